@@ -1,0 +1,207 @@
+"""Host-side helpers the sweep's callers expect (NumPy semantics).
+
+Mirrors the `jax_moseq.utils` helpers the reference imports at
+/root/reference/keypoint_moseq/fitting.py:15-16, io.py:20, util.py:15 and
+viz.py:21, and the part of `format_data` (/root/reference/keypoint_moseq/util.py:929-1089)
+that defines the (N, T, ...) layout the kernels consume.
+"""
+import warnings
+
+import numpy as np
+import torch
+
+__all__ = [
+    "batch", "unbatch", "get_nlags", "get_durations", "get_frequencies",
+    "check_for_nans", "find_optimal_segment_length", "format_data", "to_numpy_tree",
+]
+
+
+def _concat_stateseqs(stateseqs, mask=None):
+    if isinstance(stateseqs, dict):
+        return np.hstack([np.asarray(v) for v in stateseqs.values()])
+    stateseqs = np.asarray(stateseqs)
+    if mask is not None:
+        mask = np.asarray(mask)
+        return stateseqs[mask[:, -stateseqs.shape[1]:] > 0]
+    return stateseqs.reshape(-1)
+
+
+def get_nlags(Ab):
+    """Number of AR lags from the shape of Ab (..., d, d*L+1) (fitting.py:543)."""
+    return int(Ab.shape[-1] // Ab.shape[-2])
+
+
+def get_durations(stateseqs, mask=None):
+    """Run lengths of the (masked, concatenated) state sequence (viz.py:473, :575)."""
+    z = _concat_stateseqs(stateseqs, mask)
+    if z.size == 0:
+        return np.zeros(0, dtype=int)
+    changes = np.flatnonzero(np.diff(z) != 0) + 1
+    edges = np.concatenate([[0], changes, [z.size]])
+    return np.diff(edges)
+
+
+def get_frequencies(stateseqs, mask=None, num_states=None, runlength=True):
+    """State frequencies, by run onsets when `runlength` (io.py:598, viz.py:576)."""
+    z = _concat_stateseqs(stateseqs, mask).astype(int)
+    if runlength and z.size:
+        keep = np.concatenate([[True], np.diff(z) != 0])
+        z = z[keep]
+    n = 0 if num_states is None else int(num_states)
+    counts = np.bincount(z, minlength=n) if z.size else np.zeros(n)
+    tot = counts.sum()
+    return counts / tot if tot > 0 else counts.astype(float)
+
+
+def batch(data_dict, keys=None, seg_length=None, seg_overlap=30):
+    """Stack recordings into fixed-length rows (reference call: util.py:1071, :1078).
+
+    Each recording is cut at multiples of `seg_length`; every row carries
+    `seg_overlap` extra look-ahead frames and is padded to `seg_length+seg_overlap`
+    by repeating its last frame with mask 0.  Returns (stack, mask, (keys, bounds)).
+    """
+    if keys is None:
+        keys = sorted(data_dict.keys())
+    lengths = [len(data_dict[k]) for k in keys]
+    if seg_length is None:
+        seg_length = max(lengths)
+    width = seg_length + seg_overlap
+    rows, masks, okeys, bounds = [], [], [], []
+    for key, n in zip(keys, lengths):
+        arr = np.asarray(data_dict[key])
+        for start in range(0, n, seg_length):
+            end = min(start + width, n)
+            seg = arr[start:end]
+            pad = width - (end - start)
+            if pad:
+                seg = np.concatenate([seg, np.repeat(seg[-1:], pad, axis=0)], axis=0)
+            rows.append(seg)
+            m = np.zeros(width, dtype=int)
+            m[:end - start] = 1
+            masks.append(m)
+            okeys.append(key)
+            bounds.append((start, end))
+    return np.stack(rows), np.stack(masks), (okeys, np.array(bounds, dtype=int))
+
+
+def unbatch(data, keys, bounds):
+    """Inverse of `batch` (io.py:706-711): later rows overwrite the overlap."""
+    data = np.asarray(data)
+    bounds = np.asarray(bounds)
+    out = {}
+    for key in dict.fromkeys(keys):
+        idx = [i for i, kk in enumerate(keys) if kk == key]
+        length = int(bounds[idx, 1].max())
+        seq = np.zeros((length,) + data.shape[2:], dtype=data.dtype)
+        for i in idx:
+            s, e = int(bounds[i, 0]), int(bounds[i, 1])
+            seq[s:e] = data[i, :e - s]
+        out[key] = seq
+    return out
+
+
+def to_numpy_tree(tree):
+    """Device -> host for a nested dict/list/tuple of tensors (the `device_get` role)."""
+    if isinstance(tree, torch.Tensor):
+        return tree.detach().cpu().numpy()
+    if isinstance(tree, dict):
+        return {k: to_numpy_tree(v) for k, v in tree.items()}
+    if isinstance(tree, (list, tuple)):
+        return type(tree)(to_numpy_tree(v) for v in tree)
+    return tree
+
+
+def check_for_nans(model):
+    """(any_nans, nan_info, messages) over the leaves of a model dict (fitting.py:30)."""
+    nan_info, messages = [], []
+
+    def walk(node, path):
+        if isinstance(node, dict):
+            for k, v in node.items():
+                walk(v, path + (k,))
+        elif isinstance(node, (list, tuple)):
+            for i, v in enumerate(node):
+                walk(v, path + (i,))
+        elif isinstance(node, torch.Tensor):
+            if node.is_floating_point():
+                n = int(torch.isnan(node).sum().item())
+                if n:
+                    nan_info.append((path, n))
+                    messages.append(f"{n} NaNs found in {'/'.join(map(str, path))}")
+        elif isinstance(node, np.ndarray):
+            if node.dtype.kind == "f":
+                n = int(np.isnan(node).sum())
+                if n:
+                    nan_info.append((path, n))
+                    messages.append(f"{n} NaNs found in {'/'.join(map(str, path))}")
+        elif isinstance(node, float) and node != node:
+            nan_info.append((path, 1))
+            messages.append(f"NaN found in {'/'.join(map(str, path))}")
+
+    walk(model, ())
+    return len(nan_info) > 0, nan_info, messages
+
+
+def find_optimal_segment_length(sequence_lengths, max_seg_length=10_000,
+                                max_percent_padding=50, min_fragment_length=4):
+    """Segment length rule of util.py:865-926 (longest candidate within the padding budget,
+    then grown until no remainder is shorter than `min_fragment_length`)."""
+    lens = np.asarray(sequence_lengths)
+    if not np.all(lens > min_fragment_length):
+        raise AssertionError(f"All sequences must have at least {min_fragment_length + 1} elements")
+    seg = None
+    for cand in sorted(set(np.minimum(lens, max_seg_length).tolist()), reverse=True):
+        pad = (-lens % cand).sum() / lens.sum() * 100
+        if pad <= max_percent_padding:
+            seg = int(cand)
+            break
+    if seg is None:
+        warnings.warn("No segment length found that satisfies the padding constraint. "
+                      f"Using maximum value of {max_seg_length}.")
+        seg = int(max_seg_length)
+    while True:
+        rem = lens % seg
+        rem = rem[rem != 0]
+        if rem.size == 0 or np.all(rem >= min_fragment_length):
+            return seg
+        seg += int(rem.min())
+
+
+def format_data(coordinates, confidences=None, keys=None, seg_length=None, conf_pseudocount=1e-3,
+                added_noise_level=0.1, max_seg_length=10_000, max_percent_padding=50,
+                min_fragment_length=4, device=None, **kwargs):
+    """Batch recordings into the `data` dict and `metadata` tuple (util.py:1054-1089).
+
+    NaN interpolation and bodypart re-indexing are upstream of the hot path and are not
+    reproduced: coordinates must be finite.  Arrays are returned as torch tensors on
+    `device` (CUDA when available) in float64, as the reference's x64 default.
+    """
+    if keys is None:
+        keys = sorted(coordinates.keys())
+    if confidences is None:
+        confidences = {k: np.ones_like(coordinates[k][..., 0]) for k in keys}
+    for k in keys:
+        if not np.isfinite(coordinates[k]).all():
+            raise ValueError(f"non-finite coordinates in {k!r}: interpolate before format_data")
+    if not seg_length:
+        seg_length = find_optimal_segment_length(
+            [coordinates[k].shape[0] for k in keys], max_seg_length, max_percent_padding,
+            min_fragment_length)
+    Y, mask, metadata = batch(coordinates, seg_length=seg_length, keys=keys)
+    if not np.all(mask.sum(1) >= min_fragment_length):
+        raise AssertionError(f"All segments must contain at least {min_fragment_length} frames")
+    Y = Y.astype(float)
+    conf = batch(confidences, seg_length=seg_length, keys=keys)[0].astype(float)
+    if conf.min() < 0:
+        conf = np.maximum(conf, 0)
+        warnings.warn("Negative confidence values are not allowed and will be set to 0.")
+    conf = conf + conf_pseudocount
+    if added_noise_level > 0:
+        rng = np.random.default_rng(42)
+        Y += rng.uniform(-added_noise_level, added_noise_level, Y.shape)
+    if device is None:
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+    data = {"mask": torch.as_tensor(mask, device=device),
+            "Y": torch.as_tensor(Y, device=device),
+            "conf": torch.as_tensor(conf, device=device)}
+    return data, metadata
