@@ -1,0 +1,219 @@
+// Shared device helpers for the keypoint-SLDS Gibbs kernels (sm_100a).
+//
+// Randomness contract (DESIGN.md "draws"): every sampler either consumes an
+// injected tape (verification mode, pointer != nullptr) or generates its draws
+// from Philox4x32-10 keyed by the 64-bit sweep seed, with the counter built from
+// (element index, stream id, draw index).  The transforms (Marsaglia-Tsang gamma,
+// Best-Fisher von Mises, inverse-CDF categorical) are the same in both modes and
+// are evaluated in double.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define KPMS_GAMMA_R 6
+#define KPMS_VM_R 8
+#define KPMS_GAMMA_TAPE (2 * KPMS_GAMMA_R + 1)
+#define KPMS_EPS_SHIFT 1e-2
+#define KPMS_X_PRIOR_VAR 10.0
+#define KPMS_V_PRIOR_VAR 1e6
+
+// stream ids for Philox counters (one per sampler)
+enum KpmsStream : uint32_t {
+    KPMS_STREAM_Z = 1, KPMS_STREAM_X = 2, KPMS_STREAM_S = 3, KPMS_STREAM_H = 4,
+    KPMS_STREAM_V = 5, KPMS_STREAM_AR_G = 6, KPMS_STREAM_AR_B = 7, KPMS_STREAM_AR_CHI = 8,
+    KPMS_STREAM_CRP = 9, KPMS_STREAM_BIN = 10, KPMS_STREAM_BETA = 11, KPMS_STREAM_PI = 12,
+    KPMS_STREAM_SIGMA = 13
+};
+
+namespace kpms {
+
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// One logical generator per (seed, stream, element); `draw` advances inside it.
+struct Philox {
+    uint2 key;
+    uint32_t stream;
+    uint64_t elem;
+    uint32_t draw;
+    __device__ Philox(uint64_t seed, uint32_t stream_, uint64_t elem_)
+        : key(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))), stream(stream_), elem(elem_), draw(0) {}
+    __device__ __forceinline__ uint4 next4() {
+        uint4 c = make_uint4((uint32_t)elem, (uint32_t)(elem >> 32), stream, draw++);
+        return philox4x32_10(c, key);
+    }
+};
+
+__device__ __forceinline__ double u32x2_to_unit(uint32_t a, uint32_t b) {
+    // 53-bit uniform strictly inside (0,1)
+    uint64_t m = (((uint64_t)a << 32) | b) >> 11;
+    return ((double)m + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ void philox_uniform2(Philox& g, double& u0, double& u1) {
+    uint4 r = g.next4();
+    u0 = u32x2_to_unit(r.x, r.y);
+    u1 = u32x2_to_unit(r.z, r.w);
+}
+
+__device__ __forceinline__ void philox_normal2(Philox& g, double& n0, double& n1) {
+    double u0, u1;
+    philox_uniform2(g, u0, u1);
+    double r = sqrt(-2.0 * log(u0));
+    double s, c;
+    sincospi(2.0 * u1, &s, &c);
+    n0 = r * c;
+    n1 = r * s;
+}
+
+// ---------------------------------------------------------------------------
+// Gamma(a,1), Marsaglia-Tsang.  tape: KPMS_GAMMA_TAPE values [normals R | uniforms R | boost]
+// (verification mode, bounded attempts, fallback d) or nullptr (Philox, up to 64 attempts).
+// ---------------------------------------------------------------------------
+template <typename R>
+__device__ inline double gamma_draw(double a, const R* tape, Philox& g) {
+    const bool boost = a < 1.0;
+    const double a1 = boost ? a + 1.0 : a;
+    const double dd = a1 - 1.0 / 3.0;
+    const double c = 1.0 / sqrt(9.0 * dd);
+    double out = dd;
+    if (tape) {
+#pragma unroll 1
+        for (int r = 0; r < KPMS_GAMMA_R; ++r) {
+            double x = (double)tape[r], u = (double)tape[KPMS_GAMMA_R + r];
+            double vv = 1.0 + c * x;
+            if (vv > 0) {
+                double v3 = vv * vv * vv;
+                if (log(u) < 0.5 * x * x + dd - dd * v3 + dd * log(v3)) { out = dd * v3; break; }
+            }
+        }
+        if (boost) out *= pow((double)tape[2 * KPMS_GAMMA_R], 1.0 / a);
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < 64; ++r) {
+            double x, x2, u, u2;
+            philox_normal2(g, x, x2);
+            philox_uniform2(g, u, u2);
+            double vv = 1.0 + c * x;
+            if (vv > 0) {
+                double v3 = vv * vv * vv;
+                if (log(u) < 0.5 * x * x + dd - dd * v3 + dd * log(v3)) { out = dd * v3; break; }
+            }
+        }
+        if (boost) {
+            double u, u2;
+            philox_uniform2(g, u, u2);
+            out *= pow(u, 1.0 / a);
+        }
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------
+// von Mises(mu, kappa), Best-Fisher.  tape: KPMS_VM_R x 3 uniforms, or nullptr.
+// ---------------------------------------------------------------------------
+template <typename R>
+__device__ inline double vonmises_draw(double mu, double kappa, const R* tape, Philox& g) {
+    const double PI = 3.14159265358979323846;
+    double dev = 0.0;
+    if (kappa < 1e-8) {
+        double u;
+        if (tape) u = (double)tape[0];
+        else { double u2; philox_uniform2(g, u, u2); }
+        dev = PI * (2.0 * u - 1.0);
+    } else {
+        double tau = 1.0 + sqrt(1.0 + 4.0 * kappa * kappa);
+        double rho = (tau - sqrt(2.0 * tau)) / (2.0 * kappa);
+        double r = (1.0 + rho * rho) / (2.0 * rho);
+        const int R_MAX = tape ? KPMS_VM_R : 64;
+#pragma unroll 1
+        for (int a = 0; a < R_MAX; ++a) {
+            double u1, u2, u3;
+            if (tape) { u1 = (double)tape[3 * a]; u2 = (double)tape[3 * a + 1]; u3 = (double)tape[3 * a + 2]; }
+            else { double u4; philox_uniform2(g, u1, u2); philox_uniform2(g, u3, u4); }
+            double zc = cos(PI * u1);
+            double f = (1.0 + r * zc) / (r + zc);
+            double c = kappa * (r - f);
+            if ((c * (2.0 - c) - u2 > 0) || (log(c / u2) + 1.0 - c >= 0)) {
+                double fc = fmin(1.0, fmax(-1.0, f));
+                dev = (u3 > 0.5 ? 1.0 : -1.0) * acos(fc);
+                break;
+            }
+        }
+    }
+    double out = mu + dev;
+    return out - 2.0 * PI * floor((out + PI) / (2.0 * PI));
+}
+
+// ---------------------------------------------------------------------------
+// warp helpers
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { T w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+}
+
+// block-wide sum via shared scratch of >= 32 elements; result valid in all threads
+template <typename T>
+__device__ inline T block_sum(T v, T* scratch) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    T r = (lane < nw) ? scratch[lane] : T(0);
+    r = warp_sum(r);
+    return r;
+}
+
+// 16-byte vector of R (one LDS.128 / LDG.128)
+template <typename R> struct Vec16;
+template <> struct Vec16<float> { typedef float4 type; };
+template <> struct Vec16<double> { typedef double2 type; };
+
+template <typename R> __device__ __forceinline__ R rsqrt_r(R x);
+template <> __device__ __forceinline__ float rsqrt_r<float>(float x) { return rsqrtf(x); }
+template <> __device__ __forceinline__ double rsqrt_r<double>(double x) { return 1.0 / sqrt(x); }
+
+template <typename R> __device__ __forceinline__ void sincos_r(R x, R& s, R& c);
+template <> __device__ __forceinline__ void sincos_r<float>(float x, float& s, float& c) { sincosf(x, &s, &c); }
+template <> __device__ __forceinline__ void sincos_r<double>(double x, double& s, double& c) { sincos(x, &s, &c); }
+
+}  // namespace kpms
+
+// dtype dispatch for the C-ABI: 0 = f32, 1 = f64
+#define KPMS_DISPATCH_DTYPE(dtype, FN, ...)                                            \
+    ((dtype) == 0 ? FN<float>(__VA_ARGS__)                                             \
+                  : ((dtype) == 1 ? FN<double>(__VA_ARGS__)                            \
+                                  : kpms::set_error(-2, "dtype must be 0 (f32) or 1 (f64), got %d", (int)(dtype))))
+
+// compile-time (latent_dim, nlags) instantiations
+#define KPMS_FOR_EACH_DL(X) X(2, 2) X(4, 3) X(10, 3) X(16, 3)

@@ -1,0 +1,383 @@
+// Per-frame / per-keypoint resamplers of the keypoint-SLDS sweep:
+//   resample_scales, resample_heading, resample_location, resample_obs_variance statistics
+// (jax_moseq.models.keypoint_slds.gibbs, reached from keypoint_moseq/fitting.py:25).
+//
+// Ct (k*Dk, d+1) is the lifted observation operator (Gamma kron I) Cd, so that the centred,
+// aligned pose is Ybar[j][c] = Ct[j*Dk+c][:d] . x + Ct[j*Dk+c][d].
+#include "common.cuh"
+#include "../../include/kpms_b200.h"
+
+namespace kpms {
+
+// ---------------------------------------------------------------------------
+// K4: s[n,t,j] ~ ScaledInvChi2; one thread per (frame, keypoint), fully coalesced on Y/s/prior
+// ---------------------------------------------------------------------------
+template <typename R, int DK>
+__global__ void __launch_bounds__(256)
+scales_kernel(const R* __restrict__ Y, const R* __restrict__ x, const R* __restrict__ v,
+              const R* __restrict__ h, const R* __restrict__ Ct, const R* __restrict__ sigmasq,
+              const R* __restrict__ prior, double nu_s, const R* __restrict__ g_tape, uint64_t seed,
+              long long frames, int k, int d, R* __restrict__ s_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R* Cs = reinterpret_cast<R*>(smem_raw);
+    for (int i = threadIdx.x; i < k * DK * (d + 1); i += blockDim.x) Cs[i] = Ct[i];
+    __syncthreads();
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= frames * k) return;
+    const long long ft = e / k;
+    const int j = (int)(e - ft * k);
+    R sn, cs;
+    sincos_r<R>(h[ft], sn, cs);
+    R yb[DK];
+#pragma unroll
+    for (int c = 0; c < DK; ++c) {
+        const R* crow = Cs + (size_t)(j * DK + c) * (d + 1);
+        R acc = crow[d];
+        for (int a = 0; a < d; ++a) acc = fma(crow[a], x[ft * d + a], acc);
+        yb[c] = acc;
+    }
+    R r0 = cs * yb[0] - sn * yb[1], r1 = sn * yb[0] + cs * yb[1];
+    yb[0] = r0;
+    yb[1] = r1;
+    R sq = 0;
+#pragma unroll
+    for (int c = 0; c < DK; ++c) {
+        R df = Y[e * DK + c] - yb[c] - v[ft * DK + c];
+        sq = fma(df, df, sq);
+    }
+    const double variance = (double)sq / (double)sigmasq[j] + nu_s * (double)prior[e];
+    Philox gen(seed, KPMS_STREAM_S, (uint64_t)e);
+    const double gam = gamma_draw<R>(0.5 * (nu_s + DK), g_tape ? g_tape + e * KPMS_GAMMA_TAPE : nullptr, gen);
+    s_out[e] = (R)(variance / (2.0 * gam));
+}
+
+// ---------------------------------------------------------------------------
+// K9: sum_t mask * sqerr / s per keypoint (+ number of valid frames); deterministic two-stage sum
+// ---------------------------------------------------------------------------
+template <typename R, int DK>
+__global__ void __launch_bounds__(128)
+obsvar_partial_kernel(const R* __restrict__ Y, const int* __restrict__ mask, const R* __restrict__ x,
+                      const R* __restrict__ v, const R* __restrict__ h, const R* __restrict__ s,
+                      const R* __restrict__ Ct, long long frames, int k, int d, double* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R* Cs = reinterpret_cast<R*>(smem_raw);
+    __shared__ double red[32];
+    for (int i = threadIdx.x; i < k * DK * (d + 1); i += blockDim.x) Cs[i] = Ct[i];
+    __syncthreads();
+    const long long ft = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = ft < frames && mask[ft] != 0;
+    R sn = 0, cs = 1;
+    if (on) sincos_r<R>(h[ft], sn, cs);
+    for (int j = 0; j < k; ++j) {
+        double val = 0.0;
+        if (on) {
+            R yb[DK];
+#pragma unroll
+            for (int c = 0; c < DK; ++c) {
+                const R* crow = Cs + (size_t)(j * DK + c) * (d + 1);
+                R acc = crow[d];
+                for (int a = 0; a < d; ++a) acc = fma(crow[a], x[ft * d + a], acc);
+                yb[c] = acc;
+            }
+            R r0 = cs * yb[0] - sn * yb[1], r1 = sn * yb[0] + cs * yb[1];
+            yb[0] = r0;
+            yb[1] = r1;
+            R sq = 0;
+#pragma unroll
+            for (int c = 0; c < DK; ++c) {
+                R df = Y[(ft * k + j) * DK + c] - yb[c] - v[ft * DK + c];
+                sq = fma(df, df, sq);
+            }
+            val = (double)sq / (double)s[ft * k + j];
+        }
+        double tot = block_sum(val, red);
+        if (threadIdx.x == 0) partial[(size_t)blockIdx.x * (k + 1) + j] = tot;
+    }
+    double cnt = block_sum(on ? 1.0 : 0.0, red);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * (k + 1) + k] = cnt;
+}
+
+__global__ void column_sum_kernel(const double* __restrict__ partial, int rows, int cols, double* __restrict__ out) {
+    __shared__ double red[32];
+    const int c = blockIdx.x;
+    double acc = 0.0;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) acc += partial[(size_t)r * cols + c];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[c] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// K5 + K6a: heading draw and the centroid pseudo-observation (mu_t, gamma_t^2) in one pass
+// ---------------------------------------------------------------------------
+template <typename R, int DK>
+__global__ void __launch_bounds__(128)
+heading_location_kernel(const R* __restrict__ Y, const R* __restrict__ x, const R* __restrict__ v,
+                        const R* __restrict__ h_in, const R* __restrict__ s, const R* __restrict__ Ct,
+                        const R* __restrict__ sigmasq, int fix_heading, const R* __restrict__ u_tape,
+                        uint64_t seed, long long frames, int k, int d, R* __restrict__ h_out,
+                        R* __restrict__ mu, R* __restrict__ gsq) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R* Cs = reinterpret_cast<R*>(smem_raw);
+    R* sg = Cs + (size_t)k * DK * (d + 1);
+    for (int i = threadIdx.x; i < k * DK * (d + 1); i += blockDim.x) Cs[i] = Ct[i];
+    for (int i = threadIdx.x; i < k; i += blockDim.x) sg[i] = sigmasq[i];
+    __syncthreads();
+    const long long ft = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ft >= frames) return;
+    R vv[DK], sumY[DK], sumB[DK];
+#pragma unroll
+    for (int c = 0; c < DK; ++c) { vv[c] = v[ft * DK + c]; sumY[c] = 0; sumB[c] = 0; }
+    R sumw = 0, kc = 0, ks = 0;
+    for (int j = 0; j < k; ++j) {
+        const R w = (R)1 / (s[ft * k + j] * sg[j]);
+        R yb[DK], yy[DK];
+#pragma unroll
+        for (int c = 0; c < DK; ++c) {
+            const R* crow = Cs + (size_t)(j * DK + c) * (d + 1);
+            R acc = crow[d];
+            for (int a = 0; a < d; ++a) acc = fma(crow[a], x[ft * d + a], acc);
+            yb[c] = acc;
+            yy[c] = Y[(ft * k + j) * DK + c];
+            sumY[c] = fma(w, yy[c], sumY[c]);
+            sumB[c] = fma(w, yb[c], sumB[c]);
+        }
+        const R y0 = yy[0] - vv[0], y1 = yy[1] - vv[1];
+        kc = fma(w, yb[0] * y0 + yb[1] * y1, kc);
+        ks = fma(w, yb[0] * y1 - yb[1] * y0, ks);
+        sumw += w;
+    }
+    double hn;
+    if (fix_heading) hn = (double)h_in[ft];
+    else {
+        Philox gen(seed, KPMS_STREAM_H, (uint64_t)ft);
+        const double kcd = (double)kc, ksd = (double)ks;
+        hn = vonmises_draw<R>(atan2(ksd, kcd), sqrt(kcd * kcd + ksd * ksd),
+                              u_tape ? u_tape + ft * (KPMS_VM_R * 3) : nullptr, gen);
+    }
+    const R hr = (R)hn;
+    h_out[ft] = hr;
+    R sn, cs;
+    sincos_r<R>(hr, sn, cs);
+    const R g = (R)1 / sumw;
+    R rb[DK];
+#pragma unroll
+    for (int c = 0; c < DK; ++c) rb[c] = sumB[c];
+    rb[0] = cs * sumB[0] - sn * sumB[1];
+    rb[1] = sn * sumB[0] + cs * sumB[1];
+#pragma unroll
+    for (int c = 0; c < DK; ++c) mu[ft * DK + c] = (sumY[c] - rb[c]) * g;
+    gsq[ft] = g;
+}
+
+// ---------------------------------------------------------------------------
+// K6b: random-walk FFBS of the centroid; covariances are scalar multiples of I so the
+// recursion is scalar per chain with DK independent means.  One thread per chain,
+// operands fetched in independent chunks ahead of the dependent arithmetic.
+// v_out doubles as the filtered-mean stash; fP is (N,T) scratch.
+// ---------------------------------------------------------------------------
+template <typename R, int DK>
+__global__ void __launch_bounds__(32)
+location_ffbs_kernel(const R* __restrict__ mu, const R* __restrict__ gsq, const int* __restrict__ mask,
+                     double sigmasq_loc, const R* __restrict__ w_tape, uint64_t seed, int N, int T,
+                     R* __restrict__ fP, R* __restrict__ v_out) {
+    constexpr int CH = 8;
+    const int nn = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nn >= N) return;
+    const R* mun = mu + (size_t)nn * T * DK;
+    const R* gn = gsq + (size_t)nn * T;
+    const int* mk = mask + (size_t)nn * T;
+    R* fPn = fP + (size_t)nn * T;
+    R* vn = v_out + (size_t)nn * T * DK;
+    const R sl = (R)sigmasq_loc;
+    R Pp = (R)KPMS_V_PRIOR_VAR;
+    R mp[DK];
+#pragma unroll
+    for (int c = 0; c < DK; ++c) mp[c] = 0;
+    for (int t0 = 0; t0 < T; t0 += CH) {
+        R gq[CH], mq[CH][DK];
+        int on[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+            const int t = min(t0 + q, T - 1);
+            gq[q] = gn[t];
+            on[q] = mk[t];
+#pragma unroll
+            for (int c = 0; c < DK; ++c) mq[q][c] = mun[(size_t)t * DK + c];
+        }
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+            const int t = t0 + q;
+            if (t < T) {
+                if (on[q]) {
+                    const R Pc = Pp * gq[q] / (Pp + gq[q]);
+                    const R kg = Pc / gq[q];
+#pragma unroll
+                    for (int c = 0; c < DK; ++c) mp[c] = fma(kg, mq[q][c] - mp[c], mp[c]);
+                    fPn[t] = Pc;
+                    Pp = Pc + sl;
+                } else {
+                    fPn[t] = Pp;
+                }
+#pragma unroll
+                for (int c = 0; c < DK; ++c) vn[(size_t)t * DK + c] = mp[c];
+            }
+        }
+    }
+    // backward sampling
+    auto normal = [&](int t, R* out) {
+        if (w_tape) {
+#pragma unroll
+            for (int c = 0; c < DK; ++c) out[c] = w_tape[((size_t)nn * T + t) * DK + c];
+        } else {
+            Philox gen(seed, KPMS_STREAM_V, (uint64_t)nn * T + t);
+            double a0, a1, a2, a3;
+            philox_normal2(gen, a0, a1);
+            out[0] = (R)a0;
+            out[1] = (R)a1;
+            if (DK > 2) { philox_normal2(gen, a2, a3); out[DK - 1] = (R)a2; }
+        }
+    };
+    R vc[DK], wn[DK];
+    {
+        const R Pl = fPn[T - 1];
+        normal(T - 1, wn);
+        const R sd = sqrt(Pl);
+#pragma unroll
+        for (int c = 0; c < DK; ++c) { vc[c] = fma(sd, wn[c], vn[(size_t)(T - 1) * DK + c]); vn[(size_t)(T - 1) * DK + c] = vc[c]; }
+    }
+    for (int t1 = T - 2; t1 >= 0; t1 -= CH) {
+        R pq[CH], mq[CH][DK], wq[CH][DK];
+        int on[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+            const int t = max(t1 - q, 0);
+            pq[q] = fPn[t];
+            on[q] = mk[t];
+            normal(t, wq[q]);
+#pragma unroll
+            for (int c = 0; c < DK; ++c) mq[q][c] = vn[(size_t)t * DK + c];
+        }
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+            const int t = t1 - q;
+            if (t >= 0) {
+                if (on[q]) {
+                    const R gain = pq[q] / (pq[q] + sl);
+                    const R sd = sqrt(gain * sl);
+#pragma unroll
+                    for (int c = 0; c < DK; ++c) vc[c] = fma(gain, vc[c] - mq[q][c], mq[q][c]) + sd * wq[q][c];
+                }
+#pragma unroll
+                for (int c = 0; c < DK; ++c) vn[(size_t)t * DK + c] = vc[c];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+template <typename R>
+static int scales_impl(const void* Y, const void* x, const void* v, const void* h, const void* Ct,
+                       const void* sigmasq, const void* prior, double nu_s, const void* g_tape, uint64_t seed,
+                       int N, int T, int k, int Dk, int d, void* s_out, cudaStream_t st) {
+    const long long frames = (long long)N * T;
+    const long long elems = frames * k;
+    size_t smem = (size_t)k * Dk * (d + 1) * sizeof(R);
+    int blocks = (int)((elems + 255) / 256);
+    if (Dk == 2)
+        scales_kernel<R, 2><<<blocks, 256, smem, st>>>((const R*)Y, (const R*)x, (const R*)v, (const R*)h, (const R*)Ct,
+                                                       (const R*)sigmasq, (const R*)prior, nu_s, (const R*)g_tape, seed,
+                                                       frames, k, d, (R*)s_out);
+    else if (Dk == 3)
+        scales_kernel<R, 3><<<blocks, 256, smem, st>>>((const R*)Y, (const R*)x, (const R*)v, (const R*)h, (const R*)Ct,
+                                                       (const R*)sigmasq, (const R*)prior, nu_s, (const R*)g_tape, seed,
+                                                       frames, k, d, (R*)s_out);
+    else return set_error(-3, "resample_scales: keypoint dimension must be 2 or 3, got %d", Dk);
+    return check_launch("resample_scales");
+}
+
+template <typename R>
+static int obsvar_impl(const void* Y, const int* mask, const void* x, const void* v, const void* h, const void* s,
+                       const void* Ct, int N, int T, int k, int Dk, int d, double* out, void* ws, cudaStream_t st) {
+    const long long frames = (long long)N * T;
+    size_t smem = (size_t)k * Dk * (d + 1) * sizeof(R);
+    int blocks = (int)((frames + 127) / 128);
+    double* partial = reinterpret_cast<double*>(ws);
+    if (Dk == 2)
+        obsvar_partial_kernel<R, 2><<<blocks, 128, smem, st>>>((const R*)Y, mask, (const R*)x, (const R*)v, (const R*)h,
+                                                               (const R*)s, (const R*)Ct, frames, k, d, partial);
+    else if (Dk == 3)
+        obsvar_partial_kernel<R, 3><<<blocks, 128, smem, st>>>((const R*)Y, mask, (const R*)x, (const R*)v, (const R*)h,
+                                                               (const R*)s, (const R*)Ct, frames, k, d, partial);
+    else return set_error(-3, "obsvar_suffstats: keypoint dimension must be 2 or 3, got %d", Dk);
+    column_sum_kernel<<<k + 1, 256, 0, st>>>(partial, blocks, k + 1, out);
+    return check_launch("obsvar_suffstats");
+}
+
+template <typename R>
+static int headloc_impl(const void* Y, const int* mask, const void* x, const void* v_in, const void* h_in,
+                        const void* s, const void* Ct, const void* sigmasq, double sigmasq_loc, int fix_heading,
+                        const void* u_tape, const void* w_tape, uint64_t seed, int N, int T, int k, int Dk, int d,
+                        void* h_out, void* v_out, void* ws, cudaStream_t st) {
+    const long long frames = (long long)N * T;
+    size_t smem = ((size_t)k * Dk * (d + 1) + k) * sizeof(R);
+    int blocks = (int)((frames + 127) / 128);
+    char* base = reinterpret_cast<char*>(ws);
+    R* mu = reinterpret_cast<R*>(base);
+    R* gsq = reinterpret_cast<R*>(base + align_up((size_t)frames * Dk * sizeof(R), 256));
+    R* fP = reinterpret_cast<R*>(base + align_up((size_t)frames * Dk * sizeof(R), 256) + align_up((size_t)frames * sizeof(R), 256));
+#define LAUNCH(DK)                                                                                             \
+    heading_location_kernel<R, DK><<<blocks, 128, smem, st>>>(                                                 \
+        (const R*)Y, (const R*)x, (const R*)v_in, (const R*)h_in, (const R*)s, (const R*)Ct, (const R*)sigmasq, \
+        fix_heading, (const R*)u_tape, seed, frames, k, d, (R*)h_out, mu, gsq);                                \
+    location_ffbs_kernel<R, DK><<<ceil_div(N, 32), 32, 0, st>>>(mu, gsq, mask, sigmasq_loc, (const R*)w_tape,  \
+                                                                seed, N, T, fP, (R*)v_out)
+    if (Dk == 2) { LAUNCH(2); }
+    else if (Dk == 3) { LAUNCH(3); }
+    else return set_error(-3, "resample_heading_location: keypoint dimension must be 2 or 3, got %d", Dk);
+#undef LAUNCH
+    return check_launch("resample_heading_location");
+}
+
+}  // namespace kpms
+
+using namespace kpms;
+
+extern "C" {
+
+int kpms_resample_scales(int dtype, const void* Y, const void* x, const void* v, const void* h, const void* Ct,
+                         const void* sigmasq, const void* noise_prior, double nu_s, const void* g_tape,
+                         uint64_t seed, int N, int T, int k, int Dk, int d, void* s_out, void* stream) {
+    return KPMS_DISPATCH_DTYPE(dtype, scales_impl, Y, x, v, h, Ct, sigmasq, noise_prior, nu_s, g_tape, seed, N, T,
+                               k, Dk, d, s_out, (cudaStream_t)stream);
+}
+
+size_t kpms_obsvar_workspace_bytes(int N, int T, int k) {
+    return (size_t)(((long long)N * T + 127) / 128) * (k + 1) * sizeof(double);
+}
+
+int kpms_obsvar_suffstats(int dtype, const void* Y, const int32_t* mask, const void* x, const void* v,
+                          const void* h, const void* s, const void* Ct, int N, int T, int k, int Dk, int d,
+                          double* out, void* ws, void* stream) {
+    return KPMS_DISPATCH_DTYPE(dtype, obsvar_impl, Y, mask, x, v, h, s, Ct, N, T, k, Dk, d, out, ws,
+                               (cudaStream_t)stream);
+}
+
+size_t kpms_heading_location_workspace_bytes(int dtype, int N, int T, int Dk) {
+    size_t esz = dtype == 0 ? 4 : 8;
+    size_t frames = (size_t)N * T;
+    return kpms::align_up(frames * Dk * esz, 256) + 2 * kpms::align_up(frames * esz, 256);
+}
+
+int kpms_resample_heading_location(int dtype, const void* Y, const int32_t* mask, const void* x, const void* v_in,
+                                   const void* h_in, const void* s, const void* Ct, const void* sigmasq,
+                                   double sigmasq_loc, int fix_heading, const void* u_tape, const void* w_tape,
+                                   uint64_t seed, int N, int T, int k, int Dk, int d, void* h_out, void* v_out,
+                                   void* ws, void* stream) {
+    return KPMS_DISPATCH_DTYPE(dtype, headloc_impl, Y, mask, x, v_in, h_in, s, Ct, sigmasq, sigmasq_loc,
+                               fix_heading, u_tape, w_tape, seed, N, T, k, Dk, d, h_out, v_out, ws,
+                               (cudaStream_t)stream);
+}
+
+}  // extern "C"

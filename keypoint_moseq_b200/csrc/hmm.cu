@@ -1,0 +1,505 @@
+// AR-HMM path: per-frame AR log-likelihood weights (K2) and HMM forward filter /
+// backward sampler (K3).  Replaces jax_moseq.models.arhmm.resample_discrete_stateseqs,
+// marginal_log_likelihood and stateseq_marginals, reached from
+// keypoint_moseq/fitting.py:25, :536-538, :667-673.
+//
+// Layouts (row-major):
+//   x     (N, T, d)            latent trajectories
+//   mask  (N, T) int32
+//   W     (N, K, ldT)          W[n][k][t'] = exp(ll[n][t'][k] - mx[n][t']),  t' = t - L
+//   mx    (N, ldT)             per-frame max log-likelihood (0 on masked frames)
+//   filt  (N, T', ldK)         filtered state probabilities
+//   z     (N, T') int32
+#include "common.cuh"
+#include "../../include/kpms_b200.h"
+
+namespace kpms {
+
+// ---------------------------------------------------------------------------
+// per-state whitened regression operator: G_k = Lq_k^{-1} [ -A_k | I | -b_k ]  (d x F),
+// F = n + d + 1, features f = [x_{t-L} .. x_{t-1} | x_t | 1];  c_k = -sum log diag Lq - d/2 log 2pi
+// ---------------------------------------------------------------------------
+template <typename R, int D_, int L_>
+__global__ void ar_prep_kernel(const R* __restrict__ Ab, const R* __restrict__ Q, int K,
+                               R* __restrict__ G, R* __restrict__ cst, int Fp) {
+    constexpr int n = D_ * L_;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double Lq[D_][D_], Li[D_][D_];
+    for (int i = 0; i < D_; ++i)
+        for (int j = 0; j < D_; ++j) { Lq[i][j] = (double)Q[(k * D_ + i) * D_ + j]; Li[i][j] = 0.0; }
+    double logdet = 0.0;
+    for (int j = 0; j < D_; ++j) {
+        double s = Lq[j][j];
+        for (int p = 0; p < j; ++p) s -= Lq[j][p] * Lq[j][p];
+        s = sqrt(s);
+        Lq[j][j] = s;
+        logdet += log(s);
+        for (int i = j + 1; i < D_; ++i) {
+            double v = Lq[i][j];
+            for (int p = 0; p < j; ++p) v -= Lq[i][p] * Lq[j][p];
+            Lq[i][j] = v / s;
+        }
+    }
+    for (int c = 0; c < D_; ++c) {       // Li = Lq^{-1}, column by column
+        for (int i = c; i < D_; ++i) {
+            double v = (i == c) ? 1.0 : 0.0;
+            for (int p = c; p < i; ++p) v -= Lq[i][p] * Li[p][c];
+            Li[i][c] = v / Lq[i][i];
+        }
+    }
+    const R* A = Ab + (size_t)k * D_ * (n + 1);
+    R* g = G + (size_t)k * D_ * Fp;
+    for (int i = 0; i < D_; ++i) {
+        for (int j = 0; j <= n; ++j) {
+            double v = 0.0;
+            for (int p = 0; p <= i; ++p) v += Li[i][p] * (double)A[p * (n + 1) + j];
+            if (j < n) g[i * Fp + j] = (R)(-v);
+            else g[i * Fp + n + D_] = (R)(-v);
+        }
+        for (int j = 0; j < D_; ++j) g[i * Fp + n + j] = (R)Li[i][j];
+        for (int j = n + D_ + 1; j < Fp; ++j) g[i * Fp + j] = (R)0;
+    }
+    cst[k] = (R)(-logdet - 0.5 * D_ * 1.8378770664093453);
+}
+
+// ---------------------------------------------------------------------------
+// K2: log-likelihood weights.  One thread owns FPT frames (feature vectors in
+// registers); the whitened operators stream through shared memory in state chunks
+// and are read as broadcasts.  Output is written time-contiguous per state so both
+// this kernel's stores and the filter's per-column streams are coalesced.
+// ---------------------------------------------------------------------------
+template <typename R, int D_, int L_, int FPT, int KC>
+__global__ void __launch_bounds__(128)
+ar_loglik_kernel(const R* __restrict__ x, const int* __restrict__ mask, const R* __restrict__ G,
+                 const R* __restrict__ cst, int N, int T, int K, int Fp, int ldT,
+                 R* __restrict__ W, R* __restrict__ mx) {
+    constexpr int n = D_ * L_;
+    constexpr int NF = n + D_;
+    constexpr int FR = 128 * FPT;
+    constexpr int VEC = 16 / sizeof(R);
+    typedef typename Vec16<R>::type VecT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R* xs = reinterpret_cast<R*>(smem_raw);                       // (FR + L) * d
+    R* Gs = xs + align_up((size_t)(FR + L_) * D_, 4);             // KC * d * Fp
+    R* cs = Gs + (size_t)KC * D_ * Fp;                            // KC
+    const int nn = blockIdx.y;
+    const int Tp = T - L_;
+    const int t0 = blockIdx.x * FR;                               // first t' of this tile
+    const int tid = threadIdx.x;
+    const R* xrow = x + (size_t)nn * T * D_;
+    const int tile_vals = min(FR + L_, T - t0) * D_;
+    for (int i = tid; i < tile_vals; i += 128) xs[i] = xrow[(size_t)t0 * D_ + i];
+    __syncthreads();
+    R f[FPT][NF];
+    bool valid[FPT], on[FPT];
+    R best[FPT];
+#pragma unroll
+    for (int q = 0; q < FPT; ++q) {
+        int lt = tid + q * 128;
+        valid[q] = (t0 + lt) < Tp;
+        on[q] = valid[q] && mask[(size_t)nn * T + t0 + lt + L_] != 0;
+        best[q] = (R)(-INFINITY);
+#pragma unroll
+        for (int j = 0; j < NF; ++j) f[q][j] = valid[q] ? xs[lt * D_ + j] : (R)0;
+    }
+    R* Wn = W + (size_t)nn * K * ldT;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        const int kc = min(KC, K - k0);
+        __syncthreads();
+        for (int i = tid; i < kc * D_ * Fp; i += 128) Gs[i] = G[(size_t)k0 * D_ * Fp + i];
+        for (int i = tid; i < kc; i += 128) cs[i] = cst[k0 + i];
+        __syncthreads();
+        for (int kk = 0; kk < kc; ++kk) {
+            R acc[FPT];
+#pragma unroll
+            for (int q = 0; q < FPT; ++q) acc[q] = (R)0;
+#pragma unroll 2
+            for (int i = 0; i < D_; ++i) {
+                // 16-byte broadcast loads of the operator row; index NF is the bias column
+                const VecT* g = reinterpret_cast<const VecT*>(Gs + (size_t)(kk * D_ + i) * Fp);
+                R r[FPT];
+#pragma unroll
+                for (int q = 0; q < FPT; ++q) r[q] = (R)0;
+#pragma unroll
+                for (int jv = 0; jv < (NF + VEC) / VEC; ++jv) {
+                    VecT gv = g[jv];
+                    const R* ge = reinterpret_cast<const R*>(&gv);
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) {
+                        const int j = jv * VEC + c;
+                        if (j < NF) {
+#pragma unroll
+                            for (int q = 0; q < FPT; ++q) r[q] = fma(ge[c], f[q][j], r[q]);
+                        } else if (j == NF) {
+#pragma unroll
+                            for (int q = 0; q < FPT; ++q) r[q] += ge[c];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < FPT; ++q) acc[q] = fma(r[q], r[q], acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < FPT; ++q) {
+                if (valid[q]) {
+                    R ll = on[q] ? (R)(-0.5) * acc[q] + cs[kk] : (R)0;
+                    best[q] = ll > best[q] ? ll : best[q];
+                    Wn[(size_t)(k0 + kk) * ldT + t0 + tid + q * 128] = ll;
+                }
+            }
+        }
+    }
+    // second pass over this thread's own stores: W = exp(ll - max)
+#pragma unroll
+    for (int q = 0; q < FPT; ++q) {
+        if (!valid[q]) continue;
+        int tp = t0 + tid + q * 128;
+        mx[(size_t)nn * ldT + tp] = best[q];
+        for (int k = 0; k < K; ++k) {
+            R* p = Wn + (size_t)k * ldT + tp;
+            *p = exp(*p - best[q]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3 forward: scaled filter, one CTA per chain, 4 threads per state column with the
+// transition-matrix column slices resident in registers; one barrier per step.
+// ---------------------------------------------------------------------------
+template <typename R, int RPT>
+__global__ void __launch_bounds__(4 * 128)
+hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* __restrict__ pi,
+                   int K, int Tp, int ldT, int ldK, R* __restrict__ filt, double* __restrict__ logZ) {
+    constexpr int VEC = 16 / sizeof(R);
+    constexpr int RPTP = (RPT + VEC - 1) / VEC * VEC;
+    constexpr int CH = VEC;                                  // steps per prefetched chunk
+    __shared__ __align__(16) R qbuf[2][4 * RPTP];
+    __shared__ double red[32];
+    const int nn = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int j = tid >> 2, p = tid & 3;
+    const bool col = j < K;
+    R pic[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        int i = p * RPT + r;
+        pic[r] = (col && i < K) ? pi[(size_t)i * K + j] : (R)0;
+    }
+    for (int i = tid; i < 2 * 4 * RPTP; i += blockDim.x) (&qbuf[0][0])[i] = (R)0;
+    // sum of per-frame maxima (part of the log-normaliser)
+    double msum = 0.0;
+    for (int t = tid; t < Tp; t += blockDim.x) msum += (double)mx[(size_t)nn * ldT + t];
+    msum = block_sum(msum, red);
+    const R* Wc = W + ((size_t)nn * K + (col ? j : 0)) * ldT;
+    R* fl = filt + (size_t)nn * Tp * ldK;
+    const int qslot = (j / RPT) * RPTP + (j % RPT);
+    R cur[CH], nxt[CH];
+    auto load_chunk = [&](int t0, R* dst) {
+        if (t0 + CH <= ldT) {
+            if (sizeof(R) == 4) {
+                float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(Wc) + t0);
+                dst[0] = (R)v.x; dst[1] = (R)v.y; dst[2] = (R)v.z; dst[3] = (R)v.w;
+            } else {
+                double2 v = *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(Wc) + t0);
+                dst[0] = (R)v.x; dst[1] = (R)v.y;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) dst[c] = (t0 + c < ldT) ? Wc[t0 + c] : (R)0;
+        }
+    };
+    load_chunk(0, cur);
+    R pred = (R)1 / (R)K;
+    R inv_s = (R)1;
+    R qprev = (R)0;
+    double lz = 0.0;
+    int buf = 0;
+    for (int t0 = 0; t0 < Tp; t0 += CH) {
+        load_chunk(t0 + CH, nxt);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int t = t0 + c;
+            if (t >= Tp) break;
+            R qv = pred * inv_s * cur[c];
+            if (col && p == 0) {
+                qbuf[buf][qslot] = qv;
+                if (t > 0) fl[(size_t)(t - 1) * ldK + j] = qprev * inv_s;
+            }
+            __syncthreads();
+            const R* qs = &qbuf[buf][p * RPTP];
+            R a0 = 0, a1 = 0, s0 = 0, s1 = 0;
+#pragma unroll
+            for (int r = 0; r + 1 < RPT; r += 2) {
+                R q0 = qs[r], q1 = qs[r + 1];
+                a0 = fma(pic[r], q0, a0);
+                a1 = fma(pic[r + 1], q1, a1);
+                s0 += q0;
+                s1 += q1;
+            }
+            if (RPT & 1) { R q0 = qs[RPT - 1]; a0 = fma(pic[RPT - 1], q0, a0); s0 += q0; }
+            R a = a0 + a1, s = s0 + s1;
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            pred = a;
+            inv_s = (R)1 / s;
+            qprev = qv;
+            if (tid == 0) lz += log((double)s);
+            buf ^= 1;
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) cur[c] = nxt[c];
+    }
+    if (col && p == 0) fl[(size_t)(Tp - 1) * ldK + j] = qprev * inv_s;
+    if (tid == 0) logZ[nn] = lz + msum;
+}
+
+// ---------------------------------------------------------------------------
+// K3 backward: one warp per chain, VPL states per lane, pi^T resident in shared
+// memory so the column selected by z_{t+1} is a contiguous row.
+// ---------------------------------------------------------------------------
+template <typename R, int VPL, bool PI_SMEM>
+__global__ void __launch_bounds__(32)
+hmm_backward_kernel(const R* __restrict__ filt, const R* __restrict__ piT, const R* __restrict__ u_tape,
+                    uint64_t seed, int K, int Tp, int ldK, int* __restrict__ z) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R* pis = reinterpret_cast<R*>(smem_raw);
+    const int nn = blockIdx.x;
+    const int lane = threadIdx.x;
+    if (PI_SMEM) {
+        for (int i = lane; i < K * ldK; i += 32) pis[i] = piT[i];
+        __syncwarp();
+    }
+    const R* fl = filt + (size_t)nn * Tp * ldK;
+    int* zn = z + (size_t)nn * Tp;
+    R v[VPL], nx[VPL];
+    auto load_row = [&](int t, R* dst) {
+#pragma unroll
+        for (int c = 0; c < VPL; ++c) {
+            int i = lane * VPL + c;
+            dst[c] = (t >= 0 && i < K) ? fl[(size_t)t * ldK + i] : (R)0;
+        }
+    };
+    load_row(Tp - 1, v);
+    int znext = -1;
+    for (int t = Tp - 1; t >= 0; --t) {
+        load_row(t - 1, nx);
+        double u;
+        if (u_tape) u = (double)u_tape[(size_t)nn * Tp + t];
+        else {
+            Philox g(seed, KPMS_STREAM_Z, (uint64_t)nn * Tp + t);
+            double u2;
+            philox_uniform2(g, u, u2);
+        }
+        if (znext >= 0) {
+            const R* prow = (PI_SMEM ? pis : piT) + (size_t)znext * ldK;
+#pragma unroll
+            for (int c = 0; c < VPL; ++c) {
+                int i = lane * VPL + c;
+                v[c] = (i < K) ? v[c] * prow[i] : (R)0;
+            }
+        }
+        R c[VPL];
+        R run = 0;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) { run += v[q]; c[q] = run; }
+        R incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            R y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        R excl = incl - run;
+        R total = __shfl_sync(0xffffffffu, incl, 31);
+        R r = total * (R)(1.0 - u);
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+            int i = lane * VPL + q;
+            cnt += (i < K && (excl + c[q]) < r) ? 1 : 0;
+        }
+        cnt = warp_sum(cnt);
+        znext = min(cnt, K - 1);
+        if (lane == 0) zn[t] = znext;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) v[q] = nx[q];
+    }
+}
+
+template <typename R>
+__global__ void transpose_pi_kernel(const R* __restrict__ pi, int K, int ldK, R* __restrict__ piT) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * ldK) return;
+    int jn = idx / ldK, i = idx % ldK;      // piT[jn][i] = pi[i][jn]
+    piT[idx] = (i < K) ? pi[(size_t)i * K + jn] : (R)0;
+}
+
+// ---------------------------------------------------------------------------
+// smoothed marginals (stateseq_marginals): backward recursion over the stored filter
+// ---------------------------------------------------------------------------
+template <typename R>
+__global__ void hmm_smooth_kernel(const R* __restrict__ filt, const R* __restrict__ pi, int K, int Tp,
+                                  int ldK, R* __restrict__ marg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R* pis = reinterpret_cast<R*>(smem_raw);           // K*K
+    R* sm = pis + (size_t)K * K;                       // K smoothed at t+1
+    R* ratio = sm + K;                                 // K
+    R* fcur = ratio + K;                               // K
+    __shared__ R red[32];
+    const int nn = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < K * K; i += blockDim.x) pis[i] = pi[i];
+    const R* fl = filt + (size_t)nn * Tp * ldK;
+    R* mg = marg + (size_t)nn * Tp * K;
+    for (int i = tid; i < K; i += blockDim.x) { R v = fl[(size_t)(Tp - 1) * ldK + i]; sm[i] = v; mg[(size_t)(Tp - 1) * K + i] = v; }
+    __syncthreads();
+    for (int t = Tp - 2; t >= 0; --t) {
+        for (int i = tid; i < K; i += blockDim.x) fcur[i] = fl[(size_t)t * ldK + i];
+        __syncthreads();
+        for (int jn = tid; jn < K; jn += blockDim.x) {
+            R pred = 0;
+            for (int i = 0; i < K; ++i) pred = fma(fcur[i], pis[i * K + jn], pred);
+            ratio[jn] = pred > (R)0 ? sm[jn] / pred : (R)0;
+        }
+        __syncthreads();
+        R part = 0, mine = 0;
+        if (tid < K) {
+            R acc = 0;
+            for (int jn = 0; jn < K; ++jn) acc = fma(pis[tid * K + jn], ratio[jn], acc);
+            mine = fcur[tid] * acc;
+            part = mine;
+        }
+        R tot = block_sum(part, red);
+        if (tid < K) { R v = mine / tot; sm[tid] = v; mg[(size_t)t * K + tid] = v; }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------
+static inline int fp_of(int n, int d, size_t esz) { int F = n + d + 1; int v = 16 / (int)esz; return (F + v - 1) / v * v; }
+
+template <typename R>
+static size_t hmm_ws_bytes(int K, int d, int L) {
+    int Fp = fp_of(d * L, d, sizeof(R));
+    int ldK = (K + 3) / 4 * 4;
+    size_t b = 0;
+    b += align_up((size_t)K * d * Fp * sizeof(R), 256);   // G
+    b += align_up((size_t)K * sizeof(R), 256);            // cst
+    b += align_up((size_t)K * ldK * sizeof(R), 256);      // piT
+    return b;
+}
+
+template <typename R, int D_, int L_>
+static int ar_loglik_launch(const R* x, const int* mask, const R* Ab, const R* Q, int N, int T, int K,
+                            int ldT, R* W, R* mx, void* ws, cudaStream_t st) {
+    constexpr int n = D_ * L_;
+    constexpr int FPT = sizeof(R) == 4 ? 2 : 1;
+    constexpr int KC = sizeof(R) == 4 ? 32 : 16;
+    int Fp = fp_of(n, D_, sizeof(R));
+    R* G = reinterpret_cast<R*>(ws);
+    R* cst = reinterpret_cast<R*>(reinterpret_cast<char*>(ws) + align_up((size_t)K * D_ * Fp * sizeof(R), 256));
+    ar_prep_kernel<R, D_, L_><<<ceil_div(K, 64), 64, 0, st>>>(Ab, Q, K, G, cst, Fp);
+    constexpr int FR = 128 * FPT;
+    size_t smem = (align_up((size_t)(FR + L_) * D_, 4) + (size_t)KC * D_ * Fp + KC) * sizeof(R);
+    auto kern = ar_loglik_kernel<R, D_, L_, FPT, KC>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(ceil_div(T - L_, FR), N);
+    kern<<<grid, 128, smem, st>>>(x, mask, G, cst, N, T, K, Fp, ldT, W, mx);
+    return check_launch("ar_loglik");
+}
+
+template <typename R>
+static int ar_loglik_impl(const void* x, const int* mask, const void* Ab, const void* Q, int N, int T, int d,
+                          int L, int K, int ldT, void* W, void* mx, void* ws, cudaStream_t st) {
+    if (T <= L) return set_error(-3, "ar_loglik: T (%d) must exceed nlags (%d)", T, L);
+    if (ldT < T - L || ldT % 8) return set_error(-3, "ar_loglik: ldT (%d) must be a multiple of 8 and >= T-L", ldT);
+#define X(DD, LL)                                                                                         \
+    if (d == DD && L == LL)                                                                               \
+        return ar_loglik_launch<R, DD, LL>((const R*)x, mask, (const R*)Ab, (const R*)Q, N, T, K, ldT,    \
+                                           (R*)W, (R*)mx, ws, st);
+    KPMS_FOR_EACH_DL(X)
+#undef X
+    return set_error(-3, "ar_loglik: unsupported (latent_dim, nlags) = (%d, %d)", d, L);
+}
+
+template <typename R>
+static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N, int K, int Tp, int ldT,
+                            void* filt, double* logZ, cudaStream_t st) {
+    int ldK = (K + 3) / 4 * 4;
+    int Kpad = (K + 7) / 8 * 8;
+    dim3 grid(N), block(4 * Kpad);
+#define LAUNCH(RPT)                                                                                      \
+    hmm_forward_kernel<R, RPT><<<grid, block, 0, st>>>((const R*)W, (const R*)mx, (const R*)pi, K, Tp,  \
+                                                       ldT, ldK, (R*)filt, logZ)
+    if (K <= 28) LAUNCH(7);
+    else if (K <= 52) LAUNCH(13);
+    else if (K <= 100) LAUNCH(25);
+    else if (K <= 128) LAUNCH(32);
+    else return set_error(-3, "hmm_forward: num_states %d > 128 not supported", K);
+#undef LAUNCH
+    return check_launch("hmm_forward");
+}
+
+template <typename R>
+static int hmm_backward_impl(const void* filt, const void* pi, const void* u, uint64_t seed, int N, int K,
+                             int Tp, int* z, void* ws, int d, int L, cudaStream_t st) {
+    int ldK = (K + 3) / 4 * 4;
+    int Fp = fp_of(d * L, d, sizeof(R));
+    char* base = reinterpret_cast<char*>(ws);
+    R* piT = reinterpret_cast<R*>(base + align_up((size_t)K * d * Fp * sizeof(R), 256) + align_up((size_t)K * sizeof(R), 256));
+    transpose_pi_kernel<R><<<ceil_div(K * ldK, 256), 256, 0, st>>>((const R*)pi, K, ldK, piT);
+    size_t smem = (size_t)K * ldK * sizeof(R);
+    if (K > 128) return set_error(-3, "hmm_backward: num_states %d > 128 not supported", K);
+    auto kern = hmm_backward_kernel<R, 4, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<N, 32, smem, st>>>((const R*)filt, piT, (const R*)u, seed, K, Tp, ldK, z);
+    return check_launch("hmm_backward");
+}
+
+template <typename R>
+static int hmm_smooth_impl(const void* filt, const void* pi, int N, int K, int Tp, void* marg, cudaStream_t st) {
+    int ldK = (K + 3) / 4 * 4;
+    size_t smem = ((size_t)K * K + 3 * K) * sizeof(R);
+    auto kern = hmm_smooth_kernel<R>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int threads = (K + 31) / 32 * 32;
+    kern<<<N, threads, smem, st>>>((const R*)filt, (const R*)pi, K, Tp, ldK, (R*)marg);
+    return check_launch("hmm_smooth");
+}
+
+}  // namespace kpms
+
+using namespace kpms;
+
+extern "C" {
+
+size_t kpms_hmm_workspace_bytes(int dtype, int K, int d, int L) {
+    return dtype == 0 ? hmm_ws_bytes<float>(K, d, L) : hmm_ws_bytes<double>(K, d, L);
+}
+
+int kpms_ar_loglik(int dtype, const void* x, const int* mask, const void* Ab, const void* Q, int N, int T,
+                   int d, int L, int K, int ldT, void* W, void* mx, void* ws, void* stream) {
+    return KPMS_DISPATCH_DTYPE(dtype, ar_loglik_impl, x, mask, Ab, Q, N, T, d, L, K, ldT, W, mx, ws,
+                               (cudaStream_t)stream);
+}
+
+int kpms_hmm_forward(int dtype, const void* W, const void* mx, const void* pi, int N, int K, int Tp, int ldT,
+                     void* filt, double* logZ, void* stream) {
+    return KPMS_DISPATCH_DTYPE(dtype, hmm_forward_impl, W, mx, pi, N, K, Tp, ldT, filt, logZ,
+                               (cudaStream_t)stream);
+}
+
+int kpms_hmm_backward_sample(int dtype, const void* filt, const void* pi, const void* u_tape, uint64_t seed,
+                             int N, int K, int Tp, int* z, void* ws, int d, int L, void* stream) {
+    return KPMS_DISPATCH_DTYPE(dtype, hmm_backward_impl, filt, pi, u_tape, seed, N, K, Tp, z, ws, d, L,
+                               (cudaStream_t)stream);
+}
+
+int kpms_hmm_smooth(int dtype, const void* filt, const void* pi, int N, int K, int Tp, void* marg, void* stream) {
+    return KPMS_DISPATCH_DTYPE(dtype, hmm_smooth_impl, filt, pi, N, K, Tp, marg, (cudaStream_t)stream);
+}
+
+}  // extern "C"
