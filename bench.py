@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the keypoint-SLDS Gibbs sweep (BASELINE.json metric: Gibbs sweeps/s and
+frame-sweeps/s on synthetic keypoints sampled from the generative process).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # CPU arm: float64 NumPy port of the
+                                                           # reference path (jax_moseq is not installable)
+
+One "step" is one full `resample_model` sweep (all kernels, the sufficient-statistic all-reduce
+when N > 1, and the per-sweep NaN check that `fit_model` performs, fitting.py:30).  At N = 1 the
+workload is BASELINE config C2 (20 recordings x 36k frames, 12 keypoints, latent_dim 10, nlags 3,
+100 states -> 80 chains x 10 030 frames).  For N > 1 every rank holds its own C2-sized cohort
+(weak scaling; recordings shard naturally and only the packed statistics cross GPUs).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frame_sweeps_per_sec"
+UNIT = "frame-sweeps/s"
+NOMINAL_FP32_TFLOPS = 74.0   # 148 SM x 128 FMA x 2 x 1.965 GHz
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--hmm-dtype", default="float64", choices=["float32", "float64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(name):
+    from keypoint_moseq_b200.synth import CONFIGS
+    return dict(CONFIGS[name])
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([p.strip() for p in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_throughput(cfg, seconds_hint=20.0):
+    """Times the float64 NumPy port (oracle/) of the same sweep on a bounded sample of the workload.
+    Returns (frame_sweeps_per_sec, cores, sample description)."""
+    import oracle as orc
+    from keypoint_moseq_b200.synth import sample_dataset
+    chains, frames = 40, 2000
+    data, _, model = sample_dataset(recordings=chains, frames=frames, k=cfg["k"], D=cfg["D"], d=cfg["d"],
+                                    L=cfg["L"], K=cfg["K"], seed=123, seg_length=frames)
+    N, T, k, D = data["Y"].shape
+    tape = orc.make_tape(np.random.default_rng(1), N, T, k, D, cfg["d"], cfg["L"], cfg["K"])
+    t0 = time.perf_counter()
+    sweeps = 0
+    while True:
+        orc.resample_model(data, model["states"], model["params"], model["hypparams"], model["noise_prior"], tape)
+        sweeps += 1
+        if time.perf_counter() - t0 > seconds_hint * 0.5 or sweeps >= 3:
+            break
+    dt = (time.perf_counter() - t0) / sweeps
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    sample = (f"{sweeps} full sweep(s) of the float64 NumPy port on {chains} chains x {T} frames of the {k}-keypoint, "
+              f"latent_dim {cfg['d']}, {cfg['K']}-state workload ({int(data['mask'].sum())} valid frames), "
+              f"{dt:.2f} s per sweep")
+    return float(data["mask"].sum() / dt), int(cores), sample
+
+
+def run_reference(args):
+    """CPU arm: jax_moseq (the reference's engine) cannot be installed here, so the oracle port is timed."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload(args.config)
+    best = None
+    for _ in range(max(1, min(args.steps, 2))):
+        val, cores, sample = cpu_port_throughput(cfg)
+        best = val if best is None else max(best, val)
+    frames_total = cfg["recordings"] * cfg["frames"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": best, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * frames_total / best,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {cfg['recordings']} recordings x {cfg['frames']} frames, k={cfg['k']}, "
+                               f"D={cfg['D']}, latent_dim={cfg['d']}, nlags={cfg['L']}, num_states={cfg['K']} (full sweep)"},
+        "sweeps_per_sec": best / frames_total,
+        "cpu_baseline": {"value": best, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": best, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference engine jax_moseq is an unvendored dependency and jax is not installable offline; "
+                "this arm times this repo's float64 NumPy restatement (oracle/), NOT JAX",
+    }
+    print(json.dumps(line))
+
+
+def kernel_bytes_per_frame(name, cfg, esz, hmm_esz):
+    """Algorithmic HBM bytes per (chain, frame) for each kernel."""
+    d, L, K, k, D = cfg["d"], cfg["L"], cfg["K"], cfg["k"], cfg["D"]
+    n = d * L
+    rec = d * (d + 1) // 2 + d
+    stash = n + n * (n + 1) // 2
+    gh = n * n + n
+    ldK = (K + 3) // 4 * 4
+    table = {
+        "kalman_obs_info": (k * D + k + D + 1) * esz + 4 + rec * esz,
+        "kalman_forward": (rec + stash) * esz + 8,
+        "kalman_backprep": (stash + gh) * esz + 8,
+        "kalman_affine": gh * esz + d * esz,
+        "ar_loglik": d * hmm_esz + 4 + (K + 1) * hmm_esz,
+        "hmm_forward": (K + 1 + ldK) * hmm_esz,
+        "hmm_backward": ldK * hmm_esz + 4,
+        "resample_scales": (k * D + d + D + 1 + 2 * k + k) * esz,
+        "heading_location": (k * D + d + D + k) * esz + (1 + D + 1) * esz,
+        "location_ffbs": (D + 1) * esz + 4 + 2 * (D + 1) * esz,
+        "gram_partial": d * esz + 4,
+    }
+    return table.get(name)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from keypoint_moseq_b200 import _lib, gibbs
+    from keypoint_moseq_b200.synth import sample_dataset
+    from keypoint_moseq_b200.util import check_for_nans
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    _lib.load()
+
+    cfg = workload(args.config)
+    dt = torch.float32 if args.dtype == "float32" else torch.float64
+    hdt = torch.float32 if args.hmm_dtype == "float32" else torch.float64
+    esz, hesz = (4 if dt == torch.float32 else 8), (4 if hdt == torch.float32 else 8)
+    data, metadata, model = sample_dataset(recordings=cfg["recordings"], frames=cfg["frames"], k=cfg["k"], D=cfg["D"],
+                                           d=cfg["d"], L=cfg["L"], K=cfg["K"], seed=1000 + rank, kappa=1e4)
+    valid_local = int(data["mask"].sum())
+    dd = gibbs.to_device_data(data, dev, dt)
+    dm = gibbs.to_device_model(model, dev, dt)
+    opts = dict(hmm_dtype=hdt, group=group)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step(m):
+        m = gibbs.resample_model(dd, **m, **opts)
+        any_nans, _, msgs = check_for_nans(m)
+        if any_nans:
+            raise RuntimeError("NaNs in sweep: " + "; ".join(msgs))
+        return m
+
+    m = dm
+    for _ in range(max(args.warmup, 3)):
+        m = step(m)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        m = step(m)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms, float(valid_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0])
+    valid_total = float(t[1])
+    ms_per_step = ms / args.steps
+    value = valid_total / (ms_per_step * 1e-3)
+
+    # per-kernel CUDA-event timing (separate sweeps, same stream), for the roofline of the dominant kernel
+    prof = {}
+    if rank == 0 or world == 1:
+        _lib.profile(True)
+        psteps = 2
+        for _ in range(psteps):
+            m = step(m)
+        prof = _lib.profile_report()
+        _lib.profile(False)
+        prof = {k_: (v[0] / psteps, v[1] // psteps) for k_, v in prof.items()}
+    barrier()
+
+    # end to end through the public call with HOST buffers: pinned host -> device copies of the data and
+    # model every step, device -> host read of the resampled states inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        host_data = {k_: v.cpu().pin_memory() for k_, v in dd.items()}
+        host_states = {k_: v.cpu().pin_memory() for k_, v in m["states"].items()}
+        host_prior = m["noise_prior"].cpu().pin_memory()
+        host_params = {k_: v.cpu().pin_memory() for k_, v in m["params"].items()}
+        out_host = {k_: torch.empty_like(v).pin_memory() for k_, v in host_states.items()}
+        nbytes = lambda d_: sum(v.numel() * v.element_size() for v in d_.values())
+        h2d = nbytes(host_data) + nbytes(host_states) + nbytes(host_params) + host_prior.numel() * host_prior.element_size()
+        d2h = nbytes(out_host)
+        seed = m["seed"]
+        esteps = max(1, min(args.steps, 5))
+
+        def e2e_step(seed):
+            d_dev = {k_: v.to(dev, non_blocking=True) for k_, v in host_data.items()}
+            mm = {"seed": seed, "states": {k_: v.to(dev, non_blocking=True) for k_, v in host_states.items()},
+                  "params": {k_: v.to(dev, non_blocking=True) for k_, v in host_params.items()},
+                  "hypparams": m["hypparams"], "noise_prior": host_prior.to(dev, non_blocking=True)}
+            out = gibbs.resample_model(d_dev, **mm, **opts)
+            for k_, v in out["states"].items():
+                out_host[k_].copy_(v, non_blocking=True)
+            torch.cuda.synchronize()
+            if not np.isfinite(out_host["x"].numpy()).all():
+                raise RuntimeError("NaNs in e2e sweep")
+            return out["seed"]
+
+        seed = e2e_step(seed)
+        barrier()
+        e0.record()
+        for _ in range(esteps):
+            seed = e2e_step(seed)
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1) / esteps
+        te = torch.tensor([ems], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": valid_total / (float(te[0]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te[0]), "steps": esteps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    frames_rank = dd["Y"].shape[0] * dd["Y"].shape[1]
+    roofline = None
+    kernels = {}
+    if prof:
+        total = sum(v[0] for v in prof.values())
+        for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            bpf = kernel_bytes_per_frame(name, cfg, esz, hesz)
+            kernels[name] = {"ms_per_sweep": round(kms, 4), "launches": cnt, "share": round(kms / total, 4),
+                             "gbs": None if bpf is None else round(bpf * frames_rank / (kms * 1e-3) / 1e9, 1)}
+        top = max(prof.items(), key=lambda kv: kv[1][0])[0]
+        bpf = kernel_bytes_per_frame(top, cfg, esz, hesz)
+        dur = prof[top][0] / max(prof[top][1], 1)
+        ach = bpf * frames_rank / (dur * 1e-3) / 1e9 if bpf else None
+        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": None if ach is None else ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "launch_ms": dur, "algorithmic_bytes_per_launch": None if bpf is None else bpf * frames_rank,
+                    "note": "chain-serial / FP32-issue-bound kernel: HBM fraction is reported as required, "
+                            "per-step latency is the binding resource (DESIGN.md section 5)"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        val, cores, sample = cpu_port_throughput(cfg)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if dt == torch.float32 else "f64", "data": "synthetic",
+        "config": {"workload": f"{args.config} per GPU: {cfg['recordings']} recordings x {cfg['frames']} frames, "
+                               f"k={cfg['k']}, D={cfg['D']}, latent_dim={cfg['d']}, nlags={cfg['L']}, "
+                               f"num_states={cfg['K']}; full sweep (params, z, s, x, h, v) + NaN check",
+                   "chains_per_gpu": int(dd["Y"].shape[0]), "frames_per_chain": int(dd["Y"].shape[1]),
+                   "valid_frames_total": int(valid_total), "hmm_dtype": "f32" if hdt == torch.float32 else "f64",
+                   "l2": "working set per sweep (> 4 GB of filter/backward records) exceeds the 126 MB L2"},
+        "sweeps_per_sec": 1e3 / ms_per_step,
+        "gpu_launches": int(launches),
+        "e2e": e2e,
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "clocks": clk,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,11 @@ extern "C" {
 
 int kpms_version(void);
 const char* kpms_last_error(void);
+/* launch accounting: number of kernels launched by this library so far; optional per-kernel
+ * CUDA-event timing (enable, run, then report "name total_ms count" lines; report synchronises). */
+long long kpms_launch_count(void);
+void kpms_profile_enable(int on);
+int kpms_profile_report(char* buf, size_t cap);
 
 /* ---- discrete states: jax_moseq.models.arhmm.resample_discrete_stateseqs
  *      (utils.autoregression.ar_log_likelihood + utils.distributions.sample_hmm_stateseq);

@@ -21,6 +21,9 @@ _vp, _i, _d, _u64, _sz = C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_size_t
 SIGNATURES = {
     "kpms_version": (_i, []),
     "kpms_last_error": (C.c_char_p, []),
+    "kpms_launch_count": (C.c_longlong, []),
+    "kpms_profile_enable": (None, [_i]),
+    "kpms_profile_report": (_i, [C.c_char_p, _sz]),
     "kpms_hmm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "kpms_ar_loglik": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kpms_hmm_forward": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -105,3 +108,23 @@ def call(name, *args):
 def query(name, *args):
     """Invoke a size query."""
     return int(getattr(load(), name)(*args))
+
+
+def launch_count():
+    """Kernels launched by the library so far (for bench.py's `gpu_launches`)."""
+    return int(load().kpms_launch_count())
+
+
+def profile(enable):
+    load().kpms_profile_enable(1 if enable else 0)
+
+
+def profile_report():
+    """{kernel name: (total_ms, launches)} since the last report; synchronises the device."""
+    buf = C.create_string_buffer(1 << 16)
+    call("kpms_profile_report", buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, cnt = line.split()
+        out[name] = (float(ms), int(cnt))
+    return out

@@ -1,6 +1,12 @@
 // Error reporting and version for the C-ABI (include/kpms_b200.h).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 #include "common.cuh"
 #include "../../include/kpms_b200.h"
 
@@ -22,9 +28,68 @@ int check_launch(const char* what) {
     return 0;
 }
 
+// ---- launch accounting / optional per-kernel timing ----
+struct ProfEntry { const char* name; cudaEvent_t a, b; };
+static std::mutex g_mu;
+static std::vector<ProfEntry> g_prof;
+static std::atomic<long long> g_launches{0};
+static bool g_profile = false;
+
+LaunchScope::LaunchScope(const char* name, cudaStream_t st_) : slot(-1), st(st_) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_profile) {
+        ProfEntry e;
+        e.name = name;
+        cudaEventCreate(&e.a);
+        cudaEventCreate(&e.b);
+        cudaEventRecord(e.a, st);
+        std::lock_guard<std::mutex> lk(g_mu);
+        slot = (int)g_prof.size();
+        g_prof.push_back(e);
+    }
+}
+
+LaunchScope::~LaunchScope() {
+    if (slot >= 0) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        cudaEventRecord(g_prof[slot].b, st);
+    }
+}
+
 }  // namespace kpms
 
 extern "C" {
+long long kpms_launch_count(void) { return kpms::g_launches.load(); }
+
+void kpms_profile_enable(int on) { kpms::g_profile = on != 0; }
+
+// Synchronises, then writes "name total_ms count\n" lines into buf and clears the records.
+int kpms_profile_report(char* buf, size_t cap) {
+    using namespace kpms;
+    std::lock_guard<std::mutex> lk(g_mu);
+    std::map<std::string, std::pair<double, int>> acc;
+    for (auto& e : g_prof) {
+        cudaEventSynchronize(e.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        auto& slot = acc[e.name];
+        slot.first += ms;
+        slot.second += 1;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    g_prof.clear();
+    std::string out;
+    for (auto& kv : acc) {
+        char line[160];
+        snprintf(line, sizeof(line), "%s %.6f %d\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (out.size() + 1 > cap) return set_error(-4, "profile report needs %zu bytes", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
+
 int kpms_version(void) { return 100; }
 const char* kpms_last_error(void) { return kpms::g_err; }
 }

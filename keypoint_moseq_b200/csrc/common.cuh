@@ -31,6 +31,18 @@ namespace kpms {
 int set_error(int code, const char* fmt, ...);
 int check_launch(const char* what);
 
+// Every kernel launch is bracketed by a LaunchScope: it counts launches and, when profiling is
+// enabled (kpms_profile_enable), records CUDA events on the launching stream around the kernel.
+struct LaunchScope {
+    int slot;
+    cudaStream_t st;
+    LaunchScope(const char* name, cudaStream_t st);
+    ~LaunchScope();
+};
+#define KPMS_CAT2(a, b) a##b
+#define KPMS_CAT(a, b) KPMS_CAT2(a, b)
+#define KPMS_LAUNCH(name, st) kpms::LaunchScope KPMS_CAT(_launch_scope_, __LINE__)(name, st)
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

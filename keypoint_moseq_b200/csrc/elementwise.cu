@@ -285,6 +285,7 @@ static int scales_impl(const void* Y, const void* x, const void* v, const void* 
     const long long elems = frames * k;
     size_t smem = (size_t)k * Dk * (d + 1) * sizeof(R);
     int blocks = (int)((elems + 255) / 256);
+    KPMS_LAUNCH("resample_scales", st);
     if (Dk == 2)
         scales_kernel<R, 2><<<blocks, 256, smem, st>>>((const R*)Y, (const R*)x, (const R*)v, (const R*)h, (const R*)Ct,
                                                        (const R*)sigmasq, (const R*)prior, nu_s, (const R*)g_tape, seed,
@@ -304,6 +305,8 @@ static int obsvar_impl(const void* Y, const int* mask, const void* x, const void
     size_t smem = (size_t)k * Dk * (d + 1) * sizeof(R);
     int blocks = (int)((frames + 127) / 128);
     double* partial = reinterpret_cast<double*>(ws);
+    {
+    KPMS_LAUNCH("obsvar_partial", st);
     if (Dk == 2)
         obsvar_partial_kernel<R, 2><<<blocks, 128, smem, st>>>((const R*)Y, mask, (const R*)x, (const R*)v, (const R*)h,
                                                                (const R*)s, (const R*)Ct, frames, k, d, partial);
@@ -311,7 +314,8 @@ static int obsvar_impl(const void* Y, const int* mask, const void* x, const void
         obsvar_partial_kernel<R, 3><<<blocks, 128, smem, st>>>((const R*)Y, mask, (const R*)x, (const R*)v, (const R*)h,
                                                                (const R*)s, (const R*)Ct, frames, k, d, partial);
     else return set_error(-3, "obsvar_suffstats: keypoint dimension must be 2 or 3, got %d", Dk);
-    column_sum_kernel<<<k + 1, 256, 0, st>>>(partial, blocks, k + 1, out);
+    }
+    { KPMS_LAUNCH("obsvar_reduce", st); column_sum_kernel<<<k + 1, 256, 0, st>>>(partial, blocks, k + 1, out); }
     return check_launch("obsvar_suffstats");
 }
 
@@ -328,9 +332,11 @@ static int headloc_impl(const void* Y, const int* mask, const void* x, const voi
     R* gsq = reinterpret_cast<R*>(base + align_up((size_t)frames * Dk * sizeof(R), 256));
     R* fP = reinterpret_cast<R*>(base + align_up((size_t)frames * Dk * sizeof(R), 256) + align_up((size_t)frames * sizeof(R), 256));
 #define LAUNCH(DK)                                                                                             \
+    { KPMS_LAUNCH("heading_location", st);                                                                    \
     heading_location_kernel<R, DK><<<blocks, 128, smem, st>>>(                                                 \
         (const R*)Y, (const R*)x, (const R*)v_in, (const R*)h_in, (const R*)s, (const R*)Ct, (const R*)sigmasq, \
-        fix_heading, (const R*)u_tape, seed, frames, k, d, (R*)h_out, mu, gsq);                                \
+        fix_heading, (const R*)u_tape, seed, frames, k, d, (R*)h_out, mu, gsq); }                              \
+    KPMS_LAUNCH("location_ffbs", st);                                                                          \
     location_ffbs_kernel<R, DK><<<ceil_div(N, 32), 32, 0, st>>>(mu, gsq, mask, sigmasq_loc, (const R*)w_tape,  \
                                                                 seed, N, T, fP, (R*)v_out)
     if (Dk == 2) { LAUNCH(2); }

@@ -401,13 +401,14 @@ static int ar_loglik_launch(const R* x, const int* mask, const R* Ab, const R* Q
     int Fp = fp_of(n, D_, sizeof(R));
     R* G = reinterpret_cast<R*>(ws);
     R* cst = reinterpret_cast<R*>(reinterpret_cast<char*>(ws) + align_up((size_t)K * D_ * Fp * sizeof(R), 256));
-    ar_prep_kernel<R, D_, L_><<<ceil_div(K, 64), 64, 0, st>>>(Ab, Q, K, G, cst, Fp);
+    { KPMS_LAUNCH("ar_prep", st);
+    ar_prep_kernel<R, D_, L_><<<ceil_div(K, 64), 64, 0, st>>>(Ab, Q, K, G, cst, Fp); }
     constexpr int FR = 128 * FPT;
     size_t smem = (align_up((size_t)(FR + L_) * D_, 4) + (size_t)KC * D_ * Fp + KC) * sizeof(R);
     auto kern = ar_loglik_kernel<R, D_, L_, FPT, KC>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(ceil_div(T - L_, FR), N);
-    kern<<<grid, 128, smem, st>>>(x, mask, G, cst, N, T, K, Fp, ldT, W, mx);
+    { KPMS_LAUNCH("ar_loglik", st); kern<<<grid, 128, smem, st>>>(x, mask, G, cst, N, T, K, Fp, ldT, W, mx); }
     return check_launch("ar_loglik");
 }
 
@@ -432,12 +433,13 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
     int Kpad = (K + 7) / 8 * 8;
     dim3 grid(N), block(4 * Kpad);
 #define LAUNCH(RPT)                                                                                      \
+    { KPMS_LAUNCH("hmm_forward", st);                                                                  \
     hmm_forward_kernel<R, RPT><<<grid, block, 0, st>>>((const R*)W, (const R*)mx, (const R*)pi, K, Tp,  \
-                                                       ldT, ldK, (R*)filt, logZ)
-    if (K <= 28) LAUNCH(7);
-    else if (K <= 52) LAUNCH(13);
-    else if (K <= 100) LAUNCH(25);
-    else if (K <= 128) LAUNCH(32);
+                                                       ldT, ldK, (R*)filt, logZ); }
+    if (K <= 28) { LAUNCH(7); }
+    else if (K <= 52) { LAUNCH(13); }
+    else if (K <= 100) { LAUNCH(25); }
+    else if (K <= 128) { LAUNCH(32); }
     else return set_error(-3, "hmm_forward: num_states %d > 128 not supported", K);
 #undef LAUNCH
     return check_launch("hmm_forward");
@@ -450,12 +452,12 @@ static int hmm_backward_impl(const void* filt, const void* pi, const void* u, ui
     int Fp = fp_of(d * L, d, sizeof(R));
     char* base = reinterpret_cast<char*>(ws);
     R* piT = reinterpret_cast<R*>(base + align_up((size_t)K * d * Fp * sizeof(R), 256) + align_up((size_t)K * sizeof(R), 256));
-    transpose_pi_kernel<R><<<ceil_div(K * ldK, 256), 256, 0, st>>>((const R*)pi, K, ldK, piT);
+    { KPMS_LAUNCH("transpose_pi", st); transpose_pi_kernel<R><<<ceil_div(K * ldK, 256), 256, 0, st>>>((const R*)pi, K, ldK, piT); }
     size_t smem = (size_t)K * ldK * sizeof(R);
     if (K > 128) return set_error(-3, "hmm_backward: num_states %d > 128 not supported", K);
     auto kern = hmm_backward_kernel<R, 4, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<N, 32, smem, st>>>((const R*)filt, piT, (const R*)u, seed, K, Tp, ldK, z);
+    { KPMS_LAUNCH("hmm_backward", st); kern<<<N, 32, smem, st>>>((const R*)filt, piT, (const R*)u, seed, K, Tp, ldK, z); }
     return check_launch("hmm_backward");
 }
 
@@ -466,7 +468,7 @@ static int hmm_smooth_impl(const void* filt, const void* pi, int N, int K, int T
     auto kern = hmm_smooth_kernel<R>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int threads = (K + 31) / 32 * 32;
-    kern<<<N, threads, smem, st>>>((const R*)filt, (const R*)pi, K, Tp, ldK, (R*)marg);
+    { KPMS_LAUNCH("hmm_smooth", st); kern<<<N, threads, smem, st>>>((const R*)filt, (const R*)pi, K, Tp, ldK, (R*)marg); }
     return check_launch("hmm_smooth");
 }
 

@@ -620,6 +620,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
     {
         size_t smem = ((size_t)k * Dk * (D_ + 1) + k) * sizeof(R);
         int blocks = (int)((frames + 127) / 128);
+        KPMS_LAUNCH("kalman_obs_info", st);
         if (Dk == 2)
             obs_info_kernel<R, D_, 2><<<blocks, 128, smem, st>>>(Y, mask, v, h, s, sigmasq, Ct, N, T, k, L_, info);
         else
@@ -631,7 +632,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         auto kern = kalman_forward_kernel<R, D_, L_>;
         size_t smem = FwdSmem<R, D_, L_>::bytes;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<N, 256, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, T, stash_m, stash_S);
+        { KPMS_LAUNCH("kalman_forward", st); kern<<<N, 256, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, T, stash_m, stash_S); }
         int rc = check_launch("kalman forward");
         if (rc) return rc;
     }
@@ -641,7 +642,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         size_t smem = PrepSmem<R, D_, L_>::per_warp * WARPS * sizeof(R);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int blocks = (int)((frames + WARPS - 1) / WARPS);
-        kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH);
+        { KPMS_LAUNCH("kalman_backprep", st); kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH); }
         int rc = check_launch("kalman backprep");
         if (rc) return rc;
     }
@@ -650,7 +651,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         auto kern = kalman_affine_kernel<R, D_, L_, STAGES>;
         size_t smem = ((size_t)STAGES * PrepSmem<R, D_, L_>::RECS + n) * sizeof(R);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<N, 32, smem, st>>>(GH, T, x);
+        { KPMS_LAUNCH("kalman_affine", st); kern<<<N, 32, smem, st>>>(GH, T, x); }
         int rc = check_launch("kalman affine");
         if (rc) return rc;
     }

@@ -283,7 +283,8 @@ int kpms_resample_ar_params(const double* gram, const double* K_0, const double*
     size_t smem = ((size_t)4 * p * p + 3 * d * p + 4 * d * d) * sizeof(double);
     if (smem > 220 * 1024) return set_error(-3, "resample_ar_params: (latent_dim, nlags) = (%d, %d) too large", d, L);
     cudaFuncSetAttribute(ar_params_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ar_params_kernel<<<K, 32, smem, (cudaStream_t)stream>>>(gram, K_0, M_0, S_0, nu_0, w_G, w_B, g_chi, seed, d, L, Ab, Q);
+    { cudaStream_t st = (cudaStream_t)stream; KPMS_LAUNCH("ar_params", st);
+    ar_params_kernel<<<K, 32, smem, st>>>(gram, K_0, M_0, S_0, nu_0, w_G, w_B, g_chi, seed, d, L, Ab, Q); }
     return check_launch("resample_ar_params");
 }
 
@@ -303,18 +304,20 @@ int kpms_resample_hdp_transitions(const int32_t* counts, const double* betas_in,
     long long* dstarts = reinterpret_cast<long long*>(base + kpms::align_up((size_t)K * K * sizeof(long long), 256));
     int* m = reinterpret_cast<int*>(base + kpms::align_up((size_t)K * K * sizeof(long long), 256) +
                                     kpms::align_up((size_t)K * sizeof(long long), 256));
-    count_prefix_kernel<<<1, 32, 0, st>>>(counts, K, starts, dstarts);
-    crp_tables_kernel<<<K, 256, 0, st>>>(counts, betas_in, alpha, kappa, starts, u_crp, seed, K, m);
+    { KPMS_LAUNCH("trans_prefix", st); count_prefix_kernel<<<1, 32, 0, st>>>(counts, K, starts, dstarts); }
+    { KPMS_LAUNCH("trans_crp", st); crp_tables_kernel<<<K, 256, 0, st>>>(counts, betas_in, alpha, kappa, starts, u_crp, seed, K, m); }
     int threads = (K + 31) / 32 * 32;
+    { KPMS_LAUNCH("trans_betas", st);
     betas_kernel<<<1, threads, 2 * K * sizeof(double), st>>>(m, counts, betas_in, alpha, kappa, gamma, dstarts, u_bin,
-                                                             g_beta, seed, K, betas_out);
-    pi_rows_kernel<<<K, threads, 0, st>>>(counts, betas_out, alpha, kappa, g_pi, seed, K, pi);
+                                                             g_beta, seed, K, betas_out); }
+    { KPMS_LAUNCH("trans_pi", st); pi_rows_kernel<<<K, threads, 0, st>>>(counts, betas_out, alpha, kappa, g_pi, seed, K, pi); }
     return check_launch("resample_hdp_transitions");
 }
 
 int kpms_resample_obs_variance(const double* stats, double nu_sigma, double sigmasq_0, int Dk, const double* g_sig,
                                uint64_t seed, int k, double* sigmasq, void* stream) {
-    sigmasq_kernel<<<(k + 63) / 64, 64, 0, (cudaStream_t)stream>>>(stats, nu_sigma, sigmasq_0, Dk, g_sig, seed, k, sigmasq);
+    { cudaStream_t st = (cudaStream_t)stream; KPMS_LAUNCH("obs_variance", st);
+    sigmasq_kernel<<<(k + 63) / 64, 64, 0, st>>>(stats, nu_sigma, sigmasq_0, Dk, g_sig, seed, k, sigmasq); }
     return check_launch("resample_obs_variance");
 }
 

@@ -193,13 +193,13 @@ static int ar_suffstats_impl(const void* x, const int* z, const int* mask, int N
     double* partial = reinterpret_cast<double*>(base + off[3]);
     const long long total = (long long)N * (T - L);
     const int n_tiles = (int)((total + SORT_TILE - 1) / SORT_TILE);
-    tile_hist_kernel<<<n_tiles, 256, K * sizeof(int), st>>>(z, mask, N, T, L, K, tile_hist);
-    tile_scan_kernel<<<1, 128, K * sizeof(int), st>>>(tile_hist, n_tiles, K, state_start);
-    tile_scatter_kernel<<<n_tiles, 128, 0, st>>>(z, mask, tile_hist, state_start, N, T, L, K, order);
+    { KPMS_LAUNCH("sort_tile_hist", st); tile_hist_kernel<<<n_tiles, 256, K * sizeof(int), st>>>(z, mask, N, T, L, K, tile_hist); }
+    { KPMS_LAUNCH("sort_tile_scan", st); tile_scan_kernel<<<1, 128, K * sizeof(int), st>>>(tile_hist, n_tiles, K, state_start); }
+    { KPMS_LAUNCH("sort_tile_scatter", st); tile_scatter_kernel<<<n_tiles, 128, 0, st>>>(z, mask, tile_hist, state_start, N, T, L, K, order); }
     dim3 grid(GRAM_SPLIT, K);
     size_t smem = (size_t)GRAM_FT * F * sizeof(double);
-    gram_partial_kernel<R><<<grid, 256, smem, st>>>((const R*)x, order, state_start, T, d, L, partial);
-    gram_reduce_kernel<<<K, 256, 0, st>>>(partial, F * F, gram);
+    { KPMS_LAUNCH("gram_partial", st); gram_partial_kernel<R><<<grid, 256, smem, st>>>((const R*)x, order, state_start, T, d, L, partial); }
+    { KPMS_LAUNCH("gram_reduce", st); gram_reduce_kernel<<<K, 256, 0, st>>>(partial, F * F, gram); }
     return check_launch("ar_suffstats");
 }
 
@@ -219,7 +219,7 @@ int kpms_transition_counts(const int32_t* z, const int32_t* mask, int N, int T, 
     int blocks = (int)max(1LL, min((long long)148 * 4, (total + 255) / 256));
     size_t smem = (size_t)K * K * sizeof(int);
     cudaFuncSetAttribute(transition_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    transition_count_kernel<<<blocks, 256, smem, st>>>(z, mask, N, T, L, K, counts);
+    { KPMS_LAUNCH("transition_counts", st); transition_count_kernel<<<blocks, 256, smem, st>>>(z, mask, N, T, L, K, counts); }
     return check_launch("transition_counts");
 }
 

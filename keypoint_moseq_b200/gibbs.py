@@ -205,8 +205,9 @@ def resample_scales(Y, x, v, h, Cd, sigmasq, nu_s, s_0, seed64=0, g_s=None, Ct=N
         Ct = lifted_obs_matrix(Cd, k, D)
     Ctd, sg = _dev(Ct, dt, dev), _dev(sigmasq, dt, dev)
     out = torch.empty((N, T, k), dtype=dt, device=dev)
+    tape = _dev(g_s, dt, dev)          # keep converted operands alive until the launch is enqueued
     _lib.call("kpms_resample_scales", code, _lib.ptr(Y), _lib.ptr(x), _lib.ptr(v), _lib.ptr(h), _lib.ptr(Ctd),
-              _lib.ptr(sg), _lib.ptr(s_0), float(nu_s), _lib.ptr(_dev(g_s, dt, dev)), seed64, N, T, k, D, d,
+              _lib.ptr(sg), _lib.ptr(s_0), float(nu_s), _lib.ptr(tape), seed64, N, T, k, D, d,
               _lib.ptr(out), _lib.stream_ptr())
     return out
 
@@ -224,9 +225,10 @@ def resample_heading_location(Y, mask, x, v, h, s, Cd, sigmasq, sigmasq_loc, fix
     ws = _scratch("headloc_ws", _lib.query("kpms_heading_location_workspace_bytes", code, N, T, D), dev)
     h_out = torch.empty((N, T), dtype=dt, device=dev)
     v_out = torch.empty((N, T, D), dtype=dt, device=dev)
+    tu, tw = _dev(u_h, dt, dev), _dev(w_v, dt, dev)      # both must stay alive across the launch
     _lib.call("kpms_resample_heading_location", code, _lib.ptr(Y), _lib.ptr(mask), _lib.ptr(x), _lib.ptr(v),
               _lib.ptr(h), _lib.ptr(s), _lib.ptr(Ctd), _lib.ptr(sg), float(sigmasq_loc), int(bool(fix_heading)),
-              _lib.ptr(_dev(u_h, dt, dev)), _lib.ptr(_dev(w_v, dt, dev)), seed64, N, T, k, D, d,
+              _lib.ptr(tu), _lib.ptr(tw), seed64, N, T, k, D, d,
               _lib.ptr(h_out), _lib.ptr(v_out), _lib.ptr(ws), _lib.stream_ptr())
     return h_out, v_out
 
@@ -259,8 +261,9 @@ def sufficient_statistics(x, z, mask, K, obs=None):
         k, D = Y.shape[2], Y.shape[3]
         ws2 = _scratch("obsvar_ws", _lib.query("kpms_obsvar_workspace_bytes", N, T, k), dev)
         out = packed[K * F * F + K * K:]
+        Ctd = _dev(Ct, Y.dtype, dev)
         _lib.call("kpms_obsvar_suffstats", _lib.dtype_code(Y.dtype), _lib.ptr(Y), _lib.ptr(mask), _lib.ptr(x),
-                  _lib.ptr(v), _lib.ptr(h), _lib.ptr(s), _lib.ptr(_dev(Ct, Y.dtype, dev)), N, T, k, D, d,
+                  _lib.ptr(v), _lib.ptr(h), _lib.ptr(s), _lib.ptr(Ctd), N, T, k, D, d,
                   out.data_ptr(), _lib.ptr(ws2), sp)
     return packed
 
@@ -283,9 +286,11 @@ def resample_ar_params(gram, nu_0, S_0, M_0, K_0, seed64=0, w_G=None, w_B=None, 
     S0, M0, K0 = (_dev(t, f64, dev) for t in (S_0, M_0, K_0))
     Ab = torch.empty((K, d, d * L + 1), dtype=f64, device=dev)
     Q = torch.empty((K, d, d), dtype=f64, device=dev)
-    _lib.call("kpms_resample_ar_params", _lib.ptr(gram.contiguous()), _lib.ptr(K0), _lib.ptr(M0), _lib.ptr(S0),
-              float(nu_0), _lib.ptr(_dev(w_G, f64, dev)), _lib.ptr(_dev(w_B, f64, dev)),
-              _lib.ptr(_dev(g_chi, f64, dev)), seed64, K, d, L, _lib.ptr(Ab), _lib.ptr(Q), _lib.stream_ptr())
+    gram = gram.contiguous()
+    tG, tB, tC = _dev(w_G, f64, dev), _dev(w_B, f64, dev), _dev(g_chi, f64, dev)
+    _lib.call("kpms_resample_ar_params", _lib.ptr(gram), _lib.ptr(K0), _lib.ptr(M0), _lib.ptr(S0),
+              float(nu_0), _lib.ptr(tG), _lib.ptr(tB), _lib.ptr(tC), seed64, K, d, L, _lib.ptr(Ab), _lib.ptr(Q),
+              _lib.stream_ptr())
     return Ab, Q
 
 
@@ -298,10 +303,11 @@ def resample_hdp_transitions(counts, betas, alpha, kappa, gamma, seed64=0, u_crp
     ws = _scratch("trans_ws", _lib.query("kpms_transitions_workspace_bytes", K), dev)
     b_out = torch.empty(K, dtype=f64, device=dev)
     pi = torch.empty((K, K), dtype=f64, device=dev)
-    _lib.call("kpms_resample_hdp_transitions", _lib.ptr(counts), _lib.ptr(_dev(betas, f64, dev)), float(alpha),
-              float(kappa), float(gamma), _lib.ptr(_dev(u_crp, f64, dev)), _lib.ptr(_dev(u_bin, f64, dev)),
-              _lib.ptr(_dev(g_beta, f64, dev)), _lib.ptr(_dev(g_pi, f64, dev)), seed64, K, _lib.ptr(b_out),
-              _lib.ptr(pi), _lib.ptr(ws), _lib.stream_ptr())
+    b_in = _dev(betas, f64, dev)
+    t1, t2, t3, t4 = (_dev(t, f64, dev) for t in (u_crp, u_bin, g_beta, g_pi))
+    _lib.call("kpms_resample_hdp_transitions", _lib.ptr(counts), _lib.ptr(b_in), float(alpha),
+              float(kappa), float(gamma), _lib.ptr(t1), _lib.ptr(t2), _lib.ptr(t3), _lib.ptr(t4), seed64, K,
+              _lib.ptr(b_out), _lib.ptr(pi), _lib.ptr(ws), _lib.stream_ptr())
     return b_out, pi
 
 
@@ -310,8 +316,9 @@ def resample_obs_variance(obsvar, nu_sigma, sigmasq_0, D, seed64=0, g_sig=None, 
     dev = obsvar.device
     k = obsvar.numel() - 1
     out = torch.empty(k, dtype=torch.float64, device=dev)
-    _lib.call("kpms_resample_obs_variance", _lib.ptr(obsvar.contiguous()), float(nu_sigma), float(sigmasq_0), int(D),
-              _lib.ptr(_dev(g_sig, torch.float64, dev)), seed64, k, _lib.ptr(out), _lib.stream_ptr())
+    stats, tape = obsvar.contiguous(), _dev(g_sig, torch.float64, dev)
+    _lib.call("kpms_resample_obs_variance", _lib.ptr(stats), float(nu_sigma), float(sigmasq_0), int(D),
+              _lib.ptr(tape), seed64, k, _lib.ptr(out), _lib.stream_ptr())
     return out
 
 
