@@ -51,8 +51,8 @@ int kpms_ar_loglik(int dtype, const void* x, const int32_t* mask, const void* Ab
 /* filt (N,Tp,ldK), ldK = K rounded up to 4; logZ (N) double = per-chain log normaliser. */
 int kpms_hmm_forward(int dtype, const void* W, const void* mx, const void* pi, int N, int K, int Tp,
                      int ldT, void* filt, double* logZ, void* stream);
-/* z (N,Tp) int32; u_tape (N,Tp) uniforms or NULL. */
-int kpms_hmm_backward_sample(int dtype, const void* filt, const void* pi, const void* u_tape,
+/* z (N,Tp) int32; u_tape (N,Tp) uniforms or NULL, in which case u_scratch (N,Tp) receives Philox uniforms. */
+int kpms_hmm_backward_sample(int dtype, const void* filt, const void* pi, const void* u_tape, void* u_scratch,
                              uint64_t seed, int N, int K, int Tp, int32_t* z, void* ws, int d, int L,
                              void* stream);
 /* marg (N,Tp,K) smoothed marginals from the stored filter. */

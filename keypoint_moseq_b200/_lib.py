@@ -27,7 +27,7 @@ SIGNATURES = {
     "kpms_hmm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "kpms_ar_loglik": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kpms_hmm_forward": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "kpms_hmm_backward_sample": (_i, [_i, _vp, _vp, _vp, _u64, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "kpms_hmm_backward_sample": (_i, [_i, _vp, _vp, _vp, _vp, _u64, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "kpms_hmm_smooth": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "kpms_kalman_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "kpms_kalman_sample": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _u64,

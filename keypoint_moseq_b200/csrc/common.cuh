@@ -213,7 +213,7 @@ template <> struct Vec16<double> { typedef double2 type; };
 
 template <typename R> __device__ __forceinline__ R rsqrt_r(R x);
 template <> __device__ __forceinline__ float rsqrt_r<float>(float x) { return rsqrtf(x); }
-template <> __device__ __forceinline__ double rsqrt_r<double>(double x) { return 1.0 / sqrt(x); }
+template <> __device__ __forceinline__ double rsqrt_r<double>(double x) { return rsqrt(x); }
 
 template <typename R> __device__ __forceinline__ void sincos_r(R x, R& s, R& c);
 template <> __device__ __forceinline__ void sincos_r<float>(float x, float& s, float& c) { sincosf(x, &s, &c); }

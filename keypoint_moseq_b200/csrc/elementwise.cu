@@ -115,7 +115,7 @@ heading_location_kernel(const R* __restrict__ Y, const R* __restrict__ x, const 
                         const R* __restrict__ h_in, const R* __restrict__ s, const R* __restrict__ Ct,
                         const R* __restrict__ sigmasq, int fix_heading, const R* __restrict__ u_tape,
                         uint64_t seed, long long frames, int k, int d, R* __restrict__ h_out,
-                        R* __restrict__ mu, R* __restrict__ gsq) {
+                        R* __restrict__ mu, R* __restrict__ gsq, R* __restrict__ wbuf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R* Cs = reinterpret_cast<R*>(smem_raw);
     R* sg = Cs + (size_t)k * DK * (d + 1);
@@ -167,6 +167,14 @@ heading_location_kernel(const R* __restrict__ Y, const R* __restrict__ x, const 
 #pragma unroll
     for (int c = 0; c < DK; ++c) mu[ft * DK + c] = (sumY[c] - rb[c]) * g;
     gsq[ft] = g;
+    if (wbuf) {          // standard normals for the centroid FFBS, generated here so the serial scan only loads
+        Philox gen(seed, KPMS_STREAM_V, (uint64_t)ft);
+        double a0, a1;
+        philox_normal2(gen, a0, a1);
+        wbuf[ft * DK + 0] = (R)a0;
+        wbuf[ft * DK + 1] = (R)a1;
+        if (DK > 2) { philox_normal2(gen, a0, a1); wbuf[ft * DK + 2] = (R)a0; }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -178,11 +186,11 @@ heading_location_kernel(const R* __restrict__ Y, const R* __restrict__ x, const 
 template <typename R, int DK>
 __global__ void __launch_bounds__(32)
 location_ffbs_kernel(const R* __restrict__ mu, const R* __restrict__ gsq, const int* __restrict__ mask,
-                     double sigmasq_loc, const R* __restrict__ w_tape, uint64_t seed, int N, int T,
+                     double sigmasq_loc, const R* __restrict__ w_tape, int N, int T,
                      R* __restrict__ fP, R* __restrict__ v_out) {
     constexpr int CH = 8;
-    const int nn = blockIdx.x * blockDim.x + threadIdx.x;
-    if (nn >= N) return;
+    const int nn = blockIdx.x;
+    if (nn >= N || threadIdx.x != 0) return;
     const R* mun = mu + (size_t)nn * T * DK;
     const R* gn = gsq + (size_t)nn * T;
     const int* mk = mask + (size_t)nn * T;
@@ -223,19 +231,10 @@ location_ffbs_kernel(const R* __restrict__ mu, const R* __restrict__ gsq, const 
             }
         }
     }
-    // backward sampling
+    // backward sampling (w: injected tape or the normals written by heading_location_kernel)
     auto normal = [&](int t, R* out) {
-        if (w_tape) {
 #pragma unroll
-            for (int c = 0; c < DK; ++c) out[c] = w_tape[((size_t)nn * T + t) * DK + c];
-        } else {
-            Philox gen(seed, KPMS_STREAM_V, (uint64_t)nn * T + t);
-            double a0, a1, a2, a3;
-            philox_normal2(gen, a0, a1);
-            out[0] = (R)a0;
-            out[1] = (R)a1;
-            if (DK > 2) { philox_normal2(gen, a2, a3); out[DK - 1] = (R)a2; }
-        }
+        for (int c = 0; c < DK; ++c) out[c] = w_tape[((size_t)nn * T + t) * DK + c];
     };
     R vc[DK], wn[DK];
     {
@@ -331,14 +330,16 @@ static int headloc_impl(const void* Y, const int* mask, const void* x, const voi
     R* mu = reinterpret_cast<R*>(base);
     R* gsq = reinterpret_cast<R*>(base + align_up((size_t)frames * Dk * sizeof(R), 256));
     R* fP = reinterpret_cast<R*>(base + align_up((size_t)frames * Dk * sizeof(R), 256) + align_up((size_t)frames * sizeof(R), 256));
+    R* wbuf = w_tape ? nullptr : reinterpret_cast<R*>(base + align_up((size_t)frames * Dk * sizeof(R), 256) +
+                                                      2 * align_up((size_t)frames * sizeof(R), 256));
+    const R* wsrc = w_tape ? (const R*)w_tape : wbuf;
 #define LAUNCH(DK)                                                                                             \
     { KPMS_LAUNCH("heading_location", st);                                                                    \
     heading_location_kernel<R, DK><<<blocks, 128, smem, st>>>(                                                 \
         (const R*)Y, (const R*)x, (const R*)v_in, (const R*)h_in, (const R*)s, (const R*)Ct, (const R*)sigmasq, \
-        fix_heading, (const R*)u_tape, seed, frames, k, d, (R*)h_out, mu, gsq); }                              \
+        fix_heading, (const R*)u_tape, seed, frames, k, d, (R*)h_out, mu, gsq, wbuf); }                              \
     KPMS_LAUNCH("location_ffbs", st);                                                                          \
-    location_ffbs_kernel<R, DK><<<ceil_div(N, 32), 32, 0, st>>>(mu, gsq, mask, sigmasq_loc, (const R*)w_tape,  \
-                                                                seed, N, T, fP, (R*)v_out)
+    location_ffbs_kernel<R, DK><<<N, 32, 0, st>>>(mu, gsq, mask, sigmasq_loc, wsrc, N, T, fP, (R*)v_out)
     if (Dk == 2) { LAUNCH(2); }
     else if (Dk == 3) { LAUNCH(3); }
     else return set_error(-3, "resample_heading_location: keypoint dimension must be 2 or 3, got %d", Dk);
@@ -373,7 +374,7 @@ int kpms_obsvar_suffstats(int dtype, const void* Y, const int32_t* mask, const v
 size_t kpms_heading_location_workspace_bytes(int dtype, int N, int T, int Dk) {
     size_t esz = dtype == 0 ? 4 : 8;
     size_t frames = (size_t)N * T;
-    return kpms::align_up(frames * Dk * esz, 256) + 2 * kpms::align_up(frames * esz, 256);
+    return 2 * kpms::align_up(frames * Dk * esz, 256) + 2 * kpms::align_up(frames * esz, 256);
 }
 
 int kpms_resample_heading_location(int dtype, const void* Y, const int32_t* mask, const void* x, const void* v_in,

@@ -173,7 +173,7 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
                    int K, int Tp, int ldT, int ldK, R* __restrict__ filt, double* __restrict__ logZ) {
     constexpr int VEC = 16 / sizeof(R);
     constexpr int RPTP = (RPT + VEC - 1) / VEC * VEC;
-    constexpr int CH = VEC;                                  // steps per prefetched chunk
+    constexpr int CH = 8;                                    // steps per prefetched chunk (ldT % 8 == 0)
     __shared__ __align__(16) R qbuf[2][4 * RPTP];
     __shared__ double red[32];
     const int nn = blockIdx.x;
@@ -195,18 +195,19 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
     R* fl = filt + (size_t)nn * Tp * ldK;
     const int qslot = (j / RPT) * RPTP + (j % RPT);
     R cur[CH], nxt[CH];
+    typedef typename Vec16<R>::type VecT;
     auto load_chunk = [&](int t0, R* dst) {
-        if (t0 + CH <= ldT) {
-            if (sizeof(R) == 4) {
-                float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(Wc) + t0);
-                dst[0] = (R)v.x; dst[1] = (R)v.y; dst[2] = (R)v.z; dst[3] = (R)v.w;
-            } else {
-                double2 v = *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(Wc) + t0);
-                dst[0] = (R)v.x; dst[1] = (R)v.y;
+        if (t0 < ldT) {
+#pragma unroll
+            for (int v = 0; v < CH / VEC; ++v) {
+                const VecT val = *reinterpret_cast<const VecT*>(Wc + t0 + v * VEC);
+                const R* ve = reinterpret_cast<const R*>(&val);
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) dst[v * VEC + c] = ve[c];
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < CH; ++c) dst[c] = (t0 + c < ldT) ? Wc[t0 + c] : (R)0;
+            for (int c = 0; c < CH; ++c) dst[c] = (R)0;
         }
     };
     load_chunk(0, cur);
@@ -257,47 +258,73 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
 }
 
 // ---------------------------------------------------------------------------
-// K3 backward: one warp per chain, VPL states per lane, pi^T resident in shared
-// memory so the column selected by z_{t+1} is a contiguous row.
+// K3 backward: one warp per chain, VPL states per lane, pi^T resident in shared memory so the
+// column selected by z_{t+1} is a contiguous row; filtered rows arrive through a cp.async ring
+// and the uniforms (tape or pre-generated Philox draws) are fetched 32 steps at a time.
 // ---------------------------------------------------------------------------
-template <typename R, int VPL, bool PI_SMEM>
+template <typename R>
+__global__ void fill_uniform_kernel(R* __restrict__ u, long long count, uint64_t seed, uint32_t stream) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    Philox g(seed, stream, (uint64_t)e);
+    double u0, u1;
+    philox_uniform2(g, u0, u1);
+    u[e] = (R)u0;
+}
+
+template <typename R, int VPL, int STAGES>
 __global__ void __launch_bounds__(32)
-hmm_backward_kernel(const R* __restrict__ filt, const R* __restrict__ piT, const R* __restrict__ u_tape,
-                    uint64_t seed, int K, int Tp, int ldK, int* __restrict__ z) {
+hmm_backward_kernel(const R* __restrict__ filt, const R* __restrict__ piT, const R* __restrict__ u_src,
+                    int K, int Tp, int ldK, int* __restrict__ z) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    R* pis = reinterpret_cast<R*>(smem_raw);
+    R* pis = reinterpret_cast<R*>(smem_raw);                 // K x ldK
+    R* ring = pis + (size_t)K * ldK;                         // STAGES x ldK
     const int nn = blockIdx.x;
     const int lane = threadIdx.x;
-    if (PI_SMEM) {
-        for (int i = lane; i < K * ldK; i += 32) pis[i] = piT[i];
-        __syncwarp();
-    }
+    for (int i = lane; i < K * ldK; i += 32) pis[i] = piT[i];
     const R* fl = filt + (size_t)nn * Tp * ldK;
+    const R* un = u_src + (size_t)nn * Tp;
     int* zn = z + (size_t)nn * Tp;
-    R v[VPL], nx[VPL];
-    auto load_row = [&](int t, R* dst) {
-#pragma unroll
-        for (int c = 0; c < VPL; ++c) {
-            int i = lane * VPL + c;
-            dst[c] = (t >= 0 && i < K) ? fl[(size_t)t * ldK + i] : (R)0;
+    const int chunks = ldK * (int)sizeof(R) / 16;
+    auto issue = [&](int t) {
+        if (t >= 0) {
+            char* dst = reinterpret_cast<char*>(ring + (size_t)(t % STAGES) * ldK);
+            const char* src = reinterpret_cast<const char*>(fl + (size_t)t * ldK);
+            for (int c = lane; c < chunks; c += 32) {
+                unsigned d32 = (unsigned)__cvta_generic_to_shared(dst + 16 * c);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d32), "l"(src + 16 * c));
+            }
         }
+        asm volatile("cp.async.commit_group;\n" ::);
     };
-    load_row(Tp - 1, v);
+    for (int s2 = 0; s2 < STAGES - 1; ++s2) issue(Tp - 1 - s2);
+    // uniforms: block b covers steps t = Tp-1-32b-lane
+    auto load_u = [&](int blk) {
+        const int t = Tp - 1 - 32 * blk - lane;
+        return (t >= 0) ? un[t] : (R)0.5;
+    };
+    R ucur = load_u(0), unext = load_u(1);
+    __syncwarp();
     int znext = -1;
     for (int t = Tp - 1; t >= 0; --t) {
-        load_row(t - 1, nx);
-        double u;
-        if (u_tape) u = (double)u_tape[(size_t)nn * Tp + t];
-        else {
-            Philox g(seed, KPMS_STREAM_Z, (uint64_t)nn * Tp + t);
-            double u2;
-            philox_uniform2(g, u, u2);
+        const int step = Tp - 1 - t;
+        if (step > 0 && (step & 31) == 0) { ucur = unext; unext = load_u((step >> 5) + 1); }
+        const R u = __shfl_sync(0xffffffffu, ucur, step & 31);
+        issue(t - (STAGES - 1));
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(STAGES - 1));
+        __syncwarp();
+        const R* row = ring + (size_t)(t % STAGES) * ldK;
+        R v[VPL];
+#pragma unroll
+        for (int c = 0; c < VPL; ++c) {
+            const int i = lane * VPL + c;
+            v[c] = (i < K) ? row[i] : (R)0;
         }
         if (znext >= 0) {
-            const R* prow = (PI_SMEM ? pis : piT) + (size_t)znext * ldK;
+            const R* prow = pis + (size_t)znext * ldK;
 #pragma unroll
             for (int c = 0; c < VPL; ++c) {
-                int i = lane * VPL + c;
+                const int i = lane * VPL + c;
                 v[c] = (i < K) ? v[c] * prow[i] : (R)0;
             }
         }
@@ -311,20 +338,19 @@ hmm_backward_kernel(const R* __restrict__ filt, const R* __restrict__ piT, const
             R y = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += y;
         }
-        R excl = incl - run;
-        R total = __shfl_sync(0xffffffffu, incl, 31);
-        R r = total * (R)(1.0 - u);
+        const R excl = incl - run;
+        const R total = __shfl_sync(0xffffffffu, incl, 31);
+        const R r = total * ((R)1 - u);
         int cnt = 0;
 #pragma unroll
         for (int q = 0; q < VPL; ++q) {
-            int i = lane * VPL + q;
+            const int i = lane * VPL + q;
             cnt += (i < K && (excl + c[q]) < r) ? 1 : 0;
         }
-        cnt = warp_sum(cnt);
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
         znext = min(cnt, K - 1);
         if (lane == 0) zn[t] = znext;
-#pragma unroll
-        for (int q = 0; q < VPL; ++q) v[q] = nx[q];
+        __syncwarp();
     }
 }
 
@@ -446,18 +472,27 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
 }
 
 template <typename R>
-static int hmm_backward_impl(const void* filt, const void* pi, const void* u, uint64_t seed, int N, int K,
-                             int Tp, int* z, void* ws, int d, int L, cudaStream_t st) {
+static int hmm_backward_impl(const void* filt, const void* pi, const void* u, void* u_scratch, uint64_t seed, int N,
+                             int K, int Tp, int* z, void* ws, int d, int L, cudaStream_t st) {
     int ldK = (K + 3) / 4 * 4;
     int Fp = fp_of(d * L, d, sizeof(R));
     char* base = reinterpret_cast<char*>(ws);
     R* piT = reinterpret_cast<R*>(base + align_up((size_t)K * d * Fp * sizeof(R), 256) + align_up((size_t)K * sizeof(R), 256));
-    { KPMS_LAUNCH("transpose_pi", st); transpose_pi_kernel<R><<<ceil_div(K * ldK, 256), 256, 0, st>>>((const R*)pi, K, ldK, piT); }
-    size_t smem = (size_t)K * ldK * sizeof(R);
     if (K > 128) return set_error(-3, "hmm_backward: num_states %d > 128 not supported", K);
-    auto kern = hmm_backward_kernel<R, 4, true>;
+    const R* usrc = (const R*)u;
+    if (!usrc) {
+        if (!u_scratch) return set_error(-3, "hmm_backward: u_scratch (N*Tp reals) is required when no tape is given");
+        const long long count = (long long)N * Tp;
+        KPMS_LAUNCH("hmm_uniforms", st);
+        fill_uniform_kernel<R><<<(int)((count + 255) / 256), 256, 0, st>>>((R*)u_scratch, count, seed, KPMS_STREAM_Z);
+        usrc = (const R*)u_scratch;
+    }
+    { KPMS_LAUNCH("transpose_pi", st); transpose_pi_kernel<R><<<ceil_div(K * ldK, 256), 256, 0, st>>>((const R*)pi, K, ldK, piT); }
+    constexpr int STAGES = 8;
+    size_t smem = ((size_t)K * ldK + (size_t)STAGES * ldK) * sizeof(R);
+    auto kern = hmm_backward_kernel<R, 4, STAGES>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    { KPMS_LAUNCH("hmm_backward", st); kern<<<N, 32, smem, st>>>((const R*)filt, piT, (const R*)u, seed, K, Tp, ldK, z); }
+    { KPMS_LAUNCH("hmm_backward", st); kern<<<N, 32, smem, st>>>((const R*)filt, piT, usrc, K, Tp, ldK, z); }
     return check_launch("hmm_backward");
 }
 
@@ -494,9 +529,9 @@ int kpms_hmm_forward(int dtype, const void* W, const void* mx, const void* pi, i
                                (cudaStream_t)stream);
 }
 
-int kpms_hmm_backward_sample(int dtype, const void* filt, const void* pi, const void* u_tape, uint64_t seed,
-                             int N, int K, int Tp, int* z, void* ws, int d, int L, void* stream) {
-    return KPMS_DISPATCH_DTYPE(dtype, hmm_backward_impl, filt, pi, u_tape, seed, N, K, Tp, z, ws, d, L,
+int kpms_hmm_backward_sample(int dtype, const void* filt, const void* pi, const void* u_tape, void* u_scratch,
+                             uint64_t seed, int N, int K, int Tp, int* z, void* ws, int d, int L, void* stream) {
+    return KPMS_DISPATCH_DTYPE(dtype, hmm_backward_impl, filt, pi, u_tape, u_scratch, seed, N, K, Tp, z, ws, d, L,
                                (cudaStream_t)stream);
 }
 

@@ -110,18 +110,27 @@ obs_info_kernel(const R* __restrict__ Y, const int* __restrict__ mask, const R* 
 }
 
 // ---------------------------------------------------------------------------
-// K1b: serial covariance-form filter, one CTA per chain.
-// Measurement update through the well-conditioned d x d matrix B = I + Lj' P_nn Lj:
-//   U = P[:,new] Lj, V = U chol(B)^-T, P+ = P - V V', m+ = m + P+[:,new] (r - J m_new)
-// Predict with the companion structure (shift + d dense rows).
+// K1b: serial covariance-form filter, one CTA (256 threads) per chain, 4 barriers per step.
+//
+// With P the predicted covariance, Lj = chol(J_t) and B = I + Lj' P_nn Lj (eigenvalues >= 1):
+//   U = P[:,new] Lj,  V = U chol(B)^-T,  P+ = P - V V',  m+ = m + P[:,new] c - V (V_new' c),  c = r - J m_new
+// and the next prediction is assembled directly from products of the PREDICTED covariance,
+//   A P+ A' = A P A' - (A V)(A V)',   A P+ = A P - (A V) V',
+// so the dense products A P, A P A', A U do not wait for the serial d x d factorisation: they run on
+// the other warps while warps 0/1 factor B redundantly in registers (no shuffles, no barriers).
+//   phase 1: U, Lj' m_new, A P (two half-range register tiles), A m + b
+//   phase 2: A P (sum), B, c, A U
+//   phase 3: warps 0-1: chol(B), V / A V rows, V_new' c   |   warps 2-7: A P A', P[:,new] c
+//   phase 4: P+ -> stash, next predicted covariance and mean
 // ---------------------------------------------------------------------------
 template <typename R, int D_, int L_>
 struct FwdSmem {
     static constexpr int n = D_ * L_, LD = n | 1, NP = D_ * (D_ + 1) / 2, REC = NP + D_,
-                         NP2 = n * (n + 1) / 2, NA = D_ * (n + 1);
-    static constexpr size_t elems = 2 * n * LD + 2 * n + 2 * n * D_ + D_ * LD + D_ * D_ + 2 * D_ +
-                                    2 * REC + 2 * NA + 2 * D_ * D_;
-    static constexpr size_t bytes = elems * sizeof(R) + NP2 * sizeof(unsigned short) + 16;
+                         NP2 = n * (n + 1) / 2, VEC = 16 / (int)sizeof(R),
+                         DP = (D_ + VEC - 1) / VEC * VEC, AP = (n + 1 + VEC - 1) / VEC * VEC;
+    static constexpr size_t elems = 2 * n * LD + 2 * n + 2 * n * DP + 2 * D_ * DP + 3 * D_ * LD + 2 * D_ * D_ +
+                                    3 * D_ + 2 * n + 2 * REC + 2 * D_ * AP + 2 * D_ * D_;
+    static constexpr size_t bytes = (elems + 8) * sizeof(R) + NP2 * sizeof(unsigned short) + 16;
 };
 
 template <typename R, int D_, int L_>
@@ -130,25 +139,38 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
                       const R* __restrict__ Ab, const R* __restrict__ Q, R jitter, int T,
                       R* __restrict__ stash_m, R* __restrict__ stash_S) {
     typedef FwdSmem<R, D_, L_> SM;
-    constexpr int n = SM::n, LD = SM::LD, NP = SM::NP, REC = SM::REC, NP2 = SM::NP2, NA = SM::NA;
+    typedef typename Vec16<R>::type VecT;
+    constexpr int n = SM::n, LD = SM::LD, NP = SM::NP, REC = SM::REC, NP2 = SM::NP2, VEC = SM::VEC,
+                  DP = SM::DP, AP = SM::AP;
     constexpr int NT = 256;
     constexpr int NO = n - D_;                       // first index of the newest block
+    constexpr int NA = D_ * (n + 1);
     constexpr int NPRE = (REC + NA + D_ * D_ + NT - 1) / NT;
+    constexpr int GA = (D_ % 5 == 0) ? 5 : ((D_ % 4 == 0) ? 4 : ((D_ % 2 == 0) ? 2 : 1));   // A-row tile
+    constexpr int NG = D_ / GA;
+    constexpr int ES = ((n / 2) + VEC - 1) / VEC * VEC;                                      // split of the e range
+    constexpr int DV = DP / VEC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    R* P0 = reinterpret_cast<R*>(smem_raw);          // predicted covariance
-    R* P1 = P0 + n * LD;                             // filtered covariance
-    R* m0 = P1 + n * LD;
-    R* m1 = m0 + n;
-    R* U = m1 + n;
-    R* V = U + n * D_;
-    R* Tm = V + n * D_;                              // D_ x LD
-    R* Bm = Tm + D_ * LD;
+    R* base = reinterpret_cast<R*>(smem_raw);
+    R* Az = base;                                    // 2 x D_ x AP   (16-byte aligned rows: [A | b | 0])
+    R* U = Az + 2 * D_ * AP;                         // n x DP
+    R* V = U + n * DP;                               // n x DP
+    R* AU = V + n * DP;                              // D_ x DP
+    R* AV = AU + D_ * DP;                            // D_ x DP
+    R* Pb = AV + D_ * DP;                            // 2 x n x LD  (predicted covariance, ping-pong)
+    R* TPh = Pb + 2 * n * LD;                        // 2 x D_ x LD (half-range partial A P)
+    R* TP = TPh + 2 * D_ * LD;                       // D_ x LD
+    R* APA = TP + D_ * LD;                           // D_ x D_
+    R* Bm = APA + D_ * D_;                           // D_ x D_
     R* cvec = Bm + D_ * D_;
     R* tmp1 = cvec + D_;
-    R* inf = tmp1 + D_;                              // 2 x REC
-    R* Az = inf + 2 * REC;                           // 2 x NA
-    R* Qz = Az + 2 * NA;                             // 2 x D_*D_
-    unsigned short* ij = reinterpret_cast<unsigned short*>(Qz + 2 * D_ * D_);
+    R* tvec = tmp1 + D_;
+    R* pc = tvec + D_;                               // n
+    R* mp = pc + n;                                  // n
+    R* mb = mp + n;                                  // 2 x n (predicted mean, ping-pong)
+    R* inf = mb + 2 * n;                             // 2 x REC
+    R* Qz = inf + 2 * REC;                           // 2 x D_*D_
+    unsigned short* ij = reinterpret_cast<unsigned short*>(Qz + 2 * D_ * D_ + 4);
     const int nn = blockIdx.x, tid = threadIdx.x;
     const int Tx = T - L_ + 1;
     const R* inf_g = info + (size_t)nn * Tx * REC;
@@ -159,10 +181,13 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
     const R eps = (R)KPMS_EPS_SHIFT + jitter;
 
     for (int q = tid; q < NP2; q += NT) { int i, j; tri_unpack(q, i, j); ij[q] = (unsigned short)((i << 8) | j); }
-    for (int w = tid; w < n * n; w += NT) { int i = w / n, j = w % n; P0[i * LD + j] = (i == j) ? (R)KPMS_X_PRIOR_VAR : (R)0; }
-    for (int w = tid; w < n; w += NT) m0[w] = (R)0;
+    for (int w = tid; w < n * LD; w += NT) { int i = w / LD, j = w % LD; Pb[w] = (i == j) ? (R)KPMS_X_PRIOR_VAR : (R)0; }
+    for (int w = tid; w < n; w += NT) mb[w] = (R)0;
+    for (int w = tid; w < 2 * D_ * AP; w += NT) Az[w] = (R)0;
+    for (int w = tid; w < 2 * n * DP; w += NT) U[w] = (R)0;          // U and V (contiguous), padding columns stay 0
+    for (int w = tid; w < 2 * D_ * DP; w += NT) AU[w] = (R)0;        // AU and AV
+    __syncthreads();
 
-    // staged operands for step i live in buffer (i & 1)
     auto stage_load = [&](int i, int zi, R* pre) {
 #pragma unroll
         for (int q = 0; q < NPRE; ++q) {
@@ -179,7 +204,7 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
         for (int q = 0; q < NPRE; ++q) {
             int w = tid + q * NT;
             if (w < REC) inf[b * REC + w] = pre[q];
-            else if (w < REC + NA) Az[b * NA + (w - REC)] = pre[q];
+            else if (w < REC + NA) { int e = w - REC; Az[b * D_ * AP + (e / (n + 1)) * AP + (e % (n + 1))] = pre[q]; }
             else if (w < REC + NA + D_ * D_) Qz[b * D_ * D_ + (w - REC - NA)] = pre[q];
         }
     };
@@ -189,6 +214,7 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
     stage_store(0, pre);
     z_next = (Tx > 2) ? zz[1] : -1;
     int mk_cur = mk[0];
+    int pb = 0;                                      // which Pb / mb buffer holds the current prediction
     __syncthreads();
 
     for (int i = 0; i < Tx; ++i) {
@@ -198,41 +224,110 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
         if (!last) stage_load(i + 1, z_next, pre);
         const int z_next2 = (i + 2 < Tx - 1) ? zz[i + 2] : -1;
         const R* fi = inf + b * REC;
-        const R* A = Az + b * NA;
+        const R* A = Az + b * D_ * AP;
         const R* Qs = Qz + b * D_ * D_;
+        const R* P0 = Pb + pb * n * LD;
+        R* Pn = Pb + (pb ^ 1) * n * LD;
+        const R* m0 = mb + pb * n;
+        R* mn = mb + (pb ^ 1) * n;
         if (mk_cur != 0) {
-            // ---- A: U = P[:,new] Lj ; tmp1 = Lj' m_new
-            for (int w = tid; w < n * D_ + D_; w += NT) {
-                if (w < n * D_) {
-                    int r = w / D_, c = w % D_;
+            // ---------------- phase 1
+            constexpr int TPI = NG * n * 2;
+            const int n1 = (last ? 0 : TPI);
+            for (int w = tid; w < n1 + n * D_ + D_ + (last ? 0 : n); w += NT) {
+                if (w < n1) {                                   // register tile: GA rows of A x one column of P
+                    const int hh = w / (NG * n), g = (w / n) % NG, j = w % n;
+                    R acc[GA];
+#pragma unroll
+                    for (int q = 0; q < GA; ++q) acc[q] = (R)0;
+                    const int e0 = hh ? ES : 0;
+#pragma unroll
+                    for (int ev = 0; ev < (hh ? (n - ES + VEC - 1) / VEC : ES / VEC); ++ev) {
+                        R pv[VEC];
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c) { const int e = e0 + ev * VEC + c; pv[c] = (e < n) ? P0[e * LD + j] : (R)0; }
+#pragma unroll
+                        for (int q = 0; q < GA; ++q) {
+                            const VecT av = *reinterpret_cast<const VecT*>(A + (g * GA + q) * AP + e0 + ev * VEC);
+                            const R* ae = reinterpret_cast<const R*>(&av);
+#pragma unroll
+                            for (int c = 0; c < VEC; ++c) acc[q] = fma(ae[c], pv[c], acc[q]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < GA; ++q) TPh[hh * D_ * LD + (g * GA + q) * LD + j] = acc[q];
+                } else if (w < n1 + n * D_) {                   // U = P[:,new] Lj
+                    const int u = w - n1, r = u / D_, c = u % D_;
                     R acc = 0;
-                    for (int e = c; e < D_; ++e) acc = fma(P0[r * LD + NO + e], fi[e * (e + 1) / 2 + c], acc);
-                    U[w] = acc;
-                } else {
-                    int c = w - n * D_;
+#pragma unroll
+                    for (int e = 0; e < D_; ++e)
+                        if (e >= c) acc = fma(P0[r * LD + NO + e], fi[e * (e + 1) / 2 + c], acc);
+                    U[r * DP + c] = acc;
+                } else if (w < n1 + n * D_ + D_) {              // tmp1 = Lj' m_new
+                    const int c = w - n1 - n * D_;
                     R acc = 0;
-                    for (int e = c; e < D_; ++e) acc = fma(fi[e * (e + 1) / 2 + c], m0[NO + e], acc);
+#pragma unroll
+                    for (int e = 0; e < D_; ++e)
+                        if (e >= c) acc = fma(fi[e * (e + 1) / 2 + c], m0[NO + e], acc);
                     tmp1[c] = acc;
+                } else {                                        // mp = Aaug m + b
+                    const int r = w - n1 - n * D_ - D_;
+                    if (r < NO) mp[r] = m0[r + D_];
+                    else {
+                        const int a = r - NO;
+                        R acc = A[a * AP + n];
+#pragma unroll 6
+                        for (int e = 0; e < n; ++e) acc = fma(A[a * AP + e], m0[e], acc);
+                        mp[r] = acc;
+                    }
                 }
             }
             __syncthreads();
-            // ---- B: Bm = I + Lj' U[new,:] ; cvec = r - Lj tmp1
-            for (int w = tid; w < D_ * D_ + D_; w += NT) {
-                if (w < D_ * D_) {
-                    int a = w / D_, c = w % D_;
-                    R acc = (a == c) ? (R)1 : (R)0;
-                    for (int e = a; e < D_; ++e) acc = fma(fi[e * (e + 1) / 2 + a], U[(NO + e) * D_ + c], acc);
-                    Bm[w] = acc;
-                } else {
-                    int a = w - D_ * D_;
-                    R acc = fi[NP + a];
-                    for (int c = 0; c <= a; ++c) acc = fma(-fi[a * (a + 1) / 2 + c], tmp1[c], acc);
-                    cvec[a] = acc;
+            // ---------------- phase 2
+            {
+                constexpr int AUI = D_ * DV;                    // A U tiles: one A row x VEC columns of U
+                const int nau = last ? 0 : AUI;
+                const int ntp = last ? 0 : D_ * n;
+                for (int w = tid; w < nau + D_ * D_ + D_ + ntp; w += NT) {
+                    if (w < nau) {
+                        const int a = w / DV, cv = w % DV;
+                        R acc[VEC];
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c) acc[c] = (R)0;
+#pragma unroll 6
+                        for (int e = 0; e < n; ++e) {
+                            const R ae = A[a * AP + e];
+                            const VecT uv = *reinterpret_cast<const VecT*>(U + e * DP + cv * VEC);
+                            const R* ue = reinterpret_cast<const R*>(&uv);
+#pragma unroll
+                            for (int c = 0; c < VEC; ++c) acc[c] = fma(ae, ue[c], acc[c]);
+                        }
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c) AU[a * DP + cv * VEC + c] = acc[c];
+                    } else if (w < nau + D_ * D_) {             // B = I + Lj' U[new,:]
+                        const int u = w - nau, a = u / D_, c = u % D_;
+                        R acc = (a == c) ? (R)1 : (R)0;
+#pragma unroll
+                        for (int e = 0; e < D_; ++e)
+                            if (e >= a) acc = fma(fi[e * (e + 1) / 2 + a], U[(NO + e) * DP + c], acc);
+                        Bm[u] = acc;
+                    } else if (w < nau + D_ * D_ + D_) {        // c = r - Lj tmp1
+                        const int a = w - nau - D_ * D_;
+                        R acc = fi[NP + a];
+#pragma unroll
+                        for (int c = 0; c < D_; ++c)
+                            if (c <= a) acc = fma(-fi[a * (a + 1) / 2 + c], tmp1[c], acc);
+                        cvec[a] = acc;
+                    } else {                                    // A P = sum of the two half-range partials
+                        const int u = w - nau - D_ * D_ - D_, a = u / n, j = u % n;
+                        TP[a * LD + j] = TPh[a * LD + j] + TPh[D_ * LD + a * LD + j];
+                    }
                 }
             }
             __syncthreads();
-            // ---- C: every lane of warp 0 factors B redundantly in registers, then V = U Lb^-T by rows
-            if (tid < 32) {
+            // ---------------- phase 3
+            if (tid < 64) {
+                // right-looking Cholesky of B in registers, redundantly in every lane of warps 0 and 1
                 R Lb[NP];
 #pragma unroll
                 for (int a = 0; a < D_; ++a)
@@ -240,88 +335,144 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
                     for (int c = 0; c <= a; ++c) Lb[a * (a + 1) / 2 + c] = Bm[a * D_ + c];
 #pragma unroll
                 for (int c = 0; c < D_; ++c) {
-                    R sd = Lb[c * (c + 1) / 2 + c];
-#pragma unroll
-                    for (int p = 0; p < c; ++p) sd -= Lb[c * (c + 1) / 2 + p] * Lb[c * (c + 1) / 2 + p];
-                    const R inv = rsqrt_r<R>(sd);
+                    const R inv = rsqrt_r<R>(Lb[c * (c + 1) / 2 + c]);
                     Lb[c * (c + 1) / 2 + c] = inv;               // inverse diagonal
 #pragma unroll
-                    for (int a = c + 1; a < D_; ++a) {
-                        R val = Lb[a * (a + 1) / 2 + c];
+                    for (int a = c + 1; a < D_; ++a) Lb[a * (a + 1) / 2 + c] *= inv;
 #pragma unroll
-                        for (int p = 0; p < c; ++p) val -= Lb[a * (a + 1) / 2 + p] * Lb[c * (c + 1) / 2 + p];
-                        Lb[a * (a + 1) / 2 + c] = val * inv;
-                    }
+                    for (int a = c + 1; a < D_; ++a)
+#pragma unroll
+                        for (int bb = c + 1; bb <= a; ++bb)
+                            Lb[a * (a + 1) / 2 + bb] = fma(-Lb[a * (a + 1) / 2 + c], Lb[bb * (bb + 1) / 2 + c], Lb[a * (a + 1) / 2 + bb]);
                 }
-                for (int r = tid; r < n; r += 32) {
+                // rows of V = U Lb^-T (warp 0) and of A V = (A U) Lb^-T (warp 1)
+                const int lane = tid & 31;
+                const bool w1 = tid >= 32;
+                const R* src = w1 ? AU : U;
+                R* dst = w1 ? AV : V;
+                const int rows = w1 ? (last ? 0 : D_) : n;
+                for (int r = lane; r < rows; r += 32) {
                     R vr[D_];
 #pragma unroll
                     for (int c = 0; c < D_; ++c) {
-                        R val = U[r * D_ + c];
+                        R val = src[r * DP + c];
 #pragma unroll
-                        for (int p = 0; p < c; ++p) val -= Lb[c * (c + 1) / 2 + p] * vr[p];
+                        for (int p2 = 0; p2 < c; ++p2) val = fma(-Lb[c * (c + 1) / 2 + p2], vr[p2], val);
                         vr[c] = val * Lb[c * (c + 1) / 2 + c];
-                        V[r * D_ + c] = vr[c];
+                        dst[r * DP + c] = vr[c];
+                    }
+                }
+                if (!w1) {
+                    __syncwarp();
+                    if (lane < D_) {                            // tvec = V_new' c
+                        R acc = 0;
+#pragma unroll
+                        for (int r = 0; r < D_; ++r) acc = fma(V[(NO + r) * DP + lane], cvec[r], acc);
+                        tvec[lane] = acc;
+                    }
+                }
+            } else {
+                const int t2 = tid - 64;
+                const int napa = last ? 0 : NP;
+                for (int w = t2; w < napa + n; w += NT - 64) {
+                    if (w < napa) {                             // A P A' (lower)
+                        const int a = ij[w] >> 8, c = ij[w] & 255;
+                        R a0 = 0, a1 = 0;
+#pragma unroll 5
+                        for (int e = 0; e + 1 < n; e += 2) {
+                            a0 = fma(TP[a * LD + e], A[c * AP + e], a0);
+                            a1 = fma(TP[a * LD + e + 1], A[c * AP + e + 1], a1);
+                        }
+                        if (n & 1) a0 = fma(TP[a * LD + n - 1], A[c * AP + n - 1], a0);
+                        APA[a * D_ + c] = a0 + a1;
+                    } else {                                    // pc = P[:,new] c
+                        const int r = w - napa;
+                        R acc = 0;
+#pragma unroll
+                        for (int c = 0; c < D_; ++c) acc = fma(P0[r * LD + NO + c], cvec[c], acc);
+                        pc[r] = acc;
                     }
                 }
             }
             __syncthreads();
-            // ---- D: P+ = P - V V' (lower computed, mirrored), stash packed lower
-            for (int q = tid; q < NP2; q += NT) {
-                int r = ij[q] >> 8, c = ij[q] & 255;
-                R acc = P0[r * LD + c];
-#pragma unroll
-                for (int e = 0; e < D_; ++e) acc = fma(-V[r * D_ + e], V[c * D_ + e], acc);
-                P1[r * LD + c] = acc;
-                P1[c * LD + r] = acc;
-                sS_g[(size_t)i * NP2 + q] = acc;
-            }
-            __syncthreads();
-            // ---- E: m+ = m + P+[:,new] cvec ; Tm = A P+
-            for (int w = tid; w < n + (last ? 0 : D_ * n); w += NT) {
-                if (w < n) {
-                    R acc = m0[w];
-#pragma unroll
-                    for (int c = 0; c < D_; ++c) acc = fma(P1[w * LD + NO + c], cvec[c], acc);
-                    m1[w] = acc;
-                    sm_g[(size_t)i * n + w] = acc;
-                } else {
-                    int a = (w - n) / n, c = (w - n) % n;
+            // ---------------- phase 4
+            {
+                auto rowdot = [&](const R* x, const R* y) {
                     R acc = 0;
-                    for (int e = 0; e < n; ++e) acc = fma(A[a * (n + 1) + e], P1[e * LD + c], acc);
-                    Tm[a * LD + c] = acc;
-                }
-            }
-            __syncthreads();
-            // ---- F: predict into P0 / m0
-            if (!last) {
-                for (int w = tid; w < NO * NO; w += NT) {
-                    int r = w / NO, c = w % NO;
-                    P0[r * LD + c] = P1[(r + D_) * LD + c + D_] + ((r == c) ? eps : (R)0);
-                }
-                for (int w = tid; w < D_ * NO; w += NT) {
-                    int a = w / NO, c = w % NO;
-                    R val = Tm[a * LD + c + D_];
-                    P0[(NO + a) * LD + c] = val;
-                    P0[c * LD + NO + a] = val;
-                }
-                for (int w = tid; w < NP; w += NT) {
-                    int a = ij[w] >> 8, c = ij[w] & 255;
-                    R acc = Qs[a * D_ + c] + ((a == c) ? jitter : (R)0);
-                    for (int e = 0; e < n; ++e) acc = fma(Tm[a * LD + e], A[c * (n + 1) + e], acc);
-                    P0[(NO + a) * LD + NO + c] = acc;
-                    P0[(NO + c) * LD + NO + a] = acc;
-                }
-                for (int w = tid; w < n; w += NT) {
-                    if (w < NO) m0[w] = m1[w + D_];
-                    else {
-                        int a = w - NO;
-                        R acc = A[a * (n + 1) + n];
-                        for (int e = 0; e < n; ++e) acc = fma(A[a * (n + 1) + e], m1[e], acc);
-                        m0[w] = acc;
+#pragma unroll
+                    for (int cv = 0; cv < DV; ++cv) {
+                        const VecT xa = *reinterpret_cast<const VecT*>(x + cv * VEC);
+                        const VecT ya = *reinterpret_cast<const VecT*>(y + cv * VEC);
+                        const R* xe = reinterpret_cast<const R*>(&xa);
+                        const R* ye = reinterpret_cast<const R*>(&ya);
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c) acc = fma(xe[c], ye[c], acc);
+                    }
+                    return acc;
+                };
+                const int nmn = last ? 0 : D_;                  // new-block mean rows (heaviest items first)
+                const int nno = last ? 0 : D_ * NO;
+                const int nnn = last ? 0 : NP;
+                const int nmo = last ? 0 : NO;
+                for (int w = tid; w < nmn + NP2 + nno + nnn + n + nmo; w += NT) {
+                    int u = w;
+                    if (u < nmn) {                              // m'[new] = mp + A pc - (A V) tvec
+                        const int a = u;
+                        R acc = mp[NO + a];
+#pragma unroll 6
+                        for (int e = 0; e < n; ++e) acc = fma(A[a * AP + e], pc[e], acc);
+#pragma unroll
+                        for (int c = 0; c < D_; ++c) acc = fma(-AV[a * DP + c], tvec[c], acc);
+                        mn[NO + a] = acc;
+                        continue;
+                    }
+                    u -= nmn;
+                    if (u < NP2) {                              // P+ (stash) and the shifted old-old block
+                        const int r = ij[u] >> 8, c = ij[u] & 255;
+                        const R val = P0[r * LD + c] - rowdot(V + r * DP, V + c * DP);
+                        sS_g[(size_t)i * NP2 + u] = val;
+                        if (!last && c >= D_) {
+                            const R v2 = val + ((r == c) ? eps : (R)0);
+                            Pn[(r - D_) * LD + (c - D_)] = v2;
+                            Pn[(c - D_) * LD + (r - D_)] = v2;
+                        }
+                        continue;
+                    }
+                    u -= NP2;
+                    if (u < nno) {                              // new-old block
+                        const int a = u / NO, j = u % NO;
+                        const R val = TP[a * LD + j + D_] - rowdot(AV + a * DP, V + (j + D_) * DP);
+                        Pn[(NO + a) * LD + j] = val;
+                        Pn[j * LD + NO + a] = val;
+                        continue;
+                    }
+                    u -= nno;
+                    if (u < nnn) {                              // new-new block
+                        const int a = ij[u] >> 8, c = ij[u] & 255;
+                        const R val = APA[a * D_ + c] - rowdot(AV + a * DP, AV + c * DP) + Qs[a * D_ + c] +
+                                      ((a == c) ? jitter : (R)0);
+                        Pn[(NO + a) * LD + NO + c] = val;
+                        Pn[(NO + c) * LD + NO + a] = val;
+                        continue;
+                    }
+                    u -= nnn;
+                    if (u < n) {                                // m+ (stash)
+                        R acc = m0[u] + pc[u];
+#pragma unroll
+                        for (int c = 0; c < D_; ++c) acc = fma(-V[u * DP + c], tvec[c], acc);
+                        sm_g[(size_t)i * n + u] = acc;
+                        continue;
+                    }
+                    u -= n;
+                    {                                           // m'[old] = mp + delta[shifted]
+                        R acc = mp[u] + pc[u + D_];
+#pragma unroll
+                        for (int c = 0; c < D_; ++c) acc = fma(-V[(u + D_) * DP + c], tvec[c], acc);
+                        mn[u] = acc;
                     }
                 }
             }
+            if (!last) pb ^= 1;
         } else if (last) {
             for (int q = tid; q < NP2; q += NT) {
                 int r = ij[q] >> 8, c = ij[q] & 255;
@@ -564,12 +715,18 @@ kalman_affine_kernel(const R* __restrict__ GH, int T, R* __restrict__ x) {
             R a0 = 0, a1 = 0;
             if (r < n) {
                 a0 = Gs[NN + r];
-#pragma unroll 4
-                for (int c = 0; c + 1 < n; c += 2) {
+                R a2 = 0, a3 = 0;
+#pragma unroll
+                for (int c = 0; c + 3 < n; c += 4) {
                     a0 = fma(Gs[c * n + r], xi[c], a0);
                     a1 = fma(Gs[(c + 1) * n + r], xi[c + 1], a1);
+                    a2 = fma(Gs[(c + 2) * n + r], xi[c + 2], a2);
+                    a3 = fma(Gs[(c + 3) * n + r], xi[c + 3], a3);
                 }
-                if (n & 1) a0 = fma(Gs[(n - 1) * n + r], xi[n - 1], a0);
+#pragma unroll
+                for (int c = n / 4 * 4; c < n; ++c) a0 = fma(Gs[c * n + r], xi[c], a0);
+                a0 += a2;
+                a1 += a3;
             }
             nv[q] = a0 + a1;
         }
@@ -647,7 +804,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         if (rc) return rc;
     }
     {
-        constexpr int STAGES = 4;
+        constexpr int STAGES = 8;
         auto kern = kalman_affine_kernel<R, D_, L_, STAGES>;
         size_t smem = ((size_t)STAGES * PrepSmem<R, D_, L_>::RECS + n) * sizeof(R);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

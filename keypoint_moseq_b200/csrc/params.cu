@@ -174,14 +174,29 @@ ar_params_kernel(const double* __restrict__ gram, const double* __restrict__ K_0
 // ---------------------------------------------------------------------------
 // transitions
 // ---------------------------------------------------------------------------
-// exclusive prefix of the flattened counts (tape offsets), and of the diagonal
-__global__ void count_prefix_kernel(const int* __restrict__ counts, int K, long long* __restrict__ starts,
-                                    long long* __restrict__ dstarts) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        long long run = 0;
-        for (int i = 0; i < K * K; ++i) { starts[i] = run; run += counts[i]; }
-        run = 0;
-        for (int i = 0; i < K; ++i) { dstarts[i] = run; run += counts[i * K + i]; }
+// exclusive prefix of the flattened counts (tape offsets) and of the diagonal; one block of 1024 threads
+__global__ void __launch_bounds__(1024)
+count_prefix_kernel(const int* __restrict__ counts, int K, long long* __restrict__ starts,
+                    long long* __restrict__ dstarts) {
+    __shared__ long long part[1024];
+    const int tid = threadIdx.x, total = K * K;
+    const int per = (total + 1023) / 1024;
+    const int lo = min(tid * per, total), hi = min(lo + per, total);
+    long long sum = 0;
+    for (int i = lo; i < hi; ++i) sum += counts[i];
+    part[tid] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        long long add = (tid >= off) ? part[tid - off] : 0;
+        __syncthreads();
+        part[tid] += add;
+        __syncthreads();
+    }
+    long long run = part[tid] - sum;
+    for (int i = lo; i < hi; ++i) { starts[i] = run; run += counts[i]; }
+    if (tid == 0) {
+        long long r2 = 0;
+        for (int i = 0; i < K; ++i) { dstarts[i] = r2; r2 += counts[i * K + i]; }
     }
 }
 
@@ -206,35 +221,39 @@ crp_tables_kernel(const int* __restrict__ counts, const double* __restrict__ bet
     }
 }
 
-// overrides w_i, then betas ~ Dir(gamma/K + colsum(mbar)); single block of >= K threads
-__global__ void betas_kernel(const int* __restrict__ m, const int* __restrict__ counts, const double* __restrict__ betas_in,
-                             double alpha, double kappa, double gamma, const long long* __restrict__ dstarts,
-                             const double* __restrict__ u_bin, const double* __restrict__ g_beta, uint64_t seed,
-                             int K, double* __restrict__ betas_out) {
+// overrides w_i ~ Bin(m_ii, rho / (rho + beta_i (1 - rho))): one warp per state, written into m's diagonal
+__global__ void __launch_bounds__(32)
+overrides_kernel(int* __restrict__ m, const double* __restrict__ betas_in, double alpha, double kappa,
+                 const long long* __restrict__ dstarts, const double* __restrict__ u_bin, uint64_t seed, int K,
+                 int* __restrict__ wov) {
+    const int i = blockIdx.x, lane = threadIdx.x;
+    const double rho = kappa / (alpha + kappa);
+    const int mii = m[i * K + i];
+    const double pov = rho / (rho + betas_in[i] * (1.0 - rho));
+    int w = 0;
+    for (int r = lane; r < mii; r += 32) {
+        double u;
+        if (u_bin) u = u_bin[dstarts[i] + r];
+        else { Philox gen(seed, KPMS_STREAM_BIN, ((uint64_t)i << 32) | (uint32_t)r); double u2; philox_uniform2(gen, u, u2); }
+        w += (u < pov) ? 1 : 0;
+    }
+    w = warp_sum(w);
+    if (lane == 0) wov[i] = w;
+}
+
+// betas ~ Dir(gamma/K + colsum(m) - w); single block of >= K threads
+__global__ void betas_kernel(const int* __restrict__ m, const int* __restrict__ wov, double gamma,
+                             const double* __restrict__ g_beta, uint64_t seed, int K,
+                             double* __restrict__ betas_out) {
     extern __shared__ double sh[];
-    double* wov = sh;            // K overrides
-    double* gb = sh + K;         // K gammas
+    double* gb = sh;             // K gammas
     __shared__ double red[32];
     const int tid = threadIdx.x;
-    const double rho = kappa / (alpha + kappa);
-    if (tid < K) {
-        const int mii = m[tid * K + tid];
-        const double pov = rho / (rho + betas_in[tid] * (1.0 - rho));
-        int w = 0;
-        for (int r = 0; r < mii; ++r) {
-            double u;
-            if (u_bin) u = u_bin[dstarts[tid] + r];
-            else { Philox gen(seed, KPMS_STREAM_BIN, ((uint64_t)tid << 32) | (uint32_t)r); double u2; philox_uniform2(gen, u, u2); }
-            w += (u < pov) ? 1 : 0;
-        }
-        wov[tid] = (double)w;
-    }
-    __syncthreads();
     double g = 0.0;
     if (tid < K) {
         double colsum = 0.0;
         for (int i = 0; i < K; ++i) colsum += (double)m[i * K + tid];
-        colsum -= wov[tid];
+        colsum -= (double)wov[tid];
         Philox gen(seed, KPMS_STREAM_BETA, (uint64_t)tid);
         g = gamma_draw<double>(gamma / K + colsum, g_beta ? g_beta + (size_t)tid * KPMS_GAMMA_TAPE : nullptr, gen);
         gb[tid] = g;
@@ -290,7 +309,7 @@ int kpms_resample_ar_params(const double* gram, const double* K_0, const double*
 
 size_t kpms_transitions_workspace_bytes(int K) {
     return kpms::align_up((size_t)K * K * sizeof(long long), 256) + kpms::align_up((size_t)K * sizeof(long long), 256) +
-           kpms::align_up((size_t)K * K * sizeof(int), 256);
+           kpms::align_up((size_t)K * K * sizeof(int), 256) + kpms::align_up((size_t)K * sizeof(int), 256);
 }
 
 int kpms_resample_hdp_transitions(const int32_t* counts, const double* betas_in, double alpha, double kappa,
@@ -304,12 +323,13 @@ int kpms_resample_hdp_transitions(const int32_t* counts, const double* betas_in,
     long long* dstarts = reinterpret_cast<long long*>(base + kpms::align_up((size_t)K * K * sizeof(long long), 256));
     int* m = reinterpret_cast<int*>(base + kpms::align_up((size_t)K * K * sizeof(long long), 256) +
                                     kpms::align_up((size_t)K * sizeof(long long), 256));
-    { KPMS_LAUNCH("trans_prefix", st); count_prefix_kernel<<<1, 32, 0, st>>>(counts, K, starts, dstarts); }
+    int* wov = m + kpms::align_up((size_t)K * K * sizeof(int), 256) / sizeof(int);
+    { KPMS_LAUNCH("trans_prefix", st); count_prefix_kernel<<<1, 1024, 0, st>>>(counts, K, starts, dstarts); }
     { KPMS_LAUNCH("trans_crp", st); crp_tables_kernel<<<K, 256, 0, st>>>(counts, betas_in, alpha, kappa, starts, u_crp, seed, K, m); }
     int threads = (K + 31) / 32 * 32;
+    { KPMS_LAUNCH("trans_overrides", st); overrides_kernel<<<K, 32, 0, st>>>(m, betas_in, alpha, kappa, dstarts, u_bin, seed, K, wov); }
     { KPMS_LAUNCH("trans_betas", st);
-    betas_kernel<<<1, threads, 2 * K * sizeof(double), st>>>(m, counts, betas_in, alpha, kappa, gamma, dstarts, u_bin,
-                                                             g_beta, seed, K, betas_out); }
+    betas_kernel<<<1, threads, K * sizeof(double), st>>>(m, wov, gamma, g_beta, seed, K, betas_out); }
     { KPMS_LAUNCH("trans_pi", st); pi_rows_kernel<<<K, threads, 0, st>>>(counts, betas_out, alpha, kappa, g_pi, seed, K, pi); }
     return check_launch("resample_hdp_transitions");
 }

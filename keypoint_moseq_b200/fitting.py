@@ -1,0 +1,310 @@
+"""`fit_model` / `apply_model` drivers with the reference's signatures and checkpoint behaviour,
+calling the B200 sweep instead of `jax_moseq.models.keypoint_slds.resample_model`.
+
+Mirrors /root/reference/keypoint_moseq/fitting.py: `_wrapped_resample` (:23-44), `init_model`
+(:63-106), `fit_model` (:109-287), `apply_model` (:290-425), `estimate_syllable_marginals`
+(:428-559), `update_hypparams` (:562-612), `expected_marginal_likelihoods` (:615-678).
+"""
+import os
+import warnings
+from datetime import datetime
+from textwrap import fill
+
+import numpy as np
+import torch
+
+from . import gibbs
+from .io import delete_snapshots_after, extract_results, load_checkpoint, save_hdf5
+from .util import check_for_nans, get_nlags, to_numpy_tree, unbatch
+
+try:  # progress bars are optional
+    import tqdm
+    _trange = tqdm.trange
+except Exception:  # pragma: no cover
+    def _trange(*args, **kwargs):
+        class _Bar:
+            def __init__(self, it):
+                self.it = it
+
+            def __enter__(self):
+                return self
+
+            def __exit__(self, *exc):
+                return False
+
+            def __iter__(self):
+                return iter(self.it)
+
+            def close(self):
+                pass
+        return _Bar(range(*args))
+
+__all__ = ["fit_model", "apply_model", "init_model", "init_states", "update_hypparams",
+           "estimate_syllable_marginals", "expected_marginal_likelihoods", "StopResampling"]
+
+
+class StopResampling(Exception):
+    pass
+
+
+def _wrapped_resample(resample_func, data, model, pbar=None, **resample_options):
+    """One guarded sweep: Ctrl-C and NaNs end fitting and keep the last good model (fitting.py:23-44)."""
+    try:
+        model = resample_func(data, **model, **resample_options)
+    except KeyboardInterrupt:
+        print("Early termination of fitting: user interruption")
+        raise StopResampling()
+    any_nans, nan_info, messages = check_for_nans(model)
+    if any_nans:
+        if pbar is not None:
+            pbar.close()
+        text = ["\nEarly termination of fitting: NaNs encountered"] + [f"  - {m}" for m in messages]
+        text.append("\nFor additional information, see https://keypoint-moseq.readthedocs.io/en/latest/"
+                    "troubleshooting.html#nans-during-fitting")
+        warnings.warn("\n".join(text))
+        raise StopResampling()
+    return model
+
+
+def _set_parallel_flag(parallel_message_passing):
+    """The reference picks the time-parallel Kalman sampler on GPU (fitting.py:47-60).  Here the
+    backward pass is always time-parallel, so every value is accepted and normalised to a bool."""
+    if parallel_message_passing == "force" or parallel_message_passing is None:
+        return True
+    return bool(parallel_message_passing)
+
+
+def _host_model(model):
+    out = to_numpy_tree(model)
+    out["states"]["z"] = np.asarray(out["states"]["z"]).astype(np.int64)
+    return out
+
+
+def init_states(data, params, hypparams, seed, noise_prior=None, anterior_idxs=None, posterior_idxs=None,
+                error_estimator=None, dtype=torch.float64, device="cuda", **kwargs):
+    """Data-driven initial states for fixed parameters (what `apply_model` needs, fitting.py:387-394):
+    centroid = keypoint mean, heading from the posterior->anterior axis (0 when the indices are not
+    given), x by least squares on the lifted observation operator, unit scales, then one HMM draw of z.
+    Returns (states, noise_prior)."""
+    dd = gibbs.to_device_data(data, device, dtype)
+    Y, mask = dd["Y"], dd["mask"]
+    N, T, k, D = Y.shape
+    pr = {key: gibbs._dev(val, torch.float64, Y.device) for key, val in params.items()}
+    v = Y.mean(2)
+    if anterior_idxs is not None and posterior_idxs is not None and len(anterior_idxs) and len(posterior_idxs):
+        ant = Y[:, :, list(anterior_idxs)].mean(2)
+        pos = Y[:, :, list(posterior_idxs)].mean(2)
+        h = torch.atan2(ant[..., 1] - pos[..., 1], ant[..., 0] - pos[..., 0])
+    else:
+        h = torch.zeros((N, T), dtype=dtype, device=Y.device)
+    Ct = gibbs.lifted_obs_matrix(pr["Cd"], k, D)
+    Yc = (Y - v[:, :, None, :]).to(torch.float64)
+    c, s_ = torch.cos(h).to(torch.float64)[..., None], torch.sin(h).to(torch.float64)[..., None]
+    Yr = Yc.clone()
+    Yr[..., 0] = c * Yc[..., 0] + s_ * Yc[..., 1]
+    Yr[..., 1] = -s_ * Yc[..., 0] + c * Yc[..., 1]
+    resid = Yr.reshape(N, T, k * D) - Ct[:, -1]
+    x = resid @ torch.linalg.pinv(Ct[:, :-1]).T
+    if noise_prior is None:
+        if error_estimator is not None and "conf" in dd:
+            slope, intercept = error_estimator["slope"], error_estimator["intercept"]
+            noise_prior = (10.0 ** (torch.log10(dd["conf"] + 1e-6) * slope + intercept)) ** 2
+        else:
+            noise_prior = torch.ones((N, T, k), dtype=dtype, device=Y.device)
+    noise_prior = gibbs._dev(noise_prior, dtype, Y.device)
+    z, _ = gibbs.resample_discrete_stateseqs(x.to(dtype).contiguous(), mask, pr["Ab"], pr["Q"], pr["pi"],
+                                             gibbs.seed_to_u64(seed))
+    states = {"x": x.to(dtype).contiguous(), "v": v.contiguous(), "h": h.contiguous(),
+              "s": torch.ones((N, T, k), dtype=dtype, device=Y.device), "z": z}
+    return states, noise_prior
+
+
+def init_model(data=None, states=None, params=None, hypparams=None, noise_prior=None, seed=None,
+               location_aware=False, allo_hypparams=None, trans_hypparams=None, **kwargs):
+    """Model-dict constructor (fitting.py:63-106).  Parameters must be supplied (from a fitted model or
+    a checkpoint): PCA-based initialisation of `Cd` is upstream of the Gibbs sweep and not part of this
+    build.  States are re-initialised from `data` when not given."""
+    if location_aware:
+        raise NotImplementedError("location_aware=True (allo_keypoint_slds) is not implemented by the B200 sweep")
+    if params is None or hypparams is None:
+        raise NotImplementedError("init_model needs `params` and `hypparams`: PCA-based parameter "
+                                  "initialisation is outside the Gibbs-sweep scope of this build")
+    if trans_hypparams is not None:
+        hypparams = dict(hypparams, trans_hypparams=dict(hypparams["trans_hypparams"], **trans_hypparams))
+    seed = np.array([0, 0], dtype=np.uint32) if seed is None else seed
+    if states is None:
+        states, noise_prior = init_states(data, params, hypparams, seed, noise_prior=noise_prior, **kwargs)
+    elif noise_prior is None:
+        noise_prior = np.ones(np.asarray(to_numpy_tree(states["s"])).shape)
+    return {"seed": seed, "states": states, "params": params, "hypparams": hypparams, "noise_prior": noise_prior}
+
+
+def fit_model(model, data, metadata, project_dir=None, model_name=None, num_iters=50, start_iter=0,
+              verbose=False, ar_only=False, parallel_message_passing=None, jitter=0.001,
+              generate_progress_plots=True, save_every_n_iters=25, location_aware=False, **kwargs):
+    """Fit a model to data: `num_iters - start_iter + 1` Gibbs sweeps with periodic checkpoints
+    (signature and checkpoint behaviour of fitting.py:109-287).  Returns (model, model_name).
+
+    Extra keyword arguments understood here: `dtype` (torch.float32 / torch.float64 for the states and
+    the continuous-path kernels, default float64 like the reference's x64 mode), `hmm_dtype`, `group`.
+    """
+    if location_aware:
+        raise NotImplementedError("location_aware=True (allo_keypoint_slds) is not implemented by the B200 sweep")
+    if generate_progress_plots and save_every_n_iters == 0:
+        warnings.warn(fill("The `generate_progress_plots` option requires that `save_every_n_iters` be greater "
+                           "than 0. Progress plots will not be generated."))
+        generate_progress_plots = False
+    if model_name is None:
+        model_name = str(datetime.now().strftime("%Y_%m_%d-%H_%M_%S"))
+    checkpoint_path = None
+    if save_every_n_iters is not None:
+        savedir = os.path.join(project_dir, model_name)
+        os.makedirs(savedir, exist_ok=True)
+        print(fill(f"Outputs will be saved to {savedir}"))
+        checkpoint_path = os.path.join(savedir, "checkpoint.h5")
+        if not os.path.exists(checkpoint_path):
+            save_hdf5(checkpoint_path, {"model_snapshots": {f"{start_iter}": _host_model(model)},
+                                        "metadata": (np.asarray(metadata[0]), np.asarray(metadata[1])),
+                                        "data": to_numpy_tree(data)})
+        else:
+            delete_snapshots_after(checkpoint_path, start_iter)
+
+    parallel_message_passing = _set_parallel_flag(parallel_message_passing)
+    dtype = kwargs.pop("dtype", torch.float64)
+    device = kwargs.pop("device", "cuda")
+    extra = {key: kwargs[key] for key in ("hmm_dtype", "group", "fix_heading", "resample_global_noise_scale",
+                                          "resample_local_noise_scale") if key in kwargs}
+    data_dev = gibbs.to_device_data(data, device, dtype)
+    model = gibbs.to_device_model(model, device, dtype)
+    resample_func = gibbs.resample_model
+
+    with _trange(start_iter, num_iters + 1, ncols=72) as pbar:
+        for iteration in pbar:
+            try:
+                model = _wrapped_resample(resample_func, data_dev, model, pbar=pbar, ar_only=ar_only,
+                                          verbose=verbose, jitter=jitter,
+                                          parallel_message_passing=parallel_message_passing, **extra)
+            except StopResampling:
+                break
+            if save_every_n_iters is not None and iteration > start_iter:
+                if iteration == num_iters or (save_every_n_iters > 0 and iteration % save_every_n_iters == 0):
+                    save_hdf5(checkpoint_path, _host_model(model), f"model_snapshots/{iteration}", exist_ok=True)
+                    # progress plots (viz.plot_progress) are outside the sweep's scope and are skipped
+    return model, model_name
+
+
+def apply_model(model, data, metadata, project_dir=None, model_name=None, num_iters=500, ar_only=False,
+                save_results=True, verbose=False, results_path=None, parallel_message_passing=None,
+                return_model=False, location_aware=False, overwrite=False, **kwargs):
+    """Apply a fitted model to new data: states are re-initialised from the data with the parameters
+    fixed and resampled `num_iters` times with `states_only=True`; results are extracted and optionally
+    saved (fitting.py:290-425)."""
+    if location_aware:
+        raise NotImplementedError("location_aware=True (allo_keypoint_slds) is not implemented by the B200 sweep")
+    parallel_message_passing = _set_parallel_flag(parallel_message_passing)
+    dtype = kwargs.pop("dtype", torch.float64)
+    device = kwargs.pop("device", "cuda")
+    extra = {key: kwargs.pop(key) for key in ("hmm_dtype", "group", "fix_heading") if key in kwargs}
+    data_dev = gibbs.to_device_data(data, device, dtype)
+    if save_results and results_path is None:
+        assert project_dir is not None and model_name is not None, fill(
+            "The `save_results` option requires either a `results_path` or the `project_dir` and "
+            "`model_name` arguments")
+        results_path = os.path.join(project_dir, model_name, "results.h5")
+    model = init_model(data=data_dev, seed=model["seed"], params=model["params"], hypparams=model["hypparams"],
+                       dtype=dtype, device=device, **kwargs)
+    model = gibbs.to_device_model(model, device, dtype)
+    with _trange(num_iters, ncols=72) as pbar:
+        for _ in pbar:
+            try:
+                model = _wrapped_resample(gibbs.resample_model, data_dev, model, pbar=pbar, ar_only=ar_only,
+                                          states_only=True, verbose=verbose,
+                                          parallel_message_passing=parallel_message_passing, **extra)
+            except StopResampling:
+                break
+    results = extract_results(model, metadata, project_dir, model_name, save_results, results_path,
+                              overwrite=overwrite)
+    return (results, model) if return_model else results
+
+
+def estimate_syllable_marginals(model, data, metadata, burn_in_iters=200, num_samples=100, steps_per_sample=10,
+                                return_samples=False, verbose=False, parallel_message_passing=None, **kwargs):
+    """Marginal syllable distributions by averaging HMM smoother marginals over Gibbs samples of the
+    states with fixed parameters (fitting.py:428-559).  Returns {recording: (T - nlags, K) array}
+    (and the samples when `return_samples`)."""
+    parallel_message_passing = _set_parallel_flag(parallel_message_passing)
+    dtype = kwargs.pop("dtype", torch.float64)
+    device = kwargs.pop("device", "cuda")
+    data_dev = gibbs.to_device_data(data, device, dtype)
+    model = init_model(data=data_dev, seed=model["seed"], params=model["params"], hypparams=model["hypparams"],
+                       dtype=dtype, device=device, **kwargs)
+    model = gibbs.to_device_model(model, device, dtype)
+    total = burn_in_iters + num_samples * steps_per_sample
+    acc, samples = None, []
+    with _trange(total, ncols=72) as pbar:
+        for it in pbar:
+            try:
+                model = _wrapped_resample(gibbs.resample_model, data_dev, model, pbar=pbar, states_only=True,
+                                          verbose=verbose, parallel_message_passing=parallel_message_passing)
+            except StopResampling:
+                break
+            if it >= burn_in_iters and (it - burn_in_iters) % steps_per_sample == 0:
+                p = model["params"]
+                marg = gibbs.stateseq_marginals(model["states"]["x"], data_dev["mask"], p["Ab"], p["Q"], p["pi"])
+                acc = marg.clone() if acc is None else acc + marg
+                if return_samples:
+                    samples.append(model["states"]["z"].cpu().numpy())
+    nlags = get_nlags(model["params"]["Ab"])
+    keys, bounds = list(metadata[0]), np.asarray(metadata[1]) + np.array([nlags, 0])
+    est = (acc / num_samples).cpu().numpy()
+    marginals = unbatch(est, keys, bounds)
+    marginals = {k_: np.pad(v[nlags:], ((nlags, 0), (0, 0)), mode="edge") for k_, v in marginals.items()}
+    if return_samples:
+        smp = unbatch(np.moveaxis(np.asarray(samples), 0, 2), keys, bounds)
+        smp = {k_: np.pad(v[nlags:], ((nlags, 0), (0, 0)), mode="edge") for k_, v in smp.items()}
+        return marginals, smp
+    return marginals
+
+
+def update_hypparams(model_dict, **kwargs):
+    """Edit scalar hyper-parameters in place, casting to the old type (fitting.py:562-612)."""
+    assert "hypparams" in model_dict, fill("The inputted model/checkpoint does not contain any hyperparams")
+    not_updated = list(kwargs.keys())
+    for group in model_dict["hypparams"]:
+        for k, v in kwargs.items():
+            if k in model_dict["hypparams"][group]:
+                old = model_dict["hypparams"][group][k]
+                if not np.isscalar(old):
+                    print(fill(f"{k} cannot be updated since it is not a scalar hyperparam"))
+                else:
+                    if not isinstance(v, type(old)):
+                        warnings.warn(f"'{k}' with {type(v)} will be cast to {type(old)}")
+                    model_dict["hypparams"][group][k] = type(old)(v)
+                    not_updated.remove(k)
+    if len(not_updated) > 0:
+        warnings.warn(fill(f"The following hypparams were not found {not_updated}"))
+    return model_dict
+
+
+def expected_marginal_likelihoods(project_dir=None, model_names=None, checkpoint_paths=None):
+    """Expected marginal likelihood score of each model's (Ab, Q, pi) on the other models' latent
+    trajectories (fitting.py:615-678).  Returns (scores, standard_errors)."""
+    if checkpoint_paths is None:
+        assert project_dir is not None and model_names is not None, fill(
+            "Must provide either `checkpoint_paths` or `project_dir` and `model_names`")
+        checkpoint_paths = [os.path.join(project_dir, name, "checkpoint.h5") for name in model_names]
+    xs, params, data = [], [], None
+    for path in checkpoint_paths:
+        model, data, _, _ = load_checkpoint(path=path)
+        xs.append(model["states"]["x"])
+        params.append(model["params"])
+    M = len(xs)
+    mlls = np.zeros((M, M))
+    for i in range(M):
+        for j in range(M):
+            if i != j:
+                mlls[i, j] = gibbs.marginal_log_likelihood(data["mask"], xs[j], params[i]["Ab"], params[i]["Q"],
+                                                           params[i]["pi"]).item()
+    scores = mlls.sum(1) / (M - 1)
+    variances = (mlls ** 2).sum(1) / (M - 1) - scores ** 2
+    return scores, np.sqrt(variances / (M - 1))

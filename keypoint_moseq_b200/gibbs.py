@@ -138,8 +138,10 @@ def resample_discrete_stateseqs(x, mask, Ab, Q, pi, seed64=0, u_z=None, dtype=to
     filt, logZ, (N, K, Tp, d, L, code, pp), ws = _hmm_forward(x, mask, Ab, Q, pi, dtype)
     z = torch.empty((N, Tp), dtype=torch.int32, device=x.device)
     u = _dev(u_z, dtype, x.device)
-    _lib.call("kpms_hmm_backward_sample", code, _lib.ptr(filt), _lib.ptr(pp), _lib.ptr(u), seed64, N, K, Tp,
-              _lib.ptr(z), _lib.ptr(ws), d, L, _lib.stream_ptr())
+    esz = 4 if code == _lib.F32 else 8
+    u_scratch = None if u is not None else _scratch("hmm_u", N * Tp * esz, x.device)
+    _lib.call("kpms_hmm_backward_sample", code, _lib.ptr(filt), _lib.ptr(pp), _lib.ptr(u), _lib.ptr(u_scratch),
+              seed64, N, K, Tp, _lib.ptr(z), _lib.ptr(ws), d, L, _lib.stream_ptr())
     return z, logZ
 
 

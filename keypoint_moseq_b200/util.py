@@ -95,7 +95,8 @@ def unbatch(data, keys, bounds):
         seq = np.zeros((length,) + data.shape[2:], dtype=data.dtype)
         for i in idx:
             s, e = int(bounds[i, 0]), int(bounds[i, 1])
-            seq[s:e] = data[i, :e - s]
+            if e > s:
+                seq[s:e] = data[i, :e - s]
         out[key] = seq
     return out
 

@@ -1,0 +1,187 @@
+"""Host-side logic that needs no GPU: batching helpers, checkpoint tree I/O, sharding and the
+world_size-2 all-reduce of packed statistics (gloo)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as orc
+from keypoint_moseq_b200 import io as kio
+from keypoint_moseq_b200 import util
+from keypoint_moseq_b200.dist import shard_rows, shard_tree
+from keypoint_moseq_b200.fitting import update_hypparams
+from keypoint_moseq_b200.gibbs import advance_seed, seed_to_u64
+from keypoint_moseq_b200.synth import default_hypparams, sample_dataset
+
+
+def test_batch_unbatch_round_trip_and_overlap():
+    rng = np.random.default_rng(0)
+    recs = {"a": rng.standard_normal((95, 3)), "b": rng.standard_normal((40, 3)), "c": rng.standard_normal((41, 3))}
+    stack, mask, (keys, bounds) = util.batch(recs, seg_length=40, seg_overlap=5)
+    assert stack.shape == (3 + 1 + 2, 45, 3)
+    assert keys == ["a", "a", "a", "b", "c", "c"]
+    assert bounds.tolist() == [[0, 45], [40, 85], [80, 95], [0, 40], [0, 41], [40, 41]]
+    assert mask.sum(1).tolist() == [45, 45, 15, 40, 41, 1]
+    # padding repeats the last real frame
+    np.testing.assert_array_equal(stack[2, 15:], np.repeat(recs["a"][-1:], 30, axis=0))
+    back = util.unbatch(stack, keys, bounds)
+    for k in recs:
+        np.testing.assert_array_equal(back[k], recs[k])
+    # time-shortened arrays (z has T - nlags frames): shift the start bound
+    z = stack[:, 3:, 0]
+    back_z = util.unbatch(z, keys, bounds + np.array([3, 0]))
+    np.testing.assert_array_equal(back_z["a"][3:], recs["a"][3:, 0])
+
+
+def test_durations_frequencies_nlags():
+    z = np.array([[0, 0, 1, 1, 1, 2], [2, 2, 2, 0, 0, 0]])
+    mask = np.ones((2, 8), dtype=int)
+    mask[1, 6:] = 0      # last two frames of row 1 are padding -> z[1, 4:] dropped
+    assert util.get_durations(z, mask).tolist() == [2, 3, 4, 1]
+    f = util.get_frequencies(z, mask, num_states=4, runlength=True)
+    np.testing.assert_allclose(f, [2 / 4, 1 / 4, 1 / 4, 0])
+    f2 = util.get_frequencies({"a": z[0], "b": z[1]}, num_states=3, runlength=False)
+    np.testing.assert_allclose(f2, [5 / 12, 3 / 12, 4 / 12])
+    assert util.get_nlags(np.zeros((7, 4, 13))) == 3
+
+
+def test_segment_length_rule():
+    assert util.find_optimal_segment_length([36000] * 20) == 10000
+    assert util.find_optimal_segment_length([500, 800, 1200]) == 1200        # 45.6% padding <= 50%
+    seg = util.find_optimal_segment_length([10003, 20000])
+    assert all(r == 0 or r >= 4 for r in np.array([10003, 20000]) % seg)
+    with pytest.raises(AssertionError):
+        util.find_optimal_segment_length([3, 100])
+
+
+def test_format_data_layout():
+    rng = np.random.default_rng(1)
+    coords = {"r1": rng.standard_normal((120, 5, 2)), "r0": rng.standard_normal((70, 5, 2))}
+    conf = {k: rng.uniform(0, 1, v.shape[:2]) for k, v in coords.items()}
+    data, (keys, bounds) = util.format_data(coords, conf, seg_length=50, device="cpu")
+    assert keys == ["r0", "r0", "r1", "r1", "r1"]
+    assert tuple(data["Y"].shape) == (5, 80, 5, 2) and tuple(data["conf"].shape) == (5, 80, 5)
+    assert data["mask"].sum().item() == 70 + 20 + 80 + 70 + 20
+    noise = data["Y"][0, :70].numpy() - coords["r0"]
+    assert np.abs(noise).max() <= 0.1 and np.abs(noise).max() > 0.05
+    assert float(data["conf"].min()) >= 1e-3
+
+
+def test_check_for_nans():
+    model = {"states": {"x": torch.zeros(3, 4), "z": torch.zeros(3, 2, dtype=torch.int32)},
+             "params": {"Ab": np.zeros((2, 2))}, "seed": np.array([0, 1], dtype=np.uint32)}
+    assert util.check_for_nans(model)[0] is False
+    model["states"]["x"][1, 2] = float("nan")
+    any_nans, info, msgs = util.check_for_nans(model)
+    assert any_nans and "states/x" in msgs[0]
+
+
+def test_hdf5_tree_round_trip_and_guards(tmp_path):
+    _, meta, model = sample_dataset(recordings=2, frames=60, k=4, D=2, d=2, L=2, K=3, seg_length=40)
+    path = str(tmp_path / "checkpoint.h5")
+    tree = {"model_snapshots": {"0": model}, "metadata": (np.asarray(meta[0]), meta[1]), "list": [1, 2.5, "s"]}
+    kio.save_hdf5(path, tree)
+    with pytest.raises(AssertionError):
+        kio.save_hdf5(path, tree)                                   # file exists, exist_ok False
+    kio.save_hdf5(path, model, "model_snapshots/25", exist_ok=True)
+    with pytest.raises(AssertionError):
+        kio.save_hdf5(path, model, "model_snapshots/25", exist_ok=True)   # group exists, overwrite False
+    kio.save_hdf5(path, model, "model_snapshots/50", exist_ok=True)
+    m, _, md, it = None, None, None, None
+    loaded = kio.load_hdf5(path)
+    assert sorted(loaded["model_snapshots"]) == ["0", "25", "50"]
+    assert isinstance(loaded["metadata"], tuple) and list(loaded["metadata"][0]) == list(meta[0])
+    assert loaded["list"] == [1, 2.5, "s"]
+    snap = kio.load_hdf5(path, "model_snapshots/25")
+    np.testing.assert_array_equal(snap["states"]["x"], model["states"]["x"])
+    assert snap["hypparams"]["trans_hypparams"]["num_states"] == 3
+    assert isinstance(snap["hypparams"]["obs_hypparams"]["nu_s"], int)
+    kio.delete_snapshots_after(path, 25)
+    assert sorted(kio.load_hdf5(path)["model_snapshots"]) == ["0", "25"]
+
+
+def test_load_checkpoint_and_extract_results(tmp_path):
+    data, meta, model = sample_dataset(recordings=2, frames=70, k=4, D=2, d=2, L=2, K=3, seg_length=40)
+    d = tmp_path / "proj" / "m"
+    d.mkdir(parents=True)
+    kio.save_hdf5(str(d / "checkpoint.h5"), {"model_snapshots": {"0": model, "10": model},
+                                              "metadata": (np.asarray(meta[0]), meta[1]), "data": data})
+    m, dat, md, it = kio.load_checkpoint(str(tmp_path / "proj"), "m")
+    assert it == 10 and dat["Y"].shape == data["Y"].shape
+    res = kio.extract_results(m, md, str(tmp_path / "proj"), "m")
+    for name in ("rec0000", "rec0001"):
+        assert res[name]["syllable"].shape == (70,) and res[name]["latent_state"].shape == (70, 2)
+        assert res[name]["centroid"].shape == (70, 2) and res[name]["heading"].shape == (70,)
+        # the first nlags labels repeat the first sampled label
+        assert (res[name]["syllable"][:2] == res[name]["syllable"][2]).all()
+    with pytest.raises(RuntimeError):
+        kio.extract_results(m, md, str(tmp_path / "proj"), "m")     # recordings already present
+    kio.extract_results(m, md, str(tmp_path / "proj"), "m", overwrite=True)
+    again = kio.load_results(str(tmp_path / "proj"), "m")
+    np.testing.assert_array_equal(again["rec0000"]["syllable"], res["rec0000"]["syllable"])
+
+
+def test_update_hypparams_and_seed():
+    model = {"hypparams": default_hypparams(4, 3, 10)}
+    with pytest.warns(UserWarning):
+        update_hypparams(model, kappa=5, not_there=1)
+    assert model["hypparams"]["trans_hypparams"]["kappa"] == 5.0
+    assert isinstance(model["hypparams"]["trans_hypparams"]["kappa"], float)
+    s0 = np.array([3, 7], dtype=np.uint32)
+    assert seed_to_u64(s0) == (3 << 32) | 7
+    s1 = advance_seed(s0)
+    assert s1.dtype == np.uint32 and s1.shape == (2,) and not np.array_equal(s0, s1)
+    assert np.array_equal(advance_seed(s0), s1)
+
+
+def test_shard_rows_balances_and_keeps_recordings_together():
+    mask = np.zeros((7, 100), dtype=int)
+    lens = [100, 100, 30, 100, 60, 100, 10]
+    for i, n in enumerate(lens):
+        mask[i, :n] = 1
+    keys = ["a", "a", "a", "b", "b", "c", "c"]
+    shards = shard_rows(mask, 2, keys)
+    assert sorted(np.concatenate(shards).tolist()) == list(range(7))
+    loads = [mask[s].sum() for s in shards]
+    assert abs(loads[0] - loads[1]) <= 100
+    for key in "abc":
+        owners = {r for r, s in enumerate(shards) for i in s if keys[i] == key}
+        assert len(owners) == 1
+    sub = shard_tree({"Y": np.arange(7)[:, None] * np.ones((7, 3)), "m": torch.arange(7)}, shards[0])
+    assert sub["Y"].shape[0] == len(shards[0]) and sub["m"].tolist() == shards[0].tolist()
+
+
+def _gloo_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from keypoint_moseq_b200.dist import allreduce_statistics
+    data, meta, model = sample_dataset(recordings=3, frames=90, k=4, D=2, d=2, L=2, K=4, seed=5, seg_length=50)
+    K, d, L = 4, 2, 2
+    shards = shard_rows(data["mask"], world, meta[0])
+    rows = shards[rank]
+    x, z, mask = model["states"]["x"][rows], model["states"]["z"][rows], data["mask"][rows]
+    gram = orc.ar_suffstats(x, z, mask, K)        # the statistics the CUDA kernels produce, from the checker
+    counts = orc.count_transitions(z, mask, K)
+    packed = torch.tensor(np.concatenate([gram.reshape(-1), counts.reshape(-1).astype(float)]))
+    allreduce_statistics(packed)
+    np.save(os.path.join(tmp, f"packed{rank}.npy"), packed.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_statistics_allreduce_matches_single_rank(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    p0, p1 = (np.load(tmp_path / f"packed{r}.npy") for r in range(2))
+    np.testing.assert_array_equal(p0, p1)          # every rank holds the same reduced buffer
+    data, meta, model = sample_dataset(recordings=3, frames=90, k=4, D=2, d=2, L=2, K=4, seed=5, seg_length=50)
+    gram = orc.ar_suffstats(model["states"]["x"], model["states"]["z"], data["mask"], 4)
+    counts = orc.count_transitions(model["states"]["z"], data["mask"], 4)
+    F = gram.shape[-1]
+    np.testing.assert_allclose(p0[:4 * F * F].reshape(4, F, F), gram, rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(p0[4 * F * F:].reshape(4, 4), counts)
