@@ -40,6 +40,17 @@ long long kpms_launch_count(void);
 void kpms_profile_enable(int on);
 int kpms_profile_report(char* buf, size_t cap);
 
+/* Time-parallel execution of the serial recursions (Kalman filter, backward sampler, HMM filter).
+ * Each chain is cut into `chunks` pieces that run concurrently from `warmup` steps early; every
+ * boundary is checked against its neighbour and chains whose discrepancy exceeds the tolerance
+ * (tol32 for float32 calls, tol64 for float64) are re-run sequentially inside the same call.
+ * chunks = 0: automatic (fill the device), 1: sequential; a negative / non-positive argument
+ * leaves that setting unchanged.  Defaults: 0, 64, 2e-5, 1e-10.
+ * After a call the first 16 bytes of that call's workspace hold, as uint32: the largest forward
+ * boundary discrepancy (float bits), the number of chains re-run forward, and the same two for
+ * the backward recursion. */
+void kpms_set_time_chunking(int chunks, int warmup, double tol32, double tol64);
+
 /* ---- discrete states: jax_moseq.models.arhmm.resample_discrete_stateseqs
  *      (utils.autoregression.ar_log_likelihood + utils.distributions.sample_hmm_stateseq);
  *      the forward pass alone is arhmm.marginal_log_likelihood (fitting.py:667-673) and

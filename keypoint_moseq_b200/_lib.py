@@ -24,6 +24,7 @@ SIGNATURES = {
     "kpms_launch_count": (C.c_longlong, []),
     "kpms_profile_enable": (None, [_i]),
     "kpms_profile_report": (_i, [C.c_char_p, _sz]),
+    "kpms_set_time_chunking": (None, [_i, _i, _d, _d]),
     "kpms_hmm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "kpms_ar_loglik": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kpms_hmm_forward": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -108,6 +109,11 @@ def call(name, *args):
 def query(name, *args):
     """Invoke a size query."""
     return int(getattr(load(), name)(*args))
+
+
+def set_time_chunking(chunks=-1, warmup=-1, tol32=-1.0, tol64=-1.0):
+    """Time-parallel chunking of the serial recursions (see include/kpms_b200.h)."""
+    load().kpms_set_time_chunking(int(chunks), int(warmup), float(tol32), float(tol64))
 
 
 def launch_count():

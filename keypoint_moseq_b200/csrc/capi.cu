@@ -56,9 +56,27 @@ LaunchScope::~LaunchScope() {
     }
 }
 
+// ---- time-chunking configuration (common.cuh) ----
+static ChunkConfig g_chunk = {0, 64, 2e-5, 1e-10};
+ChunkConfig chunk_config() { return g_chunk; }
+int chunks_for(int N, int slots, int len, int warmup) {
+    int C = g_chunk.chunks > 0 ? g_chunk.chunks : slots / (N > 0 ? N : 1);
+    if (warmup > 0 && C > len / (4 * warmup)) C = len / (4 * warmup);
+    if (C > 64) C = 64;
+    if (C < 1) C = 1;
+    return C;
+}
+
 }  // namespace kpms
 
 extern "C" {
+void kpms_set_time_chunking(int chunks, int warmup, double tol32, double tol64) {
+    if (chunks >= 0) kpms::g_chunk.chunks = chunks;
+    if (warmup >= 0) kpms::g_chunk.warmup = warmup;
+    if (tol32 > 0) kpms::g_chunk.tol32 = tol32;
+    if (tol64 > 0) kpms::g_chunk.tol64 = tol64;
+}
+
 long long kpms_launch_count(void) { return kpms::g_launches.load(); }
 
 void kpms_profile_enable(int on) { kpms::g_profile = on != 0; }

@@ -17,6 +17,7 @@
 #define KPMS_EPS_SHIFT 1e-2
 #define KPMS_X_PRIOR_VAR 10.0
 #define KPMS_V_PRIOR_VAR 1e6
+#define KPMS_SM_COUNT 148     /* B200; the library is built for sm_100a only */
 
 // stream ids for Philox counters (one per sampler)
 enum KpmsStream : uint32_t {
@@ -218,6 +219,107 @@ template <> __device__ __forceinline__ double rsqrt_r<double>(double x) { return
 template <typename R> __device__ __forceinline__ void sincos_r(R x, R& s, R& c);
 template <> __device__ __forceinline__ void sincos_r<float>(float x, float& s, float& c) { sincosf(x, &s, &c); }
 template <> __device__ __forceinline__ void sincos_r<double>(double x, double& s, double& c) { sincos(x, &s, &c); }
+
+// ---------------------------------------------------------------------------
+// Time-parallel execution of the serial recursions ("speculative chunks with verified boundaries").
+//
+// A filter forgets its initial condition geometrically, so a chain is cut into chunks that run
+// concurrently: chunk c > 0 starts W steps before its first frame from the chain's own prior
+// (warm-up, nothing stored), and by the time it reaches its first frame its state agrees with the
+// sequential recursion's to rounding.  Nothing is assumed about the forgetting rate: every chunk
+// publishes the state it arrived with ("warm") and the state it handed to its neighbour ("exact"),
+// a check kernel compares the two at every boundary, and any chain with a discrepancy above the
+// tolerance is re-run by the sequential kernel (same code, one chunk) before anything consumes the
+// result.  Masked steps carry no information, so chunks only cut the leading run of unmasked
+// steps (vlen); the last chunk takes whatever follows.
+// Slot c of the boundary buffers is the boundary between chunks c-1 and c, for forward and
+// backward recursions alike.
+// ---------------------------------------------------------------------------
+struct ChunkRange {
+    int begin, end, start;     // outputs for steps [begin, end); forward recursions start at `start` <= begin
+    bool empty;
+};
+__host__ __device__ inline ChunkRange chunk_range(int vlen, int len, int C, int W, int c) {
+    ChunkRange r;
+    int Lc = (vlen + C - 1) / C;
+    if (Lc < 4 * W) Lc = 4 * W;
+    if (Lc < 1) Lc = 1;
+    int Cn = (vlen + Lc - 1) / Lc;
+    if (Cn < 1) Cn = 1;
+    r.empty = c >= Cn;
+    r.begin = c * Lc;
+    r.end = (c == Cn - 1) ? len : (c + 1) * Lc;
+    r.start = c > 0 ? r.begin - W : 0;
+    return r;
+}
+
+// vlen[nn] = number of leading steps i in [0, len) with mask[nn][off + i] != 0
+static __global__ void __launch_bounds__(256)
+valid_len_kernel(const int* __restrict__ mask, int T, int off, int len, int* __restrict__ vlen) {
+    __shared__ int first;
+    const int nn = blockIdx.x;
+    if (threadIdx.x == 0) first = len;
+    __syncthreads();
+    const int* mk = mask + (size_t)nn * T + off;
+    for (int i = threadIdx.x; i < len; i += blockDim.x)
+        if (mk[i] == 0) { atomicMin(&first, i); break; }
+    __syncthreads();
+    if (threadIdx.x == 0) vlen[nn] = first;
+}
+
+// Boundary check for real-valued states of `rec` numbers per boundary, in two blocks with their
+// own scales: [0, n_mean) (difference relative to 1 + max|exact|) and [n_mean, rec) (relative to
+// max|exact|).  dirty[nn] = 1 when the worst boundary discrepancy exceeds tol or is not finite.
+// stats[0] = max discrepancy seen (float bits, atomicMax), stats[1] += number of dirty chains.
+template <typename R>
+__global__ void __launch_bounds__(128)
+boundary_check_kernel(const R* __restrict__ warm, const R* __restrict__ exact, const int* __restrict__ vlen,
+                      int len, int C, int W, int n_mean, int rec, R tol, int* __restrict__ dirty,
+                      unsigned* __restrict__ stats) {
+    __shared__ R red[2][4];
+    const int nn = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    R worst = 0;
+    int bad = 0;
+    for (int c = 1; c < C; ++c) {
+        const ChunkRange r = chunk_range(vlen[nn], len, C, W, c);
+        if (r.empty) break;
+        const R* a = warm + ((size_t)nn * C + c) * rec;
+        const R* b = exact + ((size_t)nn * C + c) * rec;
+        for (int part = 0; part < 2; ++part) {
+            const int lo = part ? n_mean : 0, hi = part ? rec : n_mean;
+            if (hi <= lo) continue;
+            R diff = 0, scale = 0;
+            for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+                const R x = a[e], y = b[e];
+                const R dd = fabs(x - y);
+                if (!(dd < (R)INFINITY)) bad = 1;
+                diff = fmax(diff, dd);
+                scale = fmax(scale, fabs(y));
+            }
+            diff = warp_max(diff);
+            scale = warp_max(scale);
+            __syncthreads();
+            if (lane == 0) { red[0][warp] = diff; red[1][warp] = scale; }
+            __syncthreads();
+            const R dmax = fmax(fmax(red[0][0], red[0][1]), fmax(red[0][2], red[0][3]));
+            const R smax = fmax(fmax(red[1][0], red[1][1]), fmax(red[1][2], red[1][3]));
+            worst = fmax(worst, dmax / ((part ? (R)0 : (R)1) + smax + (R)1e-30));
+        }
+    }
+    const int any_bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        const bool d = any_bad || !(worst <= tol);
+        dirty[nn] = d ? 1 : 0;
+        atomicMax(&stats[0], __float_as_uint(any_bad ? INFINITY : (float)worst));
+        if (d) atomicAdd(&stats[1], 1u);
+    }
+}
+
+// process-wide time-chunking configuration (kpms_set_time_chunking); see capi.cu
+struct ChunkConfig { int chunks; int warmup; double tol32, tol64; };
+ChunkConfig chunk_config();
+// chunks per chain for N chains when `slots` chunk-CTAs fit on the device at once
+int chunks_for(int N, int slots, int len, int warmup);
 
 }  // namespace kpms
 

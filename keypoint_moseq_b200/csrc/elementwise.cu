@@ -178,98 +178,202 @@ heading_location_kernel(const R* __restrict__ Y, const R* __restrict__ x, const 
 }
 
 // ---------------------------------------------------------------------------
-// K6b: random-walk FFBS of the centroid; covariances are scalar multiples of I so the
-// recursion is scalar per chain with DK independent means.  One thread per chain,
-// operands fetched in independent chunks ahead of the dependent arithmetic.
+// K6b: random-walk FFBS of the centroid, parallel in time.  Covariances are scalar multiples of
+// I, so the three recursions of the sampler are scans over tiny associative elements:
+//   predicted variance   Pp' = ((g + sl) Pp + sl g) / (Pp + g)          (Moebius map, 2x2 matrix)
+//   filtered mean        m'  = (1 - kg) m + kg mu                        (affine map)
+//   backward sample      v_t = gain v_{t+1} + (1 - gain) m_t + sd w_t    (affine map, reversed)
+// One CTA per chain; every thread owns a contiguous run of frames, composes its run serially,
+// the CTA scans the per-thread composites (warp shuffles + one shared-memory hop), and each thread
+// then replays its run from the exact incoming value with the same arithmetic as the sequential
+// recursion.  All Moebius entries are positive, so the composition has no cancellation.
 // v_out doubles as the filtered-mean stash; fP is (N,T) scratch.
 // ---------------------------------------------------------------------------
-template <typename R, int DK>
-__global__ void __launch_bounds__(32)
+template <typename R, int NV>
+struct Affine {      // y = a x + b,  b has NV components
+    R a, b[NV];
+};
+template <typename R, int NV>
+__device__ __forceinline__ Affine<R, NV> affine_after(const Affine<R, NV>& second, const Affine<R, NV>& first) {
+    Affine<R, NV> o;
+    o.a = second.a * first.a;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) o.b[c] = fma(second.a, first.b[c], second.b[c]);
+    return o;
+}
+template <typename R>
+struct Moebius {     // P' = (a P + b) / (c P + d), entries > 0, scaled so the largest is 1
+    R a, b, c, d;
+};
+template <typename R>
+__device__ __forceinline__ Moebius<R> moebius_after(const Moebius<R>& s, const Moebius<R>& f) {
+    Moebius<R> o;
+    o.a = fma(s.a, f.a, s.b * f.c);
+    o.b = fma(s.a, f.b, s.b * f.d);
+    o.c = fma(s.c, f.a, s.d * f.c);
+    o.d = fma(s.c, f.b, s.d * f.d);
+    const R m = (R)1 / fmax(fmax(o.a, o.b), fmax(o.c, o.d));
+    o.a *= m; o.b *= m; o.c *= m; o.d *= m;
+    return o;
+}
+
+// Inclusive scan over the CTA of per-thread elements (thread order = application order), returned
+// as the EXCLUSIVE prefix (composition of all earlier threads' elements; identity for thread 0).
+// E is a struct of NW 32-bit or 64-bit words of type R.
+template <typename R, typename E, typename F>
+__device__ inline E block_exclusive_scan(E mine, const E& identity, F after, E* sh /* >= 32 */) {
+    constexpr int NW = sizeof(E) / sizeof(R);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    auto shfl_up = [&](const E& e, int o) {
+        E r;
+        const R* src = reinterpret_cast<const R*>(&e);
+        R* dst = reinterpret_cast<R*>(&r);
+#pragma unroll
+        for (int q = 0; q < NW; ++q) dst[q] = __shfl_up_sync(0xffffffffu, src[q], o);
+        return r;
+    };
+    E incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        E prev = shfl_up(incl, o);
+        if (lane >= o) incl = after(incl, prev);
+    }
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        E w = (lane < nwarps) ? sh[lane] : identity;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            E prev = shfl_up(w, o);
+            if (lane >= o) w = after(w, prev);
+        }
+        sh[lane] = w;                               // inclusive over warps
+    }
+    __syncthreads();
+    E excl = shfl_up(incl, 1);
+    if (lane == 0) excl = identity;
+    if (warp > 0) excl = after(excl, sh[warp - 1]);
+    __syncthreads();
+    return excl;
+}
+
+template <typename R, int DK, int NT>
+__global__ void __launch_bounds__(NT)
 location_ffbs_kernel(const R* __restrict__ mu, const R* __restrict__ gsq, const int* __restrict__ mask,
                      double sigmasq_loc, const R* __restrict__ w_tape, int N, int T,
                      R* __restrict__ fP, R* __restrict__ v_out) {
-    constexpr int CH = 8;
-    const int nn = blockIdx.x;
-    if (nn >= N || threadIdx.x != 0) return;
+    typedef Affine<R, DK> Aff;
+    typedef Moebius<R> Moe;
+    __shared__ Moe sh_m[32];
+    __shared__ Aff sh_a[32];
+    const int nn = blockIdx.x, tid = threadIdx.x;
     const R* mun = mu + (size_t)nn * T * DK;
     const R* gn = gsq + (size_t)nn * T;
     const int* mk = mask + (size_t)nn * T;
+    const R* wn = w_tape + (size_t)nn * T * DK;
     R* fPn = fP + (size_t)nn * T;
     R* vn = v_out + (size_t)nn * T * DK;
     const R sl = (R)sigmasq_loc;
-    R Pp = (R)KPMS_V_PRIOR_VAR;
+    const int per = (T + NT - 1) / NT;
+    const int lo = min(tid * per, T), hi = min(lo + per, T);
+    Moe idm; idm.a = 1; idm.b = 0; idm.c = 0; idm.d = 1;
+    Aff ida; ida.a = 1;
+#pragma unroll
+    for (int c = 0; c < DK; ++c) ida.b[c] = 0;
+
+    // ---- pass 1: predicted variance at the start of every run
+    Moe run = idm;
+    for (int t = lo; t < hi; ++t) {
+        if (mk[t]) {
+            const R g = gn[t];
+            Moe e; e.a = g + sl; e.b = sl * g; e.c = 1; e.d = g;
+            run = moebius_after(e, run);
+        }
+    }
+    const Moe pre = block_exclusive_scan<R>(run, idm, moebius_after<R>, sh_m);
+    const R P0 = (R)KPMS_V_PRIOR_VAR;
+    R Pp = fma(pre.a, P0, pre.b) / fma(pre.c, P0, pre.d);
+    // replay the run: filtered variances (stash) and the run's affine map of the mean
+    Aff runa = ida;
+    for (int t = lo; t < hi; ++t) {
+        if (mk[t]) {
+            const R g = gn[t];
+            const R Pc = Pp * g / (Pp + g);
+            const R kg = Pc / g;
+            Aff e; e.a = (R)1 - kg;
+#pragma unroll
+            for (int c = 0; c < DK; ++c) e.b[c] = kg * mun[(size_t)t * DK + c];
+            runa = affine_after(e, runa);
+            fPn[t] = Pc;
+            Pp = Pc + sl;
+        } else {
+            fPn[t] = Pp;
+        }
+    }
+    // ---- pass 2: filtered means (prior mean 0, so the incoming mean is the prefix offset)
+    const Aff prea = block_exclusive_scan<R>(runa, ida, affine_after<R, DK>, sh_a);
     R mp[DK];
 #pragma unroll
-    for (int c = 0; c < DK; ++c) mp[c] = 0;
-    for (int t0 = 0; t0 < T; t0 += CH) {
-        R gq[CH], mq[CH][DK];
-        int on[CH];
+    for (int c = 0; c < DK; ++c) mp[c] = prea.b[c];
+    for (int t = lo; t < hi; ++t) {
+        if (mk[t]) {
+            const R kg = fPn[t] / gn[t];
 #pragma unroll
-        for (int q = 0; q < CH; ++q) {
-            const int t = min(t0 + q, T - 1);
-            gq[q] = gn[t];
-            on[q] = mk[t];
-#pragma unroll
-            for (int c = 0; c < DK; ++c) mq[q][c] = mun[(size_t)t * DK + c];
+            for (int c = 0; c < DK; ++c) mp[c] = fma(kg, mun[(size_t)t * DK + c] - mp[c], mp[c]);
         }
 #pragma unroll
-        for (int q = 0; q < CH; ++q) {
-            const int t = t0 + q;
-            if (t < T) {
-                if (on[q]) {
-                    const R Pc = Pp * gq[q] / (Pp + gq[q]);
-                    const R kg = Pc / gq[q];
-#pragma unroll
-                    for (int c = 0; c < DK; ++c) mp[c] = fma(kg, mq[q][c] - mp[c], mp[c]);
-                    fPn[t] = Pc;
-                    Pp = Pc + sl;
-                } else {
-                    fPn[t] = Pp;
-                }
-#pragma unroll
-                for (int c = 0; c < DK; ++c) vn[(size_t)t * DK + c] = mp[c];
-            }
-        }
+        for (int c = 0; c < DK; ++c) vn[(size_t)t * DK + c] = mp[c];
     }
-    // backward sampling (w: injected tape or the normals written by heading_location_kernel)
-    auto normal = [&](int t, R* out) {
+    __syncthreads();
+    // ---- pass 3: backward sampling; thread order reversed so that the scan runs from T-1 down.
+    // Frame T-1 draws from its filter marginal: a constant map v = m + sqrt(P) w.
+    const int rt = NT - 1 - tid;
+    const int lo2 = min(rt * per, T), hi2 = min(lo2 + per, T);
+    auto back_elem = [&](int t) {
+        Aff e;
+        if (t == T - 1) {
+            const R sd = sqrt(fPn[t]);
+            e.a = 0;
 #pragma unroll
-        for (int c = 0; c < DK; ++c) out[c] = w_tape[((size_t)nn * T + t) * DK + c];
+            for (int c = 0; c < DK; ++c) e.b[c] = fma(sd, wn[(size_t)t * DK + c], vn[(size_t)t * DK + c]);
+        } else if (mk[t]) {
+            const R p = fPn[t];
+            const R gain = p / (p + sl);
+            const R sd = sqrt(gain * sl);
+            e.a = gain;
+#pragma unroll
+            for (int c = 0; c < DK; ++c) {
+                const R m = vn[(size_t)t * DK + c];
+                e.b[c] = fma(-gain, m, m) + sd * wn[(size_t)t * DK + c];
+            }
+        } else {
+            e = ida;
+        }
+        return e;
     };
-    R vc[DK], wn[DK];
-    {
-        const R Pl = fPn[T - 1];
-        normal(T - 1, wn);
-        const R sd = sqrt(Pl);
+    Aff runb = ida;
+    for (int t = hi2 - 1; t >= lo2; --t) runb = affine_after(back_elem(t), runb);
+    const Aff preb = block_exclusive_scan<R>(runb, ida, affine_after<R, DK>, sh_a);
+    R vc[DK];
 #pragma unroll
-        for (int c = 0; c < DK; ++c) { vc[c] = fma(sd, wn[c], vn[(size_t)(T - 1) * DK + c]); vn[(size_t)(T - 1) * DK + c] = vc[c]; }
-    }
-    for (int t1 = T - 2; t1 >= 0; t1 -= CH) {
-        R pq[CH], mq[CH][DK], wq[CH][DK];
-        int on[CH];
+    for (int c = 0; c < DK; ++c) vc[c] = preb.b[c];           // v_{hi2}: the map so far applied to anything
+    for (int t = hi2 - 1; t >= lo2; --t) {
+        if (t == T - 1) {
+            const R sd = sqrt(fPn[t]);
 #pragma unroll
-        for (int q = 0; q < CH; ++q) {
-            const int t = max(t1 - q, 0);
-            pq[q] = fPn[t];
-            on[q] = mk[t];
-            normal(t, wq[q]);
+            for (int c = 0; c < DK; ++c) vc[c] = fma(sd, wn[(size_t)t * DK + c], vn[(size_t)t * DK + c]);
+        } else if (mk[t]) {
+            const R p = fPn[t];
+            const R gain = p / (p + sl);
+            const R sd = sqrt(gain * sl);
 #pragma unroll
-            for (int c = 0; c < DK; ++c) mq[q][c] = vn[(size_t)t * DK + c];
-        }
-#pragma unroll
-        for (int q = 0; q < CH; ++q) {
-            const int t = t1 - q;
-            if (t >= 0) {
-                if (on[q]) {
-                    const R gain = pq[q] / (pq[q] + sl);
-                    const R sd = sqrt(gain * sl);
-#pragma unroll
-                    for (int c = 0; c < DK; ++c) vc[c] = fma(gain, vc[c] - mq[q][c], mq[q][c]) + sd * wq[q][c];
-                }
-#pragma unroll
-                for (int c = 0; c < DK; ++c) vn[(size_t)t * DK + c] = vc[c];
+            for (int c = 0; c < DK; ++c) {
+                const R m = vn[(size_t)t * DK + c];
+                vc[c] = fma(gain, vc[c] - m, m) + sd * wn[(size_t)t * DK + c];
             }
         }
+#pragma unroll
+        for (int c = 0; c < DK; ++c) vn[(size_t)t * DK + c] = vc[c];
     }
 }
 
@@ -339,7 +443,7 @@ static int headloc_impl(const void* Y, const int* mask, const void* x, const voi
         (const R*)Y, (const R*)x, (const R*)v_in, (const R*)h_in, (const R*)s, (const R*)Ct, (const R*)sigmasq, \
         fix_heading, (const R*)u_tape, seed, frames, k, d, (R*)h_out, mu, gsq, wbuf); }                              \
     KPMS_LAUNCH("location_ffbs", st);                                                                          \
-    location_ffbs_kernel<R, DK><<<N, 32, 0, st>>>(mu, gsq, mask, sigmasq_loc, wsrc, N, T, fP, (R*)v_out)
+    location_ffbs_kernel<R, DK, 1024><<<N, 1024, 0, st>>>(mu, gsq, mask, sigmasq_loc, wsrc, N, T, fP, (R*)v_out)
     if (Dk == 2) { LAUNCH(2); }
     else if (Dk == 3) { LAUNCH(3); }
     else return set_error(-3, "resample_heading_location: keypoint dimension must be 2 or 3, got %d", Dk);

@@ -134,10 +134,12 @@ struct FwdSmem {
 };
 
 template <typename R, int D_, int L_>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, const int* __restrict__ z,
                       const R* __restrict__ Ab, const R* __restrict__ Q, R jitter, int T,
-                      R* __restrict__ stash_m, R* __restrict__ stash_S) {
+                      R* __restrict__ stash_m, R* __restrict__ stash_S, int C, int W,
+                      const int* __restrict__ vlen, const int* __restrict__ dirty, R* __restrict__ bnd_warm,
+                      R* __restrict__ bnd_end) {
     typedef FwdSmem<R, D_, L_> SM;
     typedef typename Vec16<R>::type VecT;
     constexpr int n = SM::n, LD = SM::LD, NP = SM::NP, REC = SM::REC, NP2 = SM::NP2, VEC = SM::VEC,
@@ -171,8 +173,12 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
     R* inf = mb + 2 * n;                             // 2 x REC
     R* Qz = inf + 2 * REC;                           // 2 x D_*D_
     unsigned short* ij = reinterpret_cast<unsigned short*>(Qz + 2 * D_ * D_ + 4);
-    const int nn = blockIdx.x, tid = threadIdx.x;
+    const int nn = blockIdx.x, tid = threadIdx.x, ck = blockIdx.y;
     const int Tx = T - L_ + 1;
+    if (dirty && dirty[nn] == 0) return;             // sequential re-run of flagged chains only
+    const ChunkRange cr = chunk_range(vlen ? vlen[nn] : Tx, Tx, C, W, ck);
+    if (cr.empty) return;
+    constexpr int BREC = n + n * n;                  // boundary record: mean | covariance
     const R* inf_g = info + (size_t)nn * Tx * REC;
     const int* mk = mask + (size_t)nn * T + (L_ - 1);
     const int* zz = z + (size_t)nn * (Tx - 1);
@@ -209,19 +215,21 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
         }
     };
     R pre[NPRE];
-    int z_next = (Tx > 1) ? zz[0] : -1;              // z for step i+1 while running step i
-    stage_load(0, z_next, pre);
-    stage_store(0, pre);
-    z_next = (Tx > 2) ? zz[1] : -1;
-    int mk_cur = mk[0];
+    const int i0 = cr.start, i1 = cr.end;            // steps [i0, i1); outputs for i >= cr.begin
+    int z_next = (i0 < Tx - 1) ? zz[i0] : -1;        // z for step i+1 while running step i
+    stage_load(i0, z_next, pre);
+    stage_store(i0 & 1, pre);
+    z_next = (i0 + 1 < Tx - 1) ? zz[i0 + 1] : -1;
+    int mk_cur = mk[i0];
     int pb = 0;                                      // which Pb / mb buffer holds the current prediction
     __syncthreads();
 
-    for (int i = 0; i < Tx; ++i) {
+    for (int i = i0; i < i1; ++i) {
         const int b = i & 1;
         const bool last = (i == Tx - 1);
-        const int mk_next = last ? 0 : mk[i + 1];
-        if (!last) stage_load(i + 1, z_next, pre);
+        const bool keep = (i >= cr.begin);           // warm-up steps store nothing
+        const int mk_next = (i + 1 < Tx) ? mk[i + 1] : 0;
+        if (i + 1 < i1) stage_load(i + 1, z_next, pre);
         const int z_next2 = (i + 2 < Tx - 1) ? zz[i + 2] : -1;
         const R* fi = inf + b * REC;
         const R* A = Az + b * D_ * AP;
@@ -230,6 +238,10 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
         R* Pn = Pb + (pb ^ 1) * n * LD;
         const R* m0 = mb + pb * n;
         R* mn = mb + (pb ^ 1) * n;
+        if (ck > 0 && i == cr.begin) {               // the state this chunk arrived with
+            R* bw = bnd_warm + ((size_t)nn * C + ck) * BREC;
+            for (int w = tid; w < BREC; w += NT) bw[w] = (w < n) ? m0[w] : P0[((w - n) / n) * LD + (w - n) % n];
+        }
         if (mk_cur != 0) {
             // ---------------- phase 1
             constexpr int TPI = NG * n * 2;
@@ -430,7 +442,7 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
                     if (u < NP2) {                              // P+ (stash) and the shifted old-old block
                         const int r = ij[u] >> 8, c = ij[u] & 255;
                         const R val = P0[r * LD + c] - rowdot(V + r * DP, V + c * DP);
-                        sS_g[(size_t)i * NP2 + u] = val;
+                        if (keep) sS_g[(size_t)i * NP2 + u] = val;
                         if (!last && c >= D_) {
                             const R v2 = val + ((r == c) ? eps : (R)0);
                             Pn[(r - D_) * LD + (c - D_)] = v2;
@@ -460,7 +472,7 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
                         R acc = m0[u] + pc[u];
 #pragma unroll
                         for (int c = 0; c < D_; ++c) acc = fma(-V[u * DP + c], tvec[c], acc);
-                        sm_g[(size_t)i * n + u] = acc;
+                        if (keep) sm_g[(size_t)i * n + u] = acc;
                         continue;
                     }
                     u -= n;
@@ -480,10 +492,16 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
             }
             for (int w = tid; w < n; w += NT) sm_g[(size_t)i * n + w] = m0[w];
         }
-        if (!last) stage_store(b ^ 1, pre);
+        if (i + 1 < i1) stage_store(b ^ 1, pre);
         z_next = z_next2;
         mk_cur = mk_next;
         __syncthreads();
+    }
+    if (i1 < Tx) {                                   // the state handed to the next chunk
+        R* be = bnd_end + ((size_t)nn * C + ck + 1) * BREC;
+        const R* P0 = Pb + pb * n * LD;
+        const R* m0 = mb + pb * n;
+        for (int w = tid; w < BREC; w += NT) be[w] = (w < n) ? m0[w] : P0[((w - n) / n) * LD + (w - n) % n];
     }
 }
 
@@ -675,18 +693,29 @@ kalman_backprep_kernel(const R* __restrict__ stash_m, const R* __restrict__ stas
 // ---------------------------------------------------------------------------
 template <typename R, int D_, int L_, int STAGES>
 __global__ void __launch_bounds__(32)
-kalman_affine_kernel(const R* __restrict__ GH, int T, R* __restrict__ x) {
+kalman_affine_kernel(const R* __restrict__ GH, int T, R* __restrict__ x, int C, int W,
+                     const int* __restrict__ vlen, const int* __restrict__ dirty, R* __restrict__ bx_warm,
+                     R* __restrict__ bx_exact) {
     constexpr int n = D_ * L_, NN = n * n;
     constexpr int RECP = PrepSmem<R, D_, L_>::RECS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R* ring = reinterpret_cast<R*>(smem_raw);        // STAGES x RECP
     R* xi = ring + (size_t)STAGES * RECP;            // n
-    const int nn = blockIdx.x, lane = threadIdx.x;
+    const int nn = blockIdx.x, ck = blockIdx.y, lane = threadIdx.x;
     const int Tx = T - L_ + 1;
+    if (dirty && dirty[nn] == 0) return;
+    const ChunkRange cr = chunk_range(vlen ? vlen[nn] : Tx, Tx, C, W, ck);
+    if (cr.empty) return;
     const R* Gn = GH + (size_t)nn * Tx * RECP;
     R* xn = x + (size_t)nn * T * D_;
+    // The recursion runs downward from `top`.  The last chunk starts at the chain's terminal draw
+    // xi_{Tx-1} = h_{Tx-1}; the others start W steps above their range from an arbitrary value
+    // (warm-up) and publish the xi they reach at their upper boundary for the check.
+    const bool exact_top = (cr.end == Tx);
+    const int top = exact_top ? Tx - 1 : min(cr.end + W, Tx - 1);
+    const int lowest = cr.begin;
     auto issue = [&](int i) {
-        if (i >= 0) {
+        if (i >= lowest) {
             constexpr int CHUNKS = RECP * (int)sizeof(R) / 16;
             char* dst = reinterpret_cast<char*>(ring + (size_t)(i % STAGES) * RECP);
             const char* src = reinterpret_cast<const char*>(Gn + (size_t)i * RECP);
@@ -697,13 +726,20 @@ kalman_affine_kernel(const R* __restrict__ GH, int T, R* __restrict__ x) {
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
-    // terminal state
-    for (int r = lane; r < n; r += 32) xi[r] = Gn[(size_t)(Tx - 1) * RECP + NN + r];
-    for (int s = 0; s < STAGES - 1; ++s) issue(Tx - 2 - s);
+    auto emit = [&](int i, int r, R val) {           // x frames carried by xi_i
+        if (i == 0) xn[r] = val;                                            // frames 0..L-1 from xi_0
+        else if (r >= n - D_) xn[(size_t)(i + L_ - 1) * D_ + (r - (n - D_))] = val;
+    };
+    const bool top_known = (top == Tx - 1);
+    for (int r = lane; r < n; r += 32) xi[r] = top_known ? Gn[(size_t)top * RECP + NN + r] : (R)0;
+    for (int s = 0; s < STAGES - 1; ++s) issue(top - 1 - s);
     __syncwarp();
-    if (Tx == 1) { for (int r = lane; r < n; r += 32) xn[r] = xi[r]; }
-    else { for (int r = lane; r < D_; r += 32) xn[(size_t)(Tx - 1 + L_ - 1) * D_ + r] = xi[(n - D_) + r]; }
-    for (int i = Tx - 2; i >= 0; --i) {
+    for (int r = lane; r < n; r += 32) {
+        if (top < cr.end) emit(top, r, xi[r]);
+        if (top == cr.end) bx_warm[((size_t)nn * C + ck + 1) * n + r] = xi[r];
+        if (top == lowest && ck > 0) bx_exact[((size_t)nn * C + ck) * n + r] = xi[r];
+    }
+    for (int i = top - 1; i >= lowest; --i) {
         issue(i - (STAGES - 1));
         asm volatile("cp.async.wait_group %0;\n" ::"n"(STAGES - 1));
         __syncwarp();
@@ -736,8 +772,9 @@ kalman_affine_kernel(const R* __restrict__ GH, int T, R* __restrict__ x) {
             int r = lane + 32 * q;
             if (r < n) {
                 xi[r] = nv[q];
-                if (i == 0) xn[r] = nv[q];                                  // frames 0..L-1 from xi_0
-                else if (r >= n - D_) xn[(size_t)(i + L_ - 1) * D_ + (r - (n - D_))] = nv[q];
+                if (i < cr.end) emit(i, r, nv[q]);
+                if (i == cr.end) bx_warm[((size_t)nn * C + ck + 1) * n + r] = nv[q];
+                if (i == lowest && ck > 0) bx_exact[((size_t)nn * C + ck) * n + r] = nv[q];
             }
         }
         __syncwarp();
@@ -747,16 +784,28 @@ kalman_affine_kernel(const R* __restrict__ GH, int T, R* __restrict__ x) {
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// workspace: [diagnostics 256 B | vlen | dirty fwd | dirty bwd | info | stash_m | stash_S | GH |
+//             boundary records of the forward filter (warm, end) and of the backward recursion (warm, exact)]
+// diagnostics (unsigned[4]): max forward boundary discrepancy (float bits), forward chains re-run
+// sequentially, max backward discrepancy (float bits), backward chains re-run.
+enum { KW_DIAG, KW_VLEN, KW_DIRTY_F, KW_DIRTY_B, KW_INFO, KW_SM, KW_SS, KW_GH, KW_BFW, KW_BFE, KW_BBW, KW_BBE, KW_END };
+
 template <typename R>
-static void kalman_ws_layout(int N, int T, int d, int L, size_t off[5]) {
+static void kalman_ws_layout(int N, int T, int d, int L, int C, int Cb, size_t off[KW_END + 1]) {
     const size_t n = (size_t)d * L, Tx = T - L + 1, fr = (size_t)N * Tx;
     const size_t rec = (size_t)d * (d + 1) / 2 + d, np2 = n * (n + 1) / 2;
     const size_t recs = ((n * n + n) * sizeof(R) + 15) / 16 * 16 / sizeof(R);
+    const size_t brec = n + n * n, nb = (size_t)N * (C + 1), nbb = (size_t)N * (Cb + 1);
+    size_t sz[KW_END] = {256, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4, fr * rec * sizeof(R), fr * n * sizeof(R),
+                         fr * np2 * sizeof(R), fr * recs * sizeof(R), nb * brec * sizeof(R), nb * brec * sizeof(R),
+                         nbb * n * sizeof(R), nbb * n * sizeof(R)};
     off[0] = 0;
-    off[1] = off[0] + align_up(fr * rec * sizeof(R), 256);     // info
-    off[2] = off[1] + align_up(fr * n * sizeof(R), 256);       // stash_m
-    off[3] = off[2] + align_up(fr * np2 * sizeof(R), 256);     // stash_S
-    off[4] = off[3] + align_up(fr * recs * sizeof(R), 256);    // GH
+    for (int i = 0; i < KW_END; ++i) off[i + 1] = off[i] + align_up(sz[i], 256);
+}
+
+// chunks per chain for the Kalman recursions: enough chunk-CTAs to fill the device once
+static int kalman_chunks(int N, int T, int L, bool backward) {
+    return chunks_for(N, KPMS_SM_COUNT * (backward ? 12 : 3), T - L + 1, chunk_config().warmup);
 }
 
 template <typename R, int D_, int L_>
@@ -766,14 +815,30 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
                          cudaStream_t st) {
     constexpr int n = D_ * L_;
     const int Tx = T - L_ + 1;
-    size_t off[5];
-    kalman_ws_layout<R>(N, T, D_, L_, off);
+    const ChunkConfig cfg = chunk_config();
+    const int C = kalman_chunks(N, T, L_, false), Cb = kalman_chunks(N, T, L_, true), W = cfg.warmup;
+    const R tol = (R)(sizeof(R) == 4 ? cfg.tol32 : cfg.tol64);
+    size_t off[KW_END + 1];
+    kalman_ws_layout<R>(N, T, D_, L_, C, Cb, off);
     char* base = reinterpret_cast<char*>(ws);
-    R* info = reinterpret_cast<R*>(base + off[0]);
-    R* stash_m = reinterpret_cast<R*>(base + off[1]);
-    R* stash_S = reinterpret_cast<R*>(base + off[2]);
-    R* GH = reinterpret_cast<R*>(base + off[3]);
+    unsigned* diag = reinterpret_cast<unsigned*>(base + off[KW_DIAG]);
+    int* vlen = reinterpret_cast<int*>(base + off[KW_VLEN]);
+    int* dirty_f = reinterpret_cast<int*>(base + off[KW_DIRTY_F]);
+    int* dirty_b = reinterpret_cast<int*>(base + off[KW_DIRTY_B]);
+    R* info = reinterpret_cast<R*>(base + off[KW_INFO]);
+    R* stash_m = reinterpret_cast<R*>(base + off[KW_SM]);
+    R* stash_S = reinterpret_cast<R*>(base + off[KW_SS]);
+    R* GH = reinterpret_cast<R*>(base + off[KW_GH]);
+    R* bfw = reinterpret_cast<R*>(base + off[KW_BFW]);
+    R* bfe = reinterpret_cast<R*>(base + off[KW_BFE]);
+    R* bbw = reinterpret_cast<R*>(base + off[KW_BBW]);
+    R* bbe = reinterpret_cast<R*>(base + off[KW_BBE]);
     const long long frames = (long long)N * Tx;
+    cudaMemsetAsync(diag, 0, 256, st);
+    if (C > 1 || Cb > 1) {
+        KPMS_LAUNCH("valid_len", st);
+        valid_len_kernel<<<N, 256, 0, st>>>(mask, T, L_ - 1, Tx, vlen);
+    }
     {
         size_t smem = ((size_t)k * Dk * (D_ + 1) + k) * sizeof(R);
         int blocks = (int)((frames + 127) / 128);
@@ -789,7 +854,20 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         auto kern = kalman_forward_kernel<R, D_, L_>;
         size_t smem = FwdSmem<R, D_, L_>::bytes;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        { KPMS_LAUNCH("kalman_forward", st); kern<<<N, 256, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, T, stash_m, stash_S); }
+        if (C > 1) {
+            { KPMS_LAUNCH("kalman_forward", st);
+              kern<<<dim3(N, C), 256, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, T, stash_m, stash_S, C, W, vlen,
+                                                  nullptr, bfw, bfe); }
+            { KPMS_LAUNCH("kalman_forward_check", st);
+              boundary_check_kernel<R><<<N, 128, 0, st>>>(bfw, bfe, vlen, Tx, C, W, n, n + n * n, tol, dirty_f, diag); }
+            { KPMS_LAUNCH("kalman_forward_rerun", st);       // exits at once for chains whose boundaries agree
+              kern<<<dim3(N, 1), 256, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, T, stash_m, stash_S, 1, 0, nullptr,
+                                                  dirty_f, bfw, bfe); }
+        } else {
+            KPMS_LAUNCH("kalman_forward", st);
+            kern<<<dim3(N, 1), 256, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, T, stash_m, stash_S, 1, 0, nullptr,
+                                                nullptr, bfw, bfe);
+        }
         int rc = check_launch("kalman forward");
         if (rc) return rc;
     }
@@ -804,11 +882,21 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         if (rc) return rc;
     }
     {
-        constexpr int STAGES = 8;
+        constexpr int STAGES = 4;
         auto kern = kalman_affine_kernel<R, D_, L_, STAGES>;
         size_t smem = ((size_t)STAGES * PrepSmem<R, D_, L_>::RECS + n) * sizeof(R);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        { KPMS_LAUNCH("kalman_affine", st); kern<<<N, 32, smem, st>>>(GH, T, x); }
+        if (Cb > 1) {
+            { KPMS_LAUNCH("kalman_affine", st);
+              kern<<<dim3(N, Cb), 32, smem, st>>>(GH, T, x, Cb, W, vlen, nullptr, bbw, bbe); }
+            { KPMS_LAUNCH("kalman_affine_check", st);
+              boundary_check_kernel<R><<<N, 128, 0, st>>>(bbw, bbe, vlen, Tx, Cb, W, n, n, tol, dirty_b, diag + 2); }
+            { KPMS_LAUNCH("kalman_affine_rerun", st);
+              kern<<<dim3(N, 1), 32, smem, st>>>(GH, T, x, 1, 0, nullptr, dirty_b, bbw, bbe); }
+        } else {
+            KPMS_LAUNCH("kalman_affine", st);
+            kern<<<dim3(N, 1), 32, smem, st>>>(GH, T, x, 1, 0, nullptr, nullptr, bbw, bbe);
+        }
         int rc = check_launch("kalman affine");
         if (rc) return rc;
     }
@@ -839,10 +927,11 @@ using namespace kpms;
 extern "C" {
 
 size_t kpms_kalman_workspace_bytes(int dtype, int N, int T, int d, int L) {
-    size_t off[5];
-    if (dtype == 0) kalman_ws_layout<float>(N, T, d, L, off);
-    else kalman_ws_layout<double>(N, T, d, L, off);
-    return off[4];
+    size_t off[KW_END + 1];
+    const int C = kalman_chunks(N, T, L, false), Cb = kalman_chunks(N, T, L, true);
+    if (dtype == 0) kalman_ws_layout<float>(N, T, d, L, C, Cb, off);
+    else kalman_ws_layout<double>(N, T, d, L, C, Cb, off);
+    return off[KW_END];
 }
 
 int kpms_kalman_sample(int dtype, const void* Y, const int* mask, const void* v, const void* h, const void* s,

@@ -18,7 +18,7 @@ __all__ = [
     "resample_scales", "resample_heading_location", "resample_ar_params",
     "resample_hdp_transitions", "resample_obs_variance", "sufficient_statistics",
     "marginal_log_likelihood", "stateseq_marginals", "lifted_obs_matrix", "seed_to_u64",
-    "advance_seed", "to_device_model", "to_device_data",
+    "advance_seed", "to_device_model", "to_device_data", "chunk_diagnostics",
 ]
 
 _SCRATCH = {}
@@ -32,6 +32,23 @@ def _scratch(tag, nbytes, device):
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _SCRATCH[key] = buf
     return buf
+
+
+def chunk_diagnostics(tag="kalman_ws", device="cuda"):
+    """Diagnostics of the last time-chunked call that used scratch `tag` (synchronises):
+    largest boundary discrepancy and number of chains re-run sequentially, forward and backward."""
+    buf = _SCRATCH.get((tag, str(torch.device(device) if not isinstance(device, torch.device) else device)))
+    if buf is None:
+        for (t, _), b in _SCRATCH.items():
+            if t == tag:
+                buf = b
+    if buf is None:
+        return None
+    raw = buf[:16].cpu().numpy()
+    u = raw.view(np.uint32)
+    f = raw.view(np.float32)
+    return {"forward_max_err": float(f[0]), "forward_rerun": int(u[1]),
+            "backward_max_err": float(f[2]), "backward_rerun": int(u[3])}
 
 
 def _dev(a, dtype, device):

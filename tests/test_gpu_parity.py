@@ -210,3 +210,63 @@ def test_philox_sweeps_are_finite_and_reproducible():
                                     _np(runs[0]["states"]["h"]).astype(float), _np(runs[0]["params"]["Cd"]), 5, 2)
     resid = (data["Y"] - Yhat)[data["mask"] > 0]
     assert np.sqrt((resid ** 2).mean()) < 1.5
+
+
+# ----------------------------------------------------------------------------
+# time-parallel chunks: same answers as the sequential recursion, with and without the fallback
+# ----------------------------------------------------------------------------
+@pytest.fixture
+def chunking():
+    from keypoint_moseq_b200 import _lib
+    yield _lib.set_time_chunking
+    _lib.set_time_chunking(chunks=0, warmup=64, tol32=2e-5, tol64=1e-10)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, F64_TOL), (torch.float32, F32_TOL)])
+@pytest.mark.parametrize("mode", ["chunked", "fallback", "sequential"])
+def test_continuous_stateseqs_time_chunks(dtype, tol, mode, chunking):
+    """Long ragged chains cut into concurrent chunks: the draw must equal the oracle's sequential
+    FFBS.  `fallback` uses a warm-up too short to forget, so the boundary check must flag the
+    chains and the sequential re-run must restore the exact answer."""
+    g = _gibbs()
+    data, _, model = small_problem(seed=11, recordings=2, frames=1500, seg_length=1000, d=4, L=3, K=12, k=5, D=2)
+    tape = tape_for(data, model)
+    data, model, tape = _cast_problem(data, model, tape, dtype)
+    st, pr = model["states"], model["params"]
+    x_ref = orc.resample_continuous_stateseqs(data["Y"], data["mask"], st["v"], st["h"], st["s"], st["z"], pr["Cd"],
+                                              pr["sigmasq"], pr["Ab"], pr["Q"], 1e-3, tape["w_x"])
+    dd, dm = _to_dev(data, model, dtype)
+    s_, p_ = dm["states"], dm["params"]
+    if mode == "chunked":
+        chunking(chunks=4, warmup=48)
+    elif mode == "fallback":
+        chunking(chunks=4, warmup=1)
+    else:
+        chunking(chunks=1)
+    x = g.resample_continuous_stateseqs(dd["Y"], dd["mask"], s_["v"], s_["h"], s_["s"], s_["z"], p_["Cd"],
+                                        p_["sigmasq"], p_["Ab"], p_["Q"], 1e-3, w_x=torch.as_tensor(tape["w_x"]))
+    diag = g.chunk_diagnostics("kalman_ws")
+    assert rel_err(_np(x), x_ref) < tol, diag
+    if mode == "chunked":
+        assert diag["forward_rerun"] == 0 and diag["backward_rerun"] == 0, diag
+        assert diag["forward_max_err"] < (2e-5 if dtype == torch.float32 else 1e-10), diag
+    elif mode == "fallback":
+        assert diag["forward_rerun"] > 0, diag
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, F64_TOL), (torch.float32, F32_TOL)])
+@pytest.mark.parametrize("frames,seg", [(1500, 1000), (5200, 5000)])
+def test_location_scan_long_chains(dtype, tol, frames, seg):
+    """The centroid FFBS is a parallel scan over time: check it on chains much longer than the CTA."""
+    g = _gibbs()
+    data, _, model = small_problem(seed=12, recordings=2, frames=frames, seg_length=seg, d=4, L=3, K=8, k=6, D=2)
+    tape = tape_for(data, model)
+    data, model, tape = _cast_problem(data, model, tape, dtype)
+    st, pr = model["states"], model["params"]
+    dd, dm = _to_dev(data, model, dtype)
+    s_, p_ = dm["states"], dm["params"]
+    h, v = g.resample_heading_location(dd["Y"], dd["mask"], s_["x"], s_["v"], s_["h"], s_["s"], p_["Cd"],
+                                       p_["sigmasq"], 0.5, fix_heading=True, w_v=torch.as_tensor(tape["w_v"]))
+    v_ref = orc.resample_location(data["Y"], data["mask"], st["x"], st["h"], st["s"], pr["Cd"], pr["sigmasq"], 0.5,
+                                  tape["w_v"])
+    assert rel_err(_np(v), v_ref) < tol
