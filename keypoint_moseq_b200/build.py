@@ -40,7 +40,7 @@ def build(verbose=False, force=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if procs or not os.path.exists(LIB):
+    if procs or _stale(LIB, objs):
         subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
     return LIB
 

@@ -239,11 +239,12 @@ struct ChunkRange {
     int begin, end, start;     // outputs for steps [begin, end); forward recursions start at `start` <= begin
     bool empty;
 };
-__host__ __device__ inline ChunkRange chunk_range(int vlen, int len, int C, int W, int c) {
+__host__ __device__ inline ChunkRange chunk_range(int vlen, int len, int C, int W, int c, int align = 1) {
     ChunkRange r;
     int Lc = (vlen + C - 1) / C;
     if (Lc < 4 * W) Lc = 4 * W;
     if (Lc < 1) Lc = 1;
+    Lc = (Lc + align - 1) / align * align;           // chunk starts on a multiple of `align` (W must be one too)
     int Cn = (vlen + Lc - 1) / Lc;
     if (Cn < 1) Cn = 1;
     r.empty = c >= Cn;
@@ -274,14 +275,14 @@ valid_len_kernel(const int* __restrict__ mask, int T, int off, int len, int* __r
 template <typename R>
 __global__ void __launch_bounds__(128)
 boundary_check_kernel(const R* __restrict__ warm, const R* __restrict__ exact, const int* __restrict__ vlen,
-                      int len, int C, int W, int n_mean, int rec, R tol, int* __restrict__ dirty,
+                      int len, int C, int W, int align, int n_mean, int rec, R tol, int* __restrict__ dirty,
                       unsigned* __restrict__ stats) {
     __shared__ R red[2][4];
     const int nn = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     R worst = 0;
     int bad = 0;
     for (int c = 1; c < C; ++c) {
-        const ChunkRange r = chunk_range(vlen[nn], len, C, W, c);
+        const ChunkRange r = chunk_range(vlen[nn], len, C, W, c, align);
         if (r.empty) break;
         const R* a = warm + ((size_t)nn * C + c) * rec;
         const R* b = exact + ((size_t)nn * C + c) * rec;

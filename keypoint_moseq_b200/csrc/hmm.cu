@@ -170,14 +170,21 @@ ar_loglik_kernel(const R* __restrict__ x, const int* __restrict__ mask, const R*
 template <typename R, int RPT>
 __global__ void __launch_bounds__(4 * 128)
 hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* __restrict__ pi,
-                   int K, int Tp, int ldT, int ldK, R* __restrict__ filt, double* __restrict__ logZ) {
+                   int K, int Tp, int ldT, int ldK, R* __restrict__ filt, double* __restrict__ logZ,
+                   int C, int Wm, const int* __restrict__ vlen, const int* __restrict__ dirty,
+                   R* __restrict__ bnd_warm, R* __restrict__ bnd_end, double* __restrict__ logZ_part) {
     constexpr int VEC = 16 / sizeof(R);
     constexpr int RPTP = (RPT + VEC - 1) / VEC * VEC;
     constexpr int CH = 8;                                    // steps per prefetched chunk (ldT % 8 == 0)
     __shared__ __align__(16) R qbuf[2][4 * RPTP];
     __shared__ double red[32];
-    const int nn = blockIdx.x;
+    const int nn = blockIdx.x, ck = blockIdx.y;
     const int tid = threadIdx.x;
+    if (dirty && dirty[nn] == 0) return;
+    // time chunk (common.cuh): outputs for [cr.begin, cr.end), recursion from cr.start with the
+    // uniform prior; all three are multiples of CH except the chain end
+    const ChunkRange cr = chunk_range(vlen ? vlen[nn] : Tp, Tp, C, Wm, ck, 8);
+    if (cr.empty) return;
     const int j = tid >> 2, p = tid & 3;
     const bool col = j < K;
     R pic[RPT];
@@ -189,7 +196,7 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
     for (int i = tid; i < 2 * 4 * RPTP; i += blockDim.x) (&qbuf[0][0])[i] = (R)0;
     // sum of per-frame maxima (part of the log-normaliser)
     double msum = 0.0;
-    for (int t = tid; t < Tp; t += blockDim.x) msum += (double)mx[(size_t)nn * ldT + t];
+    for (int t = cr.begin + tid; t < cr.end; t += blockDim.x) msum += (double)mx[(size_t)nn * ldT + t];
     msum = block_sum(msum, red);
     const R* Wc = W + ((size_t)nn * K + (col ? j : 0)) * ldT;
     R* fl = filt + (size_t)nn * Tp * ldK;
@@ -210,22 +217,24 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
             for (int c = 0; c < CH; ++c) dst[c] = (R)0;
         }
     };
-    load_chunk(0, cur);
+    load_chunk(cr.start, cur);
     R pred = (R)1 / (R)K;
     R inv_s = (R)1;
     R qprev = (R)0;
     double lz = 0.0;
     int buf = 0;
-    for (int t0 = 0; t0 < Tp; t0 += CH) {
+    for (int t0 = cr.start; t0 < cr.end; t0 += CH) {
         load_chunk(t0 + CH, nxt);
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             const int t = t0 + c;
-            if (t >= Tp) break;
+            if (t >= cr.end) break;
+            if (ck > 0 && t == cr.begin && col && p == 0)          // the prediction this chunk arrived with
+                bnd_warm[((size_t)nn * C + ck) * K + j] = pred * inv_s;
             R qv = pred * inv_s * cur[c];
             if (col && p == 0) {
                 qbuf[buf][qslot] = qv;
-                if (t > 0) fl[(size_t)(t - 1) * ldK + j] = qprev * inv_s;
+                if (t > cr.begin) fl[(size_t)(t - 1) * ldK + j] = qprev * inv_s;
             }
             __syncthreads();
             const R* qs = &qbuf[buf][p * RPTP];
@@ -247,14 +256,33 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
             pred = a;
             inv_s = (R)1 / s;
             qprev = qv;
-            if (tid == 0) lz += log((double)s);
+            if (tid == 0 && t >= cr.begin) lz += log((double)s);
             buf ^= 1;
         }
 #pragma unroll
         for (int c = 0; c < CH; ++c) cur[c] = nxt[c];
     }
-    if (col && p == 0) fl[(size_t)(Tp - 1) * ldK + j] = qprev * inv_s;
-    if (tid == 0) logZ[nn] = lz + msum;
+    if (col && p == 0) {
+        fl[(size_t)(cr.end - 1) * ldK + j] = qprev * inv_s;
+        if (cr.end < Tp) bnd_end[((size_t)nn * C + ck + 1) * K + j] = pred * inv_s;   // handed to the next chunk
+    }
+    if (tid == 0) {
+        if (logZ_part) logZ_part[(size_t)nn * C + ck] = lz + msum;
+        else logZ[nn] = lz + msum;
+    }
+}
+
+// logZ[nn] = ordered sum of the chunks' parts (chains flagged dirty are overwritten by the re-run)
+__global__ void logz_sum_kernel(const double* __restrict__ part, const int* __restrict__ vlen, int N, int Tp, int C,
+                                int Wm, double* __restrict__ logZ) {
+    const int nn = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nn >= N) return;
+    double acc = 0.0;
+    for (int c = 0; c < C; ++c) {
+        if (chunk_range(vlen[nn], Tp, C, Wm, c, 8).empty) break;
+        acc += part[(size_t)nn * C + c];
+    }
+    logZ[nn] = acc;
 }
 
 // ---------------------------------------------------------------------------
@@ -275,19 +303,29 @@ __global__ void fill_uniform_kernel(R* __restrict__ u, long long count, uint64_t
 template <typename R, int VPL, int STAGES>
 __global__ void __launch_bounds__(32)
 hmm_backward_kernel(const R* __restrict__ filt, const R* __restrict__ piT, const R* __restrict__ u_src,
-                    int K, int Tp, int ldK, int* __restrict__ z) {
+                    int K, int Tp, int ldK, int* __restrict__ z, int C, int Wm, const int* __restrict__ vlen,
+                    const int* __restrict__ dirty, int* __restrict__ bz_warm, int* __restrict__ bz_exact) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R* pis = reinterpret_cast<R*>(smem_raw);                 // K x ldK
     R* ring = pis + (size_t)K * ldK;                         // STAGES x ldK
-    const int nn = blockIdx.x;
+    const int nn = blockIdx.x, ck = blockIdx.y;
     const int lane = threadIdx.x;
+    if (dirty && dirty[nn] == 0) return;
+    // Time chunk: labels for [cr.begin, cr.end).  The last chunk starts from the chain's terminal
+    // draw; the others start Wm steps above their range from an unconditioned draw and, because
+    // every step is the same deterministic map of (z_{t+1}, u_t), merge with the sequential
+    // sampler's path as soon as the two agree once.  The label used at the upper boundary is
+    // published and compared with the neighbour's own label (exact integer check).
+    const ChunkRange cr = chunk_range(vlen ? vlen[nn] : Tp, Tp, C, Wm, ck, 8);
+    if (cr.empty) return;
+    const int top = (cr.end == Tp) ? Tp : min(cr.end + Wm, Tp);   // first step taken is t = top - 1
     for (int i = lane; i < K * ldK; i += 32) pis[i] = piT[i];
     const R* fl = filt + (size_t)nn * Tp * ldK;
     const R* un = u_src + (size_t)nn * Tp;
     int* zn = z + (size_t)nn * Tp;
     const int chunks = ldK * (int)sizeof(R) / 16;
     auto issue = [&](int t) {
-        if (t >= 0) {
+        if (t >= cr.begin) {
             char* dst = reinterpret_cast<char*>(ring + (size_t)(t % STAGES) * ldK);
             const char* src = reinterpret_cast<const char*>(fl + (size_t)t * ldK);
             for (int c = lane; c < chunks; c += 32) {
@@ -297,17 +335,17 @@ hmm_backward_kernel(const R* __restrict__ filt, const R* __restrict__ piT, const
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
-    for (int s2 = 0; s2 < STAGES - 1; ++s2) issue(Tp - 1 - s2);
-    // uniforms: block b covers steps t = Tp-1-32b-lane
+    for (int s2 = 0; s2 < STAGES - 1; ++s2) issue(top - 1 - s2);
+    // uniforms: block b covers steps t = top-1-32b-lane
     auto load_u = [&](int blk) {
-        const int t = Tp - 1 - 32 * blk - lane;
-        return (t >= 0) ? un[t] : (R)0.5;
+        const int t = top - 1 - 32 * blk - lane;
+        return (t >= cr.begin) ? un[t] : (R)0.5;
     };
     R ucur = load_u(0), unext = load_u(1);
     __syncwarp();
     int znext = -1;
-    for (int t = Tp - 1; t >= 0; --t) {
-        const int step = Tp - 1 - t;
+    for (int t = top - 1; t >= cr.begin; --t) {
+        const int step = top - 1 - t;
         if (step > 0 && (step & 31) == 0) { ucur = unext; unext = load_u((step >> 5) + 1); }
         const R u = __shfl_sync(0xffffffffu, ucur, step & 31);
         issue(t - (STAGES - 1));
@@ -349,9 +387,28 @@ hmm_backward_kernel(const R* __restrict__ filt, const R* __restrict__ piT, const
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         znext = min(cnt, K - 1);
-        if (lane == 0) zn[t] = znext;
+        if (lane == 0) {
+            if (t < cr.end) zn[t] = znext;
+            if (t == cr.end) bz_warm[(size_t)nn * C + ck + 1] = znext;
+            if (t == cr.begin && ck > 0) bz_exact[(size_t)nn * C + ck] = znext;
+        }
         __syncwarp();
     }
+}
+
+// exact boundary check for the label paths
+__global__ void label_check_kernel(const int* __restrict__ warm, const int* __restrict__ exact,
+                                   const int* __restrict__ vlen, int N, int Tp, int C, int Wm,
+                                   int* __restrict__ dirty, unsigned* __restrict__ stats) {
+    const int nn = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nn >= N) return;
+    int bad = 0;
+    for (int c = 1; c < C; ++c) {
+        if (chunk_range(vlen[nn], Tp, C, Wm, c, 8).empty) break;
+        bad |= warm[(size_t)nn * C + c] != exact[(size_t)nn * C + c];
+    }
+    dirty[nn] = bad;
+    if (bad) atomicAdd(&stats[1], 1u);
 }
 
 template <typename R>
@@ -461,7 +518,8 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
 #define LAUNCH(RPT)                                                                                      \
     { KPMS_LAUNCH("hmm_forward", st);                                                                  \
     hmm_forward_kernel<R, RPT><<<grid, block, 0, st>>>((const R*)W, (const R*)mx, (const R*)pi, K, Tp,  \
-                                                       ldT, ldK, (R*)filt, logZ); }
+                                                       ldT, ldK, (R*)filt, logZ, 1, 0, nullptr, nullptr,  \
+                                                       nullptr, nullptr, nullptr); }
     if (K <= 28) { LAUNCH(7); }
     else if (K <= 52) { LAUNCH(13); }
     else if (K <= 100) { LAUNCH(25); }
@@ -492,7 +550,7 @@ static int hmm_backward_impl(const void* filt, const void* pi, const void* u, vo
     size_t smem = ((size_t)K * ldK + (size_t)STAGES * ldK) * sizeof(R);
     auto kern = hmm_backward_kernel<R, 4, STAGES>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    { KPMS_LAUNCH("hmm_backward", st); kern<<<N, 32, smem, st>>>((const R*)filt, piT, usrc, K, Tp, ldK, z); }
+    { KPMS_LAUNCH("hmm_backward", st); kern<<<N, 32, smem, st>>>((const R*)filt, piT, usrc, K, Tp, ldK, z, 1, 0, nullptr, nullptr, nullptr, nullptr); }
     return check_launch("hmm_backward");
 }
 

@@ -13,6 +13,8 @@
 // Frame index i = t - (L-1), i in [0, Tx), Tx = T - L + 1.  z[i] governs the transition i -> i+1.
 // Layouts: info (N,Tx,REC) REC = d(d+1)/2 + d;  stash_m (N,Tx,n);  stash_S (N,Tx,n(n+1)/2) packed lower;
 //          GH (N,Tx,RECS): [GT (n*n) with GT[c][r] = G[r][c] | h (n) | pad], RECS*sizeof(R) % 16 == 0.
+#include <algorithm>
+#include <type_traits>
 #include "common.cuh"
 #include "../../include/kpms_b200.h"
 
@@ -24,6 +26,10 @@ __device__ __forceinline__ void tri_unpack(int q, int& i, int& j) {
     while (i * (i + 1) / 2 > q) --i;
     j = q - i * (i + 1) / 2;
 }
+
+// filter -> backward-pass records, padded to 16 bytes so they can be moved with 16-byte cp.async
+__host__ __device__ constexpr int stash_m_stride(int n) { return (n + 3) / 4 * 4; }
+__host__ __device__ constexpr int stash_S_stride(int n) { return (n * (n + 1) / 2 + 3) / 4 * 4; }
 
 // ---------------------------------------------------------------------------
 // K1a: per-frame observation information
@@ -182,8 +188,9 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
     const R* inf_g = info + (size_t)nn * Tx * REC;
     const int* mk = mask + (size_t)nn * T + (L_ - 1);
     const int* zz = z + (size_t)nn * (Tx - 1);
-    R* sm_g = stash_m + (size_t)nn * Tx * n;
-    R* sS_g = stash_S + (size_t)nn * Tx * NP2;
+    constexpr int SMS = stash_m_stride(n), SSS = stash_S_stride(n);
+    R* sm_g = stash_m + (size_t)nn * Tx * SMS;
+    R* sS_g = stash_S + (size_t)nn * Tx * SSS;
     const R eps = (R)KPMS_EPS_SHIFT + jitter;
 
     for (int q = tid; q < NP2; q += NT) { int i, j; tri_unpack(q, i, j); ij[q] = (unsigned short)((i << 8) | j); }
@@ -442,7 +449,7 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
                     if (u < NP2) {                              // P+ (stash) and the shifted old-old block
                         const int r = ij[u] >> 8, c = ij[u] & 255;
                         const R val = P0[r * LD + c] - rowdot(V + r * DP, V + c * DP);
-                        if (keep) sS_g[(size_t)i * NP2 + u] = val;
+                        if (keep) sS_g[(size_t)i * SSS + u] = val;
                         if (!last && c >= D_) {
                             const R v2 = val + ((r == c) ? eps : (R)0);
                             Pn[(r - D_) * LD + (c - D_)] = v2;
@@ -472,7 +479,7 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
                         R acc = m0[u] + pc[u];
 #pragma unroll
                         for (int c = 0; c < D_; ++c) acc = fma(-V[u * DP + c], tvec[c], acc);
-                        if (keep) sm_g[(size_t)i * n + u] = acc;
+                        if (keep) sm_g[(size_t)i * SMS + u] = acc;
                         continue;
                     }
                     u -= n;
@@ -488,9 +495,9 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
         } else if (last) {
             for (int q = tid; q < NP2; q += NT) {
                 int r = ij[q] >> 8, c = ij[q] & 255;
-                sS_g[(size_t)i * NP2 + q] = P0[r * LD + c];
+                sS_g[(size_t)i * SSS + q] = P0[r * LD + c];
             }
-            for (int w = tid; w < n; w += NT) sm_g[(size_t)i * n + w] = m0[w];
+            for (int w = tid; w < n; w += NT) sm_g[(size_t)i * SMS + w] = m0[w];
         }
         if (i + 1 < i1) stage_store(b ^ 1, pre);
         z_next = z_next2;
@@ -572,7 +579,7 @@ kalman_backprep_kernel(const R* __restrict__ stash_m, const R* __restrict__ stas
         return;
     }
     // operands
-    const R* Sg = stash_S + (size_t)g * NP2;
+    const R* Sg = stash_S + (size_t)g * stash_S_stride(n);
     for (int q = lane; q < NP2; q += 32) {
         int r, c;
         tri_unpack(q, r, c);
@@ -581,7 +588,7 @@ kalman_backprep_kernel(const R* __restrict__ stash_m, const R* __restrict__ stas
         S[c * LD + r] = val;
     }
     for (int w = lane; w < n; w += 32) {
-        mv[w] = stash_m[(size_t)g * n + w];
+        mv[w] = stash_m[(size_t)g * stash_m_stride(n) + w];
         R wn;
         if (w_tape) wn = w_tape[(size_t)g * n + w];
         else {
@@ -685,6 +692,317 @@ kalman_backprep_kernel(const R* __restrict__ stash_m, const R* __restrict__ stas
         for (int c = 0; c <= r; ++c) acc = fma(S[r * LD + c], wv[c], acc);
         hout[r] = acc;
     }
+}
+
+// ---------------------------------------------------------------------------
+// K1c (n <= 32): backward preparation with one warp per frame and one matrix row (= column, the
+// matrices are symmetric) per lane held in registers.  Shared memory only carries what other lanes
+// must see, always as whole rows read back as 16-byte broadcasts:
+//   Wt = Aaug S          lane c: column c from its own column of S; transposed through T2
+//   Pp = Wt Aaug' + Q    lane r: row r
+//   Lp = chol(Pp)        right-looking; column j is published as row j of T1 (= Lp') and the same
+//                        broadcast drives the forward substitution V = Lp^-1 Wt on every lane's column
+//   Sigma = S - V'V      lane b: row b, V' rows published in T2
+//   Ls = chol(Sigma)     as above, Ls' rows in T2
+//   X = Lp^-T V          row-oriented back substitution against the rows of T1;  GT = X
+//   h = m - X' mp + Ls w
+// ---------------------------------------------------------------------------
+template <typename R, int D_, int L_>
+struct PrepRowsSmem {
+    static constexpr int n = D_ * L_, LS = 36, NP2 = n * (n + 1) / 2;
+    static constexpr int SB = stash_S_stride(n);
+    static constexpr size_t per_warp = 2 * 32 * LS + D_ * LS + SB + 6 * 32;
+};
+
+template <typename R> __device__ __forceinline__ R rsqrt_fast(R x);
+template <> __device__ __forceinline__ float rsqrt_fast<float>(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <> __device__ __forceinline__ double rsqrt_fast<double>(double x) { return rsqrt(x); }
+
+// asynchronous global -> shared copies (one element, or one 16-byte chunk)
+template <typename R>
+__device__ __forceinline__ void cp_async_elem(R* dst, const R* src) {
+    const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d32), "l"(src), "n"((int)sizeof(R)));
+}
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+    const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d32), "l"(src));
+}
+
+// Right-looking Cholesky of the matrix whose row `lane` is in a[]; column j is published as row j
+// of LT.  On return a[c] (c <= lane) holds L[lane][c].  With SOLVE, `col` is forward-substituted in
+// the same sweep (col <- L^-1 col) and the inverse pivots are kept in invd.
+template <typename R, int n, int LS, bool SOLVE>
+__device__ __forceinline__ void chol_rows(R (&a)[n], R* LT, R (&col)[n], R* invd, int lane) {
+    typedef typename Vec16<R>::type VecT;
+    constexpr int VEC = 16 / (int)sizeof(R), NV = (n + VEC - 1) / VEC;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+        const R dj = __shfl_sync(0xffffffffu, a[j], j);
+        const R inv = rsqrt_fast<R>(dj);
+        const R l = (lane >= j) ? a[j] * inv : (R)0;
+        a[j] = l;
+        LT[j * LS + lane] = l;
+        R vj = 0;
+        if (SOLVE) {
+            invd[j] = inv;
+            vj = col[j] * inv;
+            col[j] = vj;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int cv = (j + 1) / VEC; cv < NV; ++cv) {
+            const VecT lv = *reinterpret_cast<const VecT*>(LT + j * LS + cv * VEC);
+            const R* le = reinterpret_cast<const R*>(&lv);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+                const int c = cv * VEC + q;
+                if (c > j && c < n) {
+                    a[c] = fma(-l, le[q], a[c]);
+                    if (SOLVE) col[c] = fma(-le[q], vj, col[c]);
+                }
+            }
+        }
+    }
+}
+
+template <typename R, int D_, int L_, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, (sizeof(R) == 4 ? 4 : 1))
+kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__ stash_S,
+                            const int* __restrict__ mask, const int* __restrict__ z, const R* __restrict__ Ab,
+                            const R* __restrict__ Q, R jitter, const R* __restrict__ w_tape, uint64_t seed,
+                            int N, int T, R* __restrict__ GH) {
+    typedef PrepRowsSmem<R, D_, L_> SM;
+    typedef typename Vec16<R>::type VecT;
+    constexpr int n = SM::n, LS = SM::LS, NO = n - D_, NA1 = n + 1;
+    constexpr int VEC = 16 / (int)sizeof(R), NV = (n + VEC - 1) / VEC;
+    constexpr int SMS = stash_m_stride(n), SSS = stash_S_stride(n);
+    static_assert(n <= 32, "one matrix row per lane");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    R* T1 = reinterpret_cast<R*>(smem_raw) + (size_t)warp * SM::per_warp;   // Lp' rows (32 x LS)
+    R* T2 = T1 + 32 * LS;                                                  // Wt' / V' / Ls' rows (32 x LS)
+    R* As = T2 + 32 * LS;                                                  // D_ rows [A | b]
+    R* Sb = As + D_ * LS;                                                  // packed lower triangle of S
+    R* mvb = Sb + SM::SB;                                                  // 2 x 32 filtered means (ping-pong)
+    R* wvb = mvb + 64;                                                     // 2 x 32 normals (ping-pong)
+    R* mp = wvb + 64;
+    R* invd = mp + 32;
+    const int Tx = T - L_ + 1;
+    const long long frames = (long long)N * Tx;
+    const long long stride = (long long)gridDim.x * WARPS;
+    const bool act = lane < n;
+    const int row = act ? lane : n - 1;              // idle lanes shadow the last row; their stores land in padding
+    const R* pA = Sb + row * (row + 1) / 2;          // S[row][c] = c <= row ? pA[c] : pB[c(c+1)/2]
+    const R* pB = Sb + row;
+    const R eps = (R)KPMS_EPS_SHIFT + jitter;
+
+    // frame status: 0 = masked (identity record), 1 = regular, 2 = last frame of its chain
+    auto status = [&](long long g) {
+        const int nn = (int)(g / Tx), i = (int)(g % Tx);
+        if (i == Tx - 1) return 2;
+        return mask[(size_t)nn * T + (L_ - 1) + i] != 0 ? 1 : 0;
+    };
+    // The inputs of the next frame are requested while the current one is still being factored:
+    // A once Pp is formed, S / m / w once Sigma is formed.
+    auto issue_A = [&](long long g) {
+        if (g < frames && status(g) == 1) {
+            const int nn = (int)(g / Tx), i = (int)(g % Tx);
+            const R* A = Ab + (size_t)z[(size_t)nn * (Tx - 1) + i] * D_ * NA1;
+            for (int w = lane; w < D_ * NA1; w += 32) cp_async_elem(As + (w / NA1) * LS + (w % NA1), A + w);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    auto issue_S = [&](long long g, int buf) {
+        if (g < frames && status(g) != 0) {
+            const char* Sg = reinterpret_cast<const char*>(stash_S + (size_t)g * SSS);
+            for (int c = lane; c < SSS * (int)sizeof(R) / 16; c += 32) cp_async_16(reinterpret_cast<char*>(Sb) + 16 * c, Sg + 16 * c);
+            const char* mg = reinterpret_cast<const char*>(stash_m + (size_t)g * SMS);
+            if (lane < SMS * (int)sizeof(R) / 16) cp_async_16(reinterpret_cast<char*>(mvb + 32 * buf) + 16 * lane, mg + 16 * lane);
+            if (w_tape && act) cp_async_elem(wvb + 32 * buf + lane, w_tape + (size_t)g * n + lane);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    auto publish_row = [&](R* dst, const R (&v)[n]) {       // row `lane` of a 32 x LS buffer
+#pragma unroll
+        for (int cv = 0; cv < NV; ++cv) {
+            VecT ov;
+            R* oe = reinterpret_cast<R*>(&ov);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) oe[q] = (cv * VEC + q < n) ? v[cv * VEC + q] : (R)0;
+            *reinterpret_cast<VecT*>(dst + lane * LS + cv * VEC) = ov;
+        }
+    };
+
+    long long g = (long long)blockIdx.x * WARPS + warp;
+    int buf = 0;
+    issue_A(g);
+    issue_S(g, buf);
+    for (; g < frames; g += stride, buf ^= 1) {
+        const long long gn = g + stride;
+        const int nn = (int)(g / Tx), i = (int)(g % Tx);
+        const int stat = status(g);
+        R* Gout = GH + (size_t)g * PrepSmem<R, D_, L_>::RECS;
+        R* hout = Gout + n * n;
+        asm volatile("cp.async.wait_all;\n" ::);
+        __syncwarp();
+        if (stat == 0) {
+            for (int w = lane; w < n * n; w += 32) Gout[w] = ((w / n) == (w % n)) ? (R)1 : (R)0;
+            for (int w = lane; w < n; w += 32) hout[w] = (R)0;
+            issue_A(gn);
+            issue_S(gn, buf ^ 1);
+            continue;
+        }
+        const R* mv = mvb + 32 * buf;
+        R* wv = wvb + 32 * buf;
+        if (!w_tape && act) {
+            Philox gen(seed, KPMS_STREAM_X, (uint64_t)g * n + lane);
+            double a0, a1;
+            philox_normal2(gen, a0, a1);
+            wv[lane] = (R)a0;
+        }
+        if (stat == 2) {                             // terminal frame: draw from the filter marginal
+            R a[n], dummy[n];
+#pragma unroll
+            for (int c = 0; c < n; ++c) a[c] = (c <= row) ? pA[c] : pB[c * (c + 1) / 2];
+            __syncwarp();
+            chol_rows<R, n, LS, false>(a, T1, dummy, invd, lane);
+            R acc = mv[row];
+#pragma unroll
+            for (int c = 0; c < n; ++c) acc = fma((c <= row) ? a[c] : (R)0, wv[c], acc);
+            if (act) hout[lane] = acc;
+            __syncwarp();
+            issue_A(gn);
+            issue_S(gn, buf ^ 1);
+            continue;
+        }
+        const int zi = z[(size_t)nn * (Tx - 1) + i];
+        // Wt column `row` = Aaug S[:, row]; mp = Aaug m + b
+        R wt[n];
+        {
+            R sc[n];
+#pragma unroll
+            for (int c = 0; c < n; ++c) sc[c] = (c <= row) ? pA[c] : pB[c * (c + 1) / 2];
+#pragma unroll
+            for (int r = 0; r < NO; ++r) wt[r] = sc[r + D_];
+#pragma unroll
+            for (int a = 0; a < D_; ++a) {
+                R acc0 = 0, acc1 = 0;
+#pragma unroll
+                for (int cv = 0; cv < NV; ++cv) {
+                    const VecT av = *reinterpret_cast<const VecT*>(As + a * LS + cv * VEC);
+                    const R* ae = reinterpret_cast<const R*>(&av);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        const int e = cv * VEC + q;
+                        if (e < n) { if (e & 1) acc1 = fma(ae[q], sc[e], acc1); else acc0 = fma(ae[q], sc[e], acc0); }
+                    }
+                }
+                wt[NO + a] = acc0 + acc1;
+            }
+        }
+        {
+            R mpv;
+            if (row < NO) mpv = mv[row + D_];
+            else {
+                const R* arow = As + (row - NO) * LS;
+                mpv = arow[n];
+#pragma unroll 6
+                for (int e = 0; e < n; ++e) mpv = fma(arow[e], mv[e], mpv);
+            }
+            mp[lane] = mpv;
+        }
+        publish_row(T2, wt);                         // T2 = Wt'
+        __syncwarp();
+        // Pp row `row` = Wt[row, :] Aaug' + Qaug
+        R pp[n];
+        {
+            R wr[n];
+#pragma unroll
+            for (int e = 0; e < n; ++e) wr[e] = T2[e * LS + row];
+#pragma unroll
+            for (int c = 0; c < NO; ++c) pp[c] = wr[c + D_] + ((row == c) ? eps : (R)0);
+            const R* Qk = Q + (size_t)zi * D_ * D_;
+#pragma unroll
+            for (int a = 0; a < D_; ++a) {
+                R acc0 = (row >= NO) ? (__ldg(Qk + (row - NO) * D_ + a) + ((row - NO == a) ? jitter : (R)0)) : (R)0;
+                R acc1 = 0;
+#pragma unroll
+                for (int cv = 0; cv < NV; ++cv) {
+                    const VecT av = *reinterpret_cast<const VecT*>(As + a * LS + cv * VEC);
+                    const R* ae = reinterpret_cast<const R*>(&av);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        const int e = cv * VEC + q;
+                        if (e < n) { if (e & 1) acc1 = fma(ae[q], wr[e], acc1); else acc0 = fma(ae[q], wr[e], acc0); }
+                    }
+                }
+                pp[NO + a] = acc0 + acc1;
+            }
+        }
+        __syncwarp();                                // As and T2 (Wt') fully consumed
+        issue_A(gn);
+        chol_rows<R, n, LS, true>(pp, T1, wt, invd, lane);     // T1 = Lp', wt = V[:, row]
+        // Sigma row `row` = S[row, :] - V[:, row]' V
+        publish_row(T2, wt);                         // T2 = V'
+        __syncwarp();
+        R sig[n];
+#pragma unroll
+        for (int a = 0; a < n; ++a) {
+            R acc0 = (a <= row) ? pA[a] : pB[a * (a + 1) / 2], acc1 = 0;
+#pragma unroll
+            for (int cv = 0; cv < NV; ++cv) {
+                const VecT vv = *reinterpret_cast<const VecT*>(T2 + a * LS + cv * VEC);
+                const R* ve = reinterpret_cast<const R*>(&vv);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    const int e = cv * VEC + q;
+                    if (e < n) { if (e & 1) acc1 = fma(-ve[q], wt[e], acc1); else acc0 = fma(-ve[q], wt[e], acc0); }
+                }
+            }
+            sig[a] = acc0 + acc1;
+        }
+        __syncwarp();                                // Sb and T2 (V') fully consumed
+        issue_S(gn, buf ^ 1);
+        {
+            R dummy[n];
+            chol_rows<R, n, LS, false>(sig, T2, dummy, invd, lane);   // sig[c <= row] = Ls[row][c]
+        }
+        // X = Lp^-T V, column `row` in place over wt
+#pragma unroll
+        for (int r = n - 1; r >= 0; --r) {
+            R acc0 = wt[r], acc1 = 0;
+#pragma unroll
+            for (int cv = (r + 1) / VEC; cv < NV; ++cv) {
+                const VecT lv = *reinterpret_cast<const VecT*>(T1 + r * LS + cv * VEC);
+                const R* le = reinterpret_cast<const R*>(&lv);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    const int e = cv * VEC + q;
+                    if (e > r && e < n) { if (e & 1) acc1 = fma(-le[q], wt[e], acc1); else acc0 = fma(-le[q], wt[e], acc0); }
+                }
+            }
+            wt[r] = (acc0 + acc1) * invd[r];
+        }
+        if (act) {
+#pragma unroll
+            for (int r = 0; r < n; ++r) Gout[r * n + lane] = wt[r];
+        }
+        // h = m - X' mp + Ls w
+        R acc = mv[row], acc2 = 0;
+#pragma unroll
+        for (int c = 0; c < n; ++c) {
+            acc = fma(-wt[c], mp[c], acc);
+            acc2 = fma((c <= row) ? sig[c] : (R)0, wv[c], acc2);
+        }
+        if (act) hout[lane] = acc + acc2;
+        __syncwarp();                                // mp / invd / T1 reads done before the next frame overwrites them
+    }
+    asm volatile("cp.async.wait_all;\n" ::);
 }
 
 // ---------------------------------------------------------------------------
@@ -796,8 +1114,8 @@ static void kalman_ws_layout(int N, int T, int d, int L, int C, int Cb, size_t o
     const size_t rec = (size_t)d * (d + 1) / 2 + d, np2 = n * (n + 1) / 2;
     const size_t recs = ((n * n + n) * sizeof(R) + 15) / 16 * 16 / sizeof(R);
     const size_t brec = n + n * n, nb = (size_t)N * (C + 1), nbb = (size_t)N * (Cb + 1);
-    size_t sz[KW_END] = {256, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4, fr * rec * sizeof(R), fr * n * sizeof(R),
-                         fr * np2 * sizeof(R), fr * recs * sizeof(R), nb * brec * sizeof(R), nb * brec * sizeof(R),
+    size_t sz[KW_END] = {256, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4, fr * rec * sizeof(R), fr * stash_m_stride((int)n) * sizeof(R),
+                         fr * stash_S_stride((int)n) * sizeof(R), fr * recs * sizeof(R), nb * brec * sizeof(R), nb * brec * sizeof(R),
                          nbb * n * sizeof(R), nbb * n * sizeof(R)};
     off[0] = 0;
     for (int i = 0; i < KW_END; ++i) off[i + 1] = off[i] + align_up(sz[i], 256);
@@ -859,7 +1177,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
               kern<<<dim3(N, C), 256, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, T, stash_m, stash_S, C, W, vlen,
                                                   nullptr, bfw, bfe); }
             { KPMS_LAUNCH("kalman_forward_check", st);
-              boundary_check_kernel<R><<<N, 128, 0, st>>>(bfw, bfe, vlen, Tx, C, W, n, n + n * n, tol, dirty_f, diag); }
+              boundary_check_kernel<R><<<N, 128, 0, st>>>(bfw, bfe, vlen, Tx, C, W, 1, n, n + n * n, tol, dirty_f, diag); }
             { KPMS_LAUNCH("kalman_forward_rerun", st);       // exits at once for chains whose boundaries agree
               kern<<<dim3(N, 1), 256, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, T, stash_m, stash_S, 1, 0, nullptr,
                                                   dirty_f, bfw, bfe); }
@@ -871,7 +1189,17 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         int rc = check_launch("kalman forward");
         if (rc) return rc;
     }
-    {
+    if constexpr (n <= 32) {
+        constexpr int WARPS = 4;
+        auto kern = kalman_backprep_rows_kernel<R, D_, L_, WARPS>;
+        size_t smem = PrepRowsSmem<R, D_, L_>::per_warp * WARPS * sizeof(R);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // persistent warps: every warp walks frames g, g + stride, ... and prefetches the next one
+        int blocks = (int)std::min<long long>((frames + WARPS - 1) / WARPS, (long long)KPMS_SM_COUNT * 4);
+        { KPMS_LAUNCH("kalman_backprep", st); kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH); }
+        int rc = check_launch("kalman backprep");
+        if (rc) return rc;
+    } else {
         constexpr int WARPS = 4;
         auto kern = kalman_backprep_kernel<R, D_, L_, WARPS>;
         size_t smem = PrepSmem<R, D_, L_>::per_warp * WARPS * sizeof(R);
@@ -890,7 +1218,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
             { KPMS_LAUNCH("kalman_affine", st);
               kern<<<dim3(N, Cb), 32, smem, st>>>(GH, T, x, Cb, W, vlen, nullptr, bbw, bbe); }
             { KPMS_LAUNCH("kalman_affine_check", st);
-              boundary_check_kernel<R><<<N, 128, 0, st>>>(bbw, bbe, vlen, Tx, Cb, W, n, n, tol, dirty_b, diag + 2); }
+              boundary_check_kernel<R><<<N, 128, 0, st>>>(bbw, bbe, vlen, Tx, Cb, W, 1, n, n, tol, dirty_b, diag + 2); }
             { KPMS_LAUNCH("kalman_affine_rerun", st);
               kern<<<dim3(N, 1), 32, smem, st>>>(GH, T, x, 1, 0, nullptr, dirty_b, bbw, bbe); }
         } else {
