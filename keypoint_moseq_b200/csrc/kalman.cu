@@ -771,7 +771,7 @@ __device__ __forceinline__ void chol_rows(R (&a)[n], R* LT, R (&col)[n], R* invd
 }
 
 template <typename R, int D_, int L_, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, (sizeof(R) == 4 ? 4 : 1))
+__global__ void __launch_bounds__(32 * WARPS, 1)
 kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__ stash_S,
                             const int* __restrict__ mask, const int* __restrict__ z, const R* __restrict__ Ab,
                             const R* __restrict__ Q, R jitter, const R* __restrict__ w_tape, uint64_t seed,
@@ -838,32 +838,34 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
         }
     };
 
-    long long g = (long long)blockIdx.x * WARPS + warp;
+    // All warps of the CTA walk their frames in lockstep (one barrier per phase): the unrolled
+    // body is far larger than the instruction caches, and warps that share a scheduler then share
+    // its instruction fetches.
     int buf = 0;
-    issue_A(g);
-    issue_S(g, buf);
-    for (; g < frames; g += stride, buf ^= 1) {
-        const long long gn = g + stride;
+    {
+        const long long g0 = (long long)blockIdx.x * WARPS + warp;
+        issue_A(g0);
+        issue_S(g0, buf);
+    }
+    for (long long base = (long long)blockIdx.x * WARPS; base < frames; base += stride, buf ^= 1) {
+        const long long g = base + warp, gn = g + stride;
+        const int stat = (g < frames) ? status(g) : -1;
         const int nn = (int)(g / Tx), i = (int)(g % Tx);
-        const int stat = status(g);
         R* Gout = GH + (size_t)g * PrepSmem<R, D_, L_>::RECS;
         R* hout = Gout + n * n;
         asm volatile("cp.async.wait_all;\n" ::);
         __syncwarp();
-        if (stat == 0) {
-            for (int w = lane; w < n * n; w += 32) Gout[w] = ((w / n) == (w % n)) ? (R)1 : (R)0;
-            for (int w = lane; w < n; w += 32) hout[w] = (R)0;
-            issue_A(gn);
-            issue_S(gn, buf ^ 1);
-            continue;
-        }
         const R* mv = mvb + 32 * buf;
         R* wv = wvb + 32 * buf;
-        if (!w_tape && act) {
+        if (stat > 0 && !w_tape && act) {
             Philox gen(seed, KPMS_STREAM_X, (uint64_t)g * n + lane);
             double a0, a1;
             philox_normal2(gen, a0, a1);
             wv[lane] = (R)a0;
+        }
+        if (stat == 0) {
+            for (int w = lane; w < n * n; w += 32) Gout[w] = ((w / n) == (w % n)) ? (R)1 : (R)0;
+            for (int w = lane; w < n; w += 32) hout[w] = (R)0;
         }
         if (stat == 2) {                             // terminal frame: draw from the filter marginal
             R a[n], dummy[n];
@@ -876,14 +878,16 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
             for (int c = 0; c < n; ++c) acc = fma((c <= row) ? a[c] : (R)0, wv[c], acc);
             if (act) hout[lane] = acc;
             __syncwarp();
+        }
+        if (stat != 1) {
             issue_A(gn);
             issue_S(gn, buf ^ 1);
-            continue;
         }
-        const int zi = z[(size_t)nn * (Tx - 1) + i];
-        // Wt column `row` = Aaug S[:, row]; mp = Aaug m + b
-        R wt[n];
-        {
+        const bool on = (stat == 1);
+        const int zi = on ? z[(size_t)nn * (Tx - 1) + i] : 0;
+        R wt[n], pp[n], sig[n];
+        // ---- phase 1: Wt column `row` = Aaug S[:, row]; mp = Aaug m + b
+        if (on) {
             R sc[n];
 #pragma unroll
             for (int c = 0; c < n; ++c) sc[c] = (c <= row) ? pA[c] : pB[c * (c + 1) / 2];
@@ -904,8 +908,6 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
                 }
                 wt[NO + a] = acc0 + acc1;
             }
-        }
-        {
             R mpv;
             if (row < NO) mpv = mv[row + D_];
             else {
@@ -915,12 +917,11 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
                 for (int e = 0; e < n; ++e) mpv = fma(arow[e], mv[e], mpv);
             }
             mp[lane] = mpv;
+            publish_row(T2, wt);                     // T2 = Wt'
         }
-        publish_row(T2, wt);                         // T2 = Wt'
-        __syncwarp();
-        // Pp row `row` = Wt[row, :] Aaug' + Qaug
-        R pp[n];
-        {
+        __syncthreads();
+        // ---- phase 2: Pp row `row` = Wt[row, :] Aaug' + Qaug
+        if (on) {
             R wr[n];
 #pragma unroll
             for (int e = 0; e < n; ++e) wr[e] = T2[e * LS + row];
@@ -943,64 +944,71 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
                 }
                 pp[NO + a] = acc0 + acc1;
             }
+            __syncwarp();                            // As and T2 (Wt') fully consumed
+            issue_A(gn);
         }
-        __syncwarp();                                // As and T2 (Wt') fully consumed
-        issue_A(gn);
-        chol_rows<R, n, LS, true>(pp, T1, wt, invd, lane);     // T1 = Lp', wt = V[:, row]
-        // Sigma row `row` = S[row, :] - V[:, row]' V
-        publish_row(T2, wt);                         // T2 = V'
-        __syncwarp();
-        R sig[n];
+        __syncthreads();
+        // ---- phase 3: Lp = chol(Pp), V = Lp^-1 Wt
+        if (on) {
+            chol_rows<R, n, LS, true>(pp, T1, wt, invd, lane);   // T1 = Lp', wt = V[:, row]
+            publish_row(T2, wt);                     // T2 = V'
+        }
+        __syncthreads();
+        // ---- phase 4: Sigma row `row` = S[row, :] - V[:, row]' V
+        if (on) {
 #pragma unroll
-        for (int a = 0; a < n; ++a) {
-            R acc0 = (a <= row) ? pA[a] : pB[a * (a + 1) / 2], acc1 = 0;
+            for (int a = 0; a < n; ++a) {
+                R acc0 = (a <= row) ? pA[a] : pB[a * (a + 1) / 2], acc1 = 0;
 #pragma unroll
-            for (int cv = 0; cv < NV; ++cv) {
-                const VecT vv = *reinterpret_cast<const VecT*>(T2 + a * LS + cv * VEC);
-                const R* ve = reinterpret_cast<const R*>(&vv);
+                for (int cv = 0; cv < NV; ++cv) {
+                    const VecT vv = *reinterpret_cast<const VecT*>(T2 + a * LS + cv * VEC);
+                    const R* ve = reinterpret_cast<const R*>(&vv);
 #pragma unroll
-                for (int q = 0; q < VEC; ++q) {
-                    const int e = cv * VEC + q;
-                    if (e < n) { if (e & 1) acc1 = fma(-ve[q], wt[e], acc1); else acc0 = fma(-ve[q], wt[e], acc0); }
+                    for (int q = 0; q < VEC; ++q) {
+                        const int e = cv * VEC + q;
+                        if (e < n) { if (e & 1) acc1 = fma(-ve[q], wt[e], acc1); else acc0 = fma(-ve[q], wt[e], acc0); }
+                    }
                 }
+                sig[a] = acc0 + acc1;
             }
-            sig[a] = acc0 + acc1;
+            __syncwarp();                            // Sb and T2 (V') fully consumed
+            issue_S(gn, buf ^ 1);
         }
-        __syncwarp();                                // Sb and T2 (V') fully consumed
-        issue_S(gn, buf ^ 1);
-        {
-            R dummy[n];
-            chol_rows<R, n, LS, false>(sig, T2, dummy, invd, lane);   // sig[c <= row] = Ls[row][c]
-        }
-        // X = Lp^-T V, column `row` in place over wt
+        __syncthreads();
+        // ---- phase 5: Ls = chol(Sigma)
+        if (on) chol_rows<R, n, LS, false>(sig, T2, pp, invd, lane);   // sig[c <= row] = Ls[row][c]
+        __syncthreads();
+        // ---- phase 6: X = Lp^-T V (column `row`, in place over wt), records out
+        if (on) {
 #pragma unroll
-        for (int r = n - 1; r >= 0; --r) {
-            R acc0 = wt[r], acc1 = 0;
+            for (int r = n - 1; r >= 0; --r) {
+                R acc0 = wt[r], acc1 = 0;
 #pragma unroll
-            for (int cv = (r + 1) / VEC; cv < NV; ++cv) {
-                const VecT lv = *reinterpret_cast<const VecT*>(T1 + r * LS + cv * VEC);
-                const R* le = reinterpret_cast<const R*>(&lv);
+                for (int cv = (r + 1) / VEC; cv < NV; ++cv) {
+                    const VecT lv = *reinterpret_cast<const VecT*>(T1 + r * LS + cv * VEC);
+                    const R* le = reinterpret_cast<const R*>(&lv);
 #pragma unroll
-                for (int q = 0; q < VEC; ++q) {
-                    const int e = cv * VEC + q;
-                    if (e > r && e < n) { if (e & 1) acc1 = fma(-le[q], wt[e], acc1); else acc0 = fma(-le[q], wt[e], acc0); }
+                    for (int q = 0; q < VEC; ++q) {
+                        const int e = cv * VEC + q;
+                        if (e > r && e < n) { if (e & 1) acc1 = fma(-le[q], wt[e], acc1); else acc0 = fma(-le[q], wt[e], acc0); }
+                    }
                 }
+                wt[r] = (acc0 + acc1) * invd[r];
             }
-            wt[r] = (acc0 + acc1) * invd[r];
-        }
-        if (act) {
+            if (act) {
 #pragma unroll
-            for (int r = 0; r < n; ++r) Gout[r * n + lane] = wt[r];
-        }
-        // h = m - X' mp + Ls w
-        R acc = mv[row], acc2 = 0;
+                for (int r = 0; r < n; ++r) Gout[r * n + lane] = wt[r];
+            }
+            // h = m - X' mp + Ls w
+            R acc = mv[row], acc2 = 0;
 #pragma unroll
-        for (int c = 0; c < n; ++c) {
-            acc = fma(-wt[c], mp[c], acc);
-            acc2 = fma((c <= row) ? sig[c] : (R)0, wv[c], acc2);
+            for (int c = 0; c < n; ++c) {
+                acc = fma(-wt[c], mp[c], acc);
+                acc2 = fma((c <= row) ? sig[c] : (R)0, wv[c], acc2);
+            }
+            if (act) hout[lane] = acc + acc2;
         }
-        if (act) hout[lane] = acc + acc2;
-        __syncwarp();                                // mp / invd / T1 reads done before the next frame overwrites them
+        __syncthreads();                             // also orders this frame's shared-memory reads before the next one's writes
     }
     asm volatile("cp.async.wait_all;\n" ::);
 }
@@ -1190,12 +1198,12 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         if (rc) return rc;
     }
     if constexpr (n <= 32) {
-        constexpr int WARPS = 4;
+        constexpr int WARPS = sizeof(R) == 4 ? 16 : 8;      // one CTA per SM
         auto kern = kalman_backprep_rows_kernel<R, D_, L_, WARPS>;
         size_t smem = PrepRowsSmem<R, D_, L_>::per_warp * WARPS * sizeof(R);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         // persistent warps: every warp walks frames g, g + stride, ... and prefetches the next one
-        int blocks = (int)std::min<long long>((frames + WARPS - 1) / WARPS, (long long)KPMS_SM_COUNT * 4);
+        int blocks = (int)std::min<long long>((frames + WARPS - 1) / WARPS, (long long)KPMS_SM_COUNT);
         { KPMS_LAUNCH("kalman_backprep", st); kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH); }
         int rc = check_launch("kalman backprep");
         if (rc) return rc;
