@@ -216,6 +216,25 @@ template <typename R> __device__ __forceinline__ R rsqrt_r(R x);
 template <> __device__ __forceinline__ float rsqrt_r<float>(float x) { return rsqrtf(x); }
 template <> __device__ __forceinline__ double rsqrt_r<double>(double x) { return rsqrt(x); }
 
+template <typename R> __device__ __forceinline__ R rsqrt_fast(R x);
+template <> __device__ __forceinline__ float rsqrt_fast<float>(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <> __device__ __forceinline__ double rsqrt_fast<double>(double x) { return rsqrt(x); }
+
+// asynchronous global -> shared copies (one element, or one 16-byte chunk)
+template <typename R>
+__device__ __forceinline__ void cp_async_elem(R* dst, const R* src) {
+    const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d32), "l"(src), "n"((int)sizeof(R)));
+}
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+    const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d32), "l"(src));
+}
+
 template <typename R> __device__ __forceinline__ void sincos_r(R x, R& s, R& c);
 template <> __device__ __forceinline__ void sincos_r<float>(float x, float& s, float& c) { sincosf(x, &s, &c); }
 template <> __device__ __forceinline__ void sincos_r<double>(double x, double& s, double& c) { sincos(x, &s, &c); }

@@ -30,6 +30,10 @@ __device__ __forceinline__ void tri_unpack(int q, int& i, int& j) {
 // filter -> backward-pass records, padded to 16 bytes so they can be moved with 16-byte cp.async
 __host__ __device__ constexpr int stash_m_stride(int n) { return (n + 3) / 4 * 4; }
 __host__ __device__ constexpr int stash_S_stride(int n) { return (n * (n + 1) / 2 + 3) / 4 * 4; }
+// offset of column c in a lower triangle packed by columns (column c holds rows c..n-1)
+__host__ __device__ constexpr int col_start(int n, int c) { return c * n - c * (c - 1) / 2; }
+// per-frame observation record: [Lj packed lower (d(d+1)/2) | r (d) | Lj^-1 r (d) | pad]
+__host__ __device__ constexpr int info_stride(int d) { return (d * (d + 1) / 2 + 2 * d + 3) / 4 * 4; }
 
 // ---------------------------------------------------------------------------
 // K1a: per-frame observation information
@@ -39,7 +43,7 @@ __global__ void __launch_bounds__(128)
 obs_info_kernel(const R* __restrict__ Y, const int* __restrict__ mask, const R* __restrict__ v,
                 const R* __restrict__ h, const R* __restrict__ s, const R* __restrict__ sigmasq,
                 const R* __restrict__ Ct, int N, int T, int k, int L, R* __restrict__ info) {
-    constexpr int NP = D_ * (D_ + 1) / 2, REC = NP + D_;
+    constexpr int NP = D_ * (D_ + 1) / 2, REC = info_stride(D_);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R* Cs = reinterpret_cast<R*>(smem_raw);            // (k*DK) x (D_+1)
     R* sg = Cs + (size_t)k * DK * (D_ + 1);            // k
@@ -93,6 +97,7 @@ obs_info_kernel(const R* __restrict__ Y, const int* __restrict__ mask, const R* 
         }
     }
     // in-register Cholesky J = Lj Lj'; a non-positive pivot (rank-deficient C~) zeroes its column
+    R invp[D_];
 #pragma unroll
     for (int c = 0; c < D_; ++c) {
         R sdiag = J[c * (c + 1) / 2 + c];
@@ -100,6 +105,7 @@ obs_info_kernel(const R* __restrict__ Y, const int* __restrict__ mask, const R* 
         for (int p = 0; p < c; ++p) sdiag -= J[c * (c + 1) / 2 + p] * J[c * (c + 1) / 2 + p];
         const bool ok = sdiag > (R)0;
         const R inv = ok ? rsqrt_r<R>(sdiag) : (R)0;
+        invp[c] = inv;
         J[c * (c + 1) / 2 + c] = ok ? sdiag * inv : (R)0;
 #pragma unroll
         for (int a = c + 1; a < D_; ++a) {
@@ -113,6 +119,15 @@ obs_info_kernel(const R* __restrict__ Y, const int* __restrict__ mask, const R* 
     for (int q = 0; q < NP; ++q) out[q] = J[q];
 #pragma unroll
     for (int q = 0; q < D_; ++q) out[NP + q] = r[q];
+    // whitened pseudo-observation y~ = Lj^-1 r (unit noise, observation matrix Lj'); zero on zeroed pivots
+#pragma unroll
+    for (int c = 0; c < D_; ++c) {
+        R val = r[c];
+#pragma unroll
+        for (int p = 0; p < c; ++p) val -= J[c * (c + 1) / 2 + p] * r[p];
+        r[c] = val * invp[c];
+        out[NP + D_ + c] = r[c];
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -131,7 +146,7 @@ obs_info_kernel(const R* __restrict__ Y, const int* __restrict__ mask, const R* 
 // ---------------------------------------------------------------------------
 template <typename R, int D_, int L_>
 struct FwdSmem {
-    static constexpr int n = D_ * L_, LD = n | 1, NP = D_ * (D_ + 1) / 2, REC = NP + D_,
+    static constexpr int n = D_ * L_, LD = n | 1, NP = D_ * (D_ + 1) / 2, REC = info_stride(D_),
                          NP2 = n * (n + 1) / 2, VEC = 16 / (int)sizeof(R),
                          DP = (D_ + VEC - 1) / VEC * VEC, AP = (n + 1 + VEC - 1) / VEC * VEC;
     static constexpr size_t elems = 2 * n * LD + 2 * n + 2 * n * DP + 2 * D_ * DP + 3 * D_ * LD + 2 * D_ * D_ +
@@ -513,6 +528,383 @@ kalman_forward_kernel(const R* __restrict__ info, const int* __restrict__ mask, 
 }
 
 // ---------------------------------------------------------------------------
+// K1b (n <= 32): covariance-form filter with one warp per (chain, time chunk) and one row of the
+// predicted covariance per lane in registers (the matrix is symmetric, so the row is also the
+// column).  Per step, with Lj = chol(J_t), y~ = Lj^-1 r_t (unit-noise pseudo-observation of Lj' x_new):
+//   U = P[:,new] Lj                     own row, Lj broadcast from the prefetched record
+//   B = I + Lj' U[new,:], nu = y~ - Lj' m_new      55 + 10 entries spread over the lanes, through smem
+//   Lb = chol(B)                        redundantly in every lane's registers (no communication)
+//   V = U Lb^-T, w = Lb^-1 nu,  m+ = m + V w,  P+ = P - V V'     V rows published, read as broadcasts
+//   A P+ (lane j: column j),  m' = A m+ + b,  A P+ A' by L partial sums per lane group + shuffles,
+//   shifted blocks by shuffles from lane r + d
+// The transition parameters of the current state sit in shared memory and are reloaded only when
+// z changes; the per-frame records arrive through a cp.async ring.
+// stash_S here is the lower triangle packed by COLUMNS (column c holds rows c..n-1), which makes
+// both this kernel's stores and the backward preparation's loads contiguous across lanes.
+// ---------------------------------------------------------------------------
+template <typename R, int D_, int L_>
+struct FwdRowsSmem {
+    static constexpr int n = D_ * L_, NP = D_ * (D_ + 1) / 2, NPP = (NP + 3) / 4 * 4, RECI = info_stride(D_);
+    static constexpr int QO = (n + 1 + 3) / 4 * 4;                 // offset of the Q row inside an A row
+    static constexpr int AS = QO + (D_ + 3) / 4 * 4;               // row: [A (n) | b | pad | Q row (d)]
+    static constexpr int VS = (D_ + 3) / 4 * 4, APS = 36, STAGES = 4;
+    static constexpr int BS = NPP + (D_ + 3) / 4 * 4;
+    static constexpr size_t per_warp = STAGES * RECI + 2 * D_ * AS + 32 * VS + D_ * APS + BS + 32;
+};
+
+template <typename R, int D_, int L_, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, (sizeof(R) == 4 ? 2 : 1))
+kalman_forward_rows_kernel(const R* __restrict__ info, const int* __restrict__ mask, const int* __restrict__ z,
+                           const R* __restrict__ Ab, const R* __restrict__ Q, R jitter, int N, int T,
+                           R* __restrict__ stash_m, R* __restrict__ stash_S, int C, int W,
+                           const int* __restrict__ vlen, const int* __restrict__ dirty,
+                           R* __restrict__ bnd_warm, R* __restrict__ bnd_end) {
+    typedef FwdRowsSmem<R, D_, L_> SM;
+    typedef typename Vec16<R>::type VecT;
+    constexpr int n = SM::n, NO = n - D_, NP = SM::NP, NPP = SM::NPP, RECI = SM::RECI, AS = SM::AS, QO = SM::QO,
+                  VS = SM::VS, APS = SM::APS, STAGES = SM::STAGES;
+    constexpr int VEC = 16 / (int)sizeof(R), NV = (n + VEC - 1) / VEC, DV = (D_ + VEC - 1) / VEC;
+    constexpr int SMS = stash_m_stride(n), SSS = stash_S_stride(n), BREC = n + n * n;
+    static_assert(n <= 32, "one covariance row per lane");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long task = (long long)blockIdx.x * WARPS + warp;
+    if (task >= (long long)N * C) return;
+    const int nn = (int)(task / C), ck = (int)(task % C);
+    const int Tx = T - L_ + 1;
+    if (dirty && dirty[nn] == 0) return;
+    const ChunkRange cr = chunk_range(vlen ? vlen[nn] : Tx, Tx, C, W, ck);
+    if (cr.empty) return;
+    R* ring = reinterpret_cast<R*>(smem_raw) + (size_t)warp * SM::per_warp;   // STAGES x RECI
+    R* Asb = ring + STAGES * RECI;                   // 2 x D_ x AS
+    R* Vs = Asb + 2 * D_ * AS;                       // 32 x VS   (U rows, then V rows)
+    R* APs = Vs + 32 * VS;                           // D_ x APS  (A P+)
+    R* Bs = APs + D_ * APS;                          // [B lower packed | nu]
+    R* ms = Bs + SM::BS;                             // 32
+    const bool act = lane < n;
+    const int row = act ? lane : n - 1;              // idle lanes shadow the last row
+    const R* inf_g = info + (size_t)nn * Tx * RECI;
+    const int* mk = mask + (size_t)nn * T + (L_ - 1);
+    const int* zz = z + (size_t)nn * (Tx - 1);
+    R* sm_g = stash_m + (size_t)nn * Tx * SMS;
+    R* sS_g = stash_S + (size_t)nn * Tx * SSS;
+    const R eps = (R)KPMS_EPS_SHIFT + jitter;
+    // entries of B (lower, packed by rows) computed by this lane
+    int ba[2], bc[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        int a = 0, c = 0;
+        const int idx = lane + 32 * q;
+        if (idx < NP) tri_unpack(idx, a, c);
+        ba[q] = a;
+        bc[q] = c;
+    }
+    const int i0 = cr.start, i1 = cr.end;
+    auto issue_info = [&](int i) {
+        if (i < i1)
+            for (int c = lane; c < RECI * (int)sizeof(R) / 16; c += 32)
+                cp_async_16(reinterpret_cast<char*>(ring + (i % STAGES) * RECI) + 16 * c,
+                            reinterpret_cast<const char*>(inf_g + (size_t)i * RECI) + 16 * c);
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    auto load_A = [&](int zi, int buf) {             // joins the next committed group
+        R* dst = Asb + buf * D_ * AS;
+        const R* A = Ab + (size_t)zi * D_ * (n + 1);
+        for (int w = lane; w < D_ * (n + 1); w += 32) cp_async_elem(dst + (w / (n + 1)) * AS + (w % (n + 1)), A + w);
+        const R* Qk = Q + (size_t)zi * D_ * D_;
+        for (int w = lane; w < D_ * D_; w += 32) cp_async_elem(dst + (w / D_) * AS + QO + (w % D_), Qk + w);
+    };
+    R p[n], m = (R)0;
+#pragma unroll
+    for (int c = 0; c < n; ++c) p[c] = (c == row) ? (R)KPMS_X_PRIOR_VAR : (R)0;
+    for (int w = lane; w < 2 * D_ * AS; w += 32) Asb[w] = (R)0;     // padding is multiplied by masked zeros
+    __syncwarp();
+    int cur = 0;
+    int zc = (i0 < Tx - 1) ? zz[i0] : -1;
+    if (zc >= 0) load_A(zc, 0);
+    for (int s2 = 0; s2 < STAGES - 1; ++s2) issue_info(i0 + s2);
+    int mk_cur = mk[i0];
+    bool changed_prev = false;
+    for (int i = i0; i < i1; ++i) {
+        const bool last = (i == Tx - 1);
+        const bool keep = (i >= cr.begin);
+        const int mk_next = (i + 1 < Tx) ? mk[i + 1] : 0;
+        const int z_next = (i + 1 < Tx - 1) ? zz[i + 1] : -1;
+        const bool change = (z_next >= 0 && z_next != zc);
+        if (change) load_A(z_next, cur ^ 1);
+        issue_info(i + STAGES - 1);
+        if (changed_prev) asm volatile("cp.async.wait_all;\n" ::);
+        else asm volatile("cp.async.wait_group %0;\n" ::"n"(STAGES - 1));
+        __syncwarp();
+        if (ck > 0 && i == cr.begin && act) {        // the state this chunk arrived with
+            R* bw = bnd_warm + ((size_t)nn * C + ck) * BREC;
+            bw[lane] = m;
+#pragma unroll
+            for (int c = 0; c < n; ++c) bw[n + lane * n + c] = p[c];
+        }
+        const R* fi = ring + (i % STAGES) * RECI;
+        const R* A = Asb + cur * D_ * AS;
+        if (mk_cur != 0) {
+            // ---- U = P[:,new] Lj (own row); publish U rows and the mean
+            R u[D_];
+            {
+                R lj[NPP];
+#pragma unroll
+                for (int cv = 0; cv < NPP / VEC; ++cv) {
+                    const VecT lv = *reinterpret_cast<const VecT*>(fi + cv * VEC);
+                    const R* le = reinterpret_cast<const R*>(&lv);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) lj[cv * VEC + q] = le[q];
+                }
+#pragma unroll
+                for (int c = 0; c < D_; ++c) {
+                    R acc = 0;
+#pragma unroll
+                    for (int e = c; e < D_; ++e) acc = fma(p[NO + e], lj[e * (e + 1) / 2 + c], acc);
+                    u[c] = acc;
+                }
+            }
+            ms[lane] = m;
+#pragma unroll
+            for (int cv = 0; cv < DV; ++cv) {
+                VecT ov;
+                R* oe = reinterpret_cast<R*>(&ov);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) oe[q] = (cv * VEC + q < D_) ? u[cv * VEC + q] : (R)0;
+                *reinterpret_cast<VecT*>(Vs + lane * VS + cv * VEC) = ov;
+            }
+            __syncwarp();
+            // ---- B = I + Lj' U[new,:] (lower) and nu = y~ - Lj' m_new, spread over the lanes
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int a = ba[q], c = bc[q];
+                R acc = (a == c) ? (R)1 : (R)0;
+#pragma unroll
+                for (int e = 0; e < D_; ++e)
+                    if (e >= a) acc = fma(fi[e * (e + 1) / 2 + a], Vs[(NO + e) * VS + c], acc);
+                if (lane + 32 * q < NP) Bs[lane + 32 * q] = acc;
+            }
+            if (lane < D_) {
+                R acc = fi[NP + D_ + lane];
+#pragma unroll
+                for (int e = 0; e < D_; ++e)
+                    if (e >= lane) acc = fma(-fi[e * (e + 1) / 2 + lane], ms[NO + e], acc);
+                Bs[NPP + lane] = acc;
+            }
+            __syncwarp();
+            // ---- Lb = chol(B) in registers (inverse pivots on the diagonal); V row, w, m+
+            R v[D_];
+            {
+                R Lb[NPP], nu[DV * VEC];
+#pragma unroll
+                for (int cv = 0; cv < NPP / VEC; ++cv) {
+                    const VecT lv = *reinterpret_cast<const VecT*>(Bs + cv * VEC);
+                    const R* le = reinterpret_cast<const R*>(&lv);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) Lb[cv * VEC + q] = le[q];
+                }
+#pragma unroll
+                for (int cv = 0; cv < DV; ++cv) {
+                    const VecT lv = *reinterpret_cast<const VecT*>(Bs + NPP + cv * VEC);
+                    const R* le = reinterpret_cast<const R*>(&lv);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) nu[cv * VEC + q] = le[q];
+                }
+#pragma unroll
+                for (int c = 0; c < D_; ++c) {
+                    const R inv = rsqrt_fast<R>(Lb[c * (c + 1) / 2 + c]);
+                    Lb[c * (c + 1) / 2 + c] = inv;
+#pragma unroll
+                    for (int a = c + 1; a < D_; ++a) Lb[a * (a + 1) / 2 + c] *= inv;
+#pragma unroll
+                    for (int a = c + 1; a < D_; ++a)
+#pragma unroll
+                        for (int bb = c + 1; bb <= a; ++bb)
+                            Lb[a * (a + 1) / 2 + bb] = fma(-Lb[a * (a + 1) / 2 + c], Lb[bb * (bb + 1) / 2 + c], Lb[a * (a + 1) / 2 + bb]);
+                }
+                R dm = 0;
+#pragma unroll
+                for (int c = 0; c < D_; ++c) {
+                    R val = u[c], wv = nu[c];
+#pragma unroll
+                    for (int p2 = 0; p2 < c; ++p2) {
+                        val = fma(-Lb[c * (c + 1) / 2 + p2], v[p2], val);
+                        wv = fma(-Lb[c * (c + 1) / 2 + p2], nu[p2], wv);
+                    }
+                    v[c] = val * Lb[c * (c + 1) / 2 + c];
+                    nu[c] = wv * Lb[c * (c + 1) / 2 + c];
+                    dm = fma(v[c], nu[c], dm);
+                }
+                m += dm;
+            }
+#pragma unroll
+            for (int cv = 0; cv < DV; ++cv) {
+                VecT ov;
+                R* oe = reinterpret_cast<R*>(&ov);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) oe[q] = (cv * VEC + q < D_) ? v[cv * VEC + q] : (R)0;
+                *reinterpret_cast<VecT*>(Vs + lane * VS + cv * VEC) = ov;
+            }
+            __syncwarp();
+            // ---- P+ = P - V V' (own row)
+#pragma unroll
+            for (int c = 0; c < n; ++c) {
+                R acc = p[c];
+#pragma unroll
+                for (int cv = 0; cv < DV; ++cv) {
+                    const VecT vv = *reinterpret_cast<const VecT*>(Vs + c * VS + cv * VEC);
+                    const R* ve = reinterpret_cast<const R*>(&vv);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q)
+                        if (cv * VEC + q < D_) acc = fma(-v[cv * VEC + q], ve[q], acc);
+                }
+                p[c] = acc;
+            }
+            if (keep && act) {
+                sm_g[(size_t)i * SMS + lane] = m;
+                R* so = sS_g + (size_t)i * SSS + lane;
+#pragma unroll
+                for (int c = 0; c < n; ++c)
+                    if (c <= lane) so[col_start(n, c) - c] = p[c];
+            }
+            if (!last) {
+                // ---- A P+ (column `row`), published by rows of A
+                R ap[D_];
+#pragma unroll
+                for (int a = 0; a < D_; ++a) {
+                    R acc0 = 0, acc1 = 0;
+#pragma unroll
+                    for (int cv = 0; cv < NV; ++cv) {
+                        const VecT av = *reinterpret_cast<const VecT*>(A + a * AS + cv * VEC);
+                        const R* ae = reinterpret_cast<const R*>(&av);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) {
+                            const int e = cv * VEC + q;
+                            if (e < n) { if (e & 1) acc1 = fma(ae[q], p[e], acc1); else acc0 = fma(ae[q], p[e], acc0); }
+                        }
+                    }
+                    ap[a] = acc0 + acc1;
+                    APs[a * APS + lane] = ap[a];
+                }
+                ms[lane] = m;
+                __syncwarp();
+                // ---- next mean: shifted blocks by shuffle, newest block = A m+ + b
+                const int arow = (row >= NO) ? row - NO : 0;
+                const int grp = row / D_;                         // lane group = block of the augmented state
+                {
+                    const R* Ar = A + arow * AS;
+                    R acc0 = Ar[n], acc1 = 0;
+#pragma unroll
+                    for (int cv = 0; cv < NV; ++cv) {
+                        const VecT av = *reinterpret_cast<const VecT*>(Ar + cv * VEC);
+                        const VecT mv = *reinterpret_cast<const VecT*>(ms + cv * VEC);
+                        const R* ae = reinterpret_cast<const R*>(&av);
+                        const R* me = reinterpret_cast<const R*>(&mv);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) {
+                            const int e = cv * VEC + q;
+                            if (e < n) { if (e & 1) acc1 = fma(ae[q], me[q], acc1); else acc0 = fma(ae[q], me[q], acc0); }
+                        }
+                    }
+                    const R mshift = __shfl_down_sync(0xffffffffu, m, D_);
+                    m = (row < NO) ? mshift : (acc0 + acc1);
+                }
+                // ---- A P+ A': lane (grp, a' = row - grp d) sums its block of the contraction for every
+                //      column a; the L partial sums meet in the last lane group by shuffles
+                R apa[D_];
+                {
+                    constexpr int WN = (D_ + 2 * VEC - 2) / VEC;         // aligned window covering any block
+                    const int e0 = grp * D_;
+                    const int w0 = e0 / VEC * VEC;
+                    const R* aprow = APs + (row - e0) * APS + w0;
+                    R aw[WN * VEC];
+#pragma unroll
+                    for (int cv = 0; cv < WN; ++cv) {
+                        const VecT lv = *reinterpret_cast<const VecT*>(aprow + cv * VEC);
+                        const R* le = reinterpret_cast<const R*>(&lv);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) {
+                            const int e = w0 + cv * VEC + q;
+                            aw[cv * VEC + q] = (e >= e0 && e < e0 + D_) ? le[q] : (R)0;
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < D_; ++a) {
+                        R acc = 0;
+#pragma unroll
+                        for (int cv = 0; cv < WN; ++cv) {
+                            const VecT av = *reinterpret_cast<const VecT*>(A + a * AS + w0 + cv * VEC);
+                            const R* ae = reinterpret_cast<const R*>(&av);
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) acc = fma(aw[cv * VEC + q], ae[q], acc);
+                        }
+                        R tot = acc;
+#pragma unroll
+                        for (int gq = 1; gq < L_; ++gq) tot += __shfl_up_sync(0xffffffffu, acc, D_ * gq);
+                        apa[a] = tot;                                   // complete in the last group (rows >= NO)
+                    }
+                    // Keep the covariance symmetric to the last bit: every other block of P' is mirrored
+                    // by construction, this one is computed twice in different orders.  An antisymmetric
+                    // rounding residue is not contracted by the measurement update and grows with |A| > 1.
+                    if (act && row >= NO) {                  // idle lanes hold partial sums of the wrong lanes
+#pragma unroll
+                        for (int a = 0; a < D_; ++a) Vs[arow * VS + a] = apa[a];
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int a = 0; a < D_; ++a) apa[a] = (R)0.5 * (apa[a] + Vs[a * VS + arow]);
+                }
+                // ---- next predicted covariance: rows < NO are shifted rows of P+ / columns of A P+
+                //      (from lane r + d), rows >= NO are A P+ and A P+ A' + Q
+                {
+                    const R* aprow = APs + arow * APS;
+                    R nv[NV * VEC];
+#pragma unroll
+                    for (int cv = 0; cv < NV; ++cv) {
+                        const VecT lv = *reinterpret_cast<const VecT*>(aprow + cv * VEC);
+                        const R* le = reinterpret_cast<const R*>(&lv);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) nv[cv * VEC + q] = le[q];
+                    }
+                    R pn[n];
+#pragma unroll
+                    for (int c = 0; c < NO; ++c) {
+                        const R sh = __shfl_down_sync(0xffffffffu, p[c + D_], D_);
+                        pn[c] = (row < NO) ? sh + ((row == c) ? eps : (R)0) : nv[c + D_];
+                    }
+                    const R* qrow = A + arow * AS + QO;
+#pragma unroll
+                    for (int a = 0; a < D_; ++a) {
+                        const R sh = __shfl_down_sync(0xffffffffu, ap[a], D_);
+                        const R nw = apa[a] + qrow[a] + ((arow == a) ? jitter : (R)0);
+                        pn[NO + a] = (row < NO) ? sh : nw;
+                    }
+#pragma unroll
+                    for (int c = 0; c < n; ++c) p[c] = pn[c];
+                }
+            }
+        } else if (last && keep && act) {
+            sm_g[(size_t)i * SMS + lane] = m;
+            R* so = sS_g + (size_t)i * SSS + lane;
+#pragma unroll
+            for (int c = 0; c < n; ++c)
+                if (c <= lane) so[col_start(n, c) - c] = p[c];
+        }
+        if (change) { cur ^= 1; zc = z_next; }
+        changed_prev = change;
+        mk_cur = mk_next;
+        __syncwarp();
+    }
+    asm volatile("cp.async.wait_all;\n" ::);
+    if (i1 < Tx && act) {                            // the state handed to the next chunk
+        R* be = bnd_end + ((size_t)nn * C + ck + 1) * BREC;
+        be[lane] = m;
+#pragma unroll
+        for (int c = 0; c < n; ++c) be[n + lane * n + c] = p[c];
+    }
+}
+
+// ---------------------------------------------------------------------------
 // warp-level dense kernels on shared-memory matrices (leading dimension LD odd)
 // ---------------------------------------------------------------------------
 template <typename R, int n, int LD>
@@ -714,25 +1106,6 @@ struct PrepRowsSmem {
     static constexpr size_t per_warp = 2 * 32 * LS + D_ * LS + SB + 6 * 32;
 };
 
-template <typename R> __device__ __forceinline__ R rsqrt_fast(R x);
-template <> __device__ __forceinline__ float rsqrt_fast<float>(float x) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-template <> __device__ __forceinline__ double rsqrt_fast<double>(double x) { return rsqrt(x); }
-
-// asynchronous global -> shared copies (one element, or one 16-byte chunk)
-template <typename R>
-__device__ __forceinline__ void cp_async_elem(R* dst, const R* src) {
-    const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d32), "l"(src), "n"((int)sizeof(R)));
-}
-__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
-    const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d32), "l"(src));
-}
-
 // Right-looking Cholesky of the matrix whose row `lane` is in a[]; column j is published as row j
 // of LT.  On return a[c] (c <= lane) holds L[lane][c].  With SOLVE, `col` is forward-substituted in
 // the same sweep (col <- L^-1 col) and the inverse pivots are kept in invd.
@@ -797,7 +1170,8 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
     const long long stride = (long long)gridDim.x * WARPS;
     const bool act = lane < n;
     const int row = act ? lane : n - 1;              // idle lanes shadow the last row; their stores land in padding
-    const R* pA = Sb + row * (row + 1) / 2;          // S[row][c] = c <= row ? pA[c] : pB[c(c+1)/2]
+    // S is the lower triangle packed by columns: S[row][c] = c <= row ? pB[col_start(c) - c] : pA[c]
+    const R* pA = Sb + col_start(n, row) - row;
     const R* pB = Sb + row;
     const R eps = (R)KPMS_EPS_SHIFT + jitter;
 
@@ -822,7 +1196,7 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
             const char* Sg = reinterpret_cast<const char*>(stash_S + (size_t)g * SSS);
             for (int c = lane; c < SSS * (int)sizeof(R) / 16; c += 32) cp_async_16(reinterpret_cast<char*>(Sb) + 16 * c, Sg + 16 * c);
             const char* mg = reinterpret_cast<const char*>(stash_m + (size_t)g * SMS);
-            if (lane < SMS * (int)sizeof(R) / 16) cp_async_16(reinterpret_cast<char*>(mvb + 32 * buf) + 16 * lane, mg + 16 * lane);
+            for (int c = lane; c < SMS * (int)sizeof(R) / 16; c += 32) cp_async_16(reinterpret_cast<char*>(mvb + 32 * buf) + 16 * c, mg + 16 * c);
             if (w_tape && act) cp_async_elem(wvb + 32 * buf + lane, w_tape + (size_t)g * n + lane);
         }
         asm volatile("cp.async.commit_group;\n" ::);
@@ -870,7 +1244,7 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
         if (stat == 2) {                             // terminal frame: draw from the filter marginal
             R a[n], dummy[n];
 #pragma unroll
-            for (int c = 0; c < n; ++c) a[c] = (c <= row) ? pA[c] : pB[c * (c + 1) / 2];
+            for (int c = 0; c < n; ++c) a[c] = (c <= row) ? pB[col_start(n, c) - c] : pA[c];
             __syncwarp();
             chol_rows<R, n, LS, false>(a, T1, dummy, invd, lane);
             R acc = mv[row];
@@ -890,7 +1264,7 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
         if (on) {
             R sc[n];
 #pragma unroll
-            for (int c = 0; c < n; ++c) sc[c] = (c <= row) ? pA[c] : pB[c * (c + 1) / 2];
+            for (int c = 0; c < n; ++c) sc[c] = (c <= row) ? pB[col_start(n, c) - c] : pA[c];
 #pragma unroll
             for (int r = 0; r < NO; ++r) wt[r] = sc[r + D_];
 #pragma unroll
@@ -958,7 +1332,7 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
         if (on) {
 #pragma unroll
             for (int a = 0; a < n; ++a) {
-                R acc0 = (a <= row) ? pA[a] : pB[a * (a + 1) / 2], acc1 = 0;
+                R acc0 = (a <= row) ? pB[col_start(n, a) - a] : pA[a], acc1 = 0;
 #pragma unroll
                 for (int cv = 0; cv < NV; ++cv) {
                     const VecT vv = *reinterpret_cast<const VecT*>(T2 + a * LS + cv * VEC);
@@ -1119,7 +1493,7 @@ enum { KW_DIAG, KW_VLEN, KW_DIRTY_F, KW_DIRTY_B, KW_INFO, KW_SM, KW_SS, KW_GH, K
 template <typename R>
 static void kalman_ws_layout(int N, int T, int d, int L, int C, int Cb, size_t off[KW_END + 1]) {
     const size_t n = (size_t)d * L, Tx = T - L + 1, fr = (size_t)N * Tx;
-    const size_t rec = (size_t)d * (d + 1) / 2 + d, np2 = n * (n + 1) / 2;
+    const size_t rec = info_stride(d);
     const size_t recs = ((n * n + n) * sizeof(R) + 15) / 16 * 16 / sizeof(R);
     const size_t brec = n + n * n, nb = (size_t)N * (C + 1), nbb = (size_t)N * (Cb + 1);
     size_t sz[KW_END] = {256, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4, fr * rec * sizeof(R), fr * stash_m_stride((int)n) * sizeof(R),
@@ -1130,8 +1504,8 @@ static void kalman_ws_layout(int N, int T, int d, int L, int C, int Cb, size_t o
 }
 
 // chunks per chain for the Kalman recursions: enough chunk-CTAs to fill the device once
-static int kalman_chunks(int N, int T, int L, bool backward) {
-    return chunks_for(N, KPMS_SM_COUNT * (backward ? 12 : 3), T - L + 1, chunk_config().warmup);
+static int kalman_chunks(int N, int T, int d, int L, bool backward) {
+    return chunks_for(N, KPMS_SM_COUNT * (backward ? 12 : (d * L <= 32 ? 16 : 3)), T - L + 1, chunk_config().warmup);
 }
 
 template <typename R, int D_, int L_>
@@ -1142,7 +1516,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
     constexpr int n = D_ * L_;
     const int Tx = T - L_ + 1;
     const ChunkConfig cfg = chunk_config();
-    const int C = kalman_chunks(N, T, L_, false), Cb = kalman_chunks(N, T, L_, true), W = cfg.warmup;
+    const int C = kalman_chunks(N, T, D_, L_, false), Cb = kalman_chunks(N, T, D_, L_, true), W = cfg.warmup;
     const R tol = (R)(sizeof(R) == 4 ? cfg.tol32 : cfg.tol64);
     size_t off[KW_END + 1];
     kalman_ws_layout<R>(N, T, D_, L_, C, Cb, off);
@@ -1176,7 +1550,28 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         int rc = check_launch("kalman obs_info");
         if (rc) return rc;
     }
-    {
+    if constexpr (n <= 32) {
+        constexpr int WARPS = 8;
+        auto kern = kalman_forward_rows_kernel<R, D_, L_, WARPS>;
+        size_t smem = FwdRowsSmem<R, D_, L_>::per_warp * WARPS * sizeof(R);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (C > 1) {
+            { KPMS_LAUNCH("kalman_forward", st);
+              kern<<<(int)(((long long)N * C + WARPS - 1) / WARPS), 32 * WARPS, smem, st>>>(
+                  info, mask, z, Ab, Q, (R)jitter, N, T, stash_m, stash_S, C, W, vlen, nullptr, bfw, bfe); }
+            { KPMS_LAUNCH("kalman_forward_check", st);
+              boundary_check_kernel<R><<<N, 128, 0, st>>>(bfw, bfe, vlen, Tx, C, W, 1, n, n + n * n, tol, dirty_f, diag); }
+            { KPMS_LAUNCH("kalman_forward_rerun", st);       // exits at once for chains whose boundaries agree
+              kern<<<(N + WARPS - 1) / WARPS, 32 * WARPS, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, N, T, stash_m,
+                                                                    stash_S, 1, 0, nullptr, dirty_f, bfw, bfe); }
+        } else {
+            KPMS_LAUNCH("kalman_forward", st);
+            kern<<<(N + WARPS - 1) / WARPS, 32 * WARPS, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, N, T, stash_m,
+                                                                  stash_S, 1, 0, nullptr, nullptr, bfw, bfe);
+        }
+        int rc = check_launch("kalman forward");
+        if (rc) return rc;
+    } else {
         auto kern = kalman_forward_kernel<R, D_, L_>;
         size_t smem = FwdSmem<R, D_, L_>::bytes;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1264,7 +1659,7 @@ extern "C" {
 
 size_t kpms_kalman_workspace_bytes(int dtype, int N, int T, int d, int L) {
     size_t off[KW_END + 1];
-    const int C = kalman_chunks(N, T, L, false), Cb = kalman_chunks(N, T, L, true);
+    const int C = kalman_chunks(N, T, d, L, false), Cb = kalman_chunks(N, T, d, L, true);
     if (dtype == 0) kalman_ws_layout<float>(N, T, d, L, C, Cb, off);
     else kalman_ws_layout<double>(N, T, d, L, C, Cb, off);
     return off[KW_END];
