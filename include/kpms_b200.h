@@ -55,14 +55,16 @@ void kpms_set_time_chunking(int chunks, int warmup, double tol32, double tol64);
  *      (utils.autoregression.ar_log_likelihood + utils.distributions.sample_hmm_stateseq);
  *      the forward pass alone is arhmm.marginal_log_likelihood (fitting.py:667-673) and
  *      forward + smooth is arhmm.stateseq_marginals (fitting.py:536-538). */
-size_t kpms_hmm_workspace_bytes(int dtype, int K, int d, int L);
+/* one workspace serves kpms_ar_loglik, kpms_hmm_forward and kpms_hmm_backward_sample of the same (N, T, K, d, L) */
+size_t kpms_hmm_workspace_bytes(int dtype, int N, int T, int K, int d, int L);
 /* W (N,K,ldT) <- exp(ll - max_k ll), mx (N,ldT) <- max_k ll; masked frames have ll = 0. ldT % 8 == 0. */
 int kpms_ar_loglik(int dtype, const void* x, const int32_t* mask, const void* Ab, const void* Q, int N,
                    int T, int d, int L, int K, int ldT, void* W, void* mx, void* ws, void* stream);
 /* filt (N,Tp,ldK), ldK = K rounded up to 4; logZ (N) double = per-chain log normaliser. */
 int kpms_hmm_forward(int dtype, const void* W, const void* mx, const void* pi, int N, int K, int Tp,
-                     int ldT, void* filt, double* logZ, void* stream);
-/* z (N,Tp) int32; u_tape (N,Tp) uniforms or NULL, in which case u_scratch (N,Tp) receives Philox uniforms. */
+                     int ldT, void* filt, double* logZ, void* ws, int d, int L, void* stream);
+/* z (N,Tp) int32; u_tape (N,Tp) uniforms or NULL, in which case u_scratch (N,Tp) receives Philox uniforms.
+ * Exact and parallel in time: every step's map z_{t+1} -> z_t is tabulated, then the maps are composed. */
 int kpms_hmm_backward_sample(int dtype, const void* filt, const void* pi, const void* u_tape, void* u_scratch,
                              uint64_t seed, int N, int K, int Tp, int32_t* z, void* ws, int d, int L,
                              void* stream);

@@ -10,6 +10,7 @@
 //   mx    (N, ldT)             per-frame max log-likelihood (0 on masked frames)
 //   filt  (N, T', ldK)         filtered state probabilities
 //   z     (N, T') int32
+#include <algorithm>
 #include "common.cuh"
 #include "../../include/kpms_b200.h"
 
@@ -300,115 +301,162 @@ __global__ void fill_uniform_kernel(R* __restrict__ u, long long count, uint64_t
     u[e] = (R)u0;
 }
 
-template <typename R, int VPL, int STAGES>
-__global__ void __launch_bounds__(32)
-hmm_backward_kernel(const R* __restrict__ filt, const R* __restrict__ piT, const R* __restrict__ u_src,
-                    int K, int Tp, int ldK, int* __restrict__ z, int C, int Wm, const int* __restrict__ vlen,
-                    const int* __restrict__ dirty, int* __restrict__ bz_warm, int* __restrict__ bz_exact) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    R* pis = reinterpret_cast<R*>(smem_raw);                 // K x ldK
-    R* ring = pis + (size_t)K * ldK;                         // STAGES x ldK
-    const int nn = blockIdx.x, ck = blockIdx.y;
-    const int lane = threadIdx.x;
-    if (dirty && dirty[nn] == 0) return;
-    // Time chunk: labels for [cr.begin, cr.end).  The last chunk starts from the chain's terminal
-    // draw; the others start Wm steps above their range from an unconditioned draw and, because
-    // every step is the same deterministic map of (z_{t+1}, u_t), merge with the sequential
-    // sampler's path as soon as the two agree once.  The label used at the upper boundary is
-    // published and compared with the neighbour's own label (exact integer check).
-    const ChunkRange cr = chunk_range(vlen ? vlen[nn] : Tp, Tp, C, Wm, ck, 8);
-    if (cr.empty) return;
-    const int top = (cr.end == Tp) ? Tp : min(cr.end + Wm, Tp);   // first step taken is t = top - 1
-    for (int i = lane; i < K * ldK; i += 32) pis[i] = piT[i];
-    const R* fl = filt + (size_t)nn * Tp * ldK;
-    const R* un = u_src + (size_t)nn * Tp;
-    int* zn = z + (size_t)nn * Tp;
-    const int chunks = ldK * (int)sizeof(R) / 16;
-    auto issue = [&](int t) {
-        if (t >= cr.begin) {
-            char* dst = reinterpret_cast<char*>(ring + (size_t)(t % STAGES) * ldK);
-            const char* src = reinterpret_cast<const char*>(fl + (size_t)t * ldK);
-            for (int c = lane; c < chunks; c += 32) {
-                unsigned d32 = (unsigned)__cvta_generic_to_shared(dst + 16 * c);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d32), "l"(src + 16 * c));
+// ---------------------------------------------------------------------------
+// K3 backward, parallel in time and exact.  Backward sampling is z_t = f_t(z_{t+1}) with
+//   f_t(j) = #{ i : c_i(j) < (1 - u_t) c_{K-1}(j) },   c_i(j) = sum_{i' <= i} filt_t[i'] pi[i'][j],
+// a deterministic map of the next label once u_t is fixed.  All maps are built independently
+// (one thread per (t, j), the column of pi in registers, filt_t broadcast from shared memory),
+// then composed: per 256-step segment every starting label is walked through the segment's maps
+// (label_compose), the segment boundaries are resolved per chain from the terminal draw
+// (label_boundaries), and every segment replays its own path (label_walk).  Integer composition
+// is exact, so the labels are those of the sequential sampler that uses the same summation order.
+// The cumulative sum is blocked: c_i = P_b + a_{b,e} with P_b the sum of the blocks before block b
+// and a_{b,e} the running sum inside it (both accumulated left to right from 0).
+// ---------------------------------------------------------------------------
+constexpr int LABEL_TS = 16;        // steps per tile of the map builder
+constexpr int LABEL_SEG = 256;      // steps per composition segment
+
+template <typename R, int KP, int BS>
+__global__ void __launch_bounds__(128, 1)
+hmm_label_maps_kernel(const R* __restrict__ filt, const R* __restrict__ pi, const R* __restrict__ u,
+                      int N, int K, int Tp, int ldK, int KB, unsigned char* __restrict__ tbl) {
+    constexpr int NB = KP / BS, TS = LABEL_TS, VEC = 16 / (int)sizeof(R);
+    static_assert(KP % BS == 0 && KP % VEC == 0, "padded state count");
+    typedef typename Vec16<R>::type VecT;
+    __shared__ __align__(16) R ft[TS * KP];
+    __shared__ R us[TS];
+    const int tid = threadIdx.x, j = tid;
+    R pic[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) pic[i] = (i < K && j < K) ? pi[(size_t)i * K + j] : (R)0;
+    const int steps = Tp - 1;                         // maps for t = 0 .. Tp-2; t = Tp-1 is the terminal draw
+    const int tpc = (steps + TS - 1) / TS;
+    for (long long tile = blockIdx.x; tile < (long long)N * tpc; tile += gridDim.x) {
+        const int nn = (int)(tile / tpc), t0 = (int)(tile % tpc) * TS;
+        const int nts = min(TS, steps - t0);
+        __syncthreads();
+        for (int idx = tid; idx < TS * KP; idx += 128) {
+            const int ts = idx / KP, i = idx % KP;
+            ft[idx] = (ts < nts && i < K) ? filt[((size_t)nn * Tp + t0 + ts) * ldK + i] : (R)0;
+        }
+        if (tid < TS) us[tid] = (tid < nts) ? u[(size_t)nn * Tp + t0 + tid] : (R)0.5;
+        __syncthreads();
+        for (int ts = 0; ts < nts; ++ts) {
+            const R* f = ft + ts * KP;
+            R acc[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[b] = (R)0;
+#pragma unroll
+            for (int iv = 0; iv < KP / VEC; ++iv) {
+                const VecT fv = *reinterpret_cast<const VecT*>(f + iv * VEC);
+                const R* fe = reinterpret_cast<const R*>(&fv);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    const int i = iv * VEC + q;
+                    acc[i / BS] = fma(fe[q], pic[i], acc[i / BS]);
+                }
             }
-        }
-        asm volatile("cp.async.commit_group;\n" ::);
-    };
-    for (int s2 = 0; s2 < STAGES - 1; ++s2) issue(top - 1 - s2);
-    // uniforms: block b covers steps t = top-1-32b-lane
-    auto load_u = [&](int blk) {
-        const int t = top - 1 - 32 * blk - lane;
-        return (t >= cr.begin) ? un[t] : (R)0.5;
-    };
-    R ucur = load_u(0), unext = load_u(1);
-    __syncwarp();
-    int znext = -1;
-    for (int t = top - 1; t >= cr.begin; --t) {
-        const int step = top - 1 - t;
-        if (step > 0 && (step & 31) == 0) { ucur = unext; unext = load_u((step >> 5) + 1); }
-        const R u = __shfl_sync(0xffffffffu, ucur, step & 31);
-        issue(t - (STAGES - 1));
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(STAGES - 1));
-        __syncwarp();
-        const R* row = ring + (size_t)(t % STAGES) * ldK;
-        R v[VPL];
+            R run = (R)0, Pb = (R)0;
+            R pref[NB];
 #pragma unroll
-        for (int c = 0; c < VPL; ++c) {
-            const int i = lane * VPL + c;
-            v[c] = (i < K) ? row[i] : (R)0;
-        }
-        if (znext >= 0) {
-            const R* prow = pis + (size_t)znext * ldK;
+            for (int b = 0; b < NB; ++b) { run += acc[b]; pref[b] = run; }
+            const R r = run * ((R)1 - us[ts]);
+            int bstar = 0;
 #pragma unroll
-            for (int c = 0; c < VPL; ++c) {
-                const int i = lane * VPL + c;
-                v[c] = (i < K) ? v[c] * prow[i] : (R)0;
+            for (int b = 0; b < NB; ++b)
+                if (pref[b] < r) { bstar = b + 1; Pb = pref[b]; }
+            int cnt = bstar * BS;
+            if (bstar < NB) {
+                R a = (R)0;
+#pragma unroll
+                for (int e = 0; e < BS; ++e) {
+                    const int i = bstar * BS + e;
+                    const R pv = (i < K && j < K) ? __ldg(pi + (size_t)i * K + j) : (R)0;
+                    a = fma(f[i], pv, a);
+                    cnt += ((Pb + a) < r) ? 1 : 0;
+                }
             }
+            cnt = min(cnt, K - 1);
+            if (j < K) tbl[((size_t)nn * Tp + t0 + ts) * KB + j] = (unsigned char)cnt;
         }
-        R c[VPL];
-        R run = 0;
-#pragma unroll
-        for (int q = 0; q < VPL; ++q) { run += v[q]; c[q] = run; }
-        R incl = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            R y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        const R excl = incl - run;
-        const R total = __shfl_sync(0xffffffffu, incl, 31);
-        const R r = total * ((R)1 - u);
-        int cnt = 0;
-#pragma unroll
-        for (int q = 0; q < VPL; ++q) {
-            const int i = lane * VPL + q;
-            cnt += (i < K && (excl + c[q]) < r) ? 1 : 0;
-        }
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        znext = min(cnt, K - 1);
-        if (lane == 0) {
-            if (t < cr.end) zn[t] = znext;
-            if (t == cr.end) bz_warm[(size_t)nn * C + ck + 1] = znext;
-            if (t == cr.begin && ck > 0) bz_exact[(size_t)nn * C + ck] = znext;
-        }
-        __syncwarp();
     }
 }
 
-// exact boundary check for the label paths
-__global__ void label_check_kernel(const int* __restrict__ warm, const int* __restrict__ exact,
-                                   const int* __restrict__ vlen, int N, int Tp, int C, int Wm,
-                                   int* __restrict__ dirty, unsigned* __restrict__ stats) {
-    const int nn = blockIdx.x * blockDim.x + threadIdx.x;
-    if (nn >= N) return;
-    int bad = 0;
-    for (int c = 1; c < C; ++c) {
-        if (chunk_range(vlen[nn], Tp, C, Wm, c, 8).empty) break;
-        bad |= warm[(size_t)nn * C + c] != exact[(size_t)nn * C + c];
+// segment s of a chain covers steps [s*SEG, min((s+1)*SEG, Tp-1)); comp[nn][s][j] = label at the
+// segment's first step when the label just above the segment is j
+__global__ void __launch_bounds__(128)
+label_compose_kernel(const unsigned char* __restrict__ tbl, int K, int Tp, int KB, int nseg,
+                     unsigned char* __restrict__ comp) {
+    extern __shared__ unsigned char seg[];            // SEG x KB
+    const int nn = blockIdx.x / nseg, sg = blockIdx.x % nseg;
+    const int lo = sg * LABEL_SEG, hi = min(lo + LABEL_SEG, Tp - 1);
+    const unsigned char* src = tbl + ((size_t)nn * Tp + lo) * KB;
+    const int bytes = (hi - lo) * KB;
+    for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16)
+        *reinterpret_cast<uint4*>(seg + i) = *reinterpret_cast<const uint4*>(src + i);
+    __syncthreads();
+    const int j = threadIdx.x;
+    if (j < K) {
+        int v = j;
+        for (int t = hi - 1; t >= lo; --t) v = seg[(t - lo) * KB + v];
+        comp[((size_t)nn * nseg + sg) * KB + j] = (unsigned char)v;
     }
-    dirty[nn] = bad;
-    if (bad) atomicAdd(&stats[1], 1u);
+}
+
+// one warp per chain: terminal draw z_{Tp-1} ~ Cat(filt_{Tp-1}) (blocked cumulative sum as above),
+// then the label above every segment, top down.  zb[nn][s] = label at step min((s+1)*SEG, Tp-1).
+template <typename R, int BS>
+__global__ void __launch_bounds__(32)
+label_boundaries_kernel(const R* __restrict__ filt, const R* __restrict__ u, const unsigned char* __restrict__ comp,
+                        int K, int Tp, int ldK, int KB, int nseg, int* __restrict__ z, int* __restrict__ zb) {
+    const int nn = blockIdx.x, lane = threadIdx.x;
+    if (lane != 0) return;
+    const R* f = filt + ((size_t)nn * Tp + Tp - 1) * ldK;
+    const int NBk = (K + BS - 1) / BS;
+    R total = 0;
+    for (int b = 0; b < NBk; ++b) {
+        R a = 0;
+        for (int e = 0; e < BS; ++e) { const int i = b * BS + e; a = fma(i < K ? f[i] : (R)0, (R)1, a); }
+        total += a;
+    }
+    const R r = total * ((R)1 - u[(size_t)nn * Tp + Tp - 1]);
+    int cnt = 0;
+    R Pb = 0;
+    for (int b = 0; b < NBk; ++b) {
+        R a = 0;
+        for (int e = 0; e < BS; ++e) {
+            const int i = b * BS + e;
+            a = fma(i < K ? f[i] : (R)0, (R)1, a);
+            cnt += (i < K && (Pb + a) < r) ? 1 : 0;
+        }
+        Pb += a;
+    }
+    int v = min(cnt, K - 1);
+    z[(size_t)nn * Tp + Tp - 1] = v;
+    for (int sg = nseg - 1; sg >= 0; --sg) {
+        zb[(size_t)nn * nseg + sg] = v;
+        v = comp[((size_t)nn * nseg + sg) * KB + v];
+    }
+}
+
+__global__ void __launch_bounds__(128)
+label_walk_kernel(const unsigned char* __restrict__ tbl, const int* __restrict__ zb, int Tp, int KB, int nseg,
+                  int* __restrict__ z) {
+    extern __shared__ unsigned char seg[];
+    __shared__ int path[LABEL_SEG];
+    const int nn = blockIdx.x / nseg, sg = blockIdx.x % nseg;
+    const int lo = sg * LABEL_SEG, hi = min(lo + LABEL_SEG, Tp - 1);
+    const unsigned char* src = tbl + ((size_t)nn * Tp + lo) * KB;
+    const int bytes = (hi - lo) * KB;
+    for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16)
+        *reinterpret_cast<uint4*>(seg + i) = *reinterpret_cast<const uint4*>(src + i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int v = zb[(size_t)nn * nseg + sg];
+        for (int t = hi - 1; t >= lo; --t) { v = seg[(t - lo) * KB + v]; path[t - lo] = v; }
+    }
+    __syncthreads();
+    for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) z[(size_t)nn * Tp + t] = path[t - lo];
 }
 
 template <typename R>
@@ -464,15 +512,34 @@ __global__ void hmm_smooth_kernel(const R* __restrict__ filt, const R* __restric
 // ---------------------------------------------------------------------------
 static inline int fp_of(int n, int d, size_t esz) { int F = n + d + 1; int v = 16 / (int)esz; return (F + v - 1) / v * v; }
 
+// workspace shared by the three HMM entry points of one call sequence
+enum { HW_DIAG, HW_G, HW_CST, HW_VLEN, HW_DIRTY, HW_BW, HW_BE, HW_LZP, HW_TBL, HW_COMP, HW_ZB, HW_END };
+
+static int hmm_chunks(int N, int Tp) {
+    // forward-filter time chunks: multiples of 8 steps (vector loads of the weight rows)
+    const int W = (chunk_config().warmup + 7) / 8 * 8;
+    return chunks_for(N, KPMS_SM_COUNT * 4, Tp, W);
+}
+static inline int label_row_bytes(int K) { return (K + 15) / 16 * 16; }
+static inline int label_segments(int Tp) { return (Tp - 1 + LABEL_SEG - 1) / LABEL_SEG; }
+
 template <typename R>
-static size_t hmm_ws_bytes(int K, int d, int L) {
-    int Fp = fp_of(d * L, d, sizeof(R));
-    int ldK = (K + 3) / 4 * 4;
-    size_t b = 0;
-    b += align_up((size_t)K * d * Fp * sizeof(R), 256);   // G
-    b += align_up((size_t)K * sizeof(R), 256);            // cst
-    b += align_up((size_t)K * ldK * sizeof(R), 256);      // piT
-    return b;
+static void hmm_ws_layout(int N, int T, int K, int d, int L, size_t off[HW_END + 1]) {
+    const int Fp = fp_of(d * L, d, sizeof(R));
+    const int Tp = T - L, C = hmm_chunks(N, Tp), KB = label_row_bytes(K), nseg = label_segments(Tp);
+    size_t sz[HW_END] = {256,
+                         (size_t)K * d * Fp * sizeof(R),
+                         (size_t)K * sizeof(R),
+                         (size_t)N * 4,
+                         (size_t)N * 4,
+                         (size_t)N * (C + 1) * K * sizeof(R),
+                         (size_t)N * (C + 1) * K * sizeof(R),
+                         (size_t)N * C * sizeof(double),
+                         (size_t)N * Tp * KB,
+                         (size_t)N * (nseg + 1) * KB,
+                         (size_t)N * (nseg + 1) * 4};
+    off[0] = 0;
+    for (int i = 0; i < HW_END; ++i) off[i + 1] = off[i] + align_up(sz[i], 256);
 }
 
 template <typename R, int D_, int L_>
@@ -482,8 +549,10 @@ static int ar_loglik_launch(const R* x, const int* mask, const R* Ab, const R* Q
     constexpr int FPT = sizeof(R) == 4 ? 2 : 1;
     constexpr int KC = sizeof(R) == 4 ? 32 : 16;
     int Fp = fp_of(n, D_, sizeof(R));
-    R* G = reinterpret_cast<R*>(ws);
-    R* cst = reinterpret_cast<R*>(reinterpret_cast<char*>(ws) + align_up((size_t)K * D_ * Fp * sizeof(R), 256));
+    size_t off[HW_END + 1];
+    hmm_ws_layout<R>(N, T, K, D_, L_, off);
+    R* G = reinterpret_cast<R*>(reinterpret_cast<char*>(ws) + off[HW_G]);
+    R* cst = reinterpret_cast<R*>(reinterpret_cast<char*>(ws) + off[HW_CST]);
     { KPMS_LAUNCH("ar_prep", st);
     ar_prep_kernel<R, D_, L_><<<ceil_div(K, 64), 64, 0, st>>>(Ab, Q, K, G, cst, Fp); }
     constexpr int FR = 128 * FPT;
@@ -511,7 +580,8 @@ static int ar_loglik_impl(const void* x, const int* mask, const void* Ab, const 
 
 template <typename R>
 static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N, int K, int Tp, int ldT,
-                            void* filt, double* logZ, cudaStream_t st) {
+                            void* filt, double* logZ, void* ws, int d, int L, cudaStream_t st) {
+    (void)ws; (void)d; (void)L;
     int ldK = (K + 3) / 4 * 4;
     int Kpad = (K + 7) / 8 * 8;
     dim3 grid(N), block(4 * Kpad);
@@ -532,11 +602,15 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
 template <typename R>
 static int hmm_backward_impl(const void* filt, const void* pi, const void* u, void* u_scratch, uint64_t seed, int N,
                              int K, int Tp, int* z, void* ws, int d, int L, cudaStream_t st) {
-    int ldK = (K + 3) / 4 * 4;
-    int Fp = fp_of(d * L, d, sizeof(R));
-    char* base = reinterpret_cast<char*>(ws);
-    R* piT = reinterpret_cast<R*>(base + align_up((size_t)K * d * Fp * sizeof(R), 256) + align_up((size_t)K * sizeof(R), 256));
+    const int ldK = (K + 3) / 4 * 4;
     if (K > 128) return set_error(-3, "hmm_backward: num_states %d > 128 not supported", K);
+    size_t off[HW_END + 1];
+    hmm_ws_layout<R>(N, Tp + L, K, d, L, off);
+    char* base = reinterpret_cast<char*>(ws);
+    unsigned char* tbl = reinterpret_cast<unsigned char*>(base + off[HW_TBL]);
+    unsigned char* comp = reinterpret_cast<unsigned char*>(base + off[HW_COMP]);
+    int* zb = reinterpret_cast<int*>(base + off[HW_ZB]);
+    const int KB = label_row_bytes(K), nseg = label_segments(Tp);
     const R* usrc = (const R*)u;
     if (!usrc) {
         if (!u_scratch) return set_error(-3, "hmm_backward: u_scratch (N*Tp reals) is required when no tape is given");
@@ -545,12 +619,28 @@ static int hmm_backward_impl(const void* filt, const void* pi, const void* u, vo
         fill_uniform_kernel<R><<<(int)((count + 255) / 256), 256, 0, st>>>((R*)u_scratch, count, seed, KPMS_STREAM_Z);
         usrc = (const R*)u_scratch;
     }
-    { KPMS_LAUNCH("transpose_pi", st); transpose_pi_kernel<R><<<ceil_div(K * ldK, 256), 256, 0, st>>>((const R*)pi, K, ldK, piT); }
-    constexpr int STAGES = 8;
-    size_t smem = ((size_t)K * ldK + (size_t)STAGES * ldK) * sizeof(R);
-    auto kern = hmm_backward_kernel<R, 4, STAGES>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    { KPMS_LAUNCH("hmm_backward", st); kern<<<N, 32, smem, st>>>((const R*)filt, piT, usrc, K, Tp, ldK, z, 1, 0, nullptr, nullptr, nullptr, nullptr); }
+    if (Tp > 1) {
+        const long long tiles = (long long)N * ((Tp - 1 + LABEL_TS - 1) / LABEL_TS);
+        const int grid = (int)std::min<long long>(tiles, (long long)KPMS_SM_COUNT * 2);
+        KPMS_LAUNCH("hmm_label_maps", st);
+#define MAPS(KP, BS) hmm_label_maps_kernel<R, KP, BS><<<grid, 128, 0, st>>>((const R*)filt, (const R*)pi, usrc, N, K, Tp, ldK, KB, tbl)
+        if (K <= 32) MAPS(32, 8);
+        else if (K <= 64) MAPS(64, 8);
+        else if (K <= 100) MAPS(100, 10);
+        else MAPS(128, 8);
+#undef MAPS
+    }
+    const size_t smem = (size_t)LABEL_SEG * KB;
+    if (nseg > 0) {
+        KPMS_LAUNCH("hmm_label_compose", st);
+        label_compose_kernel<<<N * nseg, 128, smem, st>>>(tbl, K, Tp, KB, nseg, comp);
+    }
+    { KPMS_LAUNCH("hmm_label_boundaries", st);
+      label_boundaries_kernel<R, 10><<<N, 32, 0, st>>>((const R*)filt, usrc, comp, K, Tp, ldK, KB, nseg, z, zb); }
+    if (nseg > 0) {
+        KPMS_LAUNCH("hmm_label_walk", st);
+        label_walk_kernel<<<N * nseg, 128, smem, st>>>(tbl, zb, Tp, KB, nseg, z);
+    }
     return check_launch("hmm_backward");
 }
 
@@ -571,8 +661,11 @@ using namespace kpms;
 
 extern "C" {
 
-size_t kpms_hmm_workspace_bytes(int dtype, int K, int d, int L) {
-    return dtype == 0 ? hmm_ws_bytes<float>(K, d, L) : hmm_ws_bytes<double>(K, d, L);
+size_t kpms_hmm_workspace_bytes(int dtype, int N, int T, int K, int d, int L) {
+    size_t off[HW_END + 1];
+    if (dtype == 0) hmm_ws_layout<float>(N, T, K, d, L, off);
+    else hmm_ws_layout<double>(N, T, K, d, L, off);
+    return off[HW_END];
 }
 
 int kpms_ar_loglik(int dtype, const void* x, const int* mask, const void* Ab, const void* Q, int N, int T,
@@ -582,8 +675,8 @@ int kpms_ar_loglik(int dtype, const void* x, const int* mask, const void* Ab, co
 }
 
 int kpms_hmm_forward(int dtype, const void* W, const void* mx, const void* pi, int N, int K, int Tp, int ldT,
-                     void* filt, double* logZ, void* stream) {
-    return KPMS_DISPATCH_DTYPE(dtype, hmm_forward_impl, W, mx, pi, N, K, Tp, ldT, filt, logZ,
+                     void* filt, double* logZ, void* ws, int d, int L, void* stream) {
+    return KPMS_DISPATCH_DTYPE(dtype, hmm_forward_impl, W, mx, pi, N, K, Tp, ldT, filt, logZ, ws, d, L,
                                (cudaStream_t)stream);
 }
 

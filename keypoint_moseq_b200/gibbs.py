@@ -133,7 +133,7 @@ def _hmm_forward(x, mask, Ab, Q, pi, dtype):
     code = _lib.dtype_code(dtype)
     esz = 4 if code == _lib.F32 else 8
     xx, AA, QQ, pp = (_dev(t, dtype, dev) for t in (x, Ab, Q, pi))
-    ws = _scratch("hmm_ws", _lib.query("kpms_hmm_workspace_bytes", code, K, d, L), dev)
+    ws = _scratch("hmm_ws", _lib.query("kpms_hmm_workspace_bytes", code, N, T, K, d, L), dev)
     W = _scratch("hmm_W", N * K * ldT * esz, dev)
     mx = _scratch("hmm_mx", N * ldT * esz, dev)
     filt = _scratch("hmm_filt", N * Tp * ldK * esz, dev)
@@ -142,7 +142,7 @@ def _hmm_forward(x, mask, Ab, Q, pi, dtype):
     _lib.call("kpms_ar_loglik", code, _lib.ptr(xx), _lib.ptr(mask), _lib.ptr(AA), _lib.ptr(QQ), N, T, d, L, K,
               ldT, _lib.ptr(W), _lib.ptr(mx), _lib.ptr(ws), sp)
     _lib.call("kpms_hmm_forward", code, _lib.ptr(W), _lib.ptr(mx), _lib.ptr(pp), N, K, Tp, ldT, _lib.ptr(filt),
-              _lib.ptr(logZ), sp)
+              _lib.ptr(logZ), _lib.ptr(ws), d, L, sp)
     return filt, logZ, (N, K, Tp, d, L, code, pp), ws
 
 
