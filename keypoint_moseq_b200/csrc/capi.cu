@@ -57,7 +57,7 @@ LaunchScope::~LaunchScope() {
 }
 
 // ---- time-chunking configuration (common.cuh) ----
-static ChunkConfig g_chunk = {0, 64, 2e-5, 1e-10};
+static ChunkConfig g_chunk = {0, 64, 2e-5, 1e-10, 1e-12};
 ChunkConfig chunk_config() { return g_chunk; }
 int chunks_for(int N, int slots, int len, int warmup) {
     int C = g_chunk.chunks > 0 ? g_chunk.chunks : slots / (N > 0 ? N : 1);

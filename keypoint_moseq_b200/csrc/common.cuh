@@ -224,6 +224,17 @@ template <> __device__ __forceinline__ float rsqrt_fast<float>(float x) {
 }
 template <> __device__ __forceinline__ double rsqrt_fast<double>(double x) { return rsqrt(x); }
 
+// reciprocal to ~1 ulp without the IEEE division sequence
+template <typename R> __device__ __forceinline__ R rcp_fast(R x);
+template <> __device__ __forceinline__ float rcp_fast<float>(float x) { return __frcp_rn(x); }
+template <> __device__ __forceinline__ double rcp_fast<double>(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+
 // asynchronous global -> shared copies (one element, or one 16-byte chunk)
 template <typename R>
 __device__ __forceinline__ void cp_async_elem(R* dst, const R* src) {
@@ -295,7 +306,7 @@ template <typename R>
 __global__ void __launch_bounds__(128)
 boundary_check_kernel(const R* __restrict__ warm, const R* __restrict__ exact, const int* __restrict__ vlen,
                       int len, int C, int W, int align, int n_mean, int rec, R tol, int* __restrict__ dirty,
-                      unsigned* __restrict__ stats) {
+                      unsigned* __restrict__ stats, const int* __restrict__ pre = nullptr) {
     __shared__ R red[2][4];
     const int nn = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     R worst = 0;
@@ -328,7 +339,7 @@ boundary_check_kernel(const R* __restrict__ warm, const R* __restrict__ exact, c
     }
     const int any_bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {
-        const bool d = any_bad || !(worst <= tol);
+        const bool d = any_bad || !(worst <= tol) || (pre && pre[nn] != 0);
         dirty[nn] = d ? 1 : 0;
         atomicMax(&stats[0], __float_as_uint(any_bad ? INFINITY : (float)worst));
         if (d) atomicAdd(&stats[1], 1u);
@@ -336,7 +347,7 @@ boundary_check_kernel(const R* __restrict__ warm, const R* __restrict__ exact, c
 }
 
 // process-wide time-chunking configuration (kpms_set_time_chunking); see capi.cu
-struct ChunkConfig { int chunks; int warmup; double tol32, tol64; };
+struct ChunkConfig { int chunks; int warmup; double tol32, tol64, tol_hmm; };
 ChunkConfig chunk_config();
 // chunks per chain for N chains when `slots` chunk-CTAs fit on the device at once
 int chunks_for(int N, int slots, int len, int warmup);

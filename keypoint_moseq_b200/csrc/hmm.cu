@@ -165,125 +165,263 @@ ar_loglik_kernel(const R* __restrict__ x, const int* __restrict__ mask, const R*
 }
 
 // ---------------------------------------------------------------------------
-// K3 forward: scaled filter, one CTA per chain, 4 threads per state column with the
-// transition-matrix column slices resident in registers; one barrier per step.
+// K3 forward: scaled filter.  One CTA advances M independent (chain, time chunk) tasks in lockstep,
+// 4 threads per state column with the transition-matrix column slices resident in registers and
+// shared by the M tasks; one barrier per step; the weight rows arrive through a cp.async ring,
+// 8 steps at a time.
+//
+// Time chunks (common.cuh).  The unmasked prefix of a chain, rounded up to 8 steps (vb), is cut into
+// C chunks that start Wm steps early from the uniform prior and are checked against their
+// neighbours (1e-12: far below the spacing of the inverse-CDF thresholds, so the labels stay those
+// of the sequential filter).  Padded frames carry no likelihood: there the prediction obeys
+// p_{t+TL} = (pi^TL)' p_t exactly, so the padded tail is cut into TL-step chunks whose starting
+// predictions are propagated with the precomputed power of pi (pass 1) - no warm-up, no check.
+// pass 0: prefix chunks, pass 1: tail chunks, pass 2: whole chains flagged dirty, sequentially.
 // ---------------------------------------------------------------------------
-template <typename R, int RPT>
+constexpr int HMM_TL = 512;         // steps per padded-tail chunk (power of two)
+
+struct HmmTask { int nn, begin, end, start, slot; bool on, given; };
+
+__device__ inline HmmTask hmm_task(long long id, int pass, int N, int Tp, int C, int CT, int Wm,
+                                   const int* __restrict__ vb, const int* __restrict__ dirty) {
+    HmmTask t;
+    t.on = false; t.given = false; t.nn = 0; t.begin = t.end = t.start = 0; t.slot = 0;
+    if (pass == 0) {
+        const int nn = (int)(id / C), ck = (int)(id % C);
+        if (nn >= N) return t;
+        const int v = vb ? vb[nn] : Tp;
+        const ChunkRange cr = chunk_range(v, v, C, Wm, ck, 8);
+        if (cr.empty || cr.begin >= cr.end) return t;
+        t.on = true; t.nn = nn; t.begin = cr.begin; t.end = cr.end; t.start = cr.start; t.slot = ck;
+    } else if (pass == 1) {
+        const int nn = (int)(id / CT), k = (int)(id % CT);
+        if (nn >= N || dirty[nn] != 0) return t;
+        const int b = vb[nn] + k * HMM_TL;
+        if (b >= Tp) return t;
+        t.on = true; t.given = true; t.nn = nn; t.begin = t.start = b; t.end = min(b + HMM_TL, Tp); t.slot = k;
+    } else {
+        const int nn = (int)id;
+        if (nn >= N || (dirty && dirty[nn] == 0)) return t;
+        t.on = true; t.nn = nn; t.begin = t.start = 0; t.end = Tp; t.slot = 0;
+    }
+    return t;
+}
+
+template <typename R, int RPT, int M>
 __global__ void __launch_bounds__(4 * 128)
-hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* __restrict__ pi,
-                   int K, int Tp, int ldT, int ldK, R* __restrict__ filt, double* __restrict__ logZ,
-                   int C, int Wm, const int* __restrict__ vlen, const int* __restrict__ dirty,
-                   R* __restrict__ bnd_warm, R* __restrict__ bnd_end, double* __restrict__ logZ_part) {
+hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* __restrict__ pi, int N, int K,
+                   int Tp, int ldT, int ldK, R* __restrict__ filt, double* __restrict__ logZ,
+                   double* __restrict__ logZ_part, int pass, int C, int CT, int Wm,
+                   const int* __restrict__ vb, const int* __restrict__ dirty, R* __restrict__ bnd_warm,
+                   R* __restrict__ bnd_end, const R* __restrict__ tail_start) {
     constexpr int VEC = 16 / sizeof(R);
     constexpr int RPTP = (RPT + VEC - 1) / VEC * VEC;
-    constexpr int CH = 8;                                    // steps per prefetched chunk (ldT % 8 == 0)
-    __shared__ __align__(16) R qbuf[2][4 * RPTP];
+    constexpr int CH = 8;                                    // steps per staged group (ldT % 8 == 0)
+    constexpr int KC = 4 * RPT;                              // columns covered by the thread grid
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R* wbuf = reinterpret_cast<R*>(smem_raw);                // 2 x M x KC x CH
+    R* qbuf = wbuf + 2 * M * KC * CH;                        // 2 x M x 4*RPTP
     __shared__ double red[32];
-    const int nn = blockIdx.x, ck = blockIdx.y;
     const int tid = threadIdx.x;
-    if (dirty && dirty[nn] == 0) return;
-    // time chunk (common.cuh): outputs for [cr.begin, cr.end), recursion from cr.start with the
-    // uniform prior; all three are multiples of CH except the chain end
-    const ChunkRange cr = chunk_range(vlen ? vlen[nn] : Tp, Tp, C, Wm, ck, 8);
-    if (cr.empty) return;
     const int j = tid >> 2, p = tid & 3;
     const bool col = j < K;
+    HmmTask tk[M];
+    int maxlen = 0;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        tk[m] = hmm_task((long long)blockIdx.x * M + m, pass, N, Tp, C, CT, Wm, vb, dirty);
+        if (tk[m].on) maxlen = max(maxlen, tk[m].end - tk[m].start);
+    }
+    if (maxlen == 0) return;
     R pic[RPT];
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
         int i = p * RPT + r;
         pic[r] = (col && i < K) ? pi[(size_t)i * K + j] : (R)0;
     }
-    for (int i = tid; i < 2 * 4 * RPTP; i += blockDim.x) (&qbuf[0][0])[i] = (R)0;
-    // sum of per-frame maxima (part of the log-normaliser)
-    double msum = 0.0;
-    for (int t = cr.begin + tid; t < cr.end; t += blockDim.x) msum += (double)mx[(size_t)nn * ldT + t];
-    msum = block_sum(msum, red);
-    const R* Wc = W + ((size_t)nn * K + (col ? j : 0)) * ldT;
-    R* fl = filt + (size_t)nn * Tp * ldK;
+    for (int i = tid; i < 2 * M * 4 * RPTP; i += blockDim.x) qbuf[i] = (R)0;
+    // sums of the per-frame maxima (part of the log-normaliser), one block reduction per task
+    double msum[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        double acc = 0.0;
+        if (tk[m].on)
+            for (int t = tk[m].begin + tid; t < tk[m].end; t += blockDim.x) acc += (double)mx[(size_t)tk[m].nn * ldT + t];
+        msum[m] = block_sum(acc, red);
+    }
     const int qslot = (j / RPT) * RPTP + (j % RPT);
-    R cur[CH], nxt[CH];
-    typedef typename Vec16<R>::type VecT;
-    auto load_chunk = [&](int t0, R* dst) {
-        if (t0 < ldT) {
+    R pred[M], inv_s[M], qprev[M];
+    double lz[M], lzp[M];
+    int lze[M];
 #pragma unroll
-            for (int v = 0; v < CH / VEC; ++v) {
-                const VecT val = *reinterpret_cast<const VecT*>(Wc + t0 + v * VEC);
-                const R* ve = reinterpret_cast<const R*>(&val);
+    for (int m = 0; m < M; ++m) {
+        pred[m] = (R)1 / (R)K;
+        if (tk[m].on && tk[m].given && col) pred[m] = tail_start[((size_t)tk[m].nn * CT + tk[m].slot) * K + j];
+        inv_s[m] = (R)1;
+        qprev[m] = (R)0;
+        lz[m] = 0.0;
+        lzp[m] = 1.0;
+        lze[m] = 0;
+    }
+    // staging of the weights: thread (j, p) moves the p-th 16-byte piece of column j's 8-step group
+    auto stage = [&](int r0, int sbuf) {
+        if (col && p < CH / VEC) {
 #pragma unroll
-                for (int c = 0; c < VEC; ++c) dst[v * VEC + c] = ve[c];
+            for (int m = 0; m < M; ++m) {
+                const int t0 = tk[m].start + r0;
+                if (tk[m].on && t0 < tk[m].end)
+                    cp_async_16(wbuf + ((size_t)(sbuf * M + m) * KC + j) * CH + p * VEC,
+                                W + ((size_t)tk[m].nn * K + j) * ldT + t0 + p * VEC);
             }
-        } else {
-#pragma unroll
-            for (int c = 0; c < CH; ++c) dst[c] = (R)0;
         }
+        asm volatile("cp.async.commit_group;\n" ::);
     };
-    load_chunk(cr.start, cur);
-    R pred = (R)1 / (R)K;
-    R inv_s = (R)1;
-    R qprev = (R)0;
-    double lz = 0.0;
+    stage(0, 0);
     int buf = 0;
-    for (int t0 = cr.start; t0 < cr.end; t0 += CH) {
-        load_chunk(t0 + CH, nxt);
+    for (int r0 = 0; r0 < maxlen; r0 += CH) {
+        const int sbuf = (r0 / CH) & 1;
+        stage(r0 + CH, sbuf ^ 1);
+        asm volatile("cp.async.wait_group 1;\n" ::);
+        __syncthreads();
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-            const int t = t0 + c;
-            if (t >= cr.end) break;
-            if (ck > 0 && t == cr.begin && col && p == 0)          // the prediction this chunk arrived with
-                bnd_warm[((size_t)nn * C + ck) * K + j] = pred * inv_s;
-            R qv = pred * inv_s * cur[c];
-            if (col && p == 0) {
-                qbuf[buf][qslot] = qv;
-                if (t > cr.begin) fl[(size_t)(t - 1) * ldK + j] = qprev * inv_s;
+            const int r = r0 + c;
+            if (r >= maxlen) break;
+            R qv[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int t = tk[m].start + r;
+                if (tk[m].on && t < tk[m].end) {
+                    if (col && p == 0 && !tk[m].given && tk[m].slot > 0 && t == tk[m].begin && pass == 0)
+                        bnd_warm[((size_t)tk[m].nn * C + tk[m].slot) * K + j] = pred[m] * inv_s[m];
+                    const R w = col ? wbuf[((size_t)(sbuf * M + m) * KC + j) * CH + c] : (R)0;
+                    qv[m] = pred[m] * inv_s[m] * w;
+                    if (col && p == 0) {
+                        qbuf[(buf * M + m) * 4 * RPTP + qslot] = qv[m];
+                        if (t > tk[m].begin) filt[((size_t)tk[m].nn * Tp + t - 1) * ldK + j] = qprev[m] * inv_s[m];
+                    }
+                }
             }
             __syncthreads();
-            const R* qs = &qbuf[buf][p * RPTP];
-            R a0 = 0, a1 = 0, s0 = 0, s1 = 0;
 #pragma unroll
-            for (int r = 0; r + 1 < RPT; r += 2) {
-                R q0 = qs[r], q1 = qs[r + 1];
-                a0 = fma(pic[r], q0, a0);
-                a1 = fma(pic[r + 1], q1, a1);
-                s0 += q0;
-                s1 += q1;
+            for (int m = 0; m < M; ++m) {
+                const int t = tk[m].start + r;
+                if (tk[m].on && t < tk[m].end) {
+                    const R* qs = qbuf + (buf * M + m) * 4 * RPTP + p * RPTP;
+                    R a0 = 0, a1 = 0, s0 = 0, s1 = 0;
+#pragma unroll
+                    for (int rr = 0; rr + 1 < RPT; rr += 2) {
+                        R q0 = qs[rr], q1 = qs[rr + 1];
+                        a0 = fma(pic[rr], q0, a0);
+                        a1 = fma(pic[rr + 1], q1, a1);
+                        s0 += q0;
+                        s1 += q1;
+                    }
+                    if (RPT & 1) { R q0 = qs[RPT - 1]; a0 = fma(pic[RPT - 1], q0, a0); s0 += q0; }
+                    R a = a0 + a1, s = s0 + s1;
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    pred[m] = a;
+                    inv_s[m] = rcp_fast<R>(s);              // any common scale of a step's row is immaterial
+                    qprev[m] = qv[m];
+                    if (tid == 4 * m && t >= tk[m].begin) {    // log s accumulated as mantissa product + exponent
+                        int ex;
+                        lzp[m] *= frexp((double)s, &ex);
+                        lze[m] += ex;
+                        if ((r & 7) == 7) { lz[m] += log(lzp[m]); lzp[m] = 1.0; }
+                    }
+                }
             }
-            if (RPT & 1) { R q0 = qs[RPT - 1]; a0 = fma(pic[RPT - 1], q0, a0); s0 += q0; }
-            R a = a0 + a1, s = s0 + s1;
-            a += __shfl_xor_sync(0xffffffffu, a, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            a += __shfl_xor_sync(0xffffffffu, a, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            pred = a;
-            inv_s = (R)1 / s;
-            qprev = qv;
-            if (tid == 0 && t >= cr.begin) lz += log((double)s);
             buf ^= 1;
         }
+    }
 #pragma unroll
-        for (int c = 0; c < CH; ++c) cur[c] = nxt[c];
-    }
-    if (col && p == 0) {
-        fl[(size_t)(cr.end - 1) * ldK + j] = qprev * inv_s;
-        if (cr.end < Tp) bnd_end[((size_t)nn * C + ck + 1) * K + j] = pred * inv_s;   // handed to the next chunk
-    }
-    if (tid == 0) {
-        if (logZ_part) logZ_part[(size_t)nn * C + ck] = lz + msum;
-        else logZ[nn] = lz + msum;
+    for (int m = 0; m < M; ++m) {
+        if (!tk[m].on) continue;
+        if (col && p == 0) {
+            filt[((size_t)tk[m].nn * Tp + tk[m].end - 1) * ldK + j] = qprev[m] * inv_s[m];
+            if (pass == 0 && tk[m].end < Tp)               // handed to the next chunk / to the padded tail
+                bnd_end[((size_t)tk[m].nn * C + tk[m].slot + 1) * K + j] = pred[m] * inv_s[m];
+        }
+        if (tid == 4 * m) {
+            const double val = lz[m] + log(lzp[m]) + 0.6931471805599453094 * (double)lze[m] + msum[m];
+            if (pass == 2) logZ[tk[m].nn] = val;
+            else logZ_part[(size_t)tk[m].nn * (C + CT) + (pass == 0 ? tk[m].slot : C + tk[m].slot)] = val;
+        }
     }
 }
 
-// logZ[nn] = ordered sum of the chunks' parts (chains flagged dirty are overwritten by the re-run)
-__global__ void logz_sum_kernel(const double* __restrict__ part, const int* __restrict__ vlen, int N, int Tp, int C,
-                                int Wm, double* __restrict__ logZ) {
+// logZ[nn] = ordered sum of the chunks' parts (zero-initialised; chains flagged dirty are
+// overwritten by the sequential pass afterwards)
+__global__ void logz_sum_kernel(const double* __restrict__ part, int N, int parts, double* __restrict__ logZ) {
     const int nn = blockIdx.x * blockDim.x + threadIdx.x;
     if (nn >= N) return;
     double acc = 0.0;
-    for (int c = 0; c < C; ++c) {
-        if (chunk_range(vlen[nn], Tp, C, Wm, c, 8).empty) break;
-        acc += part[(size_t)nn * C + c];
-    }
+    for (int c = 0; c < parts; ++c) acc += part[(size_t)nn * parts + c];
     logZ[nn] = acc;
+}
+
+// vb[nn] = length of the leading unmasked run of steps, rounded up to 8 (capped at Tp);
+// holes[nn] = 1 when a valid frame follows a masked one (such chains run sequentially)
+__global__ void __launch_bounds__(256)
+hmm_prefix_kernel(const int* __restrict__ mask, int T, int L, int Tp, int* __restrict__ vb, int* __restrict__ holes) {
+    __shared__ int first, late;
+    const int nn = blockIdx.x;
+    if (threadIdx.x == 0) { first = Tp; late = 0; }
+    __syncthreads();
+    const int* mk = mask + (size_t)nn * T + L;
+    for (int i = threadIdx.x; i < Tp; i += blockDim.x)
+        if (mk[i] == 0) { atomicMin(&first, i); break; }
+    __syncthreads();
+    const int f = first;
+    for (int i = f + threadIdx.x; i < Tp; i += blockDim.x)
+        if (mk[i] != 0) { late = 1; break; }
+    __syncthreads();
+    if (threadIdx.x == 0) { vb[nn] = min(Tp, (f + 7) / 8 * 8); holes[nn] = late; }
+}
+
+// out = A A (K x K, row-major); used to form pi^(2^k)
+template <typename R>
+__global__ void mat_square_kernel(const R* __restrict__ A, int K, R* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * K) return;
+    const int i = idx / K, jn = idx % K;
+    R acc = 0;
+    for (int k = 0; k < K; ++k) acc = fma(A[i * K + k], A[k * K + jn], acc);
+    out[idx] = acc;
+}
+
+// predictions at the start of every padded-tail chunk: start[0] = state handed over by the last prefix
+// chunk (uniform when the chain has no valid frame), start[k] = (pi^TL)' start[k-1].  One CTA per chain.
+template <typename R>
+__global__ void __launch_bounds__(128)
+hmm_tail_starts_kernel(const R* __restrict__ PTL, const R* __restrict__ bnd_end, const int* __restrict__ vb,
+                       const int* __restrict__ dirty, int K, int Tp, int C, int CT, int Wm,
+                       R* __restrict__ tail_start) {
+    __shared__ R pcur[128];
+    const int nn = blockIdx.x, jn = threadIdx.x;
+    const int v = vb[nn];
+    if (dirty[nn] != 0 || v >= Tp) return;
+    int last = -1;                                          // last non-empty prefix chunk
+    for (int c = 0; c < C; ++c) {
+        const ChunkRange cr = chunk_range(v, v, C, Wm, c, 8);
+        if (!cr.empty && cr.begin < cr.end) last = c;
+    }
+    R val = (R)1 / (R)K;
+    if (last >= 0 && jn < K) val = bnd_end[((size_t)nn * C + last + 1) * K + jn];
+    const int nk = (Tp - v + HMM_TL - 1) / HMM_TL;
+    for (int k = 0; k < nk; ++k) {
+        if (jn < K) tail_start[((size_t)nn * CT + k) * K + jn] = val;
+        __syncthreads();
+        pcur[jn] = (jn < K) ? val : (R)0;
+        __syncthreads();
+        R acc = 0;
+        if (jn < K)
+            for (int i = 0; i < K; ++i) acc = fma(pcur[i], PTL[(size_t)i * K + jn], acc);
+        val = acc;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -513,7 +651,7 @@ __global__ void hmm_smooth_kernel(const R* __restrict__ filt, const R* __restric
 static inline int fp_of(int n, int d, size_t esz) { int F = n + d + 1; int v = 16 / (int)esz; return (F + v - 1) / v * v; }
 
 // workspace shared by the three HMM entry points of one call sequence
-enum { HW_DIAG, HW_G, HW_CST, HW_VLEN, HW_DIRTY, HW_BW, HW_BE, HW_LZP, HW_TBL, HW_COMP, HW_ZB, HW_END };
+enum { HW_DIAG, HW_G, HW_CST, HW_VLEN, HW_DIRTY, HW_BW, HW_BE, HW_LZP, HW_TS, HW_PW, HW_TBL, HW_COMP, HW_ZB, HW_END };
 
 static int hmm_chunks(int N, int Tp) {
     // forward-filter time chunks: multiples of 8 steps (vector loads of the weight rows)
@@ -527,14 +665,17 @@ template <typename R>
 static void hmm_ws_layout(int N, int T, int K, int d, int L, size_t off[HW_END + 1]) {
     const int Fp = fp_of(d * L, d, sizeof(R));
     const int Tp = T - L, C = hmm_chunks(N, Tp), KB = label_row_bytes(K), nseg = label_segments(Tp);
+    const int CT = (Tp + HMM_TL - 1) / HMM_TL;
     size_t sz[HW_END] = {256,
                          (size_t)K * d * Fp * sizeof(R),
                          (size_t)K * sizeof(R),
-                         (size_t)N * 4,
+                         (size_t)N * 8,
                          (size_t)N * 4,
                          (size_t)N * (C + 1) * K * sizeof(R),
                          (size_t)N * (C + 1) * K * sizeof(R),
-                         (size_t)N * C * sizeof(double),
+                         (size_t)N * (C + CT) * sizeof(double),
+                         (size_t)N * CT * K * sizeof(R),
+                         (size_t)2 * K * K * sizeof(R),
                          (size_t)N * Tp * KB,
                          (size_t)N * (nseg + 1) * KB,
                          (size_t)N * (nseg + 1) * 4};
@@ -555,6 +696,11 @@ static int ar_loglik_launch(const R* x, const int* mask, const R* Ab, const R* Q
     R* cst = reinterpret_cast<R*>(reinterpret_cast<char*>(ws) + off[HW_CST]);
     { KPMS_LAUNCH("ar_prep", st);
     ar_prep_kernel<R, D_, L_><<<ceil_div(K, 64), 64, 0, st>>>(Ab, Q, K, G, cst, Fp); }
+    {   // unmasked prefix of every chain (time chunks of the forward filter)
+        int* vb = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + off[HW_VLEN]);
+        KPMS_LAUNCH("hmm_prefix", st);
+        hmm_prefix_kernel<<<N, 256, 0, st>>>(mask, T, L_, T - L_, vb, vb + N);
+    }
     constexpr int FR = 128 * FPT;
     size_t smem = (align_up((size_t)(FR + L_) * D_, 4) + (size_t)KC * D_ * Fp + KC) * sizeof(R);
     auto kern = ar_loglik_kernel<R, D_, L_, FPT, KC>;
@@ -581,21 +727,68 @@ static int ar_loglik_impl(const void* x, const int* mask, const void* Ab, const 
 template <typename R>
 static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N, int K, int Tp, int ldT,
                             void* filt, double* logZ, void* ws, int d, int L, cudaStream_t st) {
-    (void)ws; (void)d; (void)L;
-    int ldK = (K + 3) / 4 * 4;
-    int Kpad = (K + 7) / 8 * 8;
-    dim3 grid(N), block(4 * Kpad);
-#define LAUNCH(RPT)                                                                                      \
-    { KPMS_LAUNCH("hmm_forward", st);                                                                  \
-    hmm_forward_kernel<R, RPT><<<grid, block, 0, st>>>((const R*)W, (const R*)mx, (const R*)pi, K, Tp,  \
-                                                       ldT, ldK, (R*)filt, logZ, 1, 0, nullptr, nullptr,  \
-                                                       nullptr, nullptr, nullptr); }
-    if (K <= 28) { LAUNCH(7); }
-    else if (K <= 52) { LAUNCH(13); }
-    else if (K <= 100) { LAUNCH(25); }
-    else if (K <= 128) { LAUNCH(32); }
-    else return set_error(-3, "hmm_forward: num_states %d > 128 not supported", K);
-#undef LAUNCH
+    const int ldK = (K + 3) / 4 * 4;
+    const int Kpad = (K + 7) / 8 * 8;
+    if (K > 128) return set_error(-3, "hmm_forward: num_states %d > 128 not supported", K);
+    constexpr int M = 4;
+    size_t off[HW_END + 1];
+    hmm_ws_layout<R>(N, Tp + L, K, d, L, off);
+    char* base = reinterpret_cast<char*>(ws);
+    unsigned* diag = reinterpret_cast<unsigned*>(base + off[HW_DIAG]);
+    int* vb = reinterpret_cast<int*>(base + off[HW_VLEN]);
+    int* holes = vb + N;
+    int* dirty = reinterpret_cast<int*>(base + off[HW_DIRTY]);
+    R* bw = reinterpret_cast<R*>(base + off[HW_BW]);
+    R* be = reinterpret_cast<R*>(base + off[HW_BE]);
+    double* lzp = reinterpret_cast<double*>(base + off[HW_LZP]);
+    R* tstart = reinterpret_cast<R*>(base + off[HW_TS]);
+    R* pw = reinterpret_cast<R*>(base + off[HW_PW]);
+    const ChunkConfig cfg = chunk_config();
+    const int C = hmm_chunks(N, Tp), CT = (Tp + HMM_TL - 1) / HMM_TL, Wm = (cfg.warmup + 7) / 8 * 8;
+    const dim3 block(4 * Kpad);
+#define FWD(RPT, GRID, PASS, VB, DIRTY)                                                                       \
+    {                                                                                                         \
+        auto kern = hmm_forward_kernel<R, RPT, M>;                                                            \
+        constexpr int RPTP_ = (RPT + 16 / (int)sizeof(R) - 1) / (16 / (int)sizeof(R)) * (16 / (int)sizeof(R)); \
+        const size_t smem = ((size_t)2 * M * 4 * RPT * 8 + (size_t)2 * M * 4 * RPTP_) * sizeof(R);            \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
+        kern<<<GRID, block, smem, st>>>((const R*)W, (const R*)mx, (const R*)pi, N, K, Tp, ldT, ldK, (R*)filt, \
+                                        logZ, lzp, PASS, C, CT, Wm, VB, DIRTY, bw, be, tstart);               \
+    }
+#define FWD_K(GRID, PASS, VB, DIRTY)                                             \
+    if (K <= 28) FWD(7, GRID, PASS, VB, DIRTY)                                   \
+    else if (K <= 52) FWD(13, GRID, PASS, VB, DIRTY)                             \
+    else if (K <= 100) FWD(25, GRID, PASS, VB, DIRTY)                            \
+    else FWD(32, GRID, PASS, VB, DIRTY)
+    cudaMemsetAsync(diag, 0, 256, st);
+    if (C <= 1) {                                        // sequential: every chain is one task
+        KPMS_LAUNCH("hmm_forward", st);
+        FWD_K((N + M - 1) / M, 2, (const int*)nullptr, (const int*)nullptr)
+        return check_launch("hmm_forward");
+    }
+    const R tol = (R)(sizeof(R) == 4 ? cfg.tol32 : cfg.tol_hmm);
+    cudaMemsetAsync(lzp, 0, (size_t)N * (C + CT) * sizeof(double), st);
+    { KPMS_LAUNCH("hmm_forward", st); FWD_K((int)(((long long)N * C + M - 1) / M), 0, vb, (const int*)nullptr) }
+    { KPMS_LAUNCH("hmm_forward_check", st);
+      boundary_check_kernel<R><<<N, 128, 0, st>>>(bw, be, vb, Tp, C, Wm, 8, K, K, tol, dirty, diag, holes); }
+    // pi^TL by repeated squaring, then the starting predictions of the padded-tail chunks
+    {
+        const R* src = (const R*)pi;
+        int which = 0;
+        for (int e = 1; e < HMM_TL; e <<= 1) {
+            KPMS_LAUNCH("hmm_pi_power", st);
+            mat_square_kernel<R><<<ceil_div(K * K, 128), 128, 0, st>>>(src, K, pw + (size_t)which * K * K);
+            src = pw + (size_t)which * K * K;
+            which ^= 1;
+        }
+        KPMS_LAUNCH("hmm_tail_starts", st);
+        hmm_tail_starts_kernel<R><<<N, 128, 0, st>>>(src, be, vb, dirty, K, Tp, C, CT, Wm, tstart);
+    }
+    { KPMS_LAUNCH("hmm_forward_tail", st); FWD_K((int)(((long long)N * CT + M - 1) / M), 1, vb, dirty) }
+    { KPMS_LAUNCH("hmm_logz_sum", st); logz_sum_kernel<<<ceil_div(N, 128), 128, 0, st>>>(lzp, N, C + CT, logZ); }
+    { KPMS_LAUNCH("hmm_forward_rerun", st); FWD_K((N + M - 1) / M, 2, (const int*)nullptr, dirty) }
+#undef FWD_K
+#undef FWD
     return check_launch("hmm_forward");
 }
 

@@ -270,3 +270,35 @@ def test_location_scan_long_chains(dtype, tol, frames, seg):
     v_ref = orc.resample_location(data["Y"], data["mask"], st["x"], st["h"], st["s"], pr["Cd"], pr["sigmasq"], 0.5,
                                   tape["w_v"])
     assert rel_err(_np(v), v_ref) < tol
+
+
+@pytest.mark.parametrize("mode", ["chunked", "fallback", "sequential"])
+@pytest.mark.parametrize("shape", [dict(d=4, L=3, K=12, k=5, D=2), dict(d=10, L=3, K=100, k=12, D=2)])
+def test_discrete_stateseqs_time_chunks(mode, shape, chunking):
+    """HMM FFBS on long ragged chains: forward filter in concurrent time chunks (prefix) and
+    power-of-pi chunks (padded tail), backward sampling by composed label maps.  Labels must stay
+    bit-exact, also when a too-short warm-up forces the sequential re-run."""
+    g = _gibbs()
+    data, _, model = small_problem(seed=13, recordings=2, frames=1500, seg_length=1000, **shape)
+    tape = tape_for(data, model)
+    st, pr = model["states"], model["params"]
+    z_ref, logZ_ref = orc.resample_discrete_stateseqs(st["x"], data["mask"], pr["Ab"], pr["Q"], pr["pi"], tape["u_z"])
+    dd, dm = _to_dev(data, model, torch.float64)
+    if mode == "chunked":
+        chunking(chunks=3, warmup=64)
+    elif mode == "fallback":
+        chunking(chunks=3, warmup=0)
+    else:
+        chunking(chunks=1)
+    z, logZ = g.resample_discrete_stateseqs(dm["states"]["x"], dd["mask"], dm["params"]["Ab"], dm["params"]["Q"],
+                                            dm["params"]["pi"], u_z=torch.as_tensor(tape["u_z"]))
+    diag = g.chunk_diagnostics("hmm_ws")
+    assert np.array_equal(_np(z), z_ref), (f"{(_np(z) != z_ref).sum()} of {z_ref.size} labels differ", diag)
+    assert rel_err(_np(logZ), logZ_ref) < 1e-9, diag
+    if mode == "chunked":
+        assert diag["forward_rerun"] == 0 and diag["forward_max_err"] < 1e-12, diag
+    elif mode == "fallback":
+        assert diag["forward_rerun"] > 0, diag
+    marg = g.stateseq_marginals(dm["states"]["x"], dd["mask"], dm["params"]["Ab"], dm["params"]["Q"], dm["params"]["pi"])
+    ref = orc.stateseq_marginals(st["x"], data["mask"].astype(float), pr["Ab"], pr["Q"], pr["pi"])
+    assert np.abs(_np(marg) - ref).max() < 1e-9
