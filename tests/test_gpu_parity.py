@@ -302,3 +302,25 @@ def test_discrete_stateseqs_time_chunks(mode, shape, chunking):
     marg = g.stateseq_marginals(dm["states"]["x"], dd["mask"], dm["params"]["Ab"], dm["params"]["Q"], dm["params"]["pi"])
     ref = orc.stateseq_marginals(st["x"], data["mask"].astype(float), pr["Ab"], pr["Q"], pr["pi"])
     assert np.abs(_np(marg) - ref).max() < 1e-9
+
+
+def test_host_operands_are_staged_and_streamed_back():
+    """resample_model given pinned HOST tensors (staged uploads, states streamed into `host_out`)
+    returns exactly what the device-resident call returns."""
+    g = _gibbs()
+    data, _, model = small_problem(seed=11, d=4, L=3, K=12, k=5, D=2)
+    tape = tape_for(data, model)
+    dd, dm = _to_dev(data, model, torch.float32)
+    ref = g.resample_model(dd, **dm, draws=tape)
+    pin = lambda t: t.cpu().pin_memory()
+    hd = {key: pin(val) for key, val in dd.items()}
+    hm = dict(dm, states={key: pin(val) for key, val in dm["states"].items()},
+              params={key: pin(val) for key, val in dm["params"].items()}, noise_prior=pin(dm["noise_prior"]))
+    sink = {key: torch.empty_like(val).pin_memory() for key, val in hm["states"].items()}
+    out = g.resample_model(hd, **hm, draws=tape, host_out=sink)
+    torch.cuda.synchronize()
+    for key in ("x", "v", "h", "s", "z"):
+        assert torch.equal(out["states"][key], ref["states"][key]), key
+        assert torch.equal(sink[key], ref["states"][key].cpu()), key
+    for key in ("Ab", "Q", "pi", "betas"):
+        assert torch.equal(out["params"][key], ref["params"][key]), key
