@@ -268,13 +268,11 @@ def main():
         esteps = max(1, min(args.steps, 5))
 
         def e2e_step(seed):
-            d_dev = {k_: v.to(dev, non_blocking=True) for k_, v in host_data.items()}
-            mm = {"seed": seed, "states": {k_: v.to(dev, non_blocking=True) for k_, v in host_states.items()},
-                  "params": {k_: v.to(dev, non_blocking=True) for k_, v in host_params.items()},
-                  "hypparams": m["hypparams"], "noise_prior": host_prior.to(dev, non_blocking=True)}
-            out = gibbs.resample_model(d_dev, **mm, **opts)
-            for k_, v in out["states"].items():
-                out_host[k_].copy_(v, non_blocking=True)
+            # the public call with HOST operands: resample_model uploads them on its copy stream in
+            # order of first use and streams each resampled state back into `out_host` as it completes
+            mm = {"seed": seed, "states": host_states, "params": host_params, "hypparams": m["hypparams"],
+                  "noise_prior": host_prior}
+            out = gibbs.resample_model(host_data, **mm, host_out=out_host, **opts)
             torch.cuda.synchronize()
             if not np.isfinite(out_host["x"].numpy()).all():
                 raise RuntimeError("NaNs in e2e sweep")

@@ -51,6 +51,80 @@ def chunk_diagnostics(tag="kalman_ws", device="cuda"):
             "backward_max_err": float(f[2]), "backward_rerun": int(u[3])}
 
 
+_STREAMS = {}
+
+
+def _side_stream(dev, tag):
+    key = (str(dev), tag)
+    if key not in _STREAMS:
+        _STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _STREAMS[key]
+
+
+class _Stager:
+    """Uploads host operands on a copy stream in the order they are registered; `get` makes the
+    compute stream wait for that operand only.  Device operands pass through (converted if needed)."""
+
+    def __init__(self, dev):
+        self.dev, self.items, self.copy = dev, {}, None
+        self.main = torch.cuda.current_stream(dev)
+
+    def put(self, key, a, dtype):
+        if a is None:
+            self.items[key] = (None, None)
+            return
+        if not isinstance(a, torch.Tensor):
+            a = torch.as_tensor(np.asarray(a))
+        if a.is_cuda:
+            self.items[key] = (a.to(device=self.dev, dtype=dtype).contiguous(), None)
+            return
+        if self.copy is None:
+            self.copy = _side_stream(self.dev, "h2d")
+        with torch.cuda.stream(self.copy):
+            t = a.to(self.dev, non_blocking=True)
+            if t.dtype != dtype:
+                t = t.to(dtype)
+            t = t.contiguous()
+            ev = torch.cuda.Event()
+            ev.record(self.copy)
+        t.record_stream(self.main)
+        self.items[key] = (t, ev)
+
+    def get(self, key):
+        t, ev = self.items[key]
+        if ev is not None:
+            self.main.wait_event(ev)
+            self.items[key] = (t, None)
+        return t
+
+
+class _HostSink:
+    """Copies finished states into caller-provided host tensors on a side stream."""
+
+    def __init__(self, dev, host_out):
+        self.out, self.done = host_out, set()
+        if host_out is not None:
+            self.main = torch.cuda.current_stream(dev)
+            self.side = _side_stream(dev, "d2h")
+
+    def emit(self, key, t):
+        if self.out is None or key not in self.out or key in self.done:
+            return
+        self.done.add(key)
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            self.out[key].copy_(t, non_blocking=True)
+        t.record_stream(self.side)
+
+    def finish(self, states):
+        if self.out is None:
+            return
+        for key, t in states.items():
+            self.emit(key, t)
+
+
 def _dev(a, dtype, device):
     """Tensor on `device` with `dtype`, contiguous; no copy when already so."""
     if a is None:
@@ -347,32 +421,50 @@ def resample_obs_variance(obsvar, nu_sigma, sigmasq_0, D, seed64=0, g_sig=None, 
 def resample_model(data, seed, states, params, hypparams, noise_prior, ar_only=False, states_only=False,
                    resample_global_noise_scale=False, resample_local_noise_scale=True, fix_heading=False,
                    verbose=False, jitter=1e-3, parallel_message_passing=False, draws=None,
-                   hmm_dtype=torch.float64, group=None, **kwargs):
+                   hmm_dtype=torch.float64, group=None, host_out=None, **kwargs):
     """One Gibbs sweep; same keywords and return layout as
     jax_moseq.models.keypoint_slds.resample_model.
 
     Extra keywords (all optional): `draws` = dict of injected tapes (verification mode, keys as
     in oracle.make_tape); `hmm_dtype` = arithmetic type of the discrete-state path (float64 keeps
     z bit-exact against a float64 reference); `group` = torch.distributed process group over which
-    the chains are sharded (sufficient statistics are all-reduced once per sweep).
+    the chains are sharded (sufficient statistics are all-reduced once per sweep); `host_out` =
+    dict of (pinned) host tensors keyed like `states`: each resampled state is copied into it on a
+    side stream as soon as its sampler has finished (the caller synchronises before reading).
+    Operands given as host tensors are uploaded on a copy stream in order of first use.
     `parallel_message_passing` is accepted for signature compatibility: the backward pass is
     always parallel in time here and the filter recursion always serial.
     """
     tp = draws or {}
     dev = data["Y"].device if isinstance(data["Y"], torch.Tensor) and data["Y"].is_cuda else torch.device("cuda")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
     x = states["x"]
     dt = x.dtype if isinstance(x, torch.Tensor) and x.dtype in (torch.float32, torch.float64) else torch.float64
-    Y = _dev(data["Y"], dt, dev)
-    mask = _dev(data["mask"], torch.int32, dev)
-    st = {key: _dev(val, torch.int32 if key == "z" else dt, dev) for key, val in states.items()}
-    pr = {key: _dev(val, torch.float64, dev) for key, val in params.items()}
-    prior = _dev(noise_prior, dt, dev)
+    # Host operands are staged in order of first use on a copy stream; every sampler waits only for
+    # what it reads, so the bulk of the transfer (Y, noise_prior, s) hides behind the HMM kernels.
+    stage = _Stager(dev)
+    stage.put("x", states["x"], dt)
+    stage.put("z", states["z"], torch.int32)
+    stage.put("mask", data["mask"], torch.int32)
+    for key, val in params.items():
+        stage.put("p:" + key, val, torch.float64)
+    rest = [key for key in states if key not in ("x", "z")]
+    for key in rest:
+        stage.put(key, states[key], dt)
+    if not ar_only:
+        stage.put("Y", data["Y"], dt)
+        stage.put("prior", noise_prior, dt)
+    mask = stage.get("mask")
+    st = {"x": stage.get("x"), "z": stage.get("z")}
+    pr = {key: stage.get("p:" + key) for key in params}
     th, ah = hypparams["trans_hypparams"], hypparams["ar_hypparams"]
     oh, ch = hypparams["obs_hypparams"], hypparams["cen_hypparams"]
     K = int(th["num_states"])
-    N, T, k, D = Y.shape
+    N, T, k, D = data["Y"].shape
     d = st["x"].shape[-1]
     L = T - st["z"].shape[1]
+    sink = _HostSink(dev, host_out)
 
     seed64 = seed_to_u64(seed)
     rank = 0
@@ -385,7 +477,7 @@ def resample_model(data, seed, states, params, hypparams, noise_prior, ar_only=F
     if not states_only:
         obs = None
         if resample_global_noise_scale and not ar_only:
-            obs = (Y, st["v"], st["h"], st["s"], Ct)
+            obs = (stage.get("Y"), stage.get("v"), stage.get("h"), stage.get("s"), Ct)
         packed = sufficient_statistics(st["x"], st["z"], mask, K, obs)
         if group is not None:
             import torch.distributed as dist
@@ -402,15 +494,22 @@ def resample_model(data, seed, states, params, hypparams, noise_prior, ar_only=F
 
     st["z"], _ = resample_discrete_stateseqs(st["x"], mask, pr["Ab"], pr["Q"], pr["pi"], seed_loc, tp.get("u_z"),
                                              dtype=hmm_dtype)
+    sink.emit("z", st["z"])
+    for key in rest:
+        st[key] = stage.get(key)
     if not ar_only:
+        Y, prior = stage.get("Y"), stage.get("prior")
         if resample_local_noise_scale:
             st["s"] = resample_scales(Y, st["x"], st["v"], st["h"], pr["Cd"], pr["sigmasq"], oh["nu_s"], prior,
                                       seed_loc, tp.get("g_s"), Ct=Ct)
+        sink.emit("s", st["s"])
         st["x"] = resample_continuous_stateseqs(Y, mask, st["v"], st["h"], st["s"], st["z"], pr["Cd"],
                                                 pr["sigmasq"], pr["Ab"], pr["Q"], jitter, seed_loc, tp.get("w_x"),
                                                 Ct=Ct)
+        sink.emit("x", st["x"])
         st["h"], st["v"] = resample_heading_location(Y, mask, st["x"], st["v"], st["h"], st["s"], pr["Cd"],
                                                      pr["sigmasq"], ch["sigmasq_loc"], fix_heading, seed_loc,
                                                      tp.get("u_h"), tp.get("w_v"), Ct=Ct)
+    sink.finish(st)
     return {"seed": advance_seed(seed), "states": st, "params": pr, "hypparams": hypparams,
             "noise_prior": noise_prior}
