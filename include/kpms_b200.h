@@ -57,7 +57,11 @@ void kpms_set_time_chunking(int chunks, int warmup, double tol32, double tol64);
  *      forward + smooth is arhmm.stateseq_marginals (fitting.py:536-538). */
 /* one workspace serves kpms_ar_loglik, kpms_hmm_forward and kpms_hmm_backward_sample of the same (N, T, K, d, L) */
 size_t kpms_hmm_workspace_bytes(int dtype, int N, int T, int K, int d, int L);
-/* W (N,K,ldT) <- exp(ll - max_k ll), mx (N,ldT) <- max_k ll; masked frames have ll = 0. ldT % 8 == 0. */
+/* W <- exp(ll - max_k ll), mx (N,ldT) <- max_k ll; masked frames have ll = 0. ldT % 8 == 0.
+ * W is an opaque buffer of kpms_hmm_weights_bytes() handed from kpms_ar_loglik to kpms_hmm_forward
+ * of the same dtype: (N,K,ldT) time-contiguous in float32, (N,Tp,K rounded up to whole 8-state tiles)
+ * state-contiguous in float64 (operand layout of the FP64 tensor-pipe kernels). */
+size_t kpms_hmm_weights_bytes(int dtype, int N, int T, int K, int L);
 int kpms_ar_loglik(int dtype, const void* x, const int32_t* mask, const void* Ab, const void* Q, int N,
                    int T, int d, int L, int K, int ldT, void* W, void* mx, void* ws, void* stream);
 /* filt (N,Tp,ldK), ldK = K rounded up to 4; logZ (N) double = per-chain log normaliser. */

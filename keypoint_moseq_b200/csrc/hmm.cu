@@ -178,7 +178,7 @@ ar_loglik_kernel(const R* __restrict__ x, const int* __restrict__ mask, const R*
 // predictions are propagated with the precomputed power of pi (pass 1) - no warm-up, no check.
 // pass 0: prefix chunks, pass 1: tail chunks, pass 2: whole chains flagged dirty, sequentially.
 // ---------------------------------------------------------------------------
-constexpr int HMM_TL = 512;         // steps per padded-tail chunk (power of two)
+constexpr int HMM_TL = 128;         // steps per padded-tail chunk (power of two)
 
 struct HmmTask { int nn, begin, end, start, slot; bool on, given; };
 
@@ -352,6 +352,8 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
         }
     }
 }
+
+#include "hmm_f64.cuh"
 
 // logZ[nn] = ordered sum of the chunks' parts (zero-initialised; chains flagged dirty are
 // overwritten by the sequential pass afterwards)
@@ -651,12 +653,16 @@ __global__ void hmm_smooth_kernel(const R* __restrict__ filt, const R* __restric
 static inline int fp_of(int n, int d, size_t esz) { int F = n + d + 1; int v = 16 / (int)esz; return (F + v - 1) / v * v; }
 
 // workspace shared by the three HMM entry points of one call sequence
-enum { HW_DIAG, HW_G, HW_CST, HW_VLEN, HW_DIRTY, HW_BW, HW_BE, HW_LZP, HW_TS, HW_PW, HW_TBL, HW_COMP, HW_ZB, HW_END };
+enum { HW_DIAG, HW_G, HW_GF, HW_CST, HW_VLEN, HW_DIRTY, HW_BW, HW_BE, HW_LZP, HW_TS, HW_PW, HW_TBL, HW_COMP, HW_ZB, HW_END };
 
-static int hmm_chunks(int N, int Tp) {
+// float64 path: state tiles of 8 columns (one warp each) for the tensor-pipe kernels; 0 = unsupported
+static inline int state_tiles(int K) { return K <= 32 ? 4 : K <= 56 ? 7 : K <= 104 ? 13 : K <= 128 ? 16 : 0; }
+constexpr int HMM_MT = 1;           // 8-task tiles per CTA of the float64 forward kernel
+
+static int hmm_chunks(int N, int Tp, bool f64) {
     // forward-filter time chunks: multiples of 8 steps (vector loads of the weight rows)
     const int W = (chunk_config().warmup + 7) / 8 * 8;
-    return chunks_for(N, KPMS_SM_COUNT * 4, Tp, W);
+    return chunks_for(N, f64 ? KPMS_SM_COUNT * 8 * HMM_MT : KPMS_SM_COUNT * 4, Tp, W);
 }
 static inline int label_row_bytes(int K) { return (K + 15) / 16 * 16; }
 static inline int label_segments(int Tp) { return (Tp - 1 + LABEL_SEG - 1) / LABEL_SEG; }
@@ -664,10 +670,11 @@ static inline int label_segments(int Tp) { return (Tp - 1 + LABEL_SEG - 1) / LAB
 template <typename R>
 static void hmm_ws_layout(int N, int T, int K, int d, int L, size_t off[HW_END + 1]) {
     const int Fp = fp_of(d * L, d, sizeof(R));
-    const int Tp = T - L, C = hmm_chunks(N, Tp), KB = label_row_bytes(K), nseg = label_segments(Tp);
+    const int Tp = T - L, C = hmm_chunks(N, Tp, sizeof(R) == 8), KB = label_row_bytes(K), nseg = label_segments(Tp);
     const int CT = (Tp + HMM_TL - 1) / HMM_TL;
     size_t sz[HW_END] = {256,
                          (size_t)K * d * Fp * sizeof(R),
+                         (size_t)state_tiles(K) * (d * ((d * L + d + 3) / 4) * 32 + d * 8 + 8) * sizeof(double),
                          (size_t)K * sizeof(R),
                          (size_t)N * 8,
                          (size_t)N * 4,
@@ -701,6 +708,27 @@ static int ar_loglik_launch(const R* x, const int* mask, const R* Ab, const R* Q
         KPMS_LAUNCH("hmm_prefix", st);
         hmm_prefix_kernel<<<N, 256, 0, st>>>(mask, T, L_, T - L_, vb, vb + N);
     }
+    if constexpr (sizeof(R) == 8) {
+        // tensor-pipe path: operators repacked in fragment order, W (N, Tp, 8*KT) states-contiguous
+        typedef ArFrag<D_, L_> AF;
+        const int KT = state_tiles(K);
+        if (KT == 0) return set_error(-3, "ar_loglik: num_states %d > 128 not supported", K);
+        double* Gf = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + off[HW_GF]);
+        { KPMS_LAUNCH("ar_pack_frag", st);
+          ar_pack_frag_kernel<D_, L_><<<ceil_div(KT * AF::CHUNK, 256), 256, 0, st>>>((const double*)G, (const double*)cst, K, Fp, KT, Gf); }
+        const size_t smem = (align_up((size_t)(128 + L_) * D_, 2) + (size_t)2 * AF::CHUNK) * sizeof(double);
+        dim3 grid(ceil_div(T - L_, 128), N);
+#define ARL(KT_)                                                                                              \
+        {                                                                                                     \
+            auto kern = ar_loglik_dmma_kernel<D_, L_, KT_>;                                                   \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+            KPMS_LAUNCH("ar_loglik", st);                                                                     \
+            kern<<<grid, 512, smem, st>>>((const double*)x, mask, Gf, N, T, K, ldT, (double*)W, (double*)mx); \
+        }
+        if (KT == 4) ARL(4) else if (KT == 7) ARL(7) else if (KT == 13) ARL(13) else ARL(16)
+#undef ARL
+        return check_launch("ar_loglik");
+    }
     constexpr int FR = 128 * FPT;
     size_t smem = (align_up((size_t)(FR + L_) * D_, 4) + (size_t)KC * D_ * Fp + KC) * sizeof(R);
     auto kern = ar_loglik_kernel<R, D_, L_, FPT, KC>;
@@ -730,7 +758,7 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
     const int ldK = (K + 3) / 4 * 4;
     const int Kpad = (K + 7) / 8 * 8;
     if (K > 128) return set_error(-3, "hmm_forward: num_states %d > 128 not supported", K);
-    constexpr int M = 4;
+    constexpr int M = sizeof(R) == 8 ? 8 * HMM_MT : 4;       // tasks per CTA
     size_t off[HW_END + 1];
     hmm_ws_layout<R>(N, Tp + L, K, d, L, off);
     char* base = reinterpret_cast<char*>(ws);
@@ -744,7 +772,7 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
     R* tstart = reinterpret_cast<R*>(base + off[HW_TS]);
     R* pw = reinterpret_cast<R*>(base + off[HW_PW]);
     const ChunkConfig cfg = chunk_config();
-    const int C = hmm_chunks(N, Tp), CT = (Tp + HMM_TL - 1) / HMM_TL, Wm = (cfg.warmup + 7) / 8 * 8;
+    const int C = hmm_chunks(N, Tp, sizeof(R) == 8), CT = (Tp + HMM_TL - 1) / HMM_TL, Wm = (cfg.warmup + 7) / 8 * 8;
     const dim3 block(4 * Kpad);
 #define FWD(RPT, GRID, PASS, VB, DIRTY)                                                                       \
     {                                                                                                         \
@@ -755,8 +783,18 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
         kern<<<GRID, block, smem, st>>>((const R*)W, (const R*)mx, (const R*)pi, N, K, Tp, ldT, ldK, (R*)filt, \
                                         logZ, lzp, PASS, C, CT, Wm, VB, DIRTY, bw, be, tstart);               \
     }
+#define FWD64(KT_, GRID, PASS, VB, DIRTY)                                                                     \
+    hmm_forward_dmma_kernel<KT_, HMM_MT><<<GRID, 32 * KT_, 0, st>>>(                                          \
+        (const double*)W, (const double*)mx, (const double*)pi, N, K, Tp, ldT, ldK, (double*)filt, logZ, lzp, \
+        PASS, C, CT, Wm, VB, DIRTY, (double*)bw, (double*)be, (const double*)tstart);
 #define FWD_K(GRID, PASS, VB, DIRTY)                                             \
-    if (K <= 28) FWD(7, GRID, PASS, VB, DIRTY)                                   \
+    if (sizeof(R) == 8) {                                                        \
+        if (K <= 32) FWD64(4, GRID, PASS, VB, DIRTY)                             \
+        else if (K <= 56) FWD64(7, GRID, PASS, VB, DIRTY)                        \
+        else if (K <= 104) FWD64(13, GRID, PASS, VB, DIRTY)                      \
+        else FWD64(16, GRID, PASS, VB, DIRTY)                                    \
+    }                                                                            \
+    else if (K <= 28) FWD(7, GRID, PASS, VB, DIRTY)                              \
     else if (K <= 52) FWD(13, GRID, PASS, VB, DIRTY)                             \
     else if (K <= 100) FWD(25, GRID, PASS, VB, DIRTY)                            \
     else FWD(32, GRID, PASS, VB, DIRTY)
@@ -788,6 +826,7 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
     { KPMS_LAUNCH("hmm_logz_sum", st); logz_sum_kernel<<<ceil_div(N, 128), 128, 0, st>>>(lzp, N, C + CT, logZ); }
     { KPMS_LAUNCH("hmm_forward_rerun", st); FWD_K((N + M - 1) / M, 2, (const int*)nullptr, dirty) }
 #undef FWD_K
+#undef FWD64
 #undef FWD
     return check_launch("hmm_forward");
 }
@@ -859,6 +898,12 @@ size_t kpms_hmm_workspace_bytes(int dtype, int N, int T, int K, int d, int L) {
     if (dtype == 0) hmm_ws_layout<float>(N, T, K, d, L, off);
     else hmm_ws_layout<double>(N, T, K, d, L, off);
     return off[HW_END];
+}
+
+size_t kpms_hmm_weights_bytes(int dtype, int N, int T, int K, int L) {
+    const size_t Tp = T > L ? T - L : 0, ldT = (Tp + 7) / 8 * 8;
+    if (dtype == 0) return (size_t)N * K * ldT * sizeof(float);
+    return (size_t)N * Tp * 8 * (state_tiles(K) ? state_tiles(K) : (K + 7) / 8) * sizeof(double);
 }
 
 int kpms_ar_loglik(int dtype, const void* x, const int* mask, const void* Ab, const void* Q, int N, int T,

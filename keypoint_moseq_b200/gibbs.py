@@ -208,7 +208,7 @@ def _hmm_forward(x, mask, Ab, Q, pi, dtype):
     esz = 4 if code == _lib.F32 else 8
     xx, AA, QQ, pp = (_dev(t, dtype, dev) for t in (x, Ab, Q, pi))
     ws = _scratch("hmm_ws", _lib.query("kpms_hmm_workspace_bytes", code, N, T, K, d, L), dev)
-    W = _scratch("hmm_W", N * K * ldT * esz, dev)
+    W = _scratch("hmm_W", _lib.query("kpms_hmm_weights_bytes", code, N, T, K, L), dev)
     mx = _scratch("hmm_mx", N * ldT * esz, dev)
     filt = _scratch("hmm_filt", N * Tp * ldK * esz, dev)
     logZ = torch.empty(N, dtype=torch.float64, device=dev)
