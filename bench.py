@@ -155,9 +155,7 @@ def kernel_bytes_per_frame(name, cfg, esz, hmm_esz):
         "kalman_affine": gh * esz + d * esz,
         "ar_loglik": d * hmm_esz + 4 + (K + 1) * hmm_esz,
         "hmm_forward": (K + 1 + ldK) * hmm_esz,
-        "hmm_label_maps": ldK * hmm_esz + hmm_esz + (K + 15) // 16 * 16,
-        "hmm_label_compose": (K + 15) // 16 * 16,
-        "hmm_label_walk": (K + 15) // 16 * 16 + 4,
+        "hmm_backward": ldK * hmm_esz + hmm_esz + 4,
         "resample_scales": (k * D + d + D + 1 + 2 * k + k) * esz,
         "heading_location": (k * D + d + D + k) * esz + (1 + D + 1) * esz,
         "location_ffbs": (D + 1) * esz + 4 + 2 * (D + 1) * esz,
@@ -341,6 +339,8 @@ def main():
         "e2e": e2e,
         "roofline": roofline,
         "kernels": kernels,
+        "chunk_diagnostics": {"kalman": gibbs.chunk_diagnostics("kalman_ws", dev),
+                              "hmm": gibbs.chunk_diagnostics("hmm_ws", dev)},
         "cpu_baseline": cpu,
         "clocks": clk,
     }

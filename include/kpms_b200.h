@@ -68,7 +68,10 @@ int kpms_ar_loglik(int dtype, const void* x, const int32_t* mask, const void* Ab
 int kpms_hmm_forward(int dtype, const void* W, const void* mx, const void* pi, int N, int K, int Tp,
                      int ldT, void* filt, double* logZ, void* ws, int d, int L, void* stream);
 /* z (N,Tp) int32; u_tape (N,Tp) uniforms or NULL, in which case u_scratch (N,Tp) receives Philox uniforms.
- * Exact and parallel in time: every step's map z_{t+1} -> z_t is tabulated, then the maps are composed. */
+ * Exact and parallel in time: with the uniforms fixed the sampler is a deterministic map z_{t+1} -> z_t,
+ * so time chunks started from a guess merge with the true path; every chunk boundary is compared with
+ * the label actually produced above it and un-merged stretches are re-walked (workspace words 2, 3 =
+ * mismatched boundaries, re-walked steps).  `ws` must be the workspace kpms_ar_loglik ran on. */
 int kpms_hmm_backward_sample(int dtype, const void* filt, const void* pi, const void* u_tape, void* u_scratch,
                              uint64_t seed, int N, int K, int Tp, int32_t* z, void* ws, int d, int L,
                              void* stream);

@@ -442,169 +442,266 @@ __global__ void fill_uniform_kernel(R* __restrict__ u, long long count, uint64_t
 }
 
 // ---------------------------------------------------------------------------
-// K3 backward, parallel in time and exact.  Backward sampling is z_t = f_t(z_{t+1}) with
-//   f_t(j) = #{ i : c_i(j) < (1 - u_t) c_{K-1}(j) },   c_i(j) = sum_{i' <= i} filt_t[i'] pi[i'][j],
-// a deterministic map of the next label once u_t is fixed.  All maps are built independently
-// (one thread per (t, j), the column of pi in registers, filt_t broadcast from shared memory),
-// then composed: per 256-step segment every starting label is walked through the segment's maps
-// (label_compose), the segment boundaries are resolved per chain from the terminal draw
-// (label_boundaries), and every segment replays its own path (label_walk).  Integer composition
-// is exact, so the labels are those of the sequential sampler that uses the same summation order.
-// The cumulative sum is blocked: c_i = P_b + a_{b,e} with P_b the sum of the blocks before block b
-// and a_{b,e} the running sum inside it (both accumulated left to right from 0).
+// K3 backward: z_{Tp-1} ~ Cat(filt_{Tp-1}),  z_t ~ Cat(filt_t * pi[:, z_{t+1}]) by inverse CDF,
+//   z = #{ i : c_i < (1 - u_t) c_{K-1} },  c_i = sum_{i' <= i} filt_t[i'] pi[i'][z_{t+1}].
+// One warp per (chain, time chunk); O(K) work per step.
+//
+// Walker.  Syllables persist, so the walker tests the hypothesis "the label stays j" for 8
+// steps at once: lane group g (4 lanes) takes step t-g and forms A = c_{j-1}, B = c_j and the total
+// from its quarter of the row (pi[:, j] lives in registers, once plain and once masked to i < j);
+// the label stays iff A < r <= B.  The longest run of passing steps is accepted in one go; the
+// first failing step is resolved by a full inverse CDF (running sums piece by piece inside every
+// 4-lane group) and the walk continues with the new label.  Rows of filt and the uniforms arrive
+// through a per-warp cp.async ring, four 8-step groups in flight; pi^T is resident in shared memory.
+//
+// Exact time parallelism.  With the uniforms fixed, backward sampling is a deterministic map
+// z_{t+1} -> z_t, and two paths that meet stay together.  Chunk c (steps [begin, end)) starts W
+// steps above its range from a draw of the filtered marginal alone, walks down without storing
+// until it reaches `end` - the label it holds there (zwarm) is the one it conditions on - and then
+// stores its range.  Chunks cut the unmasked prefix only: the top chunk starts from the terminal
+// draw and takes the whole padded tail (paths do not merge where the filter carries no
+// information, and the walker crosses such stretches at a few tens of cycles per step).  A repair
+// pass (one warp per chain, top down) compares every zwarm with the label the chunk above actually
+// produced; on a mismatch it re-walks the chunk below from the true label until the new path meets
+// the stored one.  The result is the sequential sampler's path whatever the merging time;
+// mismatches only cost time (diag word 2 = mismatched boundaries, word 3 = re-walked steps).
 // ---------------------------------------------------------------------------
-constexpr int LABEL_TS = 16;        // steps per tile of the map builder
-constexpr int LABEL_SEG = 256;      // steps per composition segment
-
-template <typename R, int KP, int BS>
-__global__ void __launch_bounds__(128, 1)
-hmm_label_maps_kernel(const R* __restrict__ filt, const R* __restrict__ pi, const R* __restrict__ u,
-                      int N, int K, int Tp, int ldK, int KB, unsigned char* __restrict__ tbl) {
-    constexpr int NB = KP / BS, TS = LABEL_TS, VEC = 16 / (int)sizeof(R);
-    static_assert(KP % BS == 0 && KP % VEC == 0, "padded state count");
-    typedef typename Vec16<R>::type VecT;
-    __shared__ __align__(16) R ft[TS * KP];
-    __shared__ R us[TS];
-    const int tid = threadIdx.x, j = tid;
-    R pic[KP];
-#pragma unroll
-    for (int i = 0; i < KP; ++i) pic[i] = (i < K && j < K) ? pi[(size_t)i * K + j] : (R)0;
-    const int steps = Tp - 1;                         // maps for t = 0 .. Tp-2; t = Tp-1 is the terminal draw
-    const int tpc = (steps + TS - 1) / TS;
-    for (long long tile = blockIdx.x; tile < (long long)N * tpc; tile += gridDim.x) {
-        const int nn = (int)(tile / tpc), t0 = (int)(tile % tpc) * TS;
-        const int nts = min(TS, steps - t0);
-        __syncthreads();
-        for (int idx = tid; idx < TS * KP; idx += 128) {
-            const int ts = idx / KP, i = idx % KP;
-            ft[idx] = (ts < nts && i < K) ? filt[((size_t)nn * Tp + t0 + ts) * ldK + i] : (R)0;
-        }
-        if (tid < TS) us[tid] = (tid < nts) ? u[(size_t)nn * Tp + t0 + tid] : (R)0.5;
-        __syncthreads();
-        for (int ts = 0; ts < nts; ++ts) {
-            const R* f = ft + ts * KP;
-            R acc[NB];
-#pragma unroll
-            for (int b = 0; b < NB; ++b) acc[b] = (R)0;
-#pragma unroll
-            for (int iv = 0; iv < KP / VEC; ++iv) {
-                const VecT fv = *reinterpret_cast<const VecT*>(f + iv * VEC);
-                const R* fe = reinterpret_cast<const R*>(&fv);
-#pragma unroll
-                for (int q = 0; q < VEC; ++q) {
-                    const int i = iv * VEC + q;
-                    acc[i / BS] = fma(fe[q], pic[i], acc[i / BS]);
-                }
-            }
-            R run = (R)0, Pb = (R)0;
-            R pref[NB];
-#pragma unroll
-            for (int b = 0; b < NB; ++b) { run += acc[b]; pref[b] = run; }
-            const R r = run * ((R)1 - us[ts]);
-            int bstar = 0;
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-                if (pref[b] < r) { bstar = b + 1; Pb = pref[b]; }
-            int cnt = bstar * BS;
-            if (bstar < NB) {
-                R a = (R)0;
-#pragma unroll
-                for (int e = 0; e < BS; ++e) {
-                    const int i = bstar * BS + e;
-                    const R pv = (i < K && j < K) ? __ldg(pi + (size_t)i * K + j) : (R)0;
-                    a = fma(f[i], pv, a);
-                    cnt += ((Pb + a) < r) ? 1 : 0;
-                }
-            }
-            cnt = min(cnt, K - 1);
-            if (j < K) tbl[((size_t)nn * Tp + t0 + ts) * KB + j] = (unsigned char)cnt;
-        }
-    }
-}
-
-// segment s of a chain covers steps [s*SEG, min((s+1)*SEG, Tp-1)); comp[nn][s][j] = label at the
-// segment's first step when the label just above the segment is j
-__global__ void __launch_bounds__(128)
-label_compose_kernel(const unsigned char* __restrict__ tbl, int K, int Tp, int KB, int nseg,
-                     unsigned char* __restrict__ comp) {
-    extern __shared__ unsigned char seg[];            // SEG x KB
-    const int nn = blockIdx.x / nseg, sg = blockIdx.x % nseg;
-    const int lo = sg * LABEL_SEG, hi = min(lo + LABEL_SEG, Tp - 1);
-    const unsigned char* src = tbl + ((size_t)nn * Tp + lo) * KB;
-    const int bytes = (hi - lo) * KB;
-    for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16)
-        *reinterpret_cast<uint4*>(seg + i) = *reinterpret_cast<const uint4*>(src + i);
-    __syncthreads();
-    const int j = threadIdx.x;
-    if (j < K) {
-        int v = j;
-        for (int t = hi - 1; t >= lo; --t) v = seg[(t - lo) * KB + v];
-        comp[((size_t)nn * nseg + sg) * KB + j] = (unsigned char)v;
-    }
-}
-
-// one warp per chain: terminal draw z_{Tp-1} ~ Cat(filt_{Tp-1}) (blocked cumulative sum as above),
-// then the label above every segment, top down.  zb[nn][s] = label at step min((s+1)*SEG, Tp-1).
-template <typename R, int BS>
-__global__ void __launch_bounds__(32)
-label_boundaries_kernel(const R* __restrict__ filt, const R* __restrict__ u, const unsigned char* __restrict__ comp,
-                        int K, int Tp, int ldK, int KB, int nseg, int* __restrict__ z, int* __restrict__ zb) {
-    const int nn = blockIdx.x, lane = threadIdx.x;
-    if (lane != 0) return;
-    const R* f = filt + ((size_t)nn * Tp + Tp - 1) * ldK;
-    const int NBk = (K + BS - 1) / BS;
-    R total = 0;
-    for (int b = 0; b < NBk; ++b) {
-        R a = 0;
-        for (int e = 0; e < BS; ++e) { const int i = b * BS + e; a = fma(i < K ? f[i] : (R)0, (R)1, a); }
-        total += a;
-    }
-    const R r = total * ((R)1 - u[(size_t)nn * Tp + Tp - 1]);
-    int cnt = 0;
-    R Pb = 0;
-    for (int b = 0; b < NBk; ++b) {
-        R a = 0;
-        for (int e = 0; e < BS; ++e) {
-            const int i = b * BS + e;
-            a = fma(i < K ? f[i] : (R)0, (R)1, a);
-            cnt += (i < K && (Pb + a) < r) ? 1 : 0;
-        }
-        Pb += a;
-    }
-    int v = min(cnt, K - 1);
-    z[(size_t)nn * Tp + Tp - 1] = v;
-    for (int sg = nseg - 1; sg >= 0; --sg) {
-        zb[(size_t)nn * nseg + sg] = v;
-        v = comp[((size_t)nn * nseg + sg) * KB + v];
-    }
-}
-
-__global__ void __launch_bounds__(128)
-label_walk_kernel(const unsigned char* __restrict__ tbl, const int* __restrict__ zb, int Tp, int KB, int nseg,
-                  int* __restrict__ z) {
-    extern __shared__ unsigned char seg[];
-    __shared__ int path[LABEL_SEG];
-    const int nn = blockIdx.x / nseg, sg = blockIdx.x % nseg;
-    const int lo = sg * LABEL_SEG, hi = min(lo + LABEL_SEG, Tp - 1);
-    const unsigned char* src = tbl + ((size_t)nn * Tp + lo) * KB;
-    const int bytes = (hi - lo) * KB;
-    for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16)
-        *reinterpret_cast<uint4*>(seg + i) = *reinterpret_cast<const uint4*>(src + i);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int v = zb[(size_t)nn * nseg + sg];
-        for (int t = hi - 1; t >= lo; --t) { v = seg[(t - lo) * KB + v]; path[t - lo] = v; }
-    }
-    __syncthreads();
-    for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) z[(size_t)nn * Tp + t] = path[t - lo];
-}
-
 template <typename R>
 __global__ void transpose_pi_kernel(const R* __restrict__ pi, int K, int ldK, R* __restrict__ piT) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= K * ldK) return;
-    int jn = idx / ldK, i = idx % ldK;      // piT[jn][i] = pi[i][jn]
+    const int jn = idx / ldK, i = idx % ldK;      // piT[jn][i] = pi[i][jn]
     piT[idx] = (i < K) ? pi[(size_t)i * K + jn] : (R)0;
+}
+
+constexpr int HMM_BW_WARPS = 4;      // warps per CTA (one CTA per SM: pi^T and the rings fill shared memory)
+constexpr int HMM_BW_RING = 32;      // ring slots per warp = four groups of 8 steps
+
+// NPC = 16-byte pieces of a row per lane of a 4-lane group: ceil(ldK * sizeof(R) / 64)
+template <typename R, int NPC>
+__global__ void __launch_bounds__(32 * HMM_BW_WARPS, 1)
+hmm_backward_walk_kernel(const R* __restrict__ filt, const R* __restrict__ piT, const R* __restrict__ u, int N,
+                         int K, int Tp, int ldK, int Cb, int Wm, const int* __restrict__ vb, int repair,
+                         int* __restrict__ z, int* __restrict__ zwarm, unsigned* __restrict__ diag) {
+    typedef typename Vec16<R>::type VecT;
+    constexpr int VEC = 16 / (int)sizeof(R);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    const int slot_len = ldK + VEC;                              // row + uniform, 16-byte multiple
+    R* piTs = reinterpret_cast<R*>(smem_raw);                    // K x ldK, piTs[j][i] = pi[i][j]
+    for (int idx = threadIdx.x; idx < K * ldK / VEC; idx += blockDim.x)
+        reinterpret_cast<VecT*>(piTs)[idx] = __ldg(reinterpret_cast<const VecT*>(piT) + idx);
+    __syncthreads();
+    R* ring = piTs + (size_t)K * ldK + (size_t)warp * HMM_BW_RING * slot_len;
+    const long long id = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const int nn = repair ? (int)id : (int)(id / Cb);
+    if (nn >= N) return;
+    const int v = vb ? vb[nn] : Tp;
+    const R* fl = filt + (size_t)nn * Tp * ldK;
+    const R* un = u + (size_t)nn * Tp;
+    int* zn = z + (size_t)nn * Tp;
+    const int pieces = ldK / VEC;                                // 16-byte pieces per row
+
+    // Walk from step t_hi down to t_lo.  init < 0: the first step is drawn from the filtered marginal
+    // alone; otherwise init is the label at t_hi + 1.  Labels of steps < store_hi are stored, the label
+    // at store_hi goes to *warm_out.  merge: stop as soon as the new label equals the stored one.
+    // Returns the number of steps whose stored label changed (merge mode) / was written.
+    auto walk = [&](int t_hi, int t_lo, int init, int store_hi, int* warm_out, bool merge) -> unsigned {
+        unsigned written = 0;
+        int next_group = 0;
+        auto issue_group = [&](int k) {                          // rows t_hi - 8k - (0..7), clipped at t_lo
+            const int t = t_hi - 8 * k - g;                      // lane group g brings row g of the group
+            if (t >= t_lo) {
+                R* dst = ring + (size_t)((8 * k + g) & (HMM_BW_RING - 1)) * slot_len;
+                const R* src = fl + (size_t)t * ldK;
+#pragma unroll
+                for (int r = 0; r < NPC; ++r) {
+                    const int pc = q + 4 * r;
+                    if (pc < pieces) cp_async_16(dst + pc * VEC, src + pc * VEC);
+                }
+                if (q == 0) cp_async_elem(dst + ldK, un + t);
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+        };
+        __syncwarp();
+        for (; next_group < 4; ++next_group) issue_group(next_group);
+        int t = t_hi, j = init;
+        R pa[NPC][VEC], pl[NPC][VEC], pjj = (R)0;
+        auto load_column = [&](int jj) {
+            const R* row = piTs + (size_t)jj * ldK;
+#pragma unroll
+            for (int r = 0; r < NPC; ++r) {
+                const int pc = q + 4 * r;
+                if (pc < pieces) *reinterpret_cast<VecT*>(pa[r]) = *reinterpret_cast<const VecT*>(row + pc * VEC);
+                else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) pa[r][e] = (R)0;
+                }
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) pl[r][e] = (pc * VEC + e < jj) ? pa[r][e] : (R)0;
+            }
+            pjj = row[jj];
+        };
+        // Inverse CDF at step tt, every 4-lane group redundantly in its own layout (piece q + 4r of
+        // the row per lane): running sums piece by piece, left to right.  with_pi: weights pa (the
+        // column of the current label), else the filtered marginal alone.  `pl` is scratch here
+        // (it is reloaded with the new label's column afterwards).
+        auto full_draw = [&](int tt, bool with_pi) -> int {
+            const R* row = ring + (size_t)((t_hi - tt) & (HMM_BW_RING - 1)) * slot_len;
+            R run = (R)0;
+#pragma unroll
+            for (int r = 0; r < NPC; ++r) {
+                const int pc = q + 4 * r;
+                R pv[VEC];
+                if (pc < pieces) {
+                    const VecT fv = *reinterpret_cast<const VecT*>(row + pc * VEC);
+                    const R* fe = reinterpret_cast<const R*>(&fv);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) pv[e] = with_pi ? fe[e] * pa[r][e] : fe[e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) pv[e] = (R)0;
+                }
+#pragma unroll
+                for (int e = 1; e < VEC; ++e) pv[e] += pv[e - 1];
+                const R pt = pv[VEC - 1];
+                R s1 = __shfl_up_sync(0xffffffffu, pt, 1);
+                s1 = q >= 1 ? pt + s1 : pt;
+                R s2 = __shfl_up_sync(0xffffffffu, s1, 2);
+                s2 = q >= 2 ? s1 + s2 : s1;
+                R ex = __shfl_up_sync(0xffffffffu, s2, 1);
+                ex = q >= 1 ? ex : (R)0;
+                const R tot = __shfl_sync(0xffffffffu, s2, (lane & ~3) | 3);
+                const R base = run + ex;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) pl[r][e] = base + pv[e];
+                run += tot;
+            }
+            const R thr = run * ((R)1 - row[ldK]);
+            int c = 0;
+#pragma unroll
+            for (int r = 0; r < NPC; ++r)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) c += (q + 4 * r < pieces && pl[r][e] < thr) ? 1 : 0;
+            c += __shfl_xor_sync(0xffffffffu, c, 1);
+            c += __shfl_xor_sync(0xffffffffu, c, 2);
+            return min(c, K - 1);
+        };
+        auto commit_label = [&](int tt, int lab) -> bool {       // true = merged with the stored path
+            if (merge && zn[tt] == lab) return true;
+            __syncwarp();
+            if (lane == 0) {
+                if (tt < store_hi) zn[tt] = lab;
+                else if (tt == store_hi && warm_out) *warm_out = lab;
+            }
+            ++written;
+            return false;
+        };
+        auto advance_groups = [&]() {                            // keep four groups in flight below t
+            const int kc = (t_hi - t) >> 3;
+            if (next_group < kc + 4) {
+                __syncwarp();
+                for (; next_group < kc + 4; ++next_group) issue_group(next_group);
+            }
+        };
+        if (init < 0) {
+            asm volatile("cp.async.wait_group 2;\n" ::);
+            __syncwarp();
+            j = full_draw(t, false);
+            if (commit_label(t, j)) return written;
+            --t;
+        }
+        if (t >= t_lo) load_column(j);
+        while (t >= t_lo) {
+            advance_groups();
+            asm volatile("cp.async.wait_group 2;\n" ::);
+            __syncwarp();
+            const int s = t - g;
+            const bool in_range = s >= t_lo;
+            const R* row = ring + (size_t)((t_hi - s) & (HMM_BW_RING - 1)) * slot_len;
+            R all0 = 0, all1 = 0, lo0 = 0, lo1 = 0;
+            if (in_range) {
+#pragma unroll
+                for (int r = 0; r < NPC; ++r) {
+                    const int pc = q + 4 * r;
+                    if (pc < pieces) {
+                        const VecT fv = *reinterpret_cast<const VecT*>(row + pc * VEC);
+                        const R* fe = reinterpret_cast<const R*>(&fv);
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) {
+                            if ((r + e) & 1) { all1 = fma(fe[e], pa[r][e], all1); lo1 = fma(fe[e], pl[r][e], lo1); }
+                            else { all0 = fma(fe[e], pa[r][e], all0); lo0 = fma(fe[e], pl[r][e], lo0); }
+                        }
+                    }
+                }
+            }
+            R all = all0 + all1, lo = lo0 + lo1;
+            all += __shfl_xor_sync(0xffffffffu, all, 1);
+            lo += __shfl_xor_sync(0xffffffffu, lo, 1);
+            all += __shfl_xor_sync(0xffffffffu, all, 2);
+            lo += __shfl_xor_sync(0xffffffffu, lo, 2);
+            bool fail = false;
+            int old = -1;
+            if (in_range) {
+                const R rr = all * ((R)1 - row[ldK]);
+                const R hi = lo + row[j] * pjj;
+                fail = !((lo < rr) && !(hi < rr));
+                if (merge) old = zn[s];
+            }
+            const unsigned fmask = __ballot_sync(0xffffffffu, fail);
+            const int first = fmask ? ((__ffs(fmask) - 1) >> 2) : 8;
+            const int nacc = min(first, min(8, t - t_lo + 1));
+            if (merge) {                                         // first accepted step whose stored label is already j
+                const unsigned mm = __ballot_sync(0xffffffffu, in_range && g < nacc && old == j);
+                if (mm) {
+                    const int gm = (__ffs(mm) - 1) >> 2;
+                    if (q == 0 && g < gm) zn[s] = j;
+                    return written + (unsigned)gm;
+                }
+            }
+            if (q == 0 && g < nacc) {
+                if (s < store_hi) zn[s] = j;
+                else if (s == store_hi && warm_out) *warm_out = j;
+            }
+            written += (unsigned)nacc;
+            t -= nacc;
+            if (first < 8 && t >= t_lo && nacc == first) {       // the label changes at step t
+                const int jn = full_draw(t, true);
+                if (commit_label(t, jn)) return written;
+                j = jn;
+                --t;
+                if (t >= t_lo) load_column(j);
+            }
+        }
+        return written;
+    };
+
+    if (!repair) {
+        const int c = (int)(id % Cb);
+        const ChunkRange cr = chunk_range(v, Tp, Cb, Wm, c);
+        if (cr.empty || cr.begin >= cr.end) return;
+        const bool top = cr.end >= Tp;
+        const int t0 = top ? Tp - 1 : min(cr.end - 1 + max(Wm, 1), Tp - 1);
+        walk(t0, cr.begin, -1, cr.end, top ? nullptr : zwarm + (size_t)nn * Cb + c, false);
+        return;
+    }
+    // repair: boundaries top down
+    int Cn = 0;
+    for (int c = 0; c < Cb; ++c) {
+        const ChunkRange cr = chunk_range(v, Tp, Cb, Wm, c);
+        if (!cr.empty && cr.begin < cr.end) Cn = c + 1;
+    }
+    unsigned mism = 0, steps = 0;
+    for (int c = Cn - 2; c >= 0; --c) {
+        const ChunkRange cr = chunk_range(v, Tp, Cb, Wm, c);
+        __syncwarp();
+        const int zc = zn[cr.end];
+        if (zwarm[(size_t)nn * Cb + c] == zc) continue;
+        ++mism;
+        steps += walk(cr.end - 1, cr.begin, zc, Tp, nullptr, true);
+        asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    if (lane == 0 && mism) { atomicAdd(&diag[2], mism); atomicAdd(&diag[3], steps); }
 }
 
 // ---------------------------------------------------------------------------
@@ -653,7 +750,7 @@ __global__ void hmm_smooth_kernel(const R* __restrict__ filt, const R* __restric
 static inline int fp_of(int n, int d, size_t esz) { int F = n + d + 1; int v = 16 / (int)esz; return (F + v - 1) / v * v; }
 
 // workspace shared by the three HMM entry points of one call sequence
-enum { HW_DIAG, HW_G, HW_GF, HW_CST, HW_VLEN, HW_DIRTY, HW_BW, HW_BE, HW_LZP, HW_TS, HW_PW, HW_TBL, HW_COMP, HW_ZB, HW_END };
+enum { HW_DIAG, HW_G, HW_GF, HW_CST, HW_VLEN, HW_DIRTY, HW_BW, HW_BE, HW_LZP, HW_TS, HW_PW, HW_PIT, HW_ZB, HW_END };
 
 // float64 path: state tiles of 8 columns (one warp each) for the tensor-pipe kernels; 0 = unsupported
 static inline int state_tiles(int K) { return K <= 32 ? 4 : K <= 56 ? 7 : K <= 104 ? 13 : K <= 128 ? 16 : 0; }
@@ -664,13 +761,11 @@ static int hmm_chunks(int N, int Tp, bool f64) {
     const int W = (chunk_config().warmup + 7) / 8 * 8;
     return chunks_for(N, f64 ? KPMS_SM_COUNT * 8 * HMM_MT : KPMS_SM_COUNT * 4, Tp, W);
 }
-static inline int label_row_bytes(int K) { return (K + 15) / 16 * 16; }
-static inline int label_segments(int Tp) { return (Tp - 1 + LABEL_SEG - 1) / LABEL_SEG; }
 
 template <typename R>
 static void hmm_ws_layout(int N, int T, int K, int d, int L, size_t off[HW_END + 1]) {
     const int Fp = fp_of(d * L, d, sizeof(R));
-    const int Tp = T - L, C = hmm_chunks(N, Tp, sizeof(R) == 8), KB = label_row_bytes(K), nseg = label_segments(Tp);
+    const int Tp = T - L, C = hmm_chunks(N, Tp, sizeof(R) == 8);
     const int CT = (Tp + HMM_TL - 1) / HMM_TL;
     size_t sz[HW_END] = {256,
                          (size_t)K * d * Fp * sizeof(R),
@@ -683,9 +778,8 @@ static void hmm_ws_layout(int N, int T, int K, int d, int L, size_t off[HW_END +
                          (size_t)N * (C + CT) * sizeof(double),
                          (size_t)N * CT * K * sizeof(R),
                          (size_t)2 * K * K * sizeof(R),
-                         (size_t)N * Tp * KB,
-                         (size_t)N * (nseg + 1) * KB,
-                         (size_t)N * (nseg + 1) * 4};
+                         (size_t)K * ((K + 3) / 4 * 4) * sizeof(R),
+                         (size_t)N * 64 * 4};
     off[0] = 0;
     for (int i = 0; i < HW_END; ++i) off[i + 1] = off[i] + align_up(sz[i], 256);
 }
@@ -831,6 +925,11 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
     return check_launch("hmm_forward");
 }
 
+static int hmm_backward_chunks(int N, int Tp) {
+    const int W = chunk_config().warmup;
+    return chunks_for(N, KPMS_SM_COUNT * HMM_BW_WARPS, Tp, W);
+}
+
 template <typename R>
 static int hmm_backward_impl(const void* filt, const void* pi, const void* u, void* u_scratch, uint64_t seed, int N,
                              int K, int Tp, int* z, void* ws, int d, int L, cudaStream_t st) {
@@ -839,10 +938,9 @@ static int hmm_backward_impl(const void* filt, const void* pi, const void* u, vo
     size_t off[HW_END + 1];
     hmm_ws_layout<R>(N, Tp + L, K, d, L, off);
     char* base = reinterpret_cast<char*>(ws);
-    unsigned char* tbl = reinterpret_cast<unsigned char*>(base + off[HW_TBL]);
-    unsigned char* comp = reinterpret_cast<unsigned char*>(base + off[HW_COMP]);
-    int* zb = reinterpret_cast<int*>(base + off[HW_ZB]);
-    const int KB = label_row_bytes(K), nseg = label_segments(Tp);
+    unsigned* diag = reinterpret_cast<unsigned*>(base + off[HW_DIAG]);
+    const int* vb = reinterpret_cast<const int*>(base + off[HW_VLEN]);     // written by kpms_ar_loglik
+    int* zwarm = reinterpret_cast<int*>(base + off[HW_ZB]);
     const R* usrc = (const R*)u;
     if (!usrc) {
         if (!u_scratch) return set_error(-3, "hmm_backward: u_scratch (N*Tp reals) is required when no tape is given");
@@ -851,28 +949,32 @@ static int hmm_backward_impl(const void* filt, const void* pi, const void* u, vo
         fill_uniform_kernel<R><<<(int)((count + 255) / 256), 256, 0, st>>>((R*)u_scratch, count, seed, KPMS_STREAM_Z);
         usrc = (const R*)u_scratch;
     }
-    if (Tp > 1) {
-        const long long tiles = (long long)N * ((Tp - 1 + LABEL_TS - 1) / LABEL_TS);
-        const int grid = (int)std::min<long long>(tiles, (long long)KPMS_SM_COUNT * 2);
-        KPMS_LAUNCH("hmm_label_maps", st);
-#define MAPS(KP, BS) hmm_label_maps_kernel<R, KP, BS><<<grid, 128, 0, st>>>((const R*)filt, (const R*)pi, usrc, N, K, Tp, ldK, KB, tbl)
-        if (K <= 32) MAPS(32, 8);
-        else if (K <= 64) MAPS(64, 8);
-        else if (K <= 100) MAPS(100, 10);
-        else MAPS(128, 8);
-#undef MAPS
+    const int Cb = hmm_backward_chunks(N, Tp), Wm = chunk_config().warmup;
+    R* piT = reinterpret_cast<R*>(base + off[HW_PIT]);
+    { KPMS_LAUNCH("hmm_transpose_pi", st);
+      transpose_pi_kernel<R><<<ceil_div(K * ldK, 256), 256, 0, st>>>((const R*)pi, K, ldK, piT); }
+    cudaMemsetAsync(diag + 2, 0, 8, st);
+    const size_t warp_ring = (size_t)HMM_BW_RING * (ldK + 16 / sizeof(R)) * sizeof(R);
+    const size_t pit_bytes = (size_t)K * ldK * sizeof(R);
+    const int wpc = pit_bytes + HMM_BW_WARPS * warp_ring <= 220 * 1024 ? HMM_BW_WARPS : HMM_BW_WARPS / 2;   // warps per CTA
+    const size_t smem = pit_bytes + wpc * warp_ring;
+    const int npc = (int)((ldK * sizeof(R) + 63) / 64);
+#define BWD(NPC_)                                                                                             \
+    {                                                                                                         \
+        auto kern = hmm_backward_walk_kernel<R, NPC_>;                                                        \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
+        { KPMS_LAUNCH("hmm_backward", st);                                                                    \
+          kern<<<(int)(((long long)N * Cb + wpc - 1) / wpc), 32 * wpc, smem, st>>>(                           \
+              (const R*)filt, piT, usrc, N, K, Tp, ldK, Cb, Wm, vb, 0, z, zwarm, diag); }                     \
+        if (Cb > 1) {                                                                                         \
+            KPMS_LAUNCH("hmm_backward_repair", st);                                                           \
+            kern<<<(N + wpc - 1) / wpc, 32 * wpc, smem, st>>>(                                                \
+                (const R*)filt, piT, usrc, N, K, Tp, ldK, Cb, Wm, vb, 1, z, zwarm, diag);                     \
+        }                                                                                                     \
     }
-    const size_t smem = (size_t)LABEL_SEG * KB;
-    if (nseg > 0) {
-        KPMS_LAUNCH("hmm_label_compose", st);
-        label_compose_kernel<<<N * nseg, 128, smem, st>>>(tbl, K, Tp, KB, nseg, comp);
-    }
-    { KPMS_LAUNCH("hmm_label_boundaries", st);
-      label_boundaries_kernel<R, 10><<<N, 32, 0, st>>>((const R*)filt, usrc, comp, K, Tp, ldK, KB, nseg, z, zb); }
-    if (nseg > 0) {
-        KPMS_LAUNCH("hmm_label_walk", st);
-        label_walk_kernel<<<N * nseg, 128, smem, st>>>(tbl, zb, Tp, KB, nseg, z);
-    }
+    if (npc <= 2) BWD(2) else if (npc <= 4) BWD(4) else if (npc <= 7) BWD(7) else if (npc <= 8) BWD(8)
+    else if (npc <= 13) BWD(13) else BWD(16)
+#undef BWD
     return check_launch("hmm_backward");
 }
 

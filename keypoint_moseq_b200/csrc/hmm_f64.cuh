@@ -1,10 +1,9 @@
 // Float64 AR-HMM kernels on the FP64 tensor pipe (DMMA.8x8x4, mma.sync m8n8k4 f64; measured
 // 37.1 TFLOP/s on B200 against 34 TFLOP/s of plain DFMA at one eighth of the issue slots,
-// tools/micro/dmma_peak.cu).  The three dense contractions of the discrete-state path are real
+// tools/micro/dmma_peak.cu).  The two dense contractions of the discrete-state path are real
 // GEMMs once frames / lock-stepped chains are batched eight at a time:
 //   ar_loglik    [frames x (n+d)] x [(n+d) x K*d]   whitened residuals, squared and summed per state
 //   hmm_forward  [8 tasks x K]   x [K x K]          one filter step of eight (chain, chunk) tasks
-//   label_maps   [8 steps x 4]   x [4 x K]          running block sums of filt_t[i] pi[i][j]
 // Included by hmm.cu inside namespace kpms (uses HmmTask / hmm_task / chunk helpers from there).
 //
 // Fragment layout of mma.m8n8k4 (lane l): A[row l/4][col l%4], B[row l%4][col l/4],

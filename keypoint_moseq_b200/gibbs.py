@@ -47,6 +47,9 @@ def chunk_diagnostics(tag="kalman_ws", device="cuda"):
     raw = buf[:16].cpu().numpy()
     u = raw.view(np.uint32)
     f = raw.view(np.float32)
+    if tag == "hmm_ws":     # backward sampler: exact merge-and-repair, counts instead of a tolerance
+        return {"forward_max_err": float(f[0]), "forward_rerun": int(u[1]),
+                "backward_mismatches": int(u[2]), "backward_rewalked": int(u[3])}
     return {"forward_max_err": float(f[0]), "forward_rerun": int(u[1]),
             "backward_max_err": float(f[2]), "backward_rerun": int(u[3])}
 

@@ -276,8 +276,9 @@ def test_location_scan_long_chains(dtype, tol, frames, seg):
 @pytest.mark.parametrize("shape", [dict(d=4, L=3, K=12, k=5, D=2), dict(d=10, L=3, K=100, k=12, D=2)])
 def test_discrete_stateseqs_time_chunks(mode, shape, chunking):
     """HMM FFBS on long ragged chains: forward filter in concurrent time chunks (prefix) and
-    power-of-pi chunks (padded tail), backward sampling by composed label maps.  Labels must stay
-    bit-exact, also when a too-short warm-up forces the sequential re-run."""
+    power-of-pi chunks (padded tail), backward sampling in time chunks that merge with the true path
+    (mismatched boundaries are re-walked).  Labels must stay bit-exact, also when a too-short
+    warm-up forces the sequential re-run / the repair pass."""
     g = _gibbs()
     data, _, model = small_problem(seed=13, recordings=2, frames=1500, seg_length=1000, **shape)
     tape = tape_for(data, model)

@@ -56,12 +56,39 @@ __global__ void ffma_kernel(float* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// dependent chain of DMMAs in one warp: cycles per instruction = latency
+__global__ void dmma_latency_kernel(double* out, long long* cyc, int iters) {
+    double c0 = 1.0, c1 = 2.0, a = threadIdx.x * 1e-3, b = 1e-3;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        dmma(c0, c1, a, b); dmma(c0, c1, a, b); dmma(c0, c1, a, b); dmma(c0, c1, a, b);
+    }
+    long long t1 = clock64();
+    out[threadIdx.x] = c0 + c1;
+    if (threadIdx.x == 0) cyc[0] = t1 - t0;
+}
+__global__ void dfma_latency_kernel(double* out, long long* cyc, int iters) {
+    double c = 1.0, a = 1.0000001, b = 1e-3;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) { c = fma(a, c, b); c = fma(a, c, b); c = fma(a, c, b); c = fma(a, c, b); }
+    long long t1 = clock64();
+    out[threadIdx.x] = c;
+    if (threadIdx.x == 0) cyc[0] = t1 - t0;
+}
+
 int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     int sms = p.multiProcessorCount;
     double* out; cudaMalloc(&out, sizeof(double) * sms * 8 * 1024);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int iters = 20000;
+    {
+        long long* cyc; cudaMalloc(&cyc, 8); long long h;
+        dmma_latency_kernel<<<1, 32>>>(out, cyc, 10000); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("DMMA dependent-chain latency: %.1f cycles\n", h / 40000.0);
+        dfma_latency_kernel<<<1, 32>>>(out, cyc, 10000); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("DFMA dependent-chain latency: %.1f cycles\n", h / 40000.0);
+    }
     for (int warps = 4; warps <= 32; warps *= 2) {
         for (int rep = 0; rep < 2; ++rep) {
             cudaEventRecord(e0);
