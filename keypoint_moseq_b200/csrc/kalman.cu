@@ -1393,7 +1393,7 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
 // ---------------------------------------------------------------------------
 template <typename R, int D_, int L_, int STAGES>
 __global__ void __launch_bounds__(32)
-kalman_affine_kernel(const R* __restrict__ GH, int T, R* __restrict__ x, int C, int W,
+kalman_affine_kernel(const R* __restrict__ GH, const int* __restrict__ mask, int T, R* __restrict__ x, int C, int W,
                      const int* __restrict__ vlen, const int* __restrict__ dirty, R* __restrict__ bx_warm,
                      R* __restrict__ bx_exact) {
     constexpr int n = D_ * L_, NN = n * n;
@@ -1412,7 +1412,7 @@ kalman_affine_kernel(const R* __restrict__ GH, int T, R* __restrict__ x, int C, 
     // xi_{Tx-1} = h_{Tx-1}; the others start W steps above their range from an arbitrary value
     // (warm-up) and publish the xi they reach at their upper boundary for the check.
     const bool exact_top = (cr.end == Tx);
-    const int top = exact_top ? Tx - 1 : min(cr.end + W, Tx - 1);
+    int top = exact_top ? Tx - 1 : min(cr.end + W, Tx - 1);
     const int lowest = cr.begin;
     auto issue = [&](int i) {
         if (i >= lowest) {
@@ -1432,10 +1432,41 @@ kalman_affine_kernel(const R* __restrict__ GH, int T, R* __restrict__ x, int C, 
     };
     const bool top_known = (top == Tx - 1);
     for (int r = lane; r < n; r += 32) xi[r] = top_known ? Gn[(size_t)top * RECP + NN + r] : (R)0;
+    if (exact_top) {
+        // Masked steps carry the state through (identity records): the padded tail below the terminal
+        // draw is emitted 32 steps at a time without touching its records.
+        __syncwarp();
+        const int* mk = mask + (size_t)nn * T + (L_ - 1);
+        for (int r = lane; r < n; r += 32) emit(top, r, xi[r]);
+        int i = top - 1;
+        while (i >= lowest) {
+            const int s = i - lane;
+            const bool masked = s >= lowest && mk[s] == 0;
+            const unsigned mm = __ballot_sync(0xffffffffu, masked);
+            const int run = (mm == 0xffffffffu) ? 32 : __ffs(~mm) - 1;      // masked steps i, i-1, .. i-run+1
+            for (int e = lane; e < run * D_; e += 32) {
+                const int st = i - e / D_, c = e % D_;
+                if (st == 0) {
+                    for (int r = c; r < n; r += D_) xn[r] = xi[r];          // frames 0..L-1 from xi_0 (c-th components)
+                } else {
+                    xn[(size_t)(st + L_ - 1) * D_ + c] = xi[n - D_ + c];
+                }
+            }
+            i -= run;
+            if (run < 32) break;
+        }
+        top = i + 1;                       // the recursion proper resumes below step `top` (xi is the state at `top`)
+        if (top - 1 < lowest) {            // nothing left: the whole chunk was masked
+            if (ck > 0)
+                for (int r = lane; r < n; r += 32) bx_exact[((size_t)nn * C + ck) * n + r] = xi[r];
+            return;
+        }
+    }
+    const bool emitted_top = exact_top;
     for (int s = 0; s < STAGES - 1; ++s) issue(top - 1 - s);
     __syncwarp();
     for (int r = lane; r < n; r += 32) {
-        if (top < cr.end) emit(top, r, xi[r]);
+        if (top < cr.end && !emitted_top) emit(top, r, xi[r]);
         if (top == cr.end) bx_warm[((size_t)nn * C + ck + 1) * n + r] = xi[r];
         if (top == lowest && ck > 0) bx_exact[((size_t)nn * C + ck) * n + r] = xi[r];
     }
@@ -1619,14 +1650,14 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (Cb > 1) {
             { KPMS_LAUNCH("kalman_affine", st);
-              kern<<<dim3(N, Cb), 32, smem, st>>>(GH, T, x, Cb, W, vlen, nullptr, bbw, bbe); }
+              kern<<<dim3(N, Cb), 32, smem, st>>>(GH, mask, T, x, Cb, W, vlen, nullptr, bbw, bbe); }
             { KPMS_LAUNCH("kalman_affine_check", st);
               boundary_check_kernel<R><<<N, 128, 0, st>>>(bbw, bbe, vlen, Tx, Cb, W, 1, n, n, tol, dirty_b, diag + 2); }
             { KPMS_LAUNCH("kalman_affine_rerun", st);
-              kern<<<dim3(N, 1), 32, smem, st>>>(GH, T, x, 1, 0, nullptr, dirty_b, bbw, bbe); }
+              kern<<<dim3(N, 1), 32, smem, st>>>(GH, mask, T, x, 1, 0, nullptr, dirty_b, bbw, bbe); }
         } else {
             KPMS_LAUNCH("kalman_affine", st);
-            kern<<<dim3(N, 1), 32, smem, st>>>(GH, T, x, 1, 0, nullptr, nullptr, bbw, bbe);
+            kern<<<dim3(N, 1), 32, smem, st>>>(GH, mask, T, x, 1, 0, nullptr, nullptr, bbw, bbe);
         }
         int rc = check_launch("kalman affine");
         if (rc) return rc;
