@@ -810,14 +810,15 @@ static int ar_loglik_launch(const R* x, const int* mask, const R* Ab, const R* Q
         double* Gf = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + off[HW_GF]);
         { KPMS_LAUNCH("ar_pack_frag", st);
           ar_pack_frag_kernel<D_, L_><<<ceil_div(KT * AF::CHUNK, 256), 256, 0, st>>>((const double*)G, (const double*)cst, K, Fp, KT, Gf); }
-        const size_t smem = (align_up((size_t)(128 + L_) * D_, 2) + (size_t)2 * AF::CHUNK) * sizeof(double);
-        dim3 grid(ceil_div(T - L_, 128), N);
+        constexpr int FRD = 8 * AR_WARPS;
+        const size_t smem = (align_up((size_t)(FRD + L_) * D_, 2) + (size_t)2 * AF::CHUNK) * sizeof(double);
+        dim3 grid(ceil_div(T - L_, FRD), N);
 #define ARL(KT_)                                                                                              \
         {                                                                                                     \
             auto kern = ar_loglik_dmma_kernel<D_, L_, KT_>;                                                   \
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
             KPMS_LAUNCH("ar_loglik", st);                                                                     \
-            kern<<<grid, 512, smem, st>>>((const double*)x, mask, Gf, N, T, K, ldT, (double*)W, (double*)mx); \
+            kern<<<grid, 32 * AR_WARPS, smem, st>>>((const double*)x, mask, Gf, N, T, K, ldT, (double*)W, (double*)mx); \
         }
         if (KT == 4) ARL(4) else if (KT == 7) ARL(7) else if (KT == 13) ARL(13) else ARL(16)
 #undef ARL

@@ -55,18 +55,21 @@ __global__ void ar_pack_frag_kernel(const double* __restrict__ G, const double* 
 }
 
 // ---------------------------------------------------------------------------
-// K2 on the tensor pipe.  CTA = 16 warps x 8 frames; the operator chunks stream through a
+// K2 on the tensor pipe.  CTA = AR_WARPS warps x 8 frames, two CTAs per SM so that one CTA's
+// prologue / exp epilogue overlaps the other's DMMA stream; the operator chunks stream through a
 // two-deep cp.async ring; every warp keeps its 8 frames' features as A fragments in registers and
-// the log-likelihoods of all states in registers until the frame maximum is known.
+// the log-likelihoods of all states until the frame maximum is known.
 // W (N, Tp, ldKw) <- exp(ll - max), states contiguous per frame (ldKw = 8*KT, pad columns 0);
 // mx (N, ldT) <- max.  Masked frames: W = 1, mx = 0.
 // ---------------------------------------------------------------------------
+constexpr int AR_WARPS = 8;
+
 template <int D_, int L_, int KT>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(32 * AR_WARPS, 2)
 ar_loglik_dmma_kernel(const double* __restrict__ x, const int* __restrict__ mask, const double* __restrict__ Gf,
                       int N, int T, int K, int ldT, double* __restrict__ W, double* __restrict__ mx) {
     typedef ArFrag<D_, L_> A;
-    constexpr int FR = 128, KK = A::KK, NF = A::NF, ldKw = 8 * KT;
+    constexpr int FR = 8 * AR_WARPS, NT = 32 * AR_WARPS, KK = A::KK, NF = A::NF, ldKw = 8 * KT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* xs = reinterpret_cast<double*>(smem_raw);                 // (FR + L) * D_
     double* gs = xs + align_up((size_t)(FR + L_) * D_, 2);            // 2 x CHUNK
@@ -74,11 +77,11 @@ ar_loglik_dmma_kernel(const double* __restrict__ x, const int* __restrict__ mask
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, p = lane & 3;
     const double* xrow = x + (size_t)nn * T * D_;
     const int tile_vals = min(FR + L_, T - t0) * D_;
-    for (int i = tid; i < (FR + L_) * D_; i += 512) xs[i] = i < tile_vals ? xrow[(size_t)t0 * D_ + i] : 0.0;
+    for (int i = tid; i < (FR + L_) * D_; i += NT) xs[i] = i < tile_vals ? xrow[(size_t)t0 * D_ + i] : 0.0;
     auto stage = [&](int kt, int buf) {
         const double* src = Gf + (size_t)kt * A::CHUNK;
         double* dst = gs + (size_t)buf * A::CHUNK;
-        for (int i = tid * 2; i < A::CHUNK; i += 1024) cp_async_16(dst + i, src + i);
+        for (int i = tid * 2; i < A::CHUNK; i += 2 * NT) cp_async_16(dst + i, src + i);
         asm volatile("cp.async.commit_group;\n" ::);
     };
     stage(0, 0);

@@ -12,7 +12,6 @@ namespace kpms {
 
 constexpr int SORT_TILE = 1024;
 constexpr int GRAM_SPLIT = 8;
-constexpr int GRAM_FT = 64;
 
 // valid frame t' of chain nn: mask[nn][L + t'] != 0
 __global__ void __launch_bounds__(256)
@@ -81,79 +80,106 @@ __global__ void __launch_bounds__(128)
 tile_scatter_kernel(const int* __restrict__ z, const int* __restrict__ mask, const int* __restrict__ tile_off,
                     const int* __restrict__ state_start, int N, int T, int L, int K, int* __restrict__ order) {
     __shared__ int zs[SORT_TILE];
+    __shared__ int rowoff[SORT_TILE];                  // nn * T + t: row of x where the frame's features start
     const int Tp = T - L;
     const long long total = (long long)N * Tp;
     const long long base = (long long)blockIdx.x * SORT_TILE;
     for (int e = threadIdx.x; e < SORT_TILE; e += blockDim.x) {
         const long long f = base + e;
-        int val = -1;
+        int val = -1, ro = 0;
         if (f < total) {
             const int nn = (int)(f / Tp), t = (int)(f % Tp);
+            ro = nn * T + t;
             if (mask[(size_t)nn * T + L + t] != 0) val = z[f];
         }
         zs[e] = val;
+        rowoff[e] = ro;
     }
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         int pos = state_start[k] + tile_off[(size_t)blockIdx.x * K + k];
         for (int e = 0; e < SORT_TILE; ++e)
-            if (zs[e] == k) order[pos++] = (int)(base + e);
+            if (zs[e] == k) order[pos++] = rowoff[e];
     }
 }
 
-template <typename R>
-__global__ void __launch_bounds__(256)
+// Per-state Gram matrices on the FP64 tensor pipe (mma.sync m8n8k4 f64).  G_k = sum_f f f' over the
+// frames of state k is a GEMM F' F with the frames as the contraction dimension, 4 frames per k-step.
+// The A fragment of feature tile ta and the B fragment of feature tile tb are the same numbers
+// (lane l: feature 8*tile + l/4 of frame l%4), read straight from x through the sorted row offsets,
+// so a k-step costs NT loads and NT(NT+1)/2 DMMAs (lower tile triangle).  Grid (GRAM_SPLIT, K), four
+// warps per CTA on disjoint frame ranges, combined in warp order (deterministic).
+__device__ __forceinline__ void dmma884_stats(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <typename R, int D_, int L_>
+__global__ void __launch_bounds__(128)
 gram_partial_kernel(const R* __restrict__ x, const int* __restrict__ order, const int* __restrict__ state_start,
-                    int T, int d, int L, double* __restrict__ partial) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = d * L, F = n + d + 1, NP = F * (F + 1) / 2, Tp = T - L;
-    double* vt = reinterpret_cast<double*>(smem_raw);                 // GRAM_FT x F
-    const int k = blockIdx.y, sp = blockIdx.x;
+                    double* __restrict__ partial) {
+    constexpr int n = D_ * L_, NF = n + D_, F = NF + 1, NT = (F + 7) / 8, NPAIR = NT * (NT + 1) / 2;
+    __shared__ double red[NPAIR * 64];
+    const int k = blockIdx.y, sp = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fr = lane & 3, fe = lane >> 2;
     const int s0 = state_start[k], cnt = state_start[k + 1] - s0;
     const int per = (cnt + GRAM_SPLIT - 1) / GRAM_SPLIT;
     const int lo = s0 + min(sp * per, cnt), hi = s0 + min((sp + 1) * per, cnt);
-    constexpr int PPT = 8;                                            // pairs per thread (<= 8*256 = 2048 pairs)
-    double acc[PPT];
-    int pa[PPT], pb[PPT];
+    const int wper = ((hi - lo + 3) / 4 + 3) / 4 * 4;               // frames per warp, whole k-steps
+    const int wlo = min(lo + warp * wper, hi), whi = min(wlo + wper, hi);
+    double acc[NPAIR][2];
 #pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-        acc[q] = 0.0;
-        int p = threadIdx.x + q * 256;
-        int a = 0, b = 0;
-        if (p < NP) {
-            a = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-            while ((a + 1) * (a + 2) / 2 <= p) ++a;
-            while (a * (a + 1) / 2 > p) --a;
-            b = p - a * (a + 1) / 2;
+    for (int p = 0; p < NPAIR; ++p) acc[p][0] = acc[p][1] = 0.0;
+    auto load_row = [&](int g0) -> int { return (g0 + fr < whi) ? order[g0 + fr] : -1; };
+    auto load_feat = [&](int ro, double (&fv)[NT]) {
+        const R* xr = x + (size_t)max(ro, 0) * D_;
+#pragma unroll
+        for (int ti = 0; ti < NT; ++ti) {
+            const int e = 8 * ti + fe;
+            double v = 0.0;
+            if (ro >= 0) v = e < NF ? (double)xr[e] : (e == NF ? 1.0 : 0.0);
+            fv[ti] = v;
         }
-        pa[q] = a;
-        pb[q] = b;
+    };
+    double cur[NT], nxt[NT];
+    int ro_next = -1;
+    if (wlo < whi) {
+        load_feat(load_row(wlo), cur);
+        ro_next = load_row(wlo + 4);
     }
-    for (int f0 = lo; f0 < hi; f0 += GRAM_FT) {
-        const int nf = min(GRAM_FT, hi - f0);
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < nf * F; idx += blockDim.x) {
-            const int fr = idx / F, e = idx % F;
-            const int f = order[f0 + fr];
-            const int nn = f / Tp, t = f % Tp;
-            vt[idx] = (e < n + d) ? (double)x[((size_t)nn * T + t) * d + e] : 1.0;
-        }
-        __syncthreads();
+    for (int g0 = wlo; g0 < whi; g0 += 4) {
+        load_feat(ro_next, nxt);                                    // features of the next k-step
+        ro_next = load_row(g0 + 8);                                 // row offsets two k-steps ahead
 #pragma unroll
-        for (int q = 0; q < PPT; ++q) {
-            if (threadIdx.x + q * 256 < NP) {
-                double a = acc[q];
-                for (int fr = 0; fr < nf; ++fr) a = fma(vt[fr * F + pa[q]], vt[fr * F + pb[q]], a);
-                acc[q] = a;
+        for (int ta = 0; ta < NT; ++ta)
+#pragma unroll
+            for (int tb = 0; tb <= ta; ++tb) dmma884_stats(acc[ta * (ta + 1) / 2 + tb][0], acc[ta * (ta + 1) / 2 + tb][1], cur[ta], cur[tb]);
+#pragma unroll
+        for (int ti = 0; ti < NT; ++ti) cur[ti] = nxt[ti];
+    }
+    // combine the four warps in order
+    for (int w = 0; w < 4; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int p = 0; p < NPAIR; ++p) {
+                double2* slot = reinterpret_cast<double2*>(red) + p * 32 + lane;
+                if (w == 0) *slot = make_double2(acc[p][0], acc[p][1]);
+                else { double2 v = *slot; v.x += acc[p][0]; v.y += acc[p][1]; *slot = v; }
             }
         }
+        __syncthreads();
     }
     double* out = partial + ((size_t)k * GRAM_SPLIT + sp) * F * F;
-#pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-        if (threadIdx.x + q * 256 < NP) {
-            out[pa[q] * F + pb[q]] = acc[q];
-            out[pb[q] * F + pa[q]] = acc[q];
+    for (int idx = threadIdx.x; idx < NPAIR * 64; idx += blockDim.x) {
+        const int p = idx / 64, l = (idx % 64) / 2, c = idx % 2;
+        int ta = 0;
+        while ((ta + 1) * (ta + 2) / 2 <= p) ++ta;
+        const int tb = p - ta * (ta + 1) / 2;
+        const int a = 8 * ta + l / 4, b = 8 * tb + 2 * (l % 4) + c;
+        if (a < F && b < F && (ta != tb || a >= b)) {
+            const double v = red[idx];
+            out[a * F + b] = v;
+            out[b * F + a] = v;
         }
     }
 }
@@ -183,7 +209,6 @@ static int ar_suffstats_impl(const void* x, const int* z, const int* mask, int N
                              double* gram, void* ws, cudaStream_t st) {
     if (T - L < 1) return set_error(-3, "ar_suffstats: T (%d) must exceed nlags (%d)", T, L);
     const int F = d * L + d + 1;
-    if (F * (F + 1) / 2 > 8 * 256) return set_error(-3, "ar_suffstats: feature dimension %d too large", F);
     size_t off[5];
     stats_ws_layout(N, T, d, L, K, off);
     char* base = reinterpret_cast<char*>(ws);
@@ -197,8 +222,16 @@ static int ar_suffstats_impl(const void* x, const int* z, const int* mask, int N
     { KPMS_LAUNCH("sort_tile_scan", st); tile_scan_kernel<<<1, 128, K * sizeof(int), st>>>(tile_hist, n_tiles, K, state_start); }
     { KPMS_LAUNCH("sort_tile_scatter", st); tile_scatter_kernel<<<n_tiles, 128, 0, st>>>(z, mask, tile_hist, state_start, N, T, L, K, order); }
     dim3 grid(GRAM_SPLIT, K);
-    size_t smem = (size_t)GRAM_FT * F * sizeof(double);
-    { KPMS_LAUNCH("gram_partial", st); gram_partial_kernel<R><<<grid, 256, smem, st>>>((const R*)x, order, state_start, T, d, L, partial); }
+    bool launched = false;
+#define X(DD, LL)                                                                                              \
+    if (d == DD && L == LL) {                                                                                  \
+        KPMS_LAUNCH("gram_partial", st);                                                                       \
+        gram_partial_kernel<R, DD, LL><<<grid, 128, 0, st>>>((const R*)x, order, state_start, partial);        \
+        launched = true;                                                                                       \
+    }
+    KPMS_FOR_EACH_DL(X)
+#undef X
+    if (!launched) return set_error(-3, "ar_suffstats: unsupported (latent_dim, nlags) = (%d, %d)", d, L);
     { KPMS_LAUNCH("gram_reduce", st); gram_reduce_kernel<<<K, 256, 0, st>>>(partial, F * F, gram); }
     return check_launch("ar_suffstats");
 }
