@@ -178,12 +178,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL) print banners on fd 1: park stdout on stderr until the JSON line is due
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
         group = dist.group.WORLD
     _lib.load()
 
@@ -192,7 +197,8 @@ def main():
     hdt = torch.float32 if args.hmm_dtype == "float32" else torch.float64
     esz, hesz = (4 if dt == torch.float32 else 8), (4 if hdt == torch.float32 else 8)
     data, metadata, model = sample_dataset(recordings=cfg["recordings"], frames=cfg["frames"], k=cfg["k"], D=cfg["D"],
-                                           d=cfg["d"], L=cfg["L"], K=cfg["K"], seed=1000 + rank, kappa=1e4)
+                                           d=cfg["d"], L=cfg["L"], K=cfg["K"], seed=1000, kappa=1e4,
+                                           data_seed=None if world == 1 else 2000 + rank)
     valid_local = int(data["mask"].sum())
     dd = gibbs.to_device_data(data, dev, dt)
     dm = gibbs.to_device_model(model, dev, dt)
@@ -239,12 +245,14 @@ def main():
     value = valid_total / (ms_per_step * 1e-3)
 
     # per-kernel CUDA-event timing (separate sweeps, same stream), for the roofline of the dominant kernel
+    # (every rank steps - the sweep contains the statistics all-reduce - but only rank 0 records)
     prof = {}
-    if rank == 0 or world == 1:
+    psteps = 2
+    if rank == 0:
         _lib.profile(True)
-        psteps = 2
-        for _ in range(psteps):
-            m = step(m)
+    for _ in range(psteps):
+        m = step(m)
+    if rank == 0:
         prof = _lib.profile_report()
         _lib.profile(False)
         prof = {k_: (v[0] / psteps, v[1] // psteps) for k_, v in prof.items()}
@@ -344,7 +352,10 @@ def main():
         "cpu_baseline": cpu,
         "clocks": clk,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

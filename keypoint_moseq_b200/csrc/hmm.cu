@@ -207,7 +207,8 @@ __device__ inline HmmTask hmm_task(long long id, int pass, int N, int Tp, int C,
     return t;
 }
 
-template <typename R, int RPT, int M>
+// ROWW: the weights are (N, Tp, ldW) state-contiguous (float64 path) instead of (N, K, ldT).
+template <typename R, int RPT, int M, bool ROWW = false>
 __global__ void __launch_bounds__(4 * 128)
 hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* __restrict__ pi, int N, int K,
                    int Tp, int ldT, int ldK, R* __restrict__ filt, double* __restrict__ logZ,
@@ -217,9 +218,9 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
     constexpr int VEC = 16 / sizeof(R);
     constexpr int RPTP = (RPT + VEC - 1) / VEC * VEC;
     constexpr int CH = 8;                                    // steps per staged group (ldT % 8 == 0)
-    constexpr int KC = 4 * RPT;                              // columns covered by the thread grid
+    constexpr int KC = ROWW ? (4 * RPT + 7) / 8 * 8 : 4 * RPT;   // columns covered by the thread grid / row stride
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    R* wbuf = reinterpret_cast<R*>(smem_raw);                // 2 x M x KC x CH
+    R* wbuf = reinterpret_cast<R*>(smem_raw);                // 2 x M x KC x CH  (ROWW: 2 x M x CH x KC)
     R* qbuf = wbuf + 2 * M * KC * CH;                        // 2 x M x 4*RPTP
     __shared__ double red[32];
     const int tid = threadIdx.x;
@@ -265,7 +266,19 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
     }
     // staging of the weights: thread (j, p) moves the p-th 16-byte piece of column j's 8-step group
     auto stage = [&](int r0, int sbuf) {
-        if (col && p < CH / VEC) {
+        if (ROWW) {                                          // one 16-byte piece of the 8 x KC tile per thread
+            constexpr int PPR = KC / VEC;                    // pieces per row
+            const int rr = tid / PPR, pc = tid % PPR;
+            if (rr < CH) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const int t0 = tk[m].start + r0 + rr;
+                    if (tk[m].on && t0 < tk[m].end)
+                        cp_async_16(wbuf + ((size_t)(sbuf * M + m) * CH + rr) * KC + pc * VEC,
+                                    W + ((size_t)tk[m].nn * Tp + t0) * KC + pc * VEC);
+                }
+            }
+        } else if (col && p < CH / VEC) {
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 const int t0 = tk[m].start + r0;
@@ -294,7 +307,8 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
                 if (tk[m].on && t < tk[m].end) {
                     if (col && p == 0 && !tk[m].given && tk[m].slot > 0 && t == tk[m].begin && pass == 0)
                         bnd_warm[((size_t)tk[m].nn * C + tk[m].slot) * K + j] = pred[m] * inv_s[m];
-                    const R w = col ? wbuf[((size_t)(sbuf * M + m) * KC + j) * CH + c] : (R)0;
+                    const R w = !col ? (R)0 : ROWW ? wbuf[((size_t)(sbuf * M + m) * CH + c) * KC + j]
+                                                   : wbuf[((size_t)(sbuf * M + m) * KC + j) * CH + c];
                     qv[m] = pred[m] * inv_s[m] * w;
                     if (col && p == 0) {
                         qbuf[(buf * M + m) * 4 * RPTP + qslot] = qv[m];
@@ -919,7 +933,28 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
     }
     { KPMS_LAUNCH("hmm_forward_tail", st); FWD_K((int)(((long long)N * CT + M - 1) / M), 1, vb, dirty) }
     { KPMS_LAUNCH("hmm_logz_sum", st); logz_sum_kernel<<<ceil_div(N, 128), 128, 0, st>>>(lzp, N, C + CT, logZ); }
-    { KPMS_LAUNCH("hmm_forward_rerun", st); FWD_K((N + M - 1) / M, 2, (const int*)nullptr, dirty) }
+    if (sizeof(R) == 8) {
+        // Chains whose boundaries failed the check (slow forgetting: parameters far from the data) are
+        // re-run sequentially, one chain per CTA on the latency-lean DFMA kernel (a DMMA step costs the
+        // same pipe time for one task as for eight).
+        KPMS_LAUNCH("hmm_forward_rerun", st);
+#define SEQ64(RPT_)                                                                                           \
+        {                                                                                                     \
+            auto kern = hmm_forward_kernel<double, RPT_, 1, true>;                                            \
+            constexpr int KC_ = (4 * RPT_ + 7) / 8 * 8, RPTP_ = (RPT_ + 1) / 2 * 2;                           \
+            const size_t smem = ((size_t)2 * KC_ * 8 + (size_t)2 * 4 * RPTP_) * sizeof(double);               \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+            kern<<<N, 4 * KC_, smem, st>>>((const double*)W, (const double*)mx, (const double*)pi, N, K, Tp,  \
+                                           ldT, ldK, (double*)filt, logZ, lzp, 2, C, CT, Wm,                  \
+                                           (const int*)nullptr, dirty, (double*)bw, (double*)be,              \
+                                           (const double*)tstart);                                            \
+        }
+        const int KTs = state_tiles(K);
+        if (KTs == 4) SEQ64(8) else if (KTs == 7) SEQ64(14) else if (KTs == 13) SEQ64(26) else SEQ64(32)
+#undef SEQ64
+    } else {
+        KPMS_LAUNCH("hmm_forward_rerun", st); FWD_K((N + M - 1) / M, 2, (const int*)nullptr, dirty)
+    }
 #undef FWD_K
 #undef FWD64
 #undef FWD

@@ -61,12 +61,14 @@ def _stable_ar(rng, d, L):
 
 
 def sample_dataset(recordings=4, frames=10_000, k=10, D=2, d=4, L=3, K=100, seed=0, kappa=1e4,
-                   kappa_gen=100.0, seg_length=None, max_seg_length=10_000, dtype=np.float64):
+                   kappa_gen=100.0, seg_length=None, max_seg_length=10_000, dtype=np.float64, data_seed=None):
     """Draw params, states and keypoints; batch them like `format_data`.
 
     Returns (data, metadata, model) with NumPy leaves:
       data  = {"Y" (N,T,k,D), "conf" (N,T,k), "mask" (N,T)}
       model = {"seed", "states", "params", "hypparams", "noise_prior"}
+    `seed` draws the parameters; `data_seed` (default: continue the same stream) draws the states and
+    keypoints, so that several shards of one cohort share one generative model.
     """
     rng = np.random.default_rng(seed)
     hyp = default_hypparams(d, L, K, kappa)
@@ -86,6 +88,8 @@ def sample_dataset(recordings=4, frames=10_000, k=10, D=2, d=4, L=3, K=100, seed
     nu_s = hyp["obs_hypparams"]["nu_s"]
     sig_loc = hyp["cen_hypparams"]["sigmasq_loc"]
     cum = np.cumsum(pi, axis=1)
+    if data_seed is not None:
+        rng = np.random.default_rng(data_seed)
 
     R_, T = recordings, frames
     u = rng.random((R_, T))

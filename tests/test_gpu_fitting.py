@@ -144,6 +144,6 @@ def test_full_size_properties_c2():
 def test_two_gpu_sharded_sweep_matches_single_gpu(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29617",
-                          os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
+                          os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "dist_check ok" in out.stdout

@@ -18,7 +18,9 @@ from keypoint_moseq_b200.synth import sample_dataset  # noqa: E402
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+import datetime  # noqa: E402
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])),
+                        timeout=datetime.timedelta(seconds=120))
 data, meta, model = sample_dataset(recordings=4, frames=400, k=5, D=2, d=4, L=3, K=12, seed=7, seg_length=250, kappa=1e2)
 N, T, k, D = data["Y"].shape
 tape = orc.make_tape(np.random.default_rng(3), N, T, k, D, 4, 3, 12)
