@@ -1,0 +1,77 @@
+"""BASELINE config 5: the two FFBS samplers in isolation over chain length, state count and latent
+dimension, time-chunked (default) against the sequential recursion (chunks = 1).
+
+  python tools/kernel_sweep.py [--quick] > gpurun_out/kernel_sweep.jsonl
+
+One JSON line per (sampler, T, K, d, mode): median ms over `--reps` calls after one warm-up, frames/s and
+the chunk diagnostics.  Inputs are drawn from the generative model (synth.sample_dataset), N chosen so that
+N*T is about `--frames` frames.  num_states > 128 is outside the kernels' template range and is reported
+as unsupported."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from keypoint_moseq_b200 import _lib, gibbs  # noqa: E402
+from keypoint_moseq_b200.synth import sample_dataset  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=800_000)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--quick", action="store_true")
+a = ap.parse_args()
+
+base = dict(T=10_000, K=100, d=10)
+grid = [dict(base, T=T) for T in (1_000, 10_000, 100_000, 1_000_000)]
+grid += [dict(base, K=K) for K in (25, 50, 128, 500)]
+grid += [dict(base, d=d) for d in (4, 16)]
+if a.quick:
+    grid = [dict(base, T=1_000), base, dict(base, K=25), dict(base, d=4)]
+
+
+def timed(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    out = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1))
+    return float(np.median(out))
+
+
+for g in grid:
+    T, K, d = g["T"], g["K"], g["d"]
+    if K > 128:
+        print(json.dumps(dict(g, sampler="both", unsupported="num_states > 128 (kernel template range)")), flush=True)
+        continue
+    N = max(1, a.frames // T)
+    t0 = time.time()
+    data, _, model = sample_dataset(recordings=N, frames=T, k=12, D=2, d=d, L=3, K=K, seed=5, seg_length=T,
+                                    max_seg_length=T)
+    gen_s = time.time() - t0
+    dd = gibbs.to_device_data(data, "cuda", torch.float32)
+    m = gibbs.to_device_model(model, "cuda", torch.float32)
+    st, pr = m["states"], m["params"]
+    frames = int(data["mask"].sum())
+    for mode, chunks in (("chunked", 0), ("sequential", 1)):
+        _lib.set_time_chunking(chunks=chunks)
+        ms = timed(lambda: gibbs.resample_discrete_stateseqs(st["x"], dd["mask"], pr["Ab"], pr["Q"], pr["pi"], 11), a.reps)
+        print(json.dumps(dict(g, N=N, sampler="hmm_ffbs", mode=mode, ms=round(ms, 3), frames_per_s=round(frames / ms * 1e3),
+                              diag=gibbs.chunk_diagnostics("hmm_ws"), gen_s=round(gen_s, 1))), flush=True)
+        ms = timed(lambda: gibbs.resample_continuous_stateseqs(dd["Y"], dd["mask"], st["v"], st["h"], st["s"], st["z"],
+                                                               pr["Cd"], pr["sigmasq"], pr["Ab"], pr["Q"], 1e-3, 11), a.reps)
+        print(json.dumps(dict(g, N=N, sampler="kalman_ffbs", mode=mode, ms=round(ms, 3), frames_per_s=round(frames / ms * 1e3),
+                              diag=gibbs.chunk_diagnostics("kalman_ws"))), flush=True)
+    _lib.set_time_chunking(chunks=0)
+    del dd, m, st, pr
+    gibbs._SCRATCH.clear()
+    torch.cuda.empty_cache()
