@@ -279,9 +279,11 @@ def main():
             mm = {"seed": seed, "states": host_states, "params": host_params, "hypparams": m["hypparams"],
                   "noise_prior": host_prior}
             out = gibbs.resample_model(host_data, **mm, host_out=out_host, **opts)
-            torch.cuda.synchronize()
-            if not np.isfinite(out_host["x"].numpy()).all():
-                raise RuntimeError("NaNs in e2e sweep")
+            # the per-sweep guard of fit_model (fitting.py:30) on everything the sweep produced
+            any_nans, _, msgs = check_for_nans({"states": out["states"], "params": out["params"]})
+            torch.cuda.synchronize()                         # host copies of the states are complete
+            if any_nans:
+                raise RuntimeError("NaNs in e2e sweep: " + "; ".join(msgs))
             return out["seed"]
 
         seed = e2e_step(seed)

@@ -62,7 +62,7 @@ ChunkConfig chunk_config() { return g_chunk; }
 int chunks_for(int N, int slots, int len, int warmup) {
     int C = g_chunk.chunks > 0 ? g_chunk.chunks : slots / (N > 0 ? N : 1);
     if (warmup > 0 && C > len / (4 * warmup)) C = len / (4 * warmup);
-    if (C > 64) C = 64;
+    if (C > KPMS_MAX_CHUNKS) C = KPMS_MAX_CHUNKS;
     if (C < 1) C = 1;
     return C;
 }

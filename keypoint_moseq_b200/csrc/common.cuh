@@ -18,6 +18,7 @@
 #define KPMS_X_PRIOR_VAR 10.0
 #define KPMS_V_PRIOR_VAR 1e6
 #define KPMS_SM_COUNT 148     /* B200; the library is built for sm_100a only */
+#define KPMS_MAX_CHUNKS 1024   /* time chunks per chain at most (a single 10^6-frame chain still fills the device) */
 
 // stream ids for Philox counters (one per sampler)
 enum KpmsStream : uint32_t {
@@ -300,7 +301,8 @@ valid_len_kernel(const int* __restrict__ mask, int T, int off, int len, int* __r
 
 // Boundary check for real-valued states of `rec` numbers per boundary, in two blocks with their
 // own scales: [0, n_mean) (difference relative to 1 + max|exact|) and [n_mean, rec) (relative to
-// max|exact|).  dirty[nn] = 1 when the worst boundary discrepancy exceeds tol or is not finite.
+// max|exact|).  One CTA per (boundary, chain); dirty[nn] (zeroed by the caller) is raised when the
+// discrepancy exceeds tol or is not finite, or when pre[nn] != 0.
 // stats[0] = max discrepancy seen (float bits, atomicMax), stats[1] += number of dirty chains.
 template <typename R>
 __global__ void __launch_bounds__(128)
@@ -308,12 +310,12 @@ boundary_check_kernel(const R* __restrict__ warm, const R* __restrict__ exact, c
                       int len, int C, int W, int align, int n_mean, int rec, R tol, int* __restrict__ dirty,
                       unsigned* __restrict__ stats, const int* __restrict__ pre = nullptr) {
     __shared__ R red[2][4];
-    const int nn = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nn = blockIdx.y, c = blockIdx.x + 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     R worst = 0;
     int bad = 0;
-    for (int c = 1; c < C; ++c) {
-        const ChunkRange r = chunk_range(vlen[nn], len, C, W, c, align);
-        if (r.empty) break;
+    const bool flagged = (c == 1 && pre && pre[nn] != 0);
+    const ChunkRange r = chunk_range(vlen[nn], len, C, W, c, align);
+    if (c < C && !r.empty) {
         const R* a = warm + ((size_t)nn * C + c) * rec;
         const R* b = exact + ((size_t)nn * C + c) * rec;
         for (int part = 0; part < 2; ++part) {
@@ -339,10 +341,9 @@ boundary_check_kernel(const R* __restrict__ warm, const R* __restrict__ exact, c
     }
     const int any_bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {
-        const bool d = any_bad || !(worst <= tol) || (pre && pre[nn] != 0);
-        dirty[nn] = d ? 1 : 0;
-        atomicMax(&stats[0], __float_as_uint(any_bad ? INFINITY : (float)worst));
-        if (d) atomicAdd(&stats[1], 1u);
+        const bool d = any_bad || !(worst <= tol) || flagged;
+        if (worst > 0 || any_bad) atomicMax(&stats[0], __float_as_uint(any_bad ? INFINITY : (float)worst));
+        if (d && atomicExch(&dirty[nn], 1) == 0) atomicAdd(&stats[1], 1u);
     }
 }
 

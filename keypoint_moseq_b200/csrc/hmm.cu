@@ -21,10 +21,13 @@ namespace kpms {
 // F = n + d + 1, features f = [x_{t-L} .. x_{t-1} | x_t | 1];  c_k = -sum log diag Lq - d/2 log 2pi
 // ---------------------------------------------------------------------------
 template <typename R, int D_, int L_>
-__global__ void ar_prep_kernel(const R* __restrict__ Ab, const R* __restrict__ Q, int K,
-                               R* __restrict__ G, R* __restrict__ cst, int Fp) {
+__global__ void __launch_bounds__(32)
+ar_prep_kernel(const R* __restrict__ Ab, const R* __restrict__ Q, int K,
+               R* __restrict__ G, R* __restrict__ cst, int Fp) {
+    // one warp per state: the d x d factor and its inverse redundantly per lane (a few hundred
+    // flops), then the lanes share the columns of G
     constexpr int n = D_ * L_;
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.x, lane = threadIdx.x;
     if (k >= K) return;
     double Lq[D_][D_], Li[D_][D_];
     for (int i = 0; i < D_; ++i)
@@ -51,17 +54,20 @@ __global__ void ar_prep_kernel(const R* __restrict__ Ab, const R* __restrict__ Q
     }
     const R* A = Ab + (size_t)k * D_ * (n + 1);
     R* g = G + (size_t)k * D_ * Fp;
-    for (int i = 0; i < D_; ++i) {
-        for (int j = 0; j <= n; ++j) {
+    for (int j = lane; j <= n; j += 32) {
+        double col[D_];
+        for (int p = 0; p < D_; ++p) col[p] = (double)A[p * (n + 1) + j];
+        for (int i = 0; i < D_; ++i) {
             double v = 0.0;
-            for (int p = 0; p <= i; ++p) v += Li[i][p] * (double)A[p * (n + 1) + j];
+            for (int p = 0; p <= i; ++p) v += Li[i][p] * col[p];
             if (j < n) g[i * Fp + j] = (R)(-v);
             else g[i * Fp + n + D_] = (R)(-v);
         }
-        for (int j = 0; j < D_; ++j) g[i * Fp + n + j] = (R)Li[i][j];
-        for (int j = n + D_ + 1; j < Fp; ++j) g[i * Fp + j] = (R)0;
     }
-    cst[k] = (R)(-logdet - 0.5 * D_ * 1.8378770664093453);
+    for (int e = lane; e < D_ * D_; e += 32) g[(e / D_) * Fp + n + (e % D_)] = (R)Li[e / D_][e % D_];
+    for (int i = lane; i < D_; i += 32)
+        for (int j = n + D_ + 1; j < Fp; ++j) g[i * Fp + j] = (R)0;
+    if (lane == 0) cst[k] = (R)(-logdet - 0.5 * D_ * 1.8378770664093453);
 }
 
 // ---------------------------------------------------------------------------
@@ -793,7 +799,7 @@ static void hmm_ws_layout(int N, int T, int K, int d, int L, size_t off[HW_END +
                          (size_t)N * CT * K * sizeof(R),
                          (size_t)2 * K * K * sizeof(R),
                          (size_t)K * ((K + 3) / 4 * 4) * sizeof(R),
-                         (size_t)N * 64 * 4};
+                         (size_t)N * KPMS_MAX_CHUNKS * 4};
     off[0] = 0;
     for (int i = 0; i < HW_END; ++i) off[i + 1] = off[i] + align_up(sz[i], 256);
 }
@@ -810,7 +816,7 @@ static int ar_loglik_launch(const R* x, const int* mask, const R* Ab, const R* Q
     R* G = reinterpret_cast<R*>(reinterpret_cast<char*>(ws) + off[HW_G]);
     R* cst = reinterpret_cast<R*>(reinterpret_cast<char*>(ws) + off[HW_CST]);
     { KPMS_LAUNCH("ar_prep", st);
-    ar_prep_kernel<R, D_, L_><<<ceil_div(K, 64), 64, 0, st>>>(Ab, Q, K, G, cst, Fp); }
+    ar_prep_kernel<R, D_, L_><<<K, 32, 0, st>>>(Ab, Q, K, G, cst, Fp); }
     {   // unmasked prefix of every chain (time chunks of the forward filter)
         int* vb = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + off[HW_VLEN]);
         KPMS_LAUNCH("hmm_prefix", st);
@@ -917,7 +923,8 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
     cudaMemsetAsync(lzp, 0, (size_t)N * (C + CT) * sizeof(double), st);
     { KPMS_LAUNCH("hmm_forward", st); FWD_K((int)(((long long)N * C + M - 1) / M), 0, vb, (const int*)nullptr) }
     { KPMS_LAUNCH("hmm_forward_check", st);
-      boundary_check_kernel<R><<<N, 128, 0, st>>>(bw, be, vb, Tp, C, Wm, 8, K, K, tol, dirty, diag, holes); }
+      cudaMemsetAsync(dirty, 0, (size_t)N * sizeof(int), st);
+      boundary_check_kernel<R><<<dim3(C - 1, N), 128, 0, st>>>(bw, be, vb, Tp, C, Wm, 8, K, K, tol, dirty, diag, holes); }
     // pi^TL by repeated squaring, then the starting predictions of the padded-tail chunks
     {
         const R* src = (const R*)pi;

@@ -1591,7 +1591,8 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
               kern<<<(int)(((long long)N * C + WARPS - 1) / WARPS), 32 * WARPS, smem, st>>>(
                   info, mask, z, Ab, Q, (R)jitter, N, T, stash_m, stash_S, C, W, vlen, nullptr, bfw, bfe); }
             { KPMS_LAUNCH("kalman_forward_check", st);
-              boundary_check_kernel<R><<<N, 128, 0, st>>>(bfw, bfe, vlen, Tx, C, W, 1, n, n + n * n, tol, dirty_f, diag); }
+              cudaMemsetAsync(dirty_f, 0, (size_t)N * sizeof(int), st);
+              boundary_check_kernel<R><<<dim3(C - 1, N), 128, 0, st>>>(bfw, bfe, vlen, Tx, C, W, 1, n, n + n * n, tol, dirty_f, diag); }
             { KPMS_LAUNCH("kalman_forward_rerun", st);       // exits at once for chains whose boundaries agree
               kern<<<(N + WARPS - 1) / WARPS, 32 * WARPS, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, N, T, stash_m,
                                                                     stash_S, 1, 0, nullptr, dirty_f, bfw, bfe); }
@@ -1611,7 +1612,8 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
               kern<<<dim3(N, C), 256, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, T, stash_m, stash_S, C, W, vlen,
                                                   nullptr, bfw, bfe); }
             { KPMS_LAUNCH("kalman_forward_check", st);
-              boundary_check_kernel<R><<<N, 128, 0, st>>>(bfw, bfe, vlen, Tx, C, W, 1, n, n + n * n, tol, dirty_f, diag); }
+              cudaMemsetAsync(dirty_f, 0, (size_t)N * sizeof(int), st);
+              boundary_check_kernel<R><<<dim3(C - 1, N), 128, 0, st>>>(bfw, bfe, vlen, Tx, C, W, 1, n, n + n * n, tol, dirty_f, diag); }
             { KPMS_LAUNCH("kalman_forward_rerun", st);       // exits at once for chains whose boundaries agree
               kern<<<dim3(N, 1), 256, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, T, stash_m, stash_S, 1, 0, nullptr,
                                                   dirty_f, bfw, bfe); }
@@ -1652,7 +1654,8 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
             { KPMS_LAUNCH("kalman_affine", st);
               kern<<<dim3(N, Cb), 32, smem, st>>>(GH, mask, T, x, Cb, W, vlen, nullptr, bbw, bbe); }
             { KPMS_LAUNCH("kalman_affine_check", st);
-              boundary_check_kernel<R><<<N, 128, 0, st>>>(bbw, bbe, vlen, Tx, Cb, W, 1, n, n, tol, dirty_b, diag + 2); }
+              cudaMemsetAsync(dirty_b, 0, (size_t)N * sizeof(int), st);
+              boundary_check_kernel<R><<<dim3(Cb - 1, N), 128, 0, st>>>(bbw, bbe, vlen, Tx, Cb, W, 1, n, n, tol, dirty_b, diag + 2); }
             { KPMS_LAUNCH("kalman_affine_rerun", st);
               kern<<<dim3(N, 1), 32, smem, st>>>(GH, mask, T, x, 1, 0, nullptr, dirty_b, bbw, bbe); }
         } else {

@@ -61,10 +61,15 @@ __global__ void tile_scan_kernel(int* __restrict__ tile_hist, int n_tiles, int K
     extern __shared__ int tot[];
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         int run = 0;
-        for (int t = 0; t < n_tiles; ++t) {
-            int c = tile_hist[(size_t)t * K + k];
-            tile_hist[(size_t)t * K + k] = run;
-            run += c;
+        for (int t0 = 0; t0 < n_tiles; t0 += 16) {           // 16 independent loads in flight per round
+            int c[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) c[q] = (t0 + q < n_tiles) ? tile_hist[(size_t)(t0 + q) * K + k] : 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (t0 + q < n_tiles) tile_hist[(size_t)(t0 + q) * K + k] = run;
+                run += c[q];
+            }
         }
         tot[k] = run;
     }

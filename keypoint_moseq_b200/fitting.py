@@ -119,21 +119,50 @@ def init_states(data, params, hypparams, seed, noise_prior=None, anterior_idxs=N
     return states, noise_prior
 
 
-def init_model(data=None, states=None, params=None, hypparams=None, noise_prior=None, seed=None,
-               location_aware=False, allo_hypparams=None, trans_hypparams=None, **kwargs):
-    """Model-dict constructor (fitting.py:63-106).  Parameters must be supplied (from a fitted model or
-    a checkpoint): PCA-based initialisation of `Cd` is upstream of the Gibbs sweep and not part of this
-    build.  States are re-initialised from `data` when not given."""
+def init_model(data=None, states=None, params=None, hypparams=None, noise_prior=None, seed=None, pca=None,
+               whiten=True, location_aware=False, allo_hypparams=None, trans_hypparams=None, ar_hypparams=None,
+               obs_hypparams=None, cen_hypparams=None, error_estimator=None, anterior_idxs=None,
+               posterior_idxs=None, fix_heading=False, PCA_fitting_num_frames=1000000, conf_threshold=0.5,
+               **kwargs):
+    """Model-dict constructor (fitting.py:63-106; `kpms.init_model(data, pca=pca, **config())`).
+
+    Anything not supplied is initialised: hyper-parameters from the four `*_hypparams` dicts of the
+    config, parameters from the PCA (`Cd`, whitened latents when `whiten`) and prior draws
+    (`initialize.init_params`; the PCA is fitted here when neither `params` nor `pca` is given), states
+    from the data for the given parameters (`init_states`).  Passing `params` / `hypparams` of a fitted
+    model re-initialises only the states, which is what `apply_model` does (fitting.py:387-394)."""
+    from . import initialize
     if location_aware:
         raise NotImplementedError("location_aware=True (allo_keypoint_slds) is not implemented by the B200 sweep")
-    if params is None or hypparams is None:
-        raise NotImplementedError("init_model needs `params` and `hypparams`: PCA-based parameter "
-                                  "initialisation is outside the Gibbs-sweep scope of this build")
-    if trans_hypparams is not None:
-        hypparams = dict(hypparams, trans_hypparams=dict(hypparams["trans_hypparams"], **trans_hypparams))
     seed = np.array([0, 0], dtype=np.uint32) if seed is None else seed
+    seed_int = int(gibbs.seed_to_u64(seed) & 0x7FFFFFFF)
+    if hypparams is None:
+        missing = [n for n, v in (("trans_hypparams", trans_hypparams), ("ar_hypparams", ar_hypparams),
+                                  ("obs_hypparams", obs_hypparams), ("cen_hypparams", cen_hypparams)) if v is None]
+        if missing:
+            raise ValueError(f"init_model needs `hypparams` or the config entries {missing}")
+        hypparams = initialize.init_hyperparams(trans_hypparams, ar_hypparams, obs_hypparams, cen_hypparams)
+    elif trans_hypparams is not None:
+        hypparams = dict(hypparams, trans_hypparams=dict(hypparams["trans_hypparams"], **trans_hypparams))
+    if params is None:
+        if data is None:
+            raise ValueError("init_model needs `data` to initialise parameters")
+        Y, mask = to_numpy_tree(data["Y"]), to_numpy_tree(data["mask"])
+        if pca is None:
+            pca = initialize.fit_pca(Y, mask, conf=to_numpy_tree(data["conf"]) if "conf" in data else None,
+                                     anterior_idxs=anterior_idxs, posterior_idxs=posterior_idxs,
+                                     conf_threshold=conf_threshold, PCA_fitting_num_frames=PCA_fitting_num_frames,
+                                     fix_heading=fix_heading, seed=seed_int)
+        flat, _, _ = initialize.preprocess_for_pca(Y, anterior_idxs, posterior_idxs, fix_heading)
+        params = initialize.init_params(pca, hypparams, Y.shape[2], flat=flat[np.asarray(mask) > 0], whiten=whiten,
+                                        seed=seed_int)
     if states is None:
-        states, noise_prior = init_states(data, params, hypparams, seed, noise_prior=noise_prior, **kwargs)
+        if noise_prior is None and data is not None and "conf" in data and error_estimator is not None:
+            noise_prior = initialize.noise_prior_from_confidence(to_numpy_tree(data["conf"]), error_estimator)
+        states, noise_prior = init_states(data, params, hypparams, seed, noise_prior=noise_prior,
+                                          anterior_idxs=None if fix_heading else anterior_idxs,
+                                          posterior_idxs=None if fix_heading else posterior_idxs,
+                                          error_estimator=error_estimator, **kwargs)
     elif noise_prior is None:
         noise_prior = np.ones(np.asarray(to_numpy_tree(states["s"])).shape)
     return {"seed": seed, "states": states, "params": params, "hypparams": hypparams, "noise_prior": noise_prior}

@@ -49,6 +49,37 @@ def test_fit_model_is_deterministic_and_float32_runs(tmp_path):
     assert a["states"]["x"].dtype == torch.float32 and a["params"]["Ab"].dtype == torch.float64
 
 
+def test_init_model_from_raw_keypoints_then_fit(tmp_path):
+    """The notebook workflow without JAX: fit_pca -> init_model(data, pca=pca, **config) -> AR-only
+    sweeps -> full sweeps.  Starts from prior draws, so the verified time chunks run their fallbacks."""
+    from keypoint_moseq_b200 import fitting, initialize
+    data, meta, truth = small_problem(seed=21, d=4, L=3, K=12, k=6, D=2, kappa=1e2, frames=500, seg_length=250)
+    config = {
+        "trans_hypparams": {"num_states": 12, "gamma": 1e3, "alpha": 5.7, "kappa": 1e4},
+        "ar_hypparams": {"latent_dim": 4, "nlags": 3, "S_0_scale": 0.01, "K_0_scale": 10.0},
+        "obs_hypparams": {"sigmasq_0": 0.1, "sigmasq_C": 0.1, "nu_sigma": 1e5, "nu_s": 5},
+        "cen_hypparams": {"sigmasq_loc": 0.5},
+        "error_estimator": {"slope": -0.5, "intercept": 0.25},
+        "anterior_idxs": [0, 1], "posterior_idxs": [4, 5], "whiten": True, "fix_heading": False,
+    }
+    pca = initialize.fit_pca(**data, **config, conf_threshold=0.0)
+    model = fitting.init_model(data, pca=pca, **config, seed=np.array([0, 5], dtype=np.uint32))
+    assert set(model) == {"seed", "states", "params", "hypparams", "noise_prior"}
+    assert model["params"]["Cd"].shape == (10, 5) and model["hypparams"]["ar_hypparams"]["nu_0"] == 6
+    assert tuple(model["states"]["z"].shape) == (data["Y"].shape[0], data["Y"].shape[1] - 3)
+    m, _ = fitting.fit_model(model, data, meta, num_iters=5, ar_only=True, save_every_n_iters=None)
+    m = fitting.update_hypparams(m, kappa=1e3)
+    m, _ = fitting.fit_model(m, data, meta, num_iters=5, save_every_n_iters=None)
+    for key in ("x", "v", "h", "s"):
+        assert torch.isfinite(m["states"][key]).all(), key
+    from keypoint_moseq_b200 import gibbs
+    import oracle as orc
+    Yhat = orc.estimate_coordinates(*(m["states"][q].cpu().numpy().astype(float) for q in ("x", "v", "h")),
+                                    m["params"]["Cd"].cpu().numpy(), 6, 2)
+    resid = (data["Y"] - Yhat)[data["mask"] > 0]
+    assert np.sqrt((resid ** 2).mean()) < 2.0, "the fitted model stops reconstructing the keypoints"
+
+
 def test_apply_model_and_results_layout(tmp_path):
     from keypoint_moseq_b200 import fitting, io as kio
     data, meta, model = small_problem(seed=13, d=4, L=3, K=12, k=5, D=2, kappa=1e2)

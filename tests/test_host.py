@@ -185,3 +185,32 @@ def test_two_rank_statistics_allreduce_matches_single_rank(tmp_path):
     F = gram.shape[-1]
     np.testing.assert_allclose(p0[:4 * F * F].reshape(4, F, F), gram, rtol=1e-12, atol=1e-12)
     np.testing.assert_array_equal(p0[4 * F * F:].reshape(4, 4), counts)
+
+
+def test_fit_pca_and_init_params_recover_the_pose_subspace():
+    """fit_pca + init_params on data from the generative model: the PCA has (k-1)*D features, the
+    whitened Cd reproduces the aligned coordinates from unit-covariance latents, prior draws have the
+    checkpoint shapes."""
+    from keypoint_moseq_b200 import initialize
+    from keypoint_moseq_b200.synth import default_hypparams, sample_dataset
+    data, _, model = sample_dataset(recordings=2, frames=600, k=6, D=2, d=4, L=3, K=12, seed=3, seg_length=300)
+    pca = initialize.fit_pca(data["Y"], data["mask"], conf=data["conf"], conf_threshold=0.0,
+                             anterior_idxs=[0, 1], posterior_idxs=[4, 5])
+    assert pca.mean_.shape == (10,) and pca.components_.shape[1] == 10
+    assert pca.explained_variance_ratio_[:4].sum() > 0.8          # 4 latent dims generate the poses (plus noise)
+    cfgh = default_hypparams(4, 3, 12)
+    hyp = initialize.init_hyperparams(cfgh["trans_hypparams"], {k_: cfgh["ar_hypparams"][k_] for k_ in
+                                      ("latent_dim", "nlags", "S_0_scale", "K_0_scale")},
+                                      cfgh["obs_hypparams"], cfgh["cen_hypparams"])
+    assert hyp["ar_hypparams"]["M_0"].shape == (4, 13) and hyp["ar_hypparams"]["nu_0"] == 6
+    flat, v, h = initialize.preprocess_for_pca(data["Y"], [0, 1], [4, 5])
+    rows = flat[data["mask"] > 0]
+    pr = initialize.init_params(pca, hyp, 6, flat=rows, whiten=True, seed=1)
+    assert pr["Cd"].shape == (10, 5) and pr["Ab"].shape == (12, 4, 13) and pr["Q"].shape == (12, 4, 4)
+    assert np.allclose(pr["pi"].sum(1), 1.0) and np.all(np.linalg.eigvalsh(pr["Q"]) > 0)
+    x = (rows - pr["Cd"][:, -1]) @ np.linalg.pinv(pr["Cd"][:, :-1]).T
+    assert np.allclose(np.cov(x, rowvar=False), np.eye(4), atol=1e-6)          # whitened latents
+    recon = x @ pr["Cd"][:, :-1].T + pr["Cd"][:, -1]
+    assert np.sqrt(((recon - rows) ** 2).mean()) < 0.5 * rows.std()
+    prior = initialize.noise_prior_from_confidence(data["conf"], {"slope": -0.5, "intercept": 0.25})
+    assert prior.shape == data["conf"].shape and np.all(prior > 0)
