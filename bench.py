@@ -52,7 +52,10 @@ def workload(name):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+    """Samples nvidia-smi clocks and throttle reasons during the timed region (the profiling recipe's
+    clocks line, -lms 200).  Every query stalls kernel launches for a while (measured: one step in ten
+    takes 30-50 ms instead of 18 when polling at 100 ms, and NVML polled in-process at 20 ms is far worse),
+    so the poll period is not shortened further; `step_ms` in the JSON line shows the outliers."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
@@ -64,7 +67,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -73,14 +76,20 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([p.strip() for p in line.split(",")])
 
+    def mark(self):
+        """Start of the timed region: only rows sampled from here on are reported (the process is
+        started before the warm-up so that its start-up cost does not fall into the timed steps)."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[getattr(self, "first", 0):] or self.rows[-1:]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -217,21 +226,30 @@ def main():
         return m
 
     m = dm
+    clocks = ClockSampler(local)
+    if rank == 0 and not os.environ.get("KPMS_BENCH_NO_CLOCKS"):
+        clocks.start()
     for _ in range(max(args.warmup, 3)):
         m = step(m)
     barrier()
-    clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        time.sleep(0.25)          # let the sampler finish its start-up and first query outside the timed region
+        clocks.mark()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
-    for _ in range(args.steps):
+    host_ms = []
+    for i_ in range(args.steps):
+        t_h = time.perf_counter()
         m = step(m)
+        marks[i_].record()
+        host_ms.append(round((time.perf_counter() - t_h) * 1e3, 2))
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    step_ms = [round(([e0] + marks)[i_].elapsed_time(marks[i_]), 3) for i_ in range(args.steps)]
     launches = _lib.launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms, float(valid_local)], dtype=torch.float64, device=dev)
@@ -345,6 +363,7 @@ def main():
                    "valid_frames_total": int(valid_total), "hmm_dtype": "f32" if hdt == torch.float32 else "f64",
                    "l2": "working set per sweep (> 4 GB of filter/backward records) exceeds the 126 MB L2"},
         "sweeps_per_sec": 1e3 / ms_per_step,
+        "step_ms": step_ms, "step_host_ms": host_ms,
         "gpu_launches": int(launches),
         "e2e": e2e,
         "roofline": roofline,

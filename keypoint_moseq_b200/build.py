@@ -20,7 +20,9 @@ def _stale(out, deps):
 
 def build(verbose=False, force=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "kpms_b200.h")]
+    extra = os.environ.get("KPMS_NVCC_EXTRA", "").split()
+    hdrs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(HERE, "..", "include", "kpms_b200.h"))
     objs, procs = [], []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in SOURCES:
@@ -30,7 +32,7 @@ def build(verbose=False, force=False):
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [path] + hdrs):
-            cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            cmd = [nvcc] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

@@ -15,6 +15,8 @@
 //          GH (N,Tx,RECS): [GT (n*n) with GT[c][r] = G[r][c] | h (n) | pad], RECS*sizeof(R) % 16 == 0.
 #include <algorithm>
 #include <type_traits>
+#include <cstdlib>
+#include <string>
 #include "common.cuh"
 #include "../../include/kpms_b200.h"
 
@@ -1387,6 +1389,8 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
     asm volatile("cp.async.wait_all;\n" ::);
 }
 
+#include "kalman_rows2.cuh"
+
 // ---------------------------------------------------------------------------
 // K1d: serial affine recursion, one warp per chain, operands streamed through a
 // cp.async ring in shared memory
@@ -1625,7 +1629,20 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         int rc = check_launch("kalman forward");
         if (rc) return rc;
     }
+    static const bool rows1 = [] { const char* e = getenv("KPMS_BACKPREP"); return e && std::string(e) == "rows1"; }();
     if constexpr (n <= 32) {
+      if (!rows1) {
+        // two rows per lane, FPW frames per warp (kalman_rows2.cuh); one CTA per SM
+        typedef PrepRows2<R, D_, L_> P2;
+        constexpr int WARPS = sizeof(R) == 4 ? 8 : 4;
+        auto kern = kalman_backprep_rows2_kernel<R, D_, L_, WARPS>;
+        size_t smem = (size_t)P2::per_group * P2::FPW * WARPS * sizeof(R);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int blocks = (int)std::min<long long>((frames + WARPS * P2::FPW - 1) / (WARPS * P2::FPW), (long long)KPMS_SM_COUNT);
+        { KPMS_LAUNCH("kalman_backprep", st); kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH); }
+        int rc = check_launch("kalman backprep");
+        if (rc) return rc;
+      } else {
         constexpr int WARPS = sizeof(R) == 4 ? 16 : 8;      // one CTA per SM
         auto kern = kalman_backprep_rows_kernel<R, D_, L_, WARPS>;
         size_t smem = PrepRowsSmem<R, D_, L_>::per_warp * WARPS * sizeof(R);
@@ -1635,6 +1652,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         { KPMS_LAUNCH("kalman_backprep", st); kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH); }
         int rc = check_launch("kalman backprep");
         if (rc) return rc;
+      }
     } else {
         constexpr int WARPS = 4;
         auto kern = kalman_backprep_kernel<R, D_, L_, WARPS>;

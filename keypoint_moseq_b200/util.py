@@ -113,8 +113,28 @@ def to_numpy_tree(tree):
 
 
 def check_for_nans(model):
-    """(any_nans, nan_info, messages) over the leaves of a model dict (fitting.py:30)."""
+    """(any_nans, nan_info, messages) over the leaves of a model dict (fitting.py:30).
+
+    Device leaves are screened with one flag per leaf and ONE device->host read for the whole tree;
+    the per-leaf counts are only computed when something is wrong."""
     nan_info, messages = [], []
+    cuda_leaves = []
+
+    def collect(node):
+        if isinstance(node, dict):
+            for v in node.values():
+                collect(v)
+        elif isinstance(node, (list, tuple)):
+            for v in node:
+                collect(v)
+        elif isinstance(node, torch.Tensor) and node.is_cuda and node.is_floating_point():
+            cuda_leaves.append(node)
+
+    collect(model)
+    clean_cuda = False
+    if cuda_leaves:
+        flags = torch.stack([torch.isnan(t).any() for t in cuda_leaves])
+        clean_cuda = not bool(flags.any().item())
 
     def walk(node, path):
         if isinstance(node, dict):
@@ -124,7 +144,7 @@ def check_for_nans(model):
             for i, v in enumerate(node):
                 walk(v, path + (i,))
         elif isinstance(node, torch.Tensor):
-            if node.is_floating_point():
+            if node.is_floating_point() and not (clean_cuda and node.is_cuda):
                 n = int(torch.isnan(node).sum().item())
                 if n:
                     nan_info.append((path, n))
