@@ -1630,7 +1630,31 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         if (rc) return rc;
     }
     static const bool rows1 = [] { const char* e = getenv("KPMS_BACKPREP"); return e && std::string(e) == "rows1"; }();
-    if constexpr (n <= 32) {
+    auto launch_generic = [&]() -> int {
+        // generic shared-memory kernel, one warp per frame; as many warps per CTA as shared memory allows
+        constexpr int WARPS_MAX = (int)(220 * 1024 / (PrepSmem<R, D_, L_>::per_warp * sizeof(R)));
+        constexpr int WARPS = WARPS_MAX >= 4 ? 4 : (WARPS_MAX >= 1 ? WARPS_MAX : 1);
+        auto kern = kalman_backprep_kernel<R, D_, L_, WARPS>;
+        size_t smem = PrepSmem<R, D_, L_>::per_warp * WARPS * sizeof(R);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int blocks = (int)((frames + WARPS - 1) / WARPS);
+        { KPMS_LAUNCH("kalman_backprep", st); kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH); }
+        return check_launch("kalman backprep");
+    };
+    if constexpr (n > 32 && n <= 64 && sizeof(R) == 4) {
+      if (rows1) { int rc = launch_generic(); if (rc) return rc; } else {
+        // latent_dim 16: one frame per warp, two rows per lane (the generic shared-memory kernel is ~50x slower)
+        typedef PrepRows2<R, D_, L_> P2;
+        constexpr int WARPS = (int)(200 * 1024 / (P2::per_group * P2::FPW * sizeof(R)));
+        auto kern = kalman_backprep_rows2_kernel<R, D_, L_, WARPS>;
+        size_t smem = (size_t)P2::per_group * P2::FPW * WARPS * sizeof(R);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int blocks = (int)std::min<long long>((frames + WARPS * P2::FPW - 1) / (WARPS * P2::FPW), (long long)KPMS_SM_COUNT);
+        { KPMS_LAUNCH("kalman_backprep", st); kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH); }
+        int rc = check_launch("kalman backprep");
+        if (rc) return rc;
+      }
+    } else if constexpr (n <= 32) {
       if (!rows1) {
         // two rows per lane, FPW frames per warp (kalman_rows2.cuh); one CTA per SM
         typedef PrepRows2<R, D_, L_> P2;
@@ -1654,13 +1678,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         if (rc) return rc;
       }
     } else {
-        constexpr int WARPS = 4;
-        auto kern = kalman_backprep_kernel<R, D_, L_, WARPS>;
-        size_t smem = PrepSmem<R, D_, L_>::per_warp * WARPS * sizeof(R);
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int blocks = (int)((frames + WARPS - 1) / WARPS);
-        { KPMS_LAUNCH("kalman_backprep", st); kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH); }
-        int rc = check_launch("kalman backprep");
+        int rc = launch_generic();
         if (rc) return rc;
     }
     {

@@ -105,11 +105,14 @@ kalman_backprep_rows2_kernel(const R* __restrict__ stash_m, const R* __restrict_
     const int r0 = act ? gl : NH - 1;                    // idle lanes shadow a valid row (same values, same addresses)
     const bool has1 = act && (gl + NH < n);
     const int r1 = has1 ? gl + NH : n - 1;
-    // S is the lower triangle packed by columns: S[r][c] = c <= r ? Sb[col_start(c) + r - c] : Sb[col_start(r) + c - r]
-    const R* pA0 = Sb + col_start(n, r0) - r0;
-    const R* pB0 = Sb + r0;
-    const R* pA1 = Sb + col_start(n, r1) - r1;
-    const R* pB1 = Sb + r1;
+    // S is the lower triangle, packed by columns by the row-per-lane filter (n <= 32):
+    //   S[r][c] = c <= r ? Sb[col_start(c) + r - c] : Sb[col_start(r) + c - r],
+    // and by rows by the generic filter (n > 32): S[r][c] = c <= r ? Sb[r(r+1)/2 + c] : Sb[c(c+1)/2 + r].
+    constexpr bool ROWPACK = n > 32;
+    auto Sat = [&](int r, int c) -> R {
+        if (ROWPACK) return (c <= r) ? Sb[r * (r + 1) / 2 + c] : Sb[c * (c + 1) / 2 + r];
+        return (c <= r) ? Sb[col_start(n, c) + r - c] : Sb[col_start(n, r) + c - r];
+    };
     const R eps = (R)KPMS_EPS_SHIFT + jitter;
 
     // frame status: -1 = none, 0 = masked (identity record), 1 = regular, 2 = last frame of its chain
@@ -198,8 +201,8 @@ kalman_backprep_rows2_kernel(const R* __restrict__ stash_m, const R* __restrict_
             R s0[n], s1[n];
 #pragma unroll
             for (int c = 0; c < n; ++c) {
-                s0[c] = (c <= r0) ? pB0[col_start(n, c) - c] : pA0[c];
-                s1[c] = (c <= r1) ? pB1[col_start(n, c) - c] : pA1[c];
+                s0[c] = Sat(r0, c);
+                s1[c] = Sat(r1, c);
             }
 #pragma unroll
             for (int r = 0; r < NO; ++r) { wt0[r] = s0[r + D_]; wt1[r] = s1[r + D_]; }
@@ -295,9 +298,8 @@ kalman_backprep_rows2_kernel(const R* __restrict__ stash_m, const R* __restrict_
         // place in T2; afterwards every lane reads its own two rows back with static indices
 #pragma unroll 1
         for (int a = 0; a < n; ++a) {
-            const int ca = col_start(n, a) - a;
-            R x0 = (a <= r0) ? pB0[ca] : pA0[a], x1 = 0;
-            R y0 = (a <= r1) ? pB1[ca] : pA1[a], y1 = 0;
+            R x0 = Sat(r0, a), x1 = 0;
+            R y0 = Sat(r1, a), y1 = 0;
             if (!term) {
 #pragma unroll
                 for (int cv = 0; cv < NV; ++cv) {

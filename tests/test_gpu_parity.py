@@ -84,7 +84,8 @@ def test_discrete_stateseqs_float32_filter():
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, F64_TOL), (torch.float32, F32_TOL)])
 @pytest.mark.parametrize("shape", [dict(d=4, L=3, K=12, k=5, D=2), dict(d=10, L=3, K=20, k=12, D=2),
-                                   dict(d=4, L=3, K=8, k=6, D=3), dict(d=2, L=2, K=5, k=4, D=2)])
+                                   dict(d=4, L=3, K=8, k=6, D=3), dict(d=2, L=2, K=5, k=4, D=2),
+                                   dict(d=16, L=3, K=6, k=12, D=2)])
 def test_continuous_stateseqs(dtype, tol, shape):
     g = _gibbs()
     data, _, model = small_problem(seed=5, **shape)
