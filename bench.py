@@ -123,6 +123,11 @@ def cpu_port_throughput(cfg, seconds_hint=20.0):
     return float(data["mask"].sum() / dt), int(cores), sample
 
 
+def workload_text(name, cfg):
+    return (f"{name} per GPU: {cfg['recordings']} recordings x {cfg['frames']} frames, k={cfg['k']}, D={cfg['D']}, "
+            f"latent_dim={cfg['d']}, nlags={cfg['L']}, num_states={cfg['K']}; full sweep (params, z, s, x, h, v) + NaN check")
+
+
 def run_reference(args):
     """CPU arm: jax_moseq (the reference's engine) cannot be installed here, so the oracle port is timed."""
     rank = int(os.environ.get("RANK", "0"))
@@ -138,8 +143,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": best, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * frames_total / best,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {cfg['recordings']} recordings x {cfg['frames']} frames, k={cfg['k']}, "
-                               f"D={cfg['D']}, latent_dim={cfg['d']}, nlags={cfg['L']}, num_states={cfg['K']} (full sweep)"},
+        "config": {"workload": workload_text(args.config, cfg)},
         "sweeps_per_sec": best / frames_total,
         "cpu_baseline": {"value": best, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": best, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -356,9 +360,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if dt == torch.float32 else "f64", "data": "synthetic",
-        "config": {"workload": f"{args.config} per GPU: {cfg['recordings']} recordings x {cfg['frames']} frames, "
-                               f"k={cfg['k']}, D={cfg['D']}, latent_dim={cfg['d']}, nlags={cfg['L']}, "
-                               f"num_states={cfg['K']}; full sweep (params, z, s, x, h, v) + NaN check",
+        "config": {"workload": workload_text(args.config, cfg),
                    "chains_per_gpu": int(dd["Y"].shape[0]), "frames_per_chain": int(dd["Y"].shape[1]),
                    "valid_frames_total": int(valid_total), "hmm_dtype": "f32" if hdt == torch.float32 else "f64",
                    "l2": "working set per sweep (> 4 GB of filter/backward records) exceeds the 126 MB L2"},
