@@ -345,11 +345,17 @@ def main():
         bpf = kernel_bytes_per_frame(top, cfg, esz, hesz)
         dur = prof[top][0] / max(prof[top][1], 1)
         ach = bpf * frames_rank / (dur * 1e-3) / 1e9 if bpf else None
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr_path) and args.config == "C2":
+            traffic = json.load(open(tr_path)).get(top, {}).get("bytes")     # from the committed ncu --set full capture
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": None if ach is None else ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": None if ach is None else ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "launch_ms": dur, "algorithmic_bytes_per_launch": None if bpf is None else bpf * frames_rank,
-                    "note": "chain-serial / FP32-issue-bound kernel: HBM fraction is reported as required, "
-                            "per-step latency is the binding resource (DESIGN.md section 5)"}
+                    "note": "the dominant kernel is a batch of per-frame 30x30 factorisations bound by FP32 issue and "
+                            "shared-memory operand traffic (ncu: issue slots 41 % busy, FMA pipe 28 %, DRAM traffic = "
+                            "0.96 x algorithmic bytes); the HBM fraction is reported as the contract requires "
+                            "(DESIGN.md section 4.1)"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

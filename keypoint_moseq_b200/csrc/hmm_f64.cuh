@@ -55,7 +55,7 @@ __global__ void ar_pack_frag_kernel(const double* __restrict__ G, const double* 
 }
 
 // ---------------------------------------------------------------------------
-// K2 on the tensor pipe.  CTA = AR_WARPS warps x 8 frames, two CTAs per SM so that one CTA's
+// K2 on the tensor pipe.  CTA = AR_WARPS warps x 8 frames, three CTAs per SM so that one CTA's
 // prologue / exp epilogue overlaps the other's DMMA stream; the operator chunks stream through a
 // two-deep cp.async ring; every warp keeps its 8 frames' features as A fragments in registers and
 // the log-likelihoods of all states until the frame maximum is known.
@@ -65,7 +65,7 @@ __global__ void ar_pack_frag_kernel(const double* __restrict__ G, const double* 
 constexpr int AR_WARPS = 8;
 
 template <int D_, int L_, int KT>
-__global__ void __launch_bounds__(32 * AR_WARPS, 2)
+__global__ void __launch_bounds__(32 * AR_WARPS, 3)
 ar_loglik_dmma_kernel(const double* __restrict__ x, const int* __restrict__ mask, const double* __restrict__ Gf,
                       int N, int T, int K, int ldT, double* __restrict__ W, double* __restrict__ mx) {
     typedef ArFrag<D_, L_> A;
