@@ -236,6 +236,25 @@ template <> __device__ __forceinline__ double rcp_fast<double>(double x) {
     return y;
 }
 
+// Two independent FMAs in one issue slot: c0 += a0*b0, c1 += a1*b1.  float: fma.rn.f32x2 (SASS FFMA2,
+// sm_100+; same rounding as two fma.rn, measured 68 TFLOP/s = the scalar FFMA peak at half the issue
+// slots, tools/micro/dmma_peak.cu); the pack / unpack moves vanish when the operands sit in aligned
+// register pairs.  double: two DFMAs.
+template <typename R>
+__device__ __forceinline__ void fma2(R& c0, R& c1, R a0, R a1, R b0, R b1) {
+    c0 = fma(a0, b0, c0);
+    c1 = fma(a1, b1, c1);
+}
+template <>
+__device__ __forceinline__ void fma2<float>(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+    unsigned long long a, b, c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(c));
+}
+
 // asynchronous global -> shared copies (one element, or one 16-byte chunk)
 template <typename R>
 __device__ __forceinline__ void cp_async_elem(R* dst, const R* src) {

@@ -55,19 +55,33 @@ __device__ __forceinline__ void chol_rows2(R (&a0)[n], R (&a1)[n], R* LT, R (&c0
             c1[j] = v1;
         }
         __syncwarp();
+        const R nl0 = -l0, nl1 = -l1, nv0 = -v0, nv1 = -v1;
 #pragma unroll
         for (int cv = (j + 1) / VEC; cv < NV; ++cv) {
             const VecT lv = *reinterpret_cast<const VecT*>(LT + j * LS + cv * VEC);
             const R* le = reinterpret_cast<const R*>(&lv);
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) {
+            for (int q = 0; q < VEC; q += 2) {               // columns c, c + 1 (c even) as one packed FMA
                 const int c = cv * VEC + q;
-                if (c > j && c < n) {
-                    a0[c] = fma(-l0, le[q], a0[c]);
-                    a1[c] = fma(-l1, le[q], a1[c]);
+                if (c > j && c + 1 < n) {
+                    fma2<R>(a0[c], a0[c + 1], nl0, nl0, le[q], le[q + 1]);
+                    fma2<R>(a1[c], a1[c + 1], nl1, nl1, le[q], le[q + 1]);
                     if (SOLVE) {
-                        c0[c] = fma(-le[q], v0, c0[c]);
-                        c1[c] = fma(-le[q], v1, c1[c]);
+                        fma2<R>(c0[c], c0[c + 1], le[q], le[q + 1], nv0, nv0);
+                        fma2<R>(c1[c], c1[c + 1], le[q], le[q + 1], nv1, nv1);
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int cc = c + t;
+                        if (cc > j && cc < n) {
+                            a0[cc] = fma(nl0, le[q + t], a0[cc]);
+                            a1[cc] = fma(nl1, le[q + t], a1[cc]);
+                            if (SOLVE) {
+                                c0[cc] = fma(le[q + t], nv0, c0[cc]);
+                                c1[cc] = fma(le[q + t], nv1, c1[cc]);
+                            }
+                        }
                     }
                 }
             }
@@ -216,11 +230,14 @@ kalman_backprep_rows2_kernel(const R* __restrict__ stash_m, const R* __restrict_
                     const VecT av = *reinterpret_cast<const VecT*>(As + a * LS + cv * VEC);
                     const R* ae = reinterpret_cast<const R*>(&av);
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) {
+                    for (int q = 0; q < VEC; q += 2) {
                         const int e = cv * VEC + q;
-                        if (e < n) {
-                            if (e & 1) { x1 = fma(ae[q], s0[e], x1); y1 = fma(ae[q], s1[e], y1); }
-                            else { x0 = fma(ae[q], s0[e], x0); y0 = fma(ae[q], s1[e], y0); }
+                        if (e + 1 < n) {
+                            fma2<R>(x0, x1, ae[q], ae[q + 1], s0[e], s0[e + 1]);
+                            fma2<R>(y0, y1, ae[q], ae[q + 1], s1[e], s1[e + 1]);
+                        } else if (e < n) {
+                            x0 = fma(ae[q], s0[e], x0);
+                            y0 = fma(ae[q], s1[e], y0);
                         }
                     }
                 }
@@ -271,11 +288,14 @@ kalman_backprep_rows2_kernel(const R* __restrict__ stash_m, const R* __restrict_
                     const VecT av = *reinterpret_cast<const VecT*>(As + a * LS + cv * VEC);
                     const R* ae = reinterpret_cast<const R*>(&av);
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) {
+                    for (int q = 0; q < VEC; q += 2) {
                         const int e = cv * VEC + q;
-                        if (e < n) {
-                            if (e & 1) { x1 = fma(ae[q], w0[e], x1); y1 = fma(ae[q], w1[e], y1); }
-                            else { x0 = fma(ae[q], w0[e], x0); y0 = fma(ae[q], w1[e], y0); }
+                        if (e + 1 < n) {
+                            fma2<R>(x0, x1, ae[q], ae[q + 1], w0[e], w0[e + 1]);
+                            fma2<R>(y0, y1, ae[q], ae[q + 1], w1[e], w1[e + 1]);
+                        } else if (e < n) {
+                            x0 = fma(ae[q], w0[e], x0);
+                            y0 = fma(ae[q], w1[e], y0);
                         }
                     }
                 }
@@ -298,26 +318,29 @@ kalman_backprep_rows2_kernel(const R* __restrict__ stash_m, const R* __restrict_
         // place in T2; afterwards every lane reads its own two rows back with static indices
 #pragma unroll 1
         for (int a = 0; a < n; ++a) {
-            R x0 = Sat(r0, a), x1 = 0;
-            R y0 = Sat(r1, a), y1 = 0;
+            R x0 = 0, x1 = 0, y0 = 0, y1 = 0;
             if (!term) {
 #pragma unroll
                 for (int cv = 0; cv < NV; ++cv) {
                     const VecT vv = *reinterpret_cast<const VecT*>(T2 + a * LS + cv * VEC);
                     const R* ve = reinterpret_cast<const R*>(&vv);
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) {
+                    for (int q = 0; q < VEC; q += 2) {
                         const int e = cv * VEC + q;
-                        if (e < n) {
-                            if (e & 1) { x1 = fma(-ve[q], wt0[e], x1); y1 = fma(-ve[q], wt1[e], y1); }
-                            else { x0 = fma(-ve[q], wt0[e], x0); y0 = fma(-ve[q], wt1[e], y0); }
+                        if (e + 1 < n) {
+                            fma2<R>(x0, x1, ve[q], ve[q + 1], wt0[e], wt0[e + 1]);
+                            fma2<R>(y0, y1, ve[q], ve[q + 1], wt1[e], wt1[e + 1]);
+                        } else if (e < n) {
+                            x0 = fma(ve[q], wt0[e], x0);
+                            y0 = fma(ve[q], wt1[e], y0);
                         }
                     }
                 }
             }
+            const R sx = Sat(r0, a) - (x0 + x1), sy = Sat(r1, a) - (y0 + y1);
             __syncwarp();
-            T2[a * LS + r0] = x0 + x1;
-            T2[a * LS + r1] = y0 + y1;
+            T2[a * LS + r0] = sx;
+            T2[a * LS + r1] = sy;
         }
         __syncwarp();
 #pragma unroll
@@ -343,23 +366,30 @@ kalman_backprep_rows2_kernel(const R* __restrict__ stash_m, const R* __restrict_
         {
 #pragma unroll
             for (int r = n - 1; r >= 0; --r) {
-                R x0 = wt0[r], x1 = 0, y0 = wt1[r], y1 = 0;
+                R x0 = 0, x1 = 0, y0 = 0, y1 = 0;
 #pragma unroll
                 for (int cv = (r + 1) / VEC; cv < NV; ++cv) {
                     const VecT lv = *reinterpret_cast<const VecT*>(T1 + r * LS + cv * VEC);
                     const R* le = reinterpret_cast<const R*>(&lv);
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) {
+                    for (int q = 0; q < VEC; q += 2) {
                         const int e = cv * VEC + q;
-                        if (e > r && e < n) {
-                            if (e & 1) { x1 = fma(-le[q], wt0[e], x1); y1 = fma(-le[q], wt1[e], y1); }
-                            else { x0 = fma(-le[q], wt0[e], x0); y0 = fma(-le[q], wt1[e], y0); }
+                        if (e > r && e + 1 < n) {
+                            fma2<R>(x0, x1, le[q], le[q + 1], wt0[e], wt0[e + 1]);
+                            fma2<R>(y0, y1, le[q], le[q + 1], wt1[e], wt1[e + 1]);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 2; ++t)
+                                if (e + t > r && e + t < n) {
+                                    x0 = fma(le[q + t], wt0[e + t], x0);
+                                    y0 = fma(le[q + t], wt1[e + t], y0);
+                                }
                         }
                     }
                 }
                 const R iv = invd[r];
-                wt0[r] = (x0 + x1) * iv;
-                wt1[r] = (y0 + y1) * iv;
+                wt0[r] = (wt0[r] - (x0 + x1)) * iv;
+                wt1[r] = (wt1[r] - (y0 + y1)) * iv;
             }
             if (on) {
 #pragma unroll

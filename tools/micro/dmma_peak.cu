@@ -56,6 +56,25 @@ __global__ void ffma_kernel(float* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// packed FP32: fma.rn.f32x2 (SASS FFMA2), two FMAs per issue slot
+template <int ILP>
+__global__ void ffma2_kernel(float* out, int iters) {
+    unsigned long long c[ILP], a, b;
+    float a0 = threadIdx.x * 1e-3f, b0 = threadIdx.x * 2e-3f;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a0 + 1.f));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b0 + 1.f));
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(c[i]) : "f"((float)i), "f"((float)-i));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) asm volatile("fma.rn.f32x2 %0, %1, %0, %2;" : "+l"(c[i]) : "l"(a), "l"(b));
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(c[i])); s += x + y; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // dependent chain of DMMAs in one warp: cycles per instruction = latency
 __global__ void dmma_latency_kernel(double* out, long long* cyc, int iters) {
     double c0 = 1.0, c1 = 2.0, a = threadIdx.x * 1e-3, b = 1e-3;
@@ -105,6 +124,14 @@ int main() {
             float ms; cudaEventElapsedTime(&ms, e0, e1);
             double flops = 2.0 * 32 * 8 * (double)iters * warps * sms;
             if (rep) printf("DFMA         warps/SM=%2d  %.2f TFLOP/s\n", warps, flops / ms * 1e-9);
+        }
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(e0);
+            ffma2_kernel<8><<<sms, warps * 32>>>((float*)out, iters);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            double flops = 2.0 * 64 * 8 * (double)iters * warps * sms;
+            if (rep) printf("FFMA2        warps/SM=%2d  %.2f TFLOP/s\n", warps, flops / ms * 1e-9);
         }
         for (int rep = 0; rep < 2; ++rep) {
             cudaEventRecord(e0);
