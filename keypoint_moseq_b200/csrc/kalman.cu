@@ -748,19 +748,26 @@ kalman_forward_rows_kernel(const R* __restrict__ info, const int* __restrict__ m
                 *reinterpret_cast<VecT*>(Vs + lane * VS + cv * VEC) = ov;
             }
             __syncwarp();
-            // ---- P+ = P - V V' (own row)
+            // ---- P+ = P - V V' (own row); packed FMAs over pairs of the d contraction terms
+            {
+                R nv[DV * VEC];
 #pragma unroll
-            for (int c = 0; c < n; ++c) {
-                R acc = p[c];
+                for (int q = 0; q < DV * VEC; ++q) nv[q] = (q < D_) ? -v[q] : (R)0;
 #pragma unroll
-                for (int cv = 0; cv < DV; ++cv) {
-                    const VecT vv = *reinterpret_cast<const VecT*>(Vs + c * VS + cv * VEC);
-                    const R* ve = reinterpret_cast<const R*>(&vv);
+                for (int c = 0; c < n; ++c) {
+                    R acc0 = p[c], acc1 = 0;
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q)
-                        if (cv * VEC + q < D_) acc = fma(-v[cv * VEC + q], ve[q], acc);
+                    for (int cv = 0; cv < DV; ++cv) {
+                        const VecT vv = *reinterpret_cast<const VecT*>(Vs + c * VS + cv * VEC);
+                        const R* ve = reinterpret_cast<const R*>(&vv);
+#pragma unroll
+                        for (int q = 0; q < VEC; q += 2) {
+                            if (cv * VEC + q + 1 < D_) fma2<R>(acc0, acc1, nv[cv * VEC + q], nv[cv * VEC + q + 1], ve[q], ve[q + 1]);
+                            else if (cv * VEC + q < D_) acc0 = fma(nv[cv * VEC + q], ve[q], acc0);
+                        }
+                    }
+                    p[c] = acc0 + acc1;
                 }
-                p[c] = acc;
             }
             if (keep && act) {
                 sm_g[(size_t)i * SMS + lane] = m;
@@ -780,9 +787,10 @@ kalman_forward_rows_kernel(const R* __restrict__ info, const int* __restrict__ m
                         const VecT av = *reinterpret_cast<const VecT*>(A + a * AS + cv * VEC);
                         const R* ae = reinterpret_cast<const R*>(&av);
 #pragma unroll
-                        for (int q = 0; q < VEC; ++q) {
+                        for (int q = 0; q < VEC; q += 2) {
                             const int e = cv * VEC + q;
-                            if (e < n) { if (e & 1) acc1 = fma(ae[q], p[e], acc1); else acc0 = fma(ae[q], p[e], acc0); }
+                            if (e + 1 < n) fma2<R>(acc0, acc1, ae[q], ae[q + 1], p[e], p[e + 1]);
+                            else if (e < n) acc0 = fma(ae[q], p[e], acc0);
                         }
                     }
                     ap[a] = acc0 + acc1;
@@ -832,14 +840,15 @@ kalman_forward_rows_kernel(const R* __restrict__ info, const int* __restrict__ m
                     }
 #pragma unroll
                     for (int a = 0; a < D_; ++a) {
-                        R acc = 0;
+                        R acc = 0, acc1 = 0;
 #pragma unroll
                         for (int cv = 0; cv < WN; ++cv) {
                             const VecT av = *reinterpret_cast<const VecT*>(A + a * AS + w0 + cv * VEC);
                             const R* ae = reinterpret_cast<const R*>(&av);
 #pragma unroll
-                            for (int q = 0; q < VEC; ++q) acc = fma(aw[cv * VEC + q], ae[q], acc);
+                            for (int q = 0; q < VEC; q += 2) fma2<R>(acc, acc1, aw[cv * VEC + q], aw[cv * VEC + q + 1], ae[q], ae[q + 1]);
                         }
+                        acc += acc1;
                         R tot = acc;
 #pragma unroll
                         for (int gq = 1; gq < L_; ++gq) tot += __shfl_up_sync(0xffffffffu, acc, D_ * gq);
