@@ -56,9 +56,11 @@ class ClockSampler:
     clocks line, -lms 200).  Every query stalls kernel launches for a while (measured: one step in ten
     takes 30-50 ms instead of 18 when polling at 100 ms, and NVML polled in-process at 20 ms is far worse),
     so the poll period is not shortened further; `step_ms` in the JSON line shows the outliers."""
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    FIELDS = os.environ.get("KPMS_BENCH_CLOCK_FIELDS") or (
+        "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+        "clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = os.environ.get("KPMS_BENCH_CLOCK_MS", "200")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -67,7 +69,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", self.PERIOD_MS], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -186,7 +188,7 @@ def main():
     import torch.distributed as dist
     from keypoint_moseq_b200 import _lib, gibbs
     from keypoint_moseq_b200.synth import sample_dataset
-    from keypoint_moseq_b200.util import check_for_nans
+    from keypoint_moseq_b200.util import NanGuard, check_for_nans
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,12 +224,20 @@ def main():
         if world > 1:
             dist.barrier()
 
+    guard = NanGuard(lag=1)       # the per-sweep NaN check of fit_model, pipelined by one sweep as fit_model does
+
     def step(m):
         m = gibbs.resample_model(dd, **m, **opts)
-        any_nans, _, msgs = check_for_nans(m)
-        if any_nans:
-            raise RuntimeError("NaNs in sweep: " + "; ".join(msgs))
+        guard.submit(m)
+        failed, _ = guard.collect()
+        if failed is not None:
+            raise RuntimeError("NaNs in sweep: " + "; ".join(check_for_nans(failed)[2]))
         return m
+
+    def drain():
+        failed, _ = guard.collect(keep=0)
+        if failed is not None:
+            raise RuntimeError("NaNs in sweep: " + "; ".join(check_for_nans(failed)[2]))
 
     m = dm
     clocks = ClockSampler(local)
@@ -235,6 +245,7 @@ def main():
         clocks.start()
     for _ in range(max(args.warmup, 3)):
         m = step(m)
+    drain()
     barrier()
     if rank == 0:
         time.sleep(0.25)          # let the sampler finish its start-up and first query outside the timed region
@@ -250,6 +261,7 @@ def main():
         m = step(m)
         marks[i_].record()
         host_ms.append(round((time.perf_counter() - t_h) * 1e3, 2))
+    drain()                       # every timed sweep's check is read inside the timed region
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -274,6 +286,7 @@ def main():
         _lib.profile(True)
     for _ in range(psteps):
         m = step(m)
+    drain()
     if rank == 0:
         prof = _lib.profile_report()
         _lib.profile(False)

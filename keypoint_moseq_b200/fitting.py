@@ -15,7 +15,7 @@ import torch
 
 from . import gibbs
 from .io import delete_snapshots_after, extract_results, load_checkpoint, save_hdf5
-from .util import check_for_nans, get_nlags, to_numpy_tree, unbatch
+from .util import NanGuard, check_for_nans, get_nlags, to_numpy_tree, unbatch
 
 try:  # progress bars are optional
     import tqdm
@@ -47,23 +47,51 @@ class StopResampling(Exception):
     pass
 
 
-def _wrapped_resample(resample_func, data, model, pbar=None, **resample_options):
-    """One guarded sweep: Ctrl-C and NaNs end fitting and keep the last good model (fitting.py:23-44)."""
+def _report_nans(model, pbar=None):
+    _, _, messages = check_for_nans(model)
+    if pbar is not None:
+        pbar.close()
+    text = ["\nEarly termination of fitting: NaNs encountered"] + [f"  - {m}" for m in messages]
+    text.append("\nFor additional information, see https://keypoint-moseq.readthedocs.io/en/latest/"
+                "troubleshooting.html#nans-during-fitting")
+    warnings.warn("\n".join(text))
+
+
+def _wrapped_resample(resample_func, data, model, pbar=None, guard=None, **resample_options):
+    """One guarded sweep: Ctrl-C and NaNs end fitting and keep the last good model (fitting.py:23-44).
+
+    With a `NanGuard` the NaN check is pipelined: this sweep's flag is queued and the flag of the sweep
+    `guard.lag` iterations back is read; `guard.clean` always holds the newest model known to be clean,
+    and that is what the caller returns when StopResampling is raised."""
     try:
-        model = resample_func(data, **model, **resample_options)
+        new = resample_func(data, **model, **resample_options)
     except KeyboardInterrupt:
         print("Early termination of fitting: user interruption")
         raise StopResampling()
-    any_nans, nan_info, messages = check_for_nans(model)
-    if any_nans:
-        if pbar is not None:
-            pbar.close()
-        text = ["\nEarly termination of fitting: NaNs encountered"] + [f"  - {m}" for m in messages]
-        text.append("\nFor additional information, see https://keypoint-moseq.readthedocs.io/en/latest/"
-                    "troubleshooting.html#nans-during-fitting")
-        warnings.warn("\n".join(text))
+    if guard is None:
+        if check_for_nans(new)[0]:
+            _report_nans(new, pbar)
+            raise StopResampling()
+        return new
+    guard.submit(new)
+    failed, clean = guard.collect()
+    if clean is not None:
+        guard.clean = clean
+    if failed is not None:
+        _report_nans(failed, pbar)
         raise StopResampling()
-    return model
+    return new
+
+
+def _drain_guard(guard, pbar=None):
+    """Synchronous end of the pipelined check: True when every queued sweep was clean."""
+    failed, clean = guard.collect(keep=0)
+    if clean is not None:
+        guard.clean = clean
+    if failed is not None:
+        _report_nans(failed, pbar)
+        return False
+    return True
 
 
 def _set_parallel_flag(parallel_message_passing):
@@ -207,18 +235,29 @@ def fit_model(model, data, metadata, project_dir=None, model_name=None, num_iter
     model = gibbs.to_device_model(model, device, dtype)
     resample_func = gibbs.resample_model
 
+    # NaN check pipelined by one sweep (kwarg nan_check_lag, 0 = synchronous as in the reference): the model
+    # returned after a NaN is the last one that was checked clean, as in fitting.py:30-44, :263-264
+    guard = NanGuard(lag=int(kwargs.pop("nan_check_lag", 1)))
+    guard.clean = model
     with _trange(start_iter, num_iters + 1, ncols=72) as pbar:
         for iteration in pbar:
             try:
-                model = _wrapped_resample(resample_func, data_dev, model, pbar=pbar, ar_only=ar_only,
+                model = _wrapped_resample(resample_func, data_dev, model, pbar=pbar, guard=guard, ar_only=ar_only,
                                           verbose=verbose, jitter=jitter,
                                           parallel_message_passing=parallel_message_passing, **extra)
             except StopResampling:
+                model = guard.clean
                 break
             if save_every_n_iters is not None and iteration > start_iter:
                 if iteration == num_iters or (save_every_n_iters > 0 and iteration % save_every_n_iters == 0):
+                    if not _drain_guard(guard, pbar):           # never checkpoint an unchecked sweep
+                        model = guard.clean
+                        break
                     save_hdf5(checkpoint_path, _host_model(model), f"model_snapshots/{iteration}", exist_ok=True)
                     # progress plots (viz.plot_progress) are outside the sweep's scope and are skipped
+        else:
+            if not _drain_guard(guard, pbar):
+                model = guard.clean
     return model, model_name
 
 

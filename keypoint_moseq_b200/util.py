@@ -163,6 +163,63 @@ def check_for_nans(model):
     return len(nan_info) > 0, nan_info, messages
 
 
+class NanGuard:
+    """The per-sweep NaN check of `fit_model` (fitting.py:30), pipelined: every sweep's flag is reduced on
+    the device and copied to pinned host memory asynchronously, and is read `lag` sweeps later, so the
+    host can queue a whole sweep ahead of the GPU instead of draining it after every sweep.  A failed
+    check is reported at most `lag` sweeps late; the caller keeps the last model known to be clean.
+    `lag = 0` is the synchronous check."""
+
+    def __init__(self, lag=1):
+        import collections
+        self.lag, self.pending, self.pool = int(lag), collections.deque(), []
+
+    def submit(self, model):
+        leaves = []
+
+        def collect(node):
+            if isinstance(node, dict):
+                for v in node.values():
+                    collect(v)
+            elif isinstance(node, (list, tuple)):
+                for v in node:
+                    collect(v)
+            elif isinstance(node, torch.Tensor) and node.is_cuda and node.is_floating_point():
+                leaves.append(node)
+
+        collect(model)
+        if not leaves:
+            self.pending.append((None, None, model))
+            return
+        flag = torch.stack([torch.isnan(t).any() for t in leaves]).any()
+        host = self.pool.pop() if self.pool else torch.empty((), dtype=torch.bool).pin_memory()
+        host.copy_(flag, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((host, ev, model))
+
+    def collect(self, keep=None):
+        """Reads every pending flag except the newest `keep` (default: lag).  Returns (failed_model,
+        last_clean_model): the first model whose check failed (else None) and the newest model checked
+        clean in this call (else None)."""
+        keep = self.lag if keep is None else keep
+        clean = None
+        while len(self.pending) > keep:
+            host, ev, model = self.pending.popleft()
+            bad = False
+            if host is None:
+                bad = check_for_nans(model)[0]
+            else:
+                ev.synchronize()
+                bad = bool(host.item())
+                self.pool.append(host)
+            if bad:
+                self.pending.clear()
+                return model, clean
+            clean = model
+        return None, clean
+
+
 def find_optimal_segment_length(sequence_lengths, max_seg_length=10_000,
                                 max_percent_padding=50, min_fragment_length=4):
     """Segment length rule of util.py:865-926 (longest candidate within the padding budget,
