@@ -214,3 +214,30 @@ def test_fit_pca_and_init_params_recover_the_pose_subspace():
     assert np.sqrt(((recon - rows) ** 2).mean()) < 0.5 * rows.std()
     prior = initialize.noise_prior_from_confidence(data["conf"], {"slope": -0.5, "intercept": 0.25})
     assert prior.shape == data["conf"].shape and np.all(prior > 0)
+
+
+def test_nan_guard_pipelines_the_check_and_keeps_the_last_clean_model():
+    """NanGuard on host leaves (the device path copies one flag per sweep asynchronously): a failed
+    check is reported `lag` sweeps late and the newest clean model is handed back."""
+    from keypoint_moseq_b200.util import NanGuard
+    good = [{"states": {"x": np.ones(3) * i}} for i in range(4)]
+    bad = {"states": {"x": np.array([1.0, np.nan])}}
+    guard = NanGuard(lag=1)
+    seen = []
+    for model in (good[0], good[1], bad, good[2], good[3]):
+        guard.submit(model)
+        failed, clean = guard.collect()
+        seen.append((failed is not None, None if clean is None else float(clean["states"]["x"][0])))
+        if failed is not None:
+            assert failed is bad
+            break
+    # sweep 0: nothing old enough; sweep 1: model 0 clean; sweep 2 (the bad one): model 1 clean; sweep 3: failure
+    assert seen == [(False, None), (False, 0.0), (False, 1.0), (True, None)]
+    guard = NanGuard(lag=0)
+    guard.submit(bad)
+    assert guard.collect()[0] is bad
+    guard = NanGuard(lag=2)
+    for model in good[:3]:
+        guard.submit(model)
+    failed, clean = guard.collect(keep=0)
+    assert failed is None and clean is good[2]
