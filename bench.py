@@ -240,44 +240,14 @@ def main():
             raise RuntimeError("NaNs in sweep: " + "; ".join(check_for_nans(failed)[2]))
 
     m = dm
-    clocks = ClockSampler(local)
-    if rank == 0 and not os.environ.get("KPMS_BENCH_NO_CLOCKS"):
-        clocks.start()
     for _ in range(max(args.warmup, 3)):
         m = step(m)
     drain()
     barrier()
-    if rank == 0:
-        time.sleep(0.25)          # let the sampler finish its start-up and first query outside the timed region
-        clocks.mark()
-    launches0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    e0.record()
-    host_ms = []
-    for i_ in range(args.steps):
-        t_h = time.perf_counter()
-        m = step(m)
-        marks[i_].record()
-        host_ms.append(round((time.perf_counter() - t_h) * 1e3, 2))
-    drain()                       # every timed sweep's check is read inside the timed region
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    step_ms = [round(([e0] + marks)[i_].elapsed_time(marks[i_]), 3) for i_ in range(args.steps)]
-    launches = _lib.launch_count() - launches0
-    clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([ms, float(valid_local)], dtype=torch.float64, device=dev)
+    tv = torch.tensor([float(valid_local)], dtype=torch.float64, device=dev)
     if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ms = float(tmax[0])
-    valid_total = float(t[1])
-    ms_per_step = ms / args.steps
-    value = valid_total / (ms_per_step * 1e-3)
-
+        dist.all_reduce(tv, op=dist.ReduceOp.SUM)
+    valid_total = float(tv[0])
     # per-kernel CUDA-event timing (separate sweeps, same stream), for the roofline of the dominant kernel
     # (every rank steps - the sweep contains the statistics all-reduce - but only rank 0 records)
     prof = {}
@@ -323,17 +293,55 @@ def main():
 
         seed = e2e_step(seed)
         barrier()
-        e0.record()
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ee0.record()
         for _ in range(esteps):
             seed = e2e_step(seed)
-        e1.record()
+        ee1.record()
         barrier()
-        ems = e0.elapsed_time(e1) / esteps
+        ems = ee0.elapsed_time(ee1) / esteps
         te = torch.tensor([ems], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": valid_total / (float(te[0]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te[0]), "steps": esteps}
+
+    # ---- the timed region proper: W warm-up sweeps again (the profiling and end-to-end sections above also
+    # serve as warm-up: the first seconds on a fresh box are noisy), then exactly K timed sweeps
+    clocks = ClockSampler(local)
+    if rank == 0 and not os.environ.get("KPMS_BENCH_NO_CLOCKS"):
+        clocks.start()
+    for _ in range(max(args.warmup, 3)):
+        m = step(m)
+    drain()
+    barrier()
+    if rank == 0:
+        time.sleep(0.25)          # let the sampler finish its start-up and first query outside the timed region
+        clocks.mark()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e0.record()
+    host_ms = []
+    for i_ in range(args.steps):
+        t_h = time.perf_counter()
+        m = step(m)
+        marks[i_].record()
+        host_ms.append(round((time.perf_counter() - t_h) * 1e3, 2))
+    drain()                       # every timed sweep's check is read inside the timed region
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    step_ms = [round(([e0] + marks)[i_].elapsed_time(marks[i_]), 3) for i_ in range(args.steps)]
+    launches = _lib.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax[0])
+    ms_per_step = ms / args.steps
+    value = valid_total / (ms_per_step * 1e-3)
 
     if rank != 0:
         if world > 1:

@@ -206,16 +206,31 @@ crp_tables_kernel(const int* __restrict__ counts, const double* __restrict__ bet
                   const long long* __restrict__ starts, const double* __restrict__ u_crp, uint64_t seed, int K,
                   int* __restrict__ m) {
     const int i = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int j = warp; j < K; j += nw) {
+    constexpr int BIG = 4096;                  // entries with more customers than this are drawn by the whole CTA
+    __shared__ int red[32];
+    auto draw = [&](int j, int r, double conc) -> int {
+        double u;
+        if (u_crp) u = u_crp[starts[i * K + j] + r];
+        else { Philox gen(seed, KPMS_STREAM_CRP, ((uint64_t)(i * K + j) << 32) | (uint32_t)r); double u2; philox_uniform2(gen, u, u2); }
+        return (u < conc / ((double)r + conc)) ? 1 : 0;
+    };
+    // the sticky diagonal holds most of the transitions (tens of thousands per state on a large cohort)
+    for (int j = 0; j < K; ++j) {
         const int nn = counts[i * K + j];
+        if (nn <= BIG) continue;               // uniform across the CTA
         const double conc = alpha * betas[j] + (i == j ? kappa : 0.0);
         int cnt = 0;
-        for (int r = lane; r < nn; r += 32) {
-            double u;
-            if (u_crp) u = u_crp[starts[i * K + j] + r];
-            else { Philox gen(seed, KPMS_STREAM_CRP, ((uint64_t)(i * K + j) << 32) | (uint32_t)r); double u2; philox_uniform2(gen, u, u2); }
-            cnt += (u < conc / ((double)r + conc)) ? 1 : 0;
-        }
+        for (int r = threadIdx.x; r < nn; r += blockDim.x) cnt += draw(j, r, conc);
+        cnt = block_sum(cnt, red);
+        if (threadIdx.x == 0) m[i * K + j] = cnt;
+        __syncthreads();
+    }
+    for (int j = warp; j < K; j += nw) {
+        const int nn = counts[i * K + j];
+        if (nn > BIG) continue;
+        const double conc = alpha * betas[j] + (i == j ? kappa : 0.0);
+        int cnt = 0;
+        for (int r = lane; r < nn; r += 32) cnt += draw(j, r, conc);
         cnt = warp_sum(cnt);
         if (lane == 0) m[i * K + j] = cnt;
     }
