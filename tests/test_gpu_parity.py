@@ -45,7 +45,8 @@ def _cast_problem(data, model, tape, dtype):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, F64_TOL), (torch.float32, F32_TOL)])
 @pytest.mark.parametrize("shape", [dict(d=4, L=3, K=12, k=5, D=2), dict(d=10, L=3, K=100, k=12, D=2),
-                                   dict(d=4, L=3, K=30, k=6, D=3)])
+                                   dict(d=4, L=3, K=30, k=6, D=3), dict(d=4, L=3, K=50, k=5, D=2),
+                                   dict(d=2, L=2, K=128, k=4, D=2), dict(d=16, L=3, K=25, k=12, D=2)])
 def test_discrete_stateseqs(dtype, tol, shape):
     g = _gibbs()
     data, _, model = small_problem(seed=3, **shape)
