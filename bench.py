@@ -224,7 +224,9 @@ def main():
         if world > 1:
             dist.barrier()
 
-    guard = NanGuard(lag=1)       # the per-sweep NaN check of fit_model, pipelined by one sweep as fit_model does
+    # the per-sweep NaN check of fit_model, pipelined as fit_model does (fitting.NAN_CHECK_LAG sweeps)
+    from keypoint_moseq_b200.fitting import NAN_CHECK_LAG
+    guard = NanGuard(lag=int(os.environ.get("KPMS_NAN_LAG", NAN_CHECK_LAG)))
 
     def step(m):
         m = gibbs.resample_model(dd, **m, **opts)
@@ -273,7 +275,11 @@ def main():
         host_params = {k_: v.cpu().pin_memory() for k_, v in m["params"].items()}
         out_host = {k_: torch.empty_like(v).pin_memory() for k_, v in host_states.items()}
         nbytes = lambda d_: sum(v.numel() * v.element_size() for v in d_.values())
-        h2d = nbytes(host_data) + nbytes(host_states) + nbytes(host_params) + host_prior.numel() * host_prior.element_size()
+        # what resample_model uploads: Y and mask (conf is not an operand of the sweep), the states it reads
+        # (the old noise scales are resampled before any use), the parameters and the noise prior
+        h2d = (nbytes({k_: v for k_, v in host_data.items() if k_ != "conf"})
+               + nbytes({k_: v for k_, v in host_states.items() if k_ != "s"}) + nbytes(host_params)
+               + host_prior.numel() * host_prior.element_size())
         d2h = nbytes(out_host)
         seed = m["seed"]
         esteps = max(1, min(args.steps, 5))

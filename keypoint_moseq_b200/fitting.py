@@ -43,6 +43,9 @@ __all__ = ["fit_model", "apply_model", "init_model", "init_states", "update_hypp
            "estimate_syllable_marginals", "expected_marginal_likelihoods", "StopResampling"]
 
 
+NAN_CHECK_LAG = 1      # sweeps by which the per-sweep NaN check trails the sweep being queued (0 = synchronous)
+
+
 class StopResampling(Exception):
     pass
 
@@ -237,7 +240,7 @@ def fit_model(model, data, metadata, project_dir=None, model_name=None, num_iter
 
     # NaN check pipelined by one sweep (kwarg nan_check_lag, 0 = synchronous as in the reference): the model
     # returned after a NaN is the last one that was checked clean, as in fitting.py:30-44, :263-264
-    guard = NanGuard(lag=int(kwargs.pop("nan_check_lag", 1)))
+    guard = NanGuard(lag=int(kwargs.pop("nan_check_lag", NAN_CHECK_LAG)))
     guard.clean = model
     with _trange(start_iter, num_iters + 1, ncols=72) as pbar:
         for iteration in pbar:

@@ -452,7 +452,9 @@ def resample_model(data, seed, states, params, hypparams, noise_prior, ar_only=F
     stage.put("mask", data["mask"], torch.int32)
     for key, val in params.items():
         stage.put("p:" + key, val, torch.float64)
-    rest = [key for key in states if key not in ("x", "z")]
+    # the old noise scales are only read when they are not resampled (or feed the obs-variance statistics)
+    s_needed = ar_only or not resample_local_noise_scale or (resample_global_noise_scale and not states_only)
+    rest = [key for key in states if key not in ("x", "z") and (key != "s" or s_needed)]
     for key in rest:
         stage.put(key, states[key], dt)
     if not ar_only:
