@@ -43,7 +43,7 @@ __all__ = ["fit_model", "apply_model", "init_model", "init_states", "update_hypp
            "estimate_syllable_marginals", "expected_marginal_likelihoods", "StopResampling"]
 
 
-NAN_CHECK_LAG = 1      # sweeps by which the per-sweep NaN check trails the sweep being queued (0 = synchronous)
+NAN_CHECK_LAG = 4      # sweeps by which the per-sweep NaN check trails the sweep being queued (0 = synchronous)
 
 
 class StopResampling(Exception):
