@@ -6,7 +6,8 @@
 // Layouts (row-major):
 //   x     (N, T, d)            latent trajectories
 //   mask  (N, T) int32
-//   W     (N, K, ldT)          W[n][k][t'] = exp(ll[n][t'][k] - mx[n][t']),  t' = t - L
+//   W     float32: (N, K, ldT), W[n][k][t'] = exp(ll[n][t'][k] - mx[n][t']),  t' = t - L
+//         float64: (N, T', 8*ceil(K/8)) state-contiguous (operand layout of the tensor-pipe kernels, hmm_f64.cuh)
 //   mx    (N, ldT)             per-frame max log-likelihood (0 on masked frames)
 //   filt  (N, T', ldK)         filtered state probabilities
 //   z     (N, T') int32
