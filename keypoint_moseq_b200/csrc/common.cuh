@@ -322,8 +322,13 @@ valid_len_kernel(const int* __restrict__ mask, int T, int off, int len, int* __r
 // own scales: [0, n_mean) (difference relative to 1 + max|exact|) and [n_mean, rec) (relative to
 // max|exact|).  One CTA per (boundary, chain); dirty[nn] (zeroed by the caller) is raised when the
 // discrepancy exceeds tol or is not finite, or when pre[nn] != 0.
+// COMPONENTWISE (HMM filter): every entry is compared relative to itself, |x - y| <= tol max(|x|, |y|).
+// A probability vector that agrees component by component is within 2 tol in Hilbert's projective
+// metric, under which the filter step is non-expansive, so every later filtered probability keeps that
+// relative accuracy; an absolute comparison would let a negligible state with a large relative error
+// pass and be amplified if the likelihood later favours it.
 // stats[0] = max discrepancy seen (float bits, atomicMax), stats[1] += number of dirty chains.
-template <typename R>
+template <typename R, bool COMPONENTWISE = false>
 __global__ void __launch_bounds__(128)
 boundary_check_kernel(const R* __restrict__ warm, const R* __restrict__ exact, const int* __restrict__ vlen,
                       int len, int C, int W, int align, int n_mean, int rec, R tol, int* __restrict__ dirty,
@@ -343,8 +348,12 @@ boundary_check_kernel(const R* __restrict__ warm, const R* __restrict__ exact, c
             R diff = 0, scale = 0;
             for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
                 const R x = a[e], y = b[e];
-                const R dd = fabs(x - y);
+                R dd = fabs(x - y);
                 if (!(dd < (R)INFINITY)) bad = 1;
+                if (COMPONENTWISE) {
+                    const R big = fmax(fabs(x), fabs(y));
+                    dd = big > (R)0 ? dd / big : (R)0;          // both exactly zero: equal
+                }
                 diff = fmax(diff, dd);
                 scale = fmax(scale, fabs(y));
             }
@@ -355,7 +364,7 @@ boundary_check_kernel(const R* __restrict__ warm, const R* __restrict__ exact, c
             __syncthreads();
             const R dmax = fmax(fmax(red[0][0], red[0][1]), fmax(red[0][2], red[0][3]));
             const R smax = fmax(fmax(red[1][0], red[1][1]), fmax(red[1][2], red[1][3]));
-            worst = fmax(worst, dmax / ((part ? (R)0 : (R)1) + smax + (R)1e-30));
+            worst = fmax(worst, COMPONENTWISE ? dmax : dmax / ((part ? (R)0 : (R)1) + smax + (R)1e-30));
         }
     }
     const int any_bad = __syncthreads_or(bad);

@@ -925,7 +925,7 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
     { KPMS_LAUNCH("hmm_forward", st); FWD_K((int)(((long long)N * C + M - 1) / M), 0, vb, (const int*)nullptr) }
     { KPMS_LAUNCH("hmm_forward_check", st);
       cudaMemsetAsync(dirty, 0, (size_t)N * sizeof(int), st);
-      boundary_check_kernel<R><<<dim3(C - 1, N), 128, 0, st>>>(bw, be, vb, Tp, C, Wm, 8, K, K, tol, dirty, diag, holes); }
+      boundary_check_kernel<R, true><<<dim3(C - 1, N), 128, 0, st>>>(bw, be, vb, Tp, C, Wm, 8, K, K, tol, dirty, diag, holes); }
     // pi^TL by repeated squaring, then the starting predictions of the padded-tail chunks
     {
         const R* src = (const R*)pi;
