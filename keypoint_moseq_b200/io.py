@@ -23,7 +23,7 @@ except Exception:  # pragma: no cover
     h5py = None
     HAVE_H5PY = False
 
-__all__ = ["save_hdf5", "load_hdf5", "load_checkpoint", "extract_results", "load_results",
+__all__ = ["save_hdf5", "load_hdf5", "load_checkpoint", "reindex_syllables_in_checkpoint", "extract_results", "load_results",
            "delete_snapshots_after", "HAVE_H5PY"]
 
 _TYPES_KEY = "__tree_types__"
@@ -238,6 +238,33 @@ def load_checkpoint(project_dir=None, model_name=None, path=None, iteration=None
     metadata = load_hdf5(path, "metadata")
     data = load_hdf5(path, "data")
     return model, data, metadata, iteration
+
+
+def reindex_syllables_in_checkpoint(project_dir=None, model_name=None, path=None, index=None, runlength=True):
+    """Relabel the syllables of every snapshot of a checkpoint, in place, by their frequency in the latest
+    snapshot (most frequent -> 0) or by the permutation `index` (`index[i]` is relabelled `i`); the
+    state-indexed parameters betas, pi, Ab, Q are permuted with the labels (io.py:552-619).  Returns the
+    permutation used."""
+    from .util import get_frequencies
+    path = _get_path(project_dir, model_name, path, "checkpoint.h5")
+    saved = sorted(int(i) for i in _list_children(path, "model_snapshots"))
+    if index is None:
+        last = load_hdf5(path, f"model_snapshots/{saved[-1]}")
+        mask = load_hdf5(path, "data")["mask"]
+        num_states = np.asarray(last["params"]["pi"]).shape[0]
+        index = np.argsort(get_frequencies(np.asarray(last["states"]["z"]), np.asarray(mask), num_states, runlength))[::-1]
+    index = np.asarray(index)
+    inverse = np.argsort(index)
+    for iteration in saved:
+        model = load_hdf5(path, f"model_snapshots/{iteration}")
+        pr = model["params"]
+        pr["betas"] = np.asarray(pr["betas"])[index]
+        pr["pi"] = np.asarray(pr["pi"])[index, :][:, index]
+        pr["Ab"] = np.asarray(pr["Ab"])[index]
+        pr["Q"] = np.asarray(pr["Q"])[index]
+        model["states"]["z"] = inverse[np.asarray(model["states"]["z"])]
+        save_hdf5(path, model, f"model_snapshots/{iteration}", exist_ok=True, overwrite=True)
+    return index
 
 
 def extract_results(model, metadata, project_dir=None, model_name=None, save_results=True, path=None,

@@ -241,3 +241,32 @@ def test_nan_guard_pipelines_the_check_and_keeps_the_last_clean_model():
         guard.submit(model)
     failed, clean = guard.collect(keep=0)
     assert failed is None and clean is good[2]
+
+
+def test_reindex_syllables_in_checkpoint(tmp_path):
+    """Relabelling by frequency permutes z and the state-indexed parameters of every snapshot consistently
+    (io.py:552-619): transition structure and likelihood parameters follow their syllable."""
+    from keypoint_moseq_b200.util import get_frequencies
+    data, meta, model = sample_dataset(recordings=2, frames=200, k=4, D=2, d=2, L=2, K=5, seg_length=120)
+    d = tmp_path / "proj" / "m"
+    d.mkdir(parents=True)
+    path = str(d / "checkpoint.h5")
+    kio.save_hdf5(path, {"model_snapshots": {"0": model, "7": model}, "metadata": (np.asarray(meta[0]), meta[1]),
+                         "data": data})
+    index = kio.reindex_syllables_in_checkpoint(str(tmp_path / "proj"), "m")
+    assert sorted(index.tolist()) == list(range(5))
+    for it in (0, 7):
+        new = kio.load_hdf5(path, f"model_snapshots/{it}")
+        old = model
+        # label i now means the syllable formerly labelled index[i]
+        np.testing.assert_array_equal(index[new["states"]["z"]], old["states"]["z"])
+        np.testing.assert_allclose(new["params"]["Ab"], np.asarray(old["params"]["Ab"])[index])
+        np.testing.assert_allclose(new["params"]["pi"], np.asarray(old["params"]["pi"])[index][:, index])
+        np.testing.assert_allclose(new["params"]["betas"], np.asarray(old["params"]["betas"])[index])
+    freq = get_frequencies(kio.load_hdf5(path, "model_snapshots/7")["states"]["z"], data["mask"], 5, True)
+    assert np.all(np.diff(freq) <= 1e-12)                       # most frequent syllable first
+    # an explicit permutation is applied as given
+    perm = np.array([4, 3, 2, 1, 0])
+    kio.reindex_syllables_in_checkpoint(path=path, index=perm)
+    twice = kio.load_hdf5(path, "model_snapshots/7")
+    np.testing.assert_array_equal(index[perm[twice["states"]["z"]]], model["states"]["z"])
