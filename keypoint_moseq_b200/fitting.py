@@ -299,10 +299,13 @@ def apply_model(model, data, metadata, project_dir=None, model_name=None, num_it
 
 
 def estimate_syllable_marginals(model, data, metadata, burn_in_iters=200, num_samples=100, steps_per_sample=10,
-                                return_samples=False, verbose=False, parallel_message_passing=None, **kwargs):
+                                return_samples=False, verbose=False, parallel_message_passing=None,
+                                location_aware=False, **kwargs):
     """Marginal syllable distributions by averaging HMM smoother marginals over Gibbs samples of the
     states with fixed parameters (fitting.py:428-559).  Returns {recording: (T - nlags, K) array}
     (and the samples when `return_samples`)."""
+    if location_aware:
+        raise NotImplementedError("location_aware=True (allo_keypoint_slds) is not implemented by the B200 sweep")
     parallel_message_passing = _set_parallel_flag(parallel_message_passing)
     dtype = kwargs.pop("dtype", torch.float64)
     device = kwargs.pop("device", "cuda")

@@ -13,6 +13,7 @@ import torch
 __all__ = [
     "batch", "unbatch", "get_nlags", "get_durations", "get_frequencies",
     "check_for_nans", "find_optimal_segment_length", "format_data", "to_numpy_tree",
+    "reindex_by_bodyparts", "interpolate_keypoints", "NanGuard",
 ]
 
 
@@ -245,22 +246,69 @@ def find_optimal_segment_length(sequence_lengths, max_seg_length=10_000,
         seg += int(rem.min())
 
 
-def format_data(coordinates, confidences=None, keys=None, seg_length=None, conf_pseudocount=1e-3,
-                added_noise_level=0.1, max_seg_length=10_000, max_percent_padding=50,
-                min_fragment_length=4, device=None, **kwargs):
-    """Batch recordings into the `data` dict and `metadata` tuple (util.py:1054-1089).
+def reindex_by_bodyparts(data, bodyparts, use_bodyparts, axis=1):
+    """Select / reorder keypoints by label (util.py:404-433); `data` is an array or a dict of arrays."""
+    ix = np.array([list(bodyparts).index(bp) for bp in use_bodyparts])
+    if isinstance(data, np.ndarray):
+        return np.take(data, ix, axis)
+    return {k: np.take(v, ix, axis) for k, v in data.items()}
 
-    NaN interpolation and bodypart re-indexing are upstream of the hot path and are not
-    reproduced: coordinates must be finite.  Arrays are returned as torch tensors on
-    `device` (CUDA when available) in float64, as the reference's x64 default.
+
+def interpolate_keypoints(coordinates, outliers):
+    """Impute outlier points by linear interpolation in time, keypoint by keypoint, holding the first /
+    last good value beyond the ends; a keypoint with no good frame becomes 0 (util.py:669-690)."""
+    coordinates = np.asarray(coordinates, dtype=float)
+    out = np.zeros_like(coordinates)
+    frames = np.arange(coordinates.shape[0])
+    for i in range(coordinates.shape[1]):
+        xp = np.nonzero(~outliers[:, i])[0]
+        if len(xp) > 0:
+            for c in range(coordinates.shape[2]):
+                out[:, i, c] = np.interp(frames, xp, coordinates[xp, i, c])
+    return out
+
+
+def format_data(coordinates, confidences=None, keys=None, bodyparts=None, use_bodyparts=None,
+                conf_pseudocount=1e-3, added_noise_level=0.1, seg_length=None, max_seg_length=10_000,
+                max_percent_padding=50, min_fragment_length=4, device=None, **kwargs):
+    """Batch recordings into the `data` dict and `metadata` tuple (util.py:929-1089): keypoints selected
+    and ordered by `use_bodyparts`, NaN points imputed by interpolation with their confidence set to 0,
+    fixed-length segments (`find_optimal_segment_length`, `batch`), confidences clamped at 0 plus
+    `conf_pseudocount`, and Uniform(+-added_noise_level) noise from `default_rng(42)`.
+
+    Arrays are returned as torch tensors on `device` (CUDA when available) in float64, the reference's
+    x64 default, where the reference calls `jax.device_put`.
     """
     if keys is None:
         keys = sorted(coordinates.keys())
+    else:
+        bad_keys = set(keys) - set(coordinates.keys())
+        assert len(bad_keys) == 0, f"Keys {bad_keys} not found in coordinates"
+    assert len(keys) > 0, "No recordings found"
+    num_keypoints = [coordinates[k].shape[-2] for k in keys]
+    assert len(set(num_keypoints)) == 1, (f"All recordings must have the same number of keypoints, but "
+                                          f"found {set(num_keypoints)} keypoints across recordings.")
+    if bodyparts is not None:
+        assert len(bodyparts) == num_keypoints[0], (
+            f"The number of keypoints in `coordinates` ({num_keypoints[0]}) does not match the number of "
+            f"labels in `bodyparts` ({len(bodyparts)})")
+    if any("/" in k for k in keys):
+        warnings.warn('WARNING: Recording names should not contain "/", this will cause problems with '
+                      "saving/loading hdf5 files.")
     if confidences is None:
         confidences = {k: np.ones_like(coordinates[k][..., 0]) for k in keys}
+    coordinates = {k: np.asarray(coordinates[k], dtype=float) for k in keys}
+    confidences = {k: np.asarray(confidences[k], dtype=float) for k in keys}
+    if bodyparts is not None and use_bodyparts is not None:
+        coordinates = reindex_by_bodyparts(coordinates, bodyparts, use_bodyparts)
+        confidences = reindex_by_bodyparts(confidences, bodyparts, use_bodyparts)
     for k in keys:
+        outliers = np.isnan(coordinates[k]).any(-1)
+        if outliers.any():
+            coordinates[k] = interpolate_keypoints(coordinates[k], outliers)
+        confidences[k] = np.where(outliers, 0, np.nan_to_num(confidences[k]))
         if not np.isfinite(coordinates[k]).all():
-            raise ValueError(f"non-finite coordinates in {k!r}: interpolate before format_data")
+            raise ValueError(f"non-finite coordinates in {k!r} (infinite values are not interpolated)")
     if not seg_length:
         seg_length = find_optimal_segment_length(
             [coordinates[k].shape[0] for k in keys], max_seg_length, max_percent_padding,

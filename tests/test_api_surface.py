@@ -1,0 +1,44 @@
+"""The drop-in boundary, pinned against the reference itself: names, parameter order and defaults of every
+reference function this repo mirrors (parsed from /root/reference by tests/golden/make_signatures.py into
+tests/golden/reference_signatures.json) must be accepted unchanged here.  Extra keyword parameters with
+defaults are allowed; nothing the reference accepts may be missing, renamed, reordered or re-defaulted."""
+import ast
+import inspect
+import json
+import os
+
+import pytest
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_signatures.json")))
+
+
+def _ours(qualname):
+    mod, name = qualname.split(".")
+    module = __import__(f"keypoint_moseq_b200.{mod}", fromlist=[name])
+    return getattr(module, name)
+
+
+@pytest.mark.parametrize("qualname", sorted(GOLD))
+def test_reference_call_signature_is_accepted(qualname):
+    ref = GOLD[qualname]
+    sig = inspect.signature(_ours(qualname))
+    params = list(sig.parameters.values())
+    names = [p.name for p in params]
+    has_varkw = any(p.kind is inspect.Parameter.VAR_KEYWORD for p in params)
+    last = -1
+    for rp in ref["params"]:
+        if ref["varargs"] and rp["name"] not in names:
+            continue                      # reference forwards *args to jax_moseq (init_model): keywords are checked below
+        assert rp["name"] in names, f"{qualname}: parameter `{rp['name']}` of the reference (line {ref['line']}) is missing"
+        idx = names.index(rp["name"])
+        if not ref["varargs"]:
+            assert idx > last, f"{qualname}: `{rp['name']}` is out of the reference's positional order"
+            last = idx
+        ours = params[idx]
+        if rp["default"] is None:
+            continue
+        assert ours.default is not inspect.Parameter.empty, f"{qualname}: `{rp['name']}` lost its default"
+        assert ours.default == ast.literal_eval(rp["default"]), (
+            f"{qualname}: default of `{rp['name']}` is {ours.default!r}, the reference has {rp['default']}")
+    if ref["varkw"]:
+        assert has_varkw, f"{qualname}: the reference swallows unknown keywords (**{ref['varkw']}), so must we"

@@ -270,3 +270,33 @@ def test_reindex_syllables_in_checkpoint(tmp_path):
     kio.reindex_syllables_in_checkpoint(path=path, index=perm)
     twice = kio.load_hdf5(path, "model_snapshots/7")
     np.testing.assert_array_equal(index[perm[twice["states"]["z"]]], model["states"]["z"])
+
+
+def test_format_data_reindexes_bodyparts_and_interpolates_missing_points():
+    """format_data (util.py:929-1089): keypoints selected / ordered by use_bodyparts, NaN points imputed by
+    linear interpolation in time with confidence 0 (+ pseudocount), everything else as before."""
+    from keypoint_moseq_b200.util import format_data, interpolate_keypoints, reindex_by_bodyparts
+    rng = np.random.default_rng(0)
+    T, parts = 50, ["nose", "ear", "tail", "paw"]
+    coords = {"a": rng.standard_normal((T, 4, 2)).cumsum(0), "b": rng.standard_normal((T - 7, 4, 2)).cumsum(0)}
+    conf = {k: rng.uniform(0.5, 1, v.shape[:2]) for k, v in coords.items()}
+    truth = coords["a"].copy()
+    coords["a"][10:13, 2] = np.nan                                     # tail missing for 3 frames
+    coords["a"][0, 0] = np.nan                                         # nose missing at the start
+    use = ["tail", "nose", "paw"]
+    data, (keys, bounds) = format_data(coords, conf, bodyparts=parts, use_bodyparts=use, added_noise_level=0.0,
+                                       seg_length=30, device="cpu")
+    Y, cf, mask = data["Y"].numpy(), data["conf"].numpy(), data["mask"].numpy()
+    assert Y.shape[2:] == (3, 2) and list(keys)[:2] == ["a", "a"]
+    # reindexing: column 0 is the tail, 1 the nose
+    np.testing.assert_allclose(Y[0, 5, 1], truth[5, 0])
+    np.testing.assert_allclose(Y[0, 5, 0], truth[5, 2])
+    # interpolation between frames 9 and 13 of the tail, confidence pseudocount only
+    for t, w in ((10, 0.25), (11, 0.5), (12, 0.75)):
+        np.testing.assert_allclose(Y[0, t, 0], (1 - w) * truth[9, 2] + w * truth[13, 2])
+        assert abs(cf[0, t, 0] - 1e-3) < 1e-12
+    np.testing.assert_allclose(Y[0, 0, 1], truth[1, 0])                # held from the first good frame
+    assert np.isfinite(Y).all() and mask.sum() == 50 + 20 + 43 + 13      # windows of 30 + 30 frames of look-ahead
+    out = interpolate_keypoints(np.full((4, 1, 2), np.nan), np.ones((4, 1), bool))
+    assert (out == 0).all()
+    assert reindex_by_bodyparts(np.arange(8.0).reshape(1, 4, 2), parts, ["paw"]).tolist() == [[[6.0, 7.0]]]
