@@ -17,7 +17,33 @@ import numpy as np
 from .synth import center_embedding
 
 __all__ = ["align_egocentric", "preprocess_for_pca", "fit_pca", "init_hyperparams", "init_params",
-           "noise_prior_from_confidence"]
+           "noise_prior_from_confidence", "default_config"]
+
+
+def default_config(**overrides):
+    """The modelling entries of the reference's `config.yml` with the defaults of `generate_config`
+    (/root/reference/keypoint_moseq/io.py:62-133): the four hyper-parameter groups, the error estimator and
+    the flags `format_data` / `fit_pca` / `init_model` read.  Use as `init_model(data, pca=pca,
+    **default_config())`; like `update_config`, an override matches a key at any nesting level."""
+    cfg = {
+        "error_estimator": {"slope": -0.5, "intercept": 0.25},
+        "obs_hypparams": {"sigmasq_0": 0.1, "sigmasq_C": 0.1, "nu_sigma": 1e5, "nu_s": 5},
+        "ar_hypparams": {"latent_dim": 10, "nlags": 3, "S_0_scale": 0.01, "K_0_scale": 10.0},
+        "trans_hypparams": {"num_states": 100, "gamma": 1e3, "alpha": 5.7, "kappa": 1e6},
+        "cen_hypparams": {"sigmasq_loc": 0.5},
+        "conf_pseudocount": 1e-3, "whiten": True, "fix_heading": False,
+        "added_noise_level": 0.1, "PCA_fitting_num_frames": 1000000, "conf_threshold": 0.5,
+    }
+    for key, val in overrides.items():
+        hit = False
+        if key in cfg:
+            cfg[key], hit = val, True
+        for group in cfg.values():
+            if isinstance(group, dict) and key in group:
+                group[key], hit = val, True
+        if not hit:
+            cfg[key] = val
+    return cfg
 
 
 def _np(a):

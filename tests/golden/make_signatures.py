@@ -27,5 +27,21 @@ for fname, names in WANT.items():
                 params.append({"name": x.arg, "default": None if d is None else ast.unparse(d), "required": d is None})
             out[f"{fname[:-3]}.{node.name}"] = {"params": params, "varargs": a.vararg.arg if a.vararg else None,
                                                 "varkw": a.kwarg.arg if a.kwarg else None, "line": node.lineno}
+# default hyper-parameters: the dict literals inside generate_config (io.py:46-169)
+tree = ast.parse(open(os.path.join(REF, "io.py")).read())
+gen = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "generate_config")
+defaults = {}
+for node in ast.walk(gen):
+    if isinstance(node, ast.Dict):
+        for k, v in zip(node.keys, node.values):
+            if isinstance(k, ast.Constant) and k.value in ("error_estimator", "obs_hypparams", "ar_hypparams",
+                                                           "trans_hypparams", "cen_hypparams"):
+                defaults[k.value] = ast.literal_eval(v)
+            if isinstance(k, ast.Constant) and k.value in ("conf_pseudocount", "whiten", "fix_heading",
+                                                           "added_noise_level", "PCA_fitting_num_frames",
+                                                           "conf_threshold") and isinstance(v, ast.Constant):
+                defaults[k.value] = v.value
+out["__generate_config_defaults__"] = defaults
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_signatures.json"), "w"), indent=1)
-print({k: len(v["params"]) for k, v in out.items()})
+print({k: len(v["params"]) for k, v in out.items() if "params" in v})
+print(defaults)

@@ -18,7 +18,7 @@ def _ours(qualname):
     return getattr(module, name)
 
 
-@pytest.mark.parametrize("qualname", sorted(GOLD))
+@pytest.mark.parametrize("qualname", sorted(k for k in GOLD if not k.startswith("__")))
 def test_reference_call_signature_is_accepted(qualname):
     ref = GOLD[qualname]
     sig = inspect.signature(_ours(qualname))
@@ -42,3 +42,15 @@ def test_reference_call_signature_is_accepted(qualname):
             f"{qualname}: default of `{rp['name']}` is {ours.default!r}, the reference has {rp['default']}")
     if ref["varkw"]:
         assert has_varkw, f"{qualname}: the reference swallows unknown keywords (**{ref['varkw']}), so must we"
+
+
+def test_default_config_matches_generate_config():
+    """The default hyper-parameters are the reference's (generate_config, io.py:62-133), value for value."""
+    from keypoint_moseq_b200.initialize import default_config
+    ref = GOLD["__generate_config_defaults__"]
+    cfg = default_config()
+    assert set(ref) <= set(cfg)
+    for key, val in ref.items():
+        assert cfg[key] == val, key
+    assert default_config(kappa=1e4, latent_dim=4)["trans_hypparams"]["kappa"] == 1e4
+    assert default_config(latent_dim=4)["ar_hypparams"]["latent_dim"] == 4
