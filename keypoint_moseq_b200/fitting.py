@@ -173,8 +173,8 @@ def init_model(data=None, states=None, params=None, hypparams=None, noise_prior=
         if missing:
             raise ValueError(f"init_model needs `hypparams` or the config entries {missing}")
         hypparams = initialize.init_hyperparams(trans_hypparams, ar_hypparams, obs_hypparams, cen_hypparams)
-    elif trans_hypparams is not None:
-        hypparams = dict(hypparams, trans_hypparams=dict(hypparams["trans_hypparams"], **trans_hypparams))
+    # (a model's own `hypparams` win over the config groups, as when apply_model re-initialises the states of a
+    # fitted model with `**config()` in the call, fitting.py:387-394)
     if params is None:
         if data is None:
             raise ValueError("init_model needs `data` to initialise parameters")
