@@ -183,3 +183,53 @@ def test_affine_recursion_chunks_and_centroid_scans_are_associative_maps():
     for t in range(hi + W - 1, hi - 1, -1):
         x = G[t] @ x + h[t]
     assert np.abs(x - xi[hi]).max() < 1e-5 * (1 + np.abs(xi[hi]).max())
+
+
+def test_refinement_passes_converge_and_the_boundary_check_certifies_them():
+    """Planned fallback for chains that do not forget within the warm-up: every chunk
+    restarts from the end state its predecessor produced in the previous pass.  The boundary discrepancy
+    contracts pass after pass, and once every chunk's start agrees component by component with its
+    predecessor's new end state the whole filter equals the sequential one to that tolerance."""
+    rng = np.random.default_rng(5)
+    K, T, Lc, W = 6, 360, 60, 4
+    pi, ll = _random_hmm(rng, K, T, sticky=0.97, sharp=0.6)          # sticky, weakly informative: slow forgetting
+    _, filt = orc.hmm_filter(pi, ll)
+    filt = filt[0]
+    C = T // Lc
+
+    def run(start, pred, stop, out):
+        for t in range(start, stop):
+            q = pred * np.exp(ll[0, t] - ll[0, t].max())
+            f = q / q.sum()
+            if t >= 0:
+                out[t] = f
+            pred = f @ pi
+        return pred                                                   # prediction handed to the next chunk
+
+    est = np.zeros((T, K))
+    ends = [None] * C
+    for c in range(C):                                                # pass 0: warm-up from the uniform prior
+        tmp = {}
+        start = max(c * Lc - W, 0)
+        ends[c] = run(start, np.full(K, 1.0 / K), (c + 1) * Lc, tmp)
+        for t in range(c * Lc, (c + 1) * Lc):
+            est[t] = tmp[t]
+    err0 = np.abs(est / filt - 1).max()
+    assert err0 > 1e-6                                                # the short warm-up is not enough here
+    passes = 0
+    while True:
+        passes += 1
+        starts = [np.full(K, 1.0 / K)] + [ends[c - 1] for c in range(1, C)]
+        new_ends = list(ends)
+        for c in range(1, C):
+            tmp = {}
+            new_ends[c] = run(c * Lc, starts[c], (c + 1) * Lc, tmp)
+            for t in range(c * Lc, (c + 1) * Lc):
+                est[t] = tmp[t]
+        # the check: the start every chunk used against its predecessor's end state of THIS pass
+        disc = max(np.abs(starts[c] / new_ends[c - 1] - 1).max() for c in range(1, C))
+        ends = new_ends
+        if disc <= 1e-12 or passes > C:
+            break
+    assert passes <= C                                                # at worst one chunk per pass (sequential)
+    assert np.abs(est / filt - 1).max() < 1e-10                       # certified by the boundary check alone
