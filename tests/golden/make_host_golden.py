@@ -1,0 +1,63 @@
+"""Golden vectors for the host helpers, produced by RUNNING the reference's own functions.
+
+`keypoint_moseq.util` cannot be imported here (it imports jax at module level), but the helpers below are
+pure NumPy: their source is cut out of /root/reference/keypoint_moseq/util.py with `ast` and executed in a
+namespace that holds NumPy and `textwrap.fill` only.  Writes tests/golden/reference_host_helpers.npz.
+Run in the build container: `python tests/golden/make_host_golden.py`."""
+import ast
+import os
+import warnings
+from textwrap import fill
+
+import numpy as np
+
+SRC = open("/root/reference/keypoint_moseq/util.py").read()
+WANT = ["_get_percent_padding", "_find_optimal_segment_length", "interpolate_along_axis", "interpolate_keypoints",
+        "reindex_by_bodyparts"]
+tree = ast.parse(SRC)
+ns = {"np": np, "fill": fill, "warnings": warnings}
+for node in tree.body:
+    if isinstance(node, ast.FunctionDef) and node.name in WANT:
+        exec(compile(ast.Module(body=[node], type_ignores=[]), "reference/util.py", "exec"), ns)
+
+rng = np.random.default_rng(0)
+out = {}
+# segment-length rule on a spread of cohorts
+cases = [np.array([36000] * 20), np.array([108000] * 50), np.array([54000] * 200), np.array([10000] * 4),
+         np.array([9500, 12000, 300, 40000]), np.array([17, 23, 8]), np.array([10003, 10001, 9999]),
+         rng.integers(50, 30000, size=12), rng.integers(5, 200, size=7), np.array([10004]), np.array([20006, 5])]
+lens, segs = [], []
+for c in cases:
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        segs.append(int(ns["_find_optimal_segment_length"](np.asarray(c))))
+    lens.append(np.asarray(c))
+out["seg_cases"] = np.array([len(c) for c in lens])
+out["seg_lengths_in"] = np.concatenate(lens)
+out["seg_lengths_out"] = np.array(segs)
+# small-parameter variants
+alt = [(np.array([1000, 1500, 700]), 400, 20, 4), (np.array([90, 35, 61]), 50, 10, 8), (np.array([64, 64, 65]), 64, 50, 4)]
+out["alt_in"] = np.concatenate([a[0] for a in alt])
+out["alt_cases"] = np.array([len(a[0]) for a in alt])
+out["alt_params"] = np.array([[a[1], a[2], a[3]] for a in alt])
+res = []
+for a in alt:
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res.append(int(ns["_find_optimal_segment_length"](a[0], a[1], a[2], a[3])))
+out["alt_out"] = np.array(res)
+# interpolation of missing keypoints
+coords = rng.standard_normal((40, 5, 3)).cumsum(0)
+outl = rng.uniform(size=(40, 5)) < 0.3
+outl[:, 4] = True                       # a keypoint that is never observed
+outl[:3, 0] = True                      # missing at the start
+outl[-4:, 1] = True                     # missing at the end
+out["interp_coords"], out["interp_outliers"] = coords, outl
+out["interp_out"] = ns["interpolate_keypoints"](coords, outl)
+# bodypart reindexing
+parts = ["a", "b", "c", "d", "e"]
+use = ["d", "a", "e"]
+out["reindex_in"] = coords
+out["reindex_out"] = ns["reindex_by_bodyparts"](coords, parts, use)
+np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host_helpers.npz"), **out)
+print("segment lengths:", segs, res)

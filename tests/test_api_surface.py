@@ -54,3 +54,32 @@ def test_default_config_matches_generate_config():
         assert cfg[key] == val, key
     assert default_config(kappa=1e4, latent_dim=4)["trans_hypparams"]["kappa"] == 1e4
     assert default_config(latent_dim=4)["ar_hypparams"]["latent_dim"] == 4
+
+
+def test_host_helpers_match_the_reference_functions():
+    """tests/golden/reference_host_helpers.npz was produced by executing the reference's own pure-NumPy
+    helpers (tests/golden/make_host_golden.py): the segment-length rule, keypoint interpolation and
+    bodypart reindexing here must return exactly what the reference returns."""
+    import warnings
+
+    import numpy as np
+
+    from keypoint_moseq_b200 import util
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_host_helpers.npz"))
+    pos = 0
+    for n_seq, want in zip(g["seg_cases"], g["seg_lengths_out"]):
+        lens = g["seg_lengths_in"][pos:pos + n_seq]
+        pos += n_seq
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert util.find_optimal_segment_length(lens) == want, lens
+    pos = 0
+    for n_seq, (mx, pad, frag), want in zip(g["alt_cases"], g["alt_params"], g["alt_out"]):
+        lens = g["alt_in"][pos:pos + n_seq]
+        pos += n_seq
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert util.find_optimal_segment_length(lens, int(mx), int(pad), int(frag)) == want, lens
+    np.testing.assert_array_equal(util.interpolate_keypoints(g["interp_coords"], g["interp_outliers"]), g["interp_out"])
+    np.testing.assert_array_equal(util.reindex_by_bodyparts(g["reindex_in"], list("abcde"), ["d", "a", "e"]),
+                                  g["reindex_out"])
