@@ -59,5 +59,35 @@ parts = ["a", "b", "c", "d", "e"]
 use = ["d", "a", "e"]
 out["reindex_in"] = coords
 out["reindex_out"] = ns["reindex_by_bodyparts"](coords, parts, use)
+# update_hypparams (fitting.py:562-612) is pure Python as well
+import contextlib
+import io
+import json
+fsrc = open("/root/reference/keypoint_moseq/fitting.py").read()
+fns = {"np": np, "fill": fill, "warnings": warnings}
+for node in ast.parse(fsrc).body:
+    if isinstance(node, ast.FunctionDef) and node.name == "update_hypparams":
+        exec(compile(ast.Module(body=[node], type_ignores=[]), "reference/fitting.py", "exec"), fns)
+
+
+def _hyp():
+    return {"hypparams": {"trans_hypparams": {"num_states": 100, "gamma": 1e3, "alpha": 5.7, "kappa": 1e6},
+                          "ar_hypparams": {"latent_dim": 10, "nlags": 3, "S_0_scale": 0.01, "K_0_scale": 10.0,
+                                           "S_0": np.eye(2), "nu_0": 12},
+                          "obs_hypparams": {"sigmasq_0": 0.1, "nu_s": 5},
+                          "cen_hypparams": {"sigmasq_loc": 0.5}}}
+
+
+calls = [dict(kappa=1e4), dict(kappa=7, nu_s=6.9, sigmasq_loc=2), dict(S_0=3.0, alpha=1), dict(not_a_key=1.0, gamma=5)]
+records = []
+for kw in calls:
+    with warnings.catch_warnings(record=True) as w, contextlib.redirect_stdout(io.StringIO()) as so:
+        warnings.simplefilter("always")
+        res = fns["update_hypparams"](_hyp(), **kw)["hypparams"]
+    flat = {f"{g}/{k}": (v if np.isscalar(v) else np.asarray(v).tolist()) for g, d in res.items() for k, v in d.items()}
+    types = {f"{g}/{k}": type(v).__name__ for g, d in res.items() for k, v in d.items()}
+    records.append({"kwargs": kw, "result": flat, "types": types, "n_warnings": len(w), "printed": bool(so.getvalue())})
+json.dump(records, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_update_hypparams.json"), "w"),
+          indent=1)
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host_helpers.npz"), **out)
-print("segment lengths:", segs, res)
+print("segment lengths:", segs, "update_hypparams cases:", len(records))

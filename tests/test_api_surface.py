@@ -83,3 +83,33 @@ def test_host_helpers_match_the_reference_functions():
     np.testing.assert_array_equal(util.interpolate_keypoints(g["interp_coords"], g["interp_outliers"]), g["interp_out"])
     np.testing.assert_array_equal(util.reindex_by_bodyparts(g["reindex_in"], list("abcde"), ["d", "a", "e"]),
                                   g["reindex_out"])
+
+
+def test_update_hypparams_matches_the_reference_function():
+    """Inputs and outputs of the reference's own update_hypparams (executed by make_host_golden.py): same
+    values, same types after the cast, same number of warnings, same refusal of non-scalar entries."""
+    import contextlib
+    import io
+    import warnings
+
+    import numpy as np
+
+    from keypoint_moseq_b200.fitting import update_hypparams
+    recs = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                       "reference_update_hypparams.json")))
+    for rec in recs:
+        model = {"hypparams": {"trans_hypparams": {"num_states": 100, "gamma": 1e3, "alpha": 5.7, "kappa": 1e6},
+                               "ar_hypparams": {"latent_dim": 10, "nlags": 3, "S_0_scale": 0.01, "K_0_scale": 10.0,
+                                                "S_0": np.eye(2), "nu_0": 12},
+                               "obs_hypparams": {"sigmasq_0": 0.1, "nu_s": 5},
+                               "cen_hypparams": {"sigmasq_loc": 0.5}}}
+        with warnings.catch_warnings(record=True) as w, contextlib.redirect_stdout(io.StringIO()) as so:
+            warnings.simplefilter("always")
+            out = update_hypparams(model, **rec["kwargs"])["hypparams"]
+        for key, want in rec["result"].items():
+            g_, k_ = key.split("/")
+            got = out[g_][k_]
+            assert type(got).__name__ == rec["types"][key], key
+            assert (np.asarray(got).tolist() if not np.isscalar(got) else got) == want, key
+        assert len(w) == rec["n_warnings"], rec["kwargs"]
+        assert bool(so.getvalue()) == rec["printed"], rec["kwargs"]
