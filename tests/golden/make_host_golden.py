@@ -89,5 +89,34 @@ for kw in calls:
     records.append({"kwargs": kw, "result": flat, "types": types, "n_warnings": len(w), "printed": bool(so.getvalue())})
 json.dump(records, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_update_hypparams.json"), "w"),
           indent=1)
+# format_data end to end (util.py:929-1089), executed from the reference with two substitutions it cannot do
+# without: jax_moseq.utils.batch (un-vendored) -> this repo's util.batch, jax.device_put -> identity.
+import sys
+import types
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+from keypoint_moseq_b200.util import batch as our_batch  # noqa: E402
+ns["batch"] = our_batch
+ns["jax"] = types.SimpleNamespace(device_put=lambda tree: tree)
+for node in tree.body:
+    if isinstance(node, ast.FunctionDef) and node.name == "format_data":
+        exec(compile(ast.Module(body=[node], type_ignores=[]), "reference/util.py", "exec"), ns)
+frng = np.random.default_rng(7)
+fcoords = {f"rec{i}": frng.standard_normal((n_, 6, 2)).cumsum(0) for i, n_ in enumerate((130, 95, 210))}
+fconf = {k_: frng.uniform(-0.1, 1.0, v_.shape[:2]) for k_, v_ in fcoords.items()}
+fcoords["rec1"][20:25, 3] = np.nan
+fcoords["rec2"][0:2, 0] = np.nan
+fparts = ["p0", "p1", "p2", "p3", "p4", "p5"]
+fuse = ["p5", "p0", "p3", "p1"]
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    fdata, (fkeys, fbounds) = ns["format_data"]({k_: v_.copy() for k_, v_ in fcoords.items()},
+                                                 {k_: v_.copy() for k_, v_ in fconf.items()}, bodyparts=fparts,
+                                                 use_bodyparts=fuse, seg_length=80)
+out["fd_lengths"] = np.array([130, 95, 210])
+out["fd_coords"] = np.concatenate([fcoords[f"rec{i}"] for i in range(3)])
+out["fd_conf"] = np.concatenate([fconf[f"rec{i}"] for i in range(3)])
+out["fd_Y"], out["fd_conf_out"], out["fd_mask"] = np.asarray(fdata["Y"]), np.asarray(fdata["conf"]), np.asarray(fdata["mask"])
+out["fd_keys"] = np.array(list(fkeys))
+out["fd_bounds"] = np.asarray(fbounds)
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host_helpers.npz"), **out)
 print("segment lengths:", segs, "update_hypparams cases:", len(records))

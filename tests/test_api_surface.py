@@ -113,3 +113,28 @@ def test_update_hypparams_matches_the_reference_function():
             assert (np.asarray(got).tolist() if not np.isscalar(got) else got) == want, key
         assert len(w) == rec["n_warnings"], rec["kwargs"]
         assert bool(so.getvalue()) == rec["printed"], rec["kwargs"]
+
+
+def test_format_data_matches_the_reference_function():
+    """The reference's own format_data, executed with this repo's `batch` in place of the un-vendored
+    jax_moseq one and an identity `device_put` (make_host_golden.py), against util.format_data: reindexing,
+    interpolation, confidence clamp + pseudocount and the Uniform(+-0.1) noise of default_rng(42) agree
+    to the last bit."""
+    import warnings
+
+    import numpy as np
+
+    from keypoint_moseq_b200.util import format_data
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_host_helpers.npz"))
+    edges = np.concatenate([[0], np.cumsum(g["fd_lengths"])])
+    coords = {f"rec{i}": g["fd_coords"][edges[i]:edges[i + 1]].copy() for i in range(3)}
+    conf = {f"rec{i}": g["fd_conf"][edges[i]:edges[i + 1]].copy() for i in range(3)}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        data, (keys, bounds) = format_data(coords, conf, bodyparts=["p0", "p1", "p2", "p3", "p4", "p5"],
+                                           use_bodyparts=["p5", "p0", "p3", "p1"], seg_length=80, device="cpu")
+    np.testing.assert_array_equal(data["Y"].numpy(), g["fd_Y"])
+    np.testing.assert_array_equal(data["conf"].numpy(), g["fd_conf_out"])
+    np.testing.assert_array_equal(data["mask"].numpy(), g["fd_mask"])
+    assert list(keys) == list(g["fd_keys"])
+    np.testing.assert_array_equal(np.asarray(bounds), g["fd_bounds"])
