@@ -118,5 +118,25 @@ out["fd_conf"] = np.concatenate([fconf[f"rec{i}"] for i in range(3)])
 out["fd_Y"], out["fd_conf_out"], out["fd_mask"] = np.asarray(fdata["Y"]), np.asarray(fdata["conf"]), np.asarray(fdata["mask"])
 out["fd_keys"] = np.array(list(fkeys))
 out["fd_bounds"] = np.asarray(fbounds)
+# extract_results (io.py:622-727) without saving, executed from the reference with this repo's `unbatch` in
+# place of the un-vendored jax_moseq one and an identity `device_get`
+from keypoint_moseq_b200.util import unbatch as our_unbatch  # noqa: E402
+ins = {"np": np, "os": os, "fill": fill, "unbatch": our_unbatch, "jax": types.SimpleNamespace(device_get=lambda t: t)}
+for node in ast.parse(open("/root/reference/keypoint_moseq/io.py").read()).body:
+    if isinstance(node, ast.FunctionDef) and node.name == "extract_results":
+        exec(compile(ast.Module(body=[node], type_ignores=[]), "reference/io.py", "exec"), ins)
+erng = np.random.default_rng(11)
+ecoords = {"m1": np.zeros((130, 1)), "m2": np.zeros((75, 1))}
+_, emask, (ekeys, ebounds) = our_batch(ecoords, seg_length=50, keys=["m1", "m2"])
+eN, eT = emask.shape
+estates = {"x": erng.standard_normal((eN, eT, 3)), "v": erng.standard_normal((eN, eT, 2)), "h": erng.standard_normal((eN, eT)),
+           "z": erng.integers(0, 7, size=(eN, eT - 2))}
+eres = ins["extract_results"]({"states": estates}, (ekeys, ebounds), save_results=False)
+for name_, v_ in estates.items():
+    out["er_" + name_] = v_
+out["er_keys"], out["er_bounds"] = np.array(list(ekeys)), np.asarray(ebounds)
+for rec_, d_ in eres.items():
+    for k_, v_ in d_.items():
+        out[f"er_out/{rec_}/{k_}"] = np.asarray(v_)
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host_helpers.npz"), **out)
 print("segment lengths:", segs, "update_hypparams cases:", len(records))

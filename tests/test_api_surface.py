@@ -138,3 +138,20 @@ def test_format_data_matches_the_reference_function():
     np.testing.assert_array_equal(data["mask"].numpy(), g["fd_mask"])
     assert list(keys) == list(g["fd_keys"])
     np.testing.assert_array_equal(np.asarray(bounds), g["fd_bounds"])
+
+
+def test_extract_results_matches_the_reference_function():
+    """The reference's own extract_results (run by make_host_golden.py with this repo's `unbatch` substituted
+    for jax_moseq's): syllables left-padded by repeating the first label nlags times, per-recording
+    stitching of latent state, centroid and heading."""
+    import numpy as np
+
+    from keypoint_moseq_b200.io import extract_results
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_host_helpers.npz"))
+    model = {"states": {k: g["er_" + k] for k in ("x", "v", "h", "z")}}
+    res = extract_results(model, (list(g["er_keys"]), g["er_bounds"]), save_results=False)
+    names = sorted({k.split("/")[1] for k in g.files if k.startswith("er_out/")})
+    assert sorted(res) == names
+    for rec in names:
+        for field in ("syllable", "latent_state", "centroid", "heading"):
+            np.testing.assert_array_equal(np.asarray(res[rec][field]), g[f"er_out/{rec}/{field}"])
