@@ -138,5 +138,61 @@ out["er_keys"], out["er_bounds"] = np.array(list(ekeys)), np.asarray(ebounds)
 for rec_, d_ in eres.items():
     for k_, v_ in d_.items():
         out[f"er_out/{rec_}/{k_}"] = np.asarray(v_)
+# fit_model's loop control (fitting.py:109-287 with _wrapped_resample :23-44), executed from the reference with
+# stubs for everything below the boundary: which iterations are checkpointed, how many sweeps run, which model
+# comes back when a sweep produces NaNs
+import tempfile
+ftree = ast.parse(fsrc)
+saves = []
+
+
+class _Bar:
+    def __init__(self, it):
+        self.it = it
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def __iter__(self):
+        return iter(self.it)
+
+    def close(self):
+        pass
+
+
+def _stub_resample(data, count=0, nan_at=None, **kw):
+    return {"count": count + 1, "nan_at": nan_at}
+
+
+fit_ns = {"np": np, "fill": fill, "warnings": warnings, "os": os, "datetime": __import__("datetime").datetime,
+          "save_hdf5": lambda path, d, datapath=None, **kw: saves.append(datapath or "init"),
+          "_set_parallel_flag": lambda x: x, "device_put_as_scalar": lambda m: m,
+          "keypoint_slds": types.SimpleNamespace(resample_model=_stub_resample),
+          "allo_keypoint_slds": types.SimpleNamespace(resample_model=_stub_resample),
+          "tqdm": types.SimpleNamespace(trange=lambda a, b, **kw: _Bar(range(a, b))),
+          "check_for_nans": lambda m: (m["nan_at"] is not None and m["count"] >= m["nan_at"], [], ["stub"]),
+          "plot_progress": lambda *a, **k: None}
+for node in ftree.body:
+    if (isinstance(node, ast.ClassDef) and node.name == "StopResampling") or \
+            (isinstance(node, ast.FunctionDef) and node.name in ("_wrapped_resample", "fit_model")):
+        exec(compile(ast.Module(body=[node], type_ignores=[]), "reference/fitting.py", "exec"), fit_ns)
+fit_cases = [dict(num_iters=10, start_iter=0, save_every_n_iters=3), dict(num_iters=10, start_iter=0, save_every_n_iters=-1),
+             dict(num_iters=10, start_iter=0, save_every_n_iters=None), dict(num_iters=12, start_iter=5, save_every_n_iters=5),
+             dict(num_iters=10, start_iter=0, save_every_n_iters=4, nan_at=7), dict(num_iters=3, start_iter=0, save_every_n_iters=25),
+             dict(num_iters=9, start_iter=0, save_every_n_iters=2, nan_at=1)]
+fit_records = []
+for case in fit_cases:
+    saves.clear()
+    kw = dict(case)
+    nan_at = kw.pop("nan_at", None)
+    with tempfile.TemporaryDirectory() as tmp, warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        model, name = fit_ns["fit_model"]({"count": 0, "nan_at": nan_at}, {}, ([], []), tmp, "m",
+                                          generate_progress_plots=False, **kw)
+    fit_records.append({"case": case, "saves": list(saves), "returned_count": model["count"]})
+json.dump(fit_records, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_fit_loop.json"), "w"), indent=1)
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host_helpers.npz"), **out)
 print("segment lengths:", segs, "update_hypparams cases:", len(records))

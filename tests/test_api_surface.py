@@ -155,3 +155,38 @@ def test_extract_results_matches_the_reference_function():
     for rec in names:
         for field in ("syllable", "latent_state", "centroid", "heading"):
             np.testing.assert_array_equal(np.asarray(res[rec][field]), g[f"er_out/{rec}/{field}"])
+
+
+def test_fit_model_loop_matches_the_reference_loop(tmp_path, monkeypatch):
+    """fit_model's control flow against the reference's own loop (fit_model + _wrapped_resample executed by
+    make_host_golden.py with stubs below the boundary): the same snapshots are written, and after a NaN
+    sweep the model from before it comes back - although the NaN check here trails the sweeps by
+    NAN_CHECK_LAG and may let a few extra sweeps run, it never lets an unchecked sweep be saved or returned."""
+    from keypoint_moseq_b200 import fitting
+    recs = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_fit_loop.json")))
+    saves = []
+
+    def stub_resample(data, count=0, nan_at=None, **kw):
+        import numpy as np
+        new = count + 1
+        bad = nan_at is not None and new >= nan_at
+        return {"count": new, "nan_at": nan_at, "x": np.array([float("nan") if bad else 0.0])}
+
+    monkeypatch.setattr(fitting.gibbs, "resample_model", stub_resample)
+    monkeypatch.setattr(fitting.gibbs, "to_device_data", lambda d, *a, **k: d)
+    monkeypatch.setattr(fitting.gibbs, "to_device_model", lambda m, *a, **k: m)
+    monkeypatch.setattr(fitting, "_host_model", lambda m: m)
+    monkeypatch.setattr(fitting, "to_numpy_tree", lambda t: t)
+    monkeypatch.setattr(fitting, "save_hdf5", lambda path, d, datapath=None, **kw: saves.append(datapath or "init"))
+    import warnings
+    for i, rec in enumerate(recs):
+        saves.clear()
+        kw = dict(rec["case"])
+        nan_at = kw.pop("nan_at", None)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model, name = fitting.fit_model({"count": 0, "nan_at": nan_at}, {}, ([], []), str(tmp_path / f"p{i}"), "m",
+                                            generate_progress_plots=False, **kw)
+        assert name == "m"
+        assert saves == rec["saves"], rec["case"]
+        assert model["count"] == rec["returned_count"], rec["case"]
