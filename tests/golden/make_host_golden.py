@@ -194,5 +194,39 @@ for case in fit_cases:
                                           generate_progress_plots=False, **kw)
     fit_records.append({"case": case, "saves": list(saves), "returned_count": model["count"]})
 json.dump(fit_records, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_fit_loop.json"), "w"), indent=1)
+# apply_model's control flow (fitting.py:290-425), same technique
+calls = []
+
+
+def _stub_resample2(data, count=0, **kw):
+    calls.append({k_: v_ for k_, v_ in sorted(kw.items()) if k_ not in ("tag",)})
+    return {"count": count + 1, "tag": kw.get("tag", None) or "m"}
+
+
+app_ns = dict(fit_ns)
+app_ns.update({"jax": types.SimpleNamespace(device_put=lambda t: t),
+               "init_model": lambda **kw: {"count": 0, "tag": "init:" + ",".join(sorted(kw))},
+               "keypoint_slds": types.SimpleNamespace(resample_model=_stub_resample2),
+               "allo_keypoint_slds": types.SimpleNamespace(resample_model=_stub_resample2),
+               "tqdm": types.SimpleNamespace(trange=lambda n, **kw: _Bar(range(n))),
+               "check_for_nans": lambda m: (False, [], []),
+               "extract_results": lambda model, metadata, project_dir, model_name, save_results, results_path, overwrite=False:
+                   {"count": model["count"], "save_results": save_results, "results_path": results_path, "overwrite": overwrite}})
+for node in ftree.body:
+    if isinstance(node, ast.FunctionDef) and node.name in ("_wrapped_resample", "apply_model"):
+        exec(compile(ast.Module(body=[node], type_ignores=[]), "reference/fitting.py", "exec"), app_ns)
+app_cases = [dict(num_iters=7), dict(num_iters=3, ar_only=True, save_results=False, return_model=True),
+             dict(num_iters=2, results_path="/x/y.h5", overwrite=True, verbose=True)]
+app_records = []
+for case in app_cases:
+    calls.clear()
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = app_ns["apply_model"]({"seed": 1, "params": 2, "hypparams": 3}, {}, ([], []), "/proj", "name", **case)
+    model_back = None
+    if isinstance(res, tuple):
+        res, model_back = res
+    app_records.append({"case": case, "sweeps": len(calls), "kwargs_per_sweep": calls[0], "results": res,
+                        "model_count": None if model_back is None else model_back["count"]})
+json.dump(app_records, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_apply_loop.json"), "w"), indent=1)
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host_helpers.npz"), **out)
 print("segment lengths:", segs, "update_hypparams cases:", len(records))

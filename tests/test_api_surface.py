@@ -190,3 +190,40 @@ def test_fit_model_loop_matches_the_reference_loop(tmp_path, monkeypatch):
         assert name == "m"
         assert saves == rec["saves"], rec["case"]
         assert model["count"] == rec["returned_count"], rec["case"]
+
+
+def test_apply_model_loop_matches_the_reference_loop(monkeypatch):
+    """apply_model's control flow against the reference's own (executed with stubs by make_host_golden.py):
+    the states are re-initialised, exactly num_iters states-only sweeps run with the reference's keywords
+    (no jitter), results are extracted with the reference's path / overwrite handling."""
+    from keypoint_moseq_b200 import fitting
+    recs = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_apply_loop.json")))
+    calls = []
+
+    def stub_resample(data, count=0, **kw):
+        calls.append(kw)
+        return {"count": count + 1}
+
+    monkeypatch.setattr(fitting.gibbs, "resample_model", stub_resample)
+    monkeypatch.setattr(fitting.gibbs, "to_device_data", lambda d, *a, **k: d)
+    monkeypatch.setattr(fitting.gibbs, "to_device_model", lambda m, *a, **k: m)
+    monkeypatch.setattr(fitting, "init_model", lambda **kw: {"count": 0})
+    monkeypatch.setattr(fitting, "check_for_nans", lambda m: (False, [], []))
+    monkeypatch.setattr(fitting, "extract_results",
+                        lambda model, metadata, project_dir, model_name, save_results, results_path, overwrite=False:
+                        {"count": model["count"], "save_results": save_results, "results_path": results_path,
+                         "overwrite": overwrite})
+    for rec in recs:
+        calls.clear()
+        res = fitting.apply_model({"seed": 1, "params": 2, "hypparams": 3}, {}, ([], []), "/proj", "name", **rec["case"])
+        back = None
+        if isinstance(res, tuple):
+            res, back = res
+        assert len(calls) == rec["sweeps"]
+        for key, val in rec["kwargs_per_sweep"].items():
+            if key == "parallel_message_passing":
+                continue                   # normalised to a bool here: the backward pass is always time-parallel
+            assert calls[0][key] == val, key
+        assert "jitter" not in calls[0]
+        assert res == rec["results"], rec["case"]
+        assert (None if back is None else back["count"]) == rec["model_count"]
