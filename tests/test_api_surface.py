@@ -227,3 +227,123 @@ def test_apply_model_loop_matches_the_reference_loop(monkeypatch):
         assert "jitter" not in calls[0]
         assert res == rec["results"], rec["case"]
         assert (None if back is None else back["count"]) == rec["model_count"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# HDF5 tree layout: our writer against the reference's `_savetree_hdf5`, each reader on the other's tree
+# ---------------------------------------------------------------------------------------------------
+def _io_golden():
+    here = os.path.dirname(os.path.abspath(__file__))
+    return json.load(open(os.path.join(here, "golden", "reference_hdf5_layout.json")))
+
+
+def _with_fake_h5py(monkeypatch):
+    import fake_h5py
+    from keypoint_moseq_b200 import io as kio
+    fake_h5py.reset()
+    monkeypatch.setattr(kio, "h5py", fake_h5py)
+    monkeypatch.setattr(kio, "HAVE_H5PY", True)
+    return fake_h5py, kio
+
+
+def _untag(t):
+    import numpy as np
+    (kind, val), = [(k, v) for k, v in t.items() if k not in ("dtype", "shape")]
+    if kind == "dict":
+        return {k: _untag(v) for k, v in val}
+    if kind == "list":
+        return [_untag(v) for v in val]
+    if kind == "tuple":
+        return tuple(_untag(v) for v in val)
+    if kind == "ndarray":
+        dt = str if t["dtype"] == "U" else np.dtype(t["dtype"])
+        return np.array(val, dtype=dt).reshape(t["shape"])
+    return val
+
+
+def _same_tree(a, b, path=""):
+    import numpy as np
+    assert type(a) is type(b) or (isinstance(a, (int, float, bool, np.generic)) and isinstance(b, (int, float, bool, np.generic))), (path, type(a), type(b))
+    if isinstance(a, dict):
+        assert list(a.keys()) == list(b.keys()), path
+        for k in a:
+            _same_tree(a[k], b[k], f"{path}/{k}")
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _same_tree(x, y, f"{path}[{i}]")
+    elif isinstance(a, np.ndarray):
+        assert a.shape == b.shape and a.dtype.kind == b.dtype.kind, (path, a.dtype, b.dtype)
+        if a.dtype.kind != "U":
+            assert a.dtype == b.dtype, (path, a.dtype, b.dtype)
+        assert np.array_equal(a, b), path
+    else:
+        assert a == b, (path, a, b)
+
+
+@pytest.mark.parametrize("case", ["checkpoint", "misc", "results", "long_list"])
+def test_hdf5_writer_produces_the_reference_layout(case, tmp_path, monkeypatch):
+    """Same groups, `type` attributes, `arr{k}` names, dataset dtypes / shapes / values and string encoding
+    as the reference's `save_hdf5` (io.py:1297-1400) - compared through an in-memory h5py."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_io_golden
+    fake, kio = _with_fake_h5py(monkeypatch)
+    gold = _io_golden()[case]
+    tree = make_io_golden.cases()[case] if case != "long_list" else {"seq": [int(i) for i in range(12)]}
+    path = str(tmp_path / "f.h5")
+    kio.save_hdf5(path, tree)
+    assert fake.File(path, "r").describe() == gold["stored"]
+    if case == "checkpoint":
+        snap = tree["model_snapshots"]["0"]
+        kio.save_hdf5(path, snap, "model_snapshots/25", exist_ok=True)
+        assert fake.File(path, "r").describe() == gold["stored_after_snapshot"]
+        for label, kw in [("exists", {}), ("no_overwrite", {"exist_ok": True}),
+                          ("overwrite", {"exist_ok": True, "overwrite": True})]:
+            if gold["errors"][label]:
+                with pytest.raises(AssertionError):
+                    kio.save_hdf5(path, snap, "model_snapshots/25", **kw)
+            else:
+                kio.save_hdf5(path, snap, "model_snapshots/25", **kw)
+        assert fake.File(path, "r").describe() == gold["stored_after_snapshot"]
+
+
+@pytest.mark.parametrize("case", ["checkpoint", "misc", "results"])
+def test_hdf5_reader_loads_a_reference_written_tree(case, tmp_path, monkeypatch):
+    """A tree stored by the reference's writer (the fixture) loads to what the reference's own loader
+    returns: container types, member order, scalars as Python scalars, strings decoded."""
+    fake, kio = _with_fake_h5py(monkeypatch)
+    gold = _io_golden()[case]
+    path = str(tmp_path / "f.h5")
+    fake.from_description(path, gold.get("stored_after_snapshot", gold["stored"]))
+    if case == "checkpoint":
+        _same_tree(kio.load_hdf5(path, "model_snapshots/25"), _untag(gold["loaded_datapath"]))
+        loaded = kio.load_hdf5(path)
+        del loaded["model_snapshots"]["25"]
+        _same_tree(loaded, _untag(gold["loaded"]))
+        assert kio._list_children(path, "model_snapshots") == ["0", "25"]
+    else:
+        _same_tree(kio.load_hdf5(path), _untag(gold["loaded"]))
+
+
+def test_hdf5_reader_keeps_list_order_where_the_reference_scrambles_it(tmp_path, monkeypatch):
+    """Documented divergence: h5py lists group members alphabetically, so the reference's loader returns a
+    12-element list as arr0, arr1, arr10, arr11, arr2 ...; ours orders by the index in the name."""
+    fake, kio = _with_fake_h5py(monkeypatch)
+    gold = _io_golden()["long_list"]
+    path = str(tmp_path / "f.h5")
+    fake.from_description(path, gold["stored"])
+    assert _untag(gold["loaded"])["seq"] == [0, 1, 10, 11, 2, 3, 4, 5, 6, 7, 8, 9]
+    assert kio.load_hdf5(path)["seq"] == list(range(12))
+
+
+def test_hdf5_writer_accepts_what_the_reference_refuses_only_for_numpy_scalars(tmp_path, monkeypatch):
+    fake, kio = _with_fake_h5py(monkeypatch)
+    gold = _io_golden()["refused"]
+    import numpy as np
+    assert gold == {"float32_scalar": "ValueError", "none": "ValueError", "set": "ValueError"}
+    kio.save_hdf5(str(tmp_path / "a.h5"), {"a": np.float32(1.0)})          # superset: NumPy scalars are leaves
+    for bad in (None, {1, 2}):
+        fake.reset()
+        with pytest.raises(ValueError):
+            kio.save_hdf5(str(tmp_path / "b.h5"), {"a": bad})
