@@ -20,8 +20,26 @@ sys.path.insert(0, os.path.dirname(HERE))
 import fake_h5py  # noqa: E402
 
 SRC = open("/root/reference/keypoint_moseq/io.py").read()
-WANT = ["save_hdf5", "load_hdf5", "_savetree_hdf5", "_loadtree_hdf5"]
-ns = {"np": np, "os": os, "h5py": fake_h5py, "jax": types.SimpleNamespace(device_get=lambda x: x)}
+WANT = ["save_hdf5", "load_hdf5", "_savetree_hdf5", "_loadtree_hdf5", "_get_path", "load_checkpoint",
+        "reindex_syllables_in_checkpoint"]
+
+
+def run_frequencies(z, mask, num_states, runlength=True):
+    """Stand-in for jax_moseq.utils.get_frequencies (not vendored), restating its published rule: the masked
+    frames of all rows are concatenated, then run onsets (or frames) are counted per label.  Only reached
+    by the index=None branch, whose result is recorded for the control flow, not as a pin of this function."""
+    z = np.asarray(z)
+    flat = z[np.asarray(mask)[:, -z.shape[1]:] > 0].astype(int)
+    if runlength:
+        flat = flat[np.pad(np.diff(flat).nonzero()[0] + 1, (1, 0))]
+    counts = np.bincount(flat, minlength=num_states)
+    return counts / counts.sum()
+
+
+import tqdm  # noqa: E402
+from textwrap import fill  # noqa: E402
+ns = {"np": np, "os": os, "h5py": fake_h5py, "jax": types.SimpleNamespace(device_get=lambda x: x), "tqdm": tqdm,
+      "fill": fill, "get_frequencies": run_frequencies}
 for node in ast.parse(SRC).body:
     if isinstance(node, ast.FunctionDef) and node.name in WANT:
         exec(compile(ast.Module(body=[node], type_ignores=[]), "reference/io.py", "exec"), ns)
@@ -48,6 +66,28 @@ def cases():
                          "centroid": rng.standard_normal((5, 2)), "heading": rng.standard_normal(5)}}
     return {"checkpoint": {"model_snapshots": {"0": model}, "metadata": metadata, "data": data},
             "misc": misc, "results": results}
+
+
+def reindex_checkpoint():
+    """A checkpoint with the state-indexed parameters `reindex_syllables_in_checkpoint` permutes."""
+    rng = np.random.default_rng(1)
+    K, d, n = 4, 2, 5
+
+    def snap(seed):
+        r = np.random.default_rng(seed)
+        z = np.repeat(r.integers(0, K, (2, 6)), 3, axis=1)                 # runs of three frames
+        return {"seed": np.array([0, seed], dtype=np.uint32),
+                "states": {"z": z, "x": r.standard_normal((2, 20, d))},
+                "params": {"betas": r.dirichlet(np.ones(K)), "pi": r.dirichlet(np.ones(K), K),
+                           "Ab": r.standard_normal((K, d, n)), "Q": r.standard_normal((K, d, d)),
+                           "sigmasq": np.ones(3)},
+                "hypparams": {"trans_hypparams": {"num_states": K}}, "noise_prior": 1.0}
+
+    mask = np.ones((2, 20))
+    mask[1, 14:] = 0
+    return {"model_snapshots": {"0": snap(3), "10": snap(4), "5": snap(5)},
+            "metadata": (["a", "b"], np.array([[0, 20], [0, 14]])),
+            "data": {"Y": rng.standard_normal((2, 20, 3, 2)), "mask": mask}}
 
 
 def tag(tree):
@@ -95,6 +135,25 @@ if __name__ == "__main__":
                     errors[label] = "AssertionError"
             entry["errors"] = errors
         out[name] = entry
+    # load_checkpoint / reindex_syllables_in_checkpoint (io.py:492-619) on a three-snapshot checkpoint
+    entry = {}
+    for label, kw in [("explicit", {"index": np.array([2, 0, 3, 1])}), ("by_runs", {}), ("by_frames", {"runlength": False})]:
+        fake_h5py.reset()
+        path = os.path.join(tmp, "re_" + label + ".h5")
+        ns["save_hdf5"](path, reindex_checkpoint())
+        if label == "explicit":
+            model, data, metadata, it = ns["load_checkpoint"](path=path)
+            entry["latest"] = {"iteration": int(it), "model": tag(model), "metadata": tag(metadata), "data": tag(data)}
+            model, _, _, it = ns["load_checkpoint"](path=path, iteration=5)
+            entry["at_5"] = {"iteration": int(it), "seed": tag(model["seed"])}
+            try:
+                ns["load_checkpoint"](path=path, iteration=7)
+                entry["missing"] = None
+            except AssertionError:
+                entry["missing"] = "AssertionError"
+        index = ns["reindex_syllables_in_checkpoint"](path=path, **kw)
+        entry[label] = {"index": np.asarray(index).tolist(), "stored": fake_h5py.File(path, "r").describe()}
+    out["reindex"] = entry
     # the reference's loader relies on the group's member order: alphabetical, so arr10 sorts before arr2
     fake_h5py.reset()
     path = os.path.join(tmp, "long.h5")
