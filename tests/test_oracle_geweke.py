@@ -156,3 +156,65 @@ def test_invariance_test_has_power_against_a_wrong_conditional(broken, monkeypat
         monkeypatch.setattr(mod, "ar_log_likelihood", lambda x, Ab, Q: np.roll(real(x, Ab, Q), 1, axis=1))
     zs = invariance_z_scores(replicates=1500, sweeps=2, seed=8)
     assert max(abs(v) for v in zs.values()) > 6.0, broken
+
+
+def test_ar_only_sweep_with_two_lags_and_three_states_is_invariant():
+    """The AR-HMM part (transitions, AR parameters, labels given x) is an exact Gibbs sampler for any number
+    of lags: x generated with Ab laid out [oldest lag | ... | newest lag | offset] - the layout M_0 = identity
+    on the newest lag implies - must leave labels and parameters at their joint law under
+    `resample_model(ar_only=True)`.  Pins the lag order of `get_lags` against the likelihood AND the
+    sufficient statistics at once, and the sticky-HDP update with three states."""
+    K3, L2, T2 = 3, 2, 9
+    n = d * L2
+    M_0 = np.hstack([np.zeros((d, n - d)), 0.5 * np.eye(d), np.zeros((d, 1))])
+    hyp = {"trans_hypparams": {"num_states": K3, "alpha": 3.0, "kappa": 2.0, "gamma": 2.0},
+           "ar_hypparams": {"nu_0": d + 4.0, "S_0": 0.4 * np.eye(d), "M_0": M_0, "K_0": 0.3 * np.eye(n + 1)},
+           "obs_hypparams": HYP["obs_hypparams"], "cen_hypparams": HYP["cen_hypparams"]}
+    th, ah = hyp["trans_hypparams"], hyp["ar_hypparams"]
+    rng = np.random.default_rng(21)
+    LK = np.linalg.cholesky(ah["K_0"])
+    mask = np.ones((1, T2))
+
+    def g(z, pr):
+        Ab, Q, pi, betas = pr["Ab"], pr["Q"], pr["pi"], pr["betas"]
+        ldq = np.log(np.linalg.det(Q))
+        out = {"pi diag": np.diag(pi).mean(), "pi01": pi[0, 1], "pi21": pi[2, 1], "beta0": betas[0], "beta2^2": betas[2] ** 2,
+               "logdet Q": ldq.mean(), "A old": Ab[:, 0, 0].mean(), "A new": Ab[:, 0, n - d].mean(), "A new off": Ab[:, 0, n - d + 1].mean(),
+               "A old^2": (Ab[:, :, :n - d] ** 2).mean(), "A new^2": (Ab[:, :, n - d:n] ** 2).mean(), "b^2": (Ab[:, :, -1] ** 2).mean(),
+               "occ0": (z == 0).mean(), "occ2": (z == 2).mean(), "switch": (z[:, 1:] != z[:, :-1]).mean(),
+               "logdet Q[z]": ldq[z[0]].mean(), "log pi[z,z']": np.log(pi[z[0, :-1], z[0, 1:]]).mean(),
+               "log beta[z]": np.log(betas[z[0]]).mean()}
+        for t in range(T2 - L2):
+            j = z[0, t]
+            phi = np.concatenate([x[0, t], x[0, t + 1], [1.0]])
+            r = x[0, t + 2] - Ab[j] @ phi
+            out[f"resid own {t}"] = np.log1p(r @ np.linalg.solve(Q[j], r))
+        return out
+
+    diffs = []
+    R = 5000
+    for _ in range(R):
+        betas = rng.dirichlet(np.full(K3, th["gamma"] / K3))
+        pi = np.stack([rng.dirichlet(th["alpha"] * betas + th["kappa"] * np.eye(K3)[i]) for i in range(K3)])
+        Q = np.stack([invwishart.rvs(df=ah["nu_0"], scale=ah["S_0"], random_state=rng) for _ in range(K3)])
+        Ab = np.stack([M_0 + np.linalg.cholesky(Q[j]) @ rng.standard_normal((d, n + 1)) @ LK.T for j in range(K3)])
+        x = np.empty((1, T2, d))
+        z = np.empty((1, T2 - L2), dtype=np.int64)
+        x[0, :L2] = rng.standard_normal((L2, d)) * 2.0
+        for t in range(T2 - L2):
+            z[0, t] = rng.integers(K3) if t == 0 else rng.choice(K3, p=pi[z[0, t - 1]])
+            j = z[0, t]
+            phi = np.concatenate([x[0, t], x[0, t + 1], [1.0]])           # oldest lag first
+            x[0, t + L2] = Ab[j] @ phi + np.linalg.cholesky(Q[j]) @ rng.standard_normal(d)
+        pr = {"betas": betas, "pi": pi, "Ab": Ab, "Q": Q}
+        before = g(z, pr)
+        st = {"x": x, "z": z}
+        for _ in range(2):
+            tape = orc.make_tape(rng, 1, T2, k, D, d, L2, K3)
+            st, pr, _ = orc.resample_model({"Y": None, "mask": mask}, st, pr, hyp, S_PRIOR, tape, ar_only=True)
+        after = g(st["z"], pr)
+        diffs.append([after[m] - before[m] for m in before])
+    diffs = np.array(diffs)
+    zs = dict(zip(before, diffs.mean(0) / (diffs.std(0, ddof=1) / np.sqrt(R))))
+    worst = max(zs, key=lambda m: abs(zs[m]))
+    assert abs(zs[worst]) < 4.5, {m: round(float(v), 2) for m, v in zs.items() if abs(v) > 3}
