@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--hmm-dtype", default="float64", choices=["float32", "float64"])
+    ap.add_argument("--variant", default="full", choices=["full", "ar_only", "states_only"],
+                    help="full sweep (the headline metric), or the reference's ar_only / states_only sweeps "
+                         "(fit_model's AR-HMM stage, apply_model's sweeps); SURVEY 8(d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -96,7 +99,12 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_port_throughput(cfg, seconds_hint=20.0):
+VARIANT_OPTS = {"full": {}, "ar_only": {"ar_only": True}, "states_only": {"states_only": True}}
+VARIANT_TEXT = {"full": "full sweep (params, z, s, x, h, v)", "ar_only": "ar_only sweep (transitions, AR params, z)",
+                "states_only": "states_only sweep (z, s, x, h, v; no parameter updates, no all-reduce)"}
+
+
+def cpu_port_throughput(cfg, seconds_hint=20.0, variant="full"):
     """Times the float64 NumPy port (oracle/) of the same sweep on a bounded sample of the workload.
     Returns (frame_sweeps_per_sec, cores, sample description)."""
     import oracle as orc
@@ -109,7 +117,8 @@ def cpu_port_throughput(cfg, seconds_hint=20.0):
     t0 = time.perf_counter()
     sweeps = 0
     while True:
-        orc.resample_model(data, model["states"], model["params"], model["hypparams"], model["noise_prior"], tape)
+        orc.resample_model(data, model["states"], model["params"], model["hypparams"], model["noise_prior"], tape,
+                           **VARIANT_OPTS[variant])
         sweeps += 1
         if time.perf_counter() - t0 > seconds_hint * 0.5 or sweeps >= 3:
             break
@@ -119,15 +128,15 @@ def cpu_port_throughput(cfg, seconds_hint=20.0):
         cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     except Exception:
         cores = os.cpu_count() or 1
-    sample = (f"{sweeps} full sweep(s) of the float64 NumPy port on {chains} chains x {T} frames of the {k}-keypoint, "
+    sample = (f"{sweeps} {variant} sweep(s) of the float64 NumPy port on {chains} chains x {T} frames of the {k}-keypoint, "
               f"latent_dim {cfg['d']}, {cfg['K']}-state workload ({int(data['mask'].sum())} valid frames), "
               f"{dt:.2f} s per sweep")
     return float(data["mask"].sum() / dt), int(cores), sample
 
 
-def workload_text(name, cfg):
+def workload_text(name, cfg, variant="full"):
     return (f"{name} per GPU: {cfg['recordings']} recordings x {cfg['frames']} frames, k={cfg['k']}, D={cfg['D']}, "
-            f"latent_dim={cfg['d']}, nlags={cfg['L']}, num_states={cfg['K']}; full sweep (params, z, s, x, h, v) + NaN check")
+            f"latent_dim={cfg['d']}, nlags={cfg['L']}, num_states={cfg['K']}; {VARIANT_TEXT[variant]} + NaN check")
 
 
 def run_reference(args):
@@ -138,14 +147,14 @@ def run_reference(args):
     cfg = workload(args.config)
     best = None
     for _ in range(max(1, min(args.steps, 2))):
-        val, cores, sample = cpu_port_throughput(cfg)
+        val, cores, sample = cpu_port_throughput(cfg, variant=args.variant)
         best = val if best is None else max(best, val)
     frames_total = cfg["recordings"] * cfg["frames"]
     line = {
         "impl": "reference", "metric": METRIC, "value": best, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * frames_total / best,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_text(args.config, cfg)},
+        "config": {"workload": workload_text(args.config, cfg, args.variant)},
         "sweeps_per_sec": best / frames_total,
         "cpu_baseline": {"value": best, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": best, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -217,7 +226,7 @@ def main():
     valid_local = int(data["mask"].sum())
     dd = gibbs.to_device_data(data, dev, dt)
     dm = gibbs.to_device_model(model, dev, dt)
-    opts = dict(hmm_dtype=hdt, group=group)
+    opts = dict(hmm_dtype=hdt, group=group, **VARIANT_OPTS[args.variant])
 
     def barrier():
         torch.cuda.synchronize()
@@ -277,9 +286,12 @@ def main():
         nbytes = lambda d_: sum(v.numel() * v.element_size() for v in d_.values())
         # what resample_model uploads: Y and mask (conf is not an operand of the sweep), the states it reads
         # (the old noise scales are resampled before any use), the parameters and the noise prior
-        h2d = (nbytes({k_: v for k_, v in host_data.items() if k_ != "conf"})
-               + nbytes({k_: v for k_, v in host_states.items() if k_ != "s"}) + nbytes(host_params)
-               + host_prior.numel() * host_prior.element_size())
+        if args.variant == "ar_only":       # no keypoints, no noise prior; every state rides along unchanged
+            h2d = nbytes({"mask": host_data["mask"]}) + nbytes(host_states) + nbytes(host_params)
+        else:
+            h2d = (nbytes({k_: v for k_, v in host_data.items() if k_ != "conf"})
+                   + nbytes({k_: v for k_, v in host_states.items() if k_ != "s"}) + nbytes(host_params)
+                   + host_prior.numel() * host_prior.element_size())
         d2h = nbytes(out_host)
         seed = m["seed"]
         esteps = max(1, min(args.steps, 5))
@@ -386,14 +398,14 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        val, cores, sample = cpu_port_throughput(cfg)
+        val, cores, sample = cpu_port_throughput(cfg, variant=args.variant)
         cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if dt == torch.float32 else "f64", "data": "synthetic",
-        "config": {"workload": workload_text(args.config, cfg),
+        "config": {"workload": workload_text(args.config, cfg, args.variant),
                    "chains_per_gpu": int(dd["Y"].shape[0]), "frames_per_chain": int(dd["Y"].shape[1]),
                    "valid_frames_total": int(valid_total), "hmm_dtype": "f32" if hdt == torch.float32 else "f64",
                    "l2": "working set per sweep (> 4 GB of filter/backward records) exceeds the 126 MB L2"},
