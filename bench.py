@@ -104,34 +104,111 @@ VARIANT_TEXT = {"full": "full sweep (params, z, s, x, h, v)", "ar_only": "ar_onl
                 "states_only": "states_only sweep (z, s, x, h, v; no parameter updates, no all-reduce)"}
 
 
-def cpu_port_throughput(cfg, seconds_hint=20.0, variant="full"):
-    """Times the float64 NumPy port (oracle/) of the same sweep on a bounded sample of the workload.
-    Returns (frame_sweeps_per_sec, cores, sample description)."""
+def _cpu_worker(idx, shard, dims, variant, sweeps, barrier, out_q):
+    """One host process of the CPU arm: the float64 NumPy port on its own rows of the batch."""
+    try:
+        import oracle as orc
+        data, states, params, hypparams, prior = shard
+        N, T, k, D = data["Y"].shape
+        tape = orc.make_tape(np.random.default_rng(idx + 1), N, T, k, D, dims["d"], dims["L"], dims["K"])
+        barrier.wait(timeout=600)
+        t0 = time.perf_counter()
+        for _ in range(sweeps):
+            orc.resample_model(data, states, params, hypparams, prior, tape, **VARIANT_OPTS[variant])
+        out_q.put((idx, time.perf_counter() - t0, float(data["mask"].sum()), None))
+    except Exception as e:  # noqa: BLE001
+        try:
+            barrier.abort()
+        except Exception:  # noqa: BLE001
+            pass
+        out_q.put((idx, 0.0, 0.0, repr(e)))
+
+
+def _cpu_single(cfg, variant="full", chains=40, frames=2000, sweeps=2):
+    """Fallback of the CPU arm: one process, BLAS threads as configured."""
     import oracle as orc
     from keypoint_moseq_b200.synth import sample_dataset
-    chains, frames = 40, 2000
     data, _, model = sample_dataset(recordings=chains, frames=frames, k=cfg["k"], D=cfg["D"], d=cfg["d"],
                                     L=cfg["L"], K=cfg["K"], seed=123, seg_length=frames)
     N, T, k, D = data["Y"].shape
     tape = orc.make_tape(np.random.default_rng(1), N, T, k, D, cfg["d"], cfg["L"], cfg["K"])
     t0 = time.perf_counter()
-    sweeps = 0
-    while True:
+    for _ in range(sweeps):
         orc.resample_model(data, model["states"], model["params"], model["hypparams"], model["noise_prior"], tape,
                            **VARIANT_OPTS[variant])
-        sweeps += 1
-        if time.perf_counter() - t0 > seconds_hint * 0.5 or sweeps >= 3:
-            break
     dt = (time.perf_counter() - t0) / sweeps
     try:
         from threadpoolctl import threadpool_info
         cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
+    except Exception:  # noqa: BLE001
         cores = os.cpu_count() or 1
     sample = (f"{sweeps} {variant} sweep(s) of the float64 NumPy port on {chains} chains x {T} frames of the {k}-keypoint, "
-              f"latent_dim {cfg['d']}, {cfg['K']}-state workload ({int(data['mask'].sum())} valid frames), "
+              f"latent_dim {cfg['d']}, {cfg['K']}-state workload ({int(data['mask'].sum())} valid frames), one process, "
               f"{dt:.2f} s per sweep")
     return float(data["mask"].sum() / dt), int(cores), sample
+
+
+def cpu_port_throughput(cfg, variant="full"):
+    try:
+        return _cpu_multi(cfg, variant)
+    except Exception as e:  # noqa: BLE001
+        print(f"bench: multi-process CPU arm failed ({e!r}); timing one process instead", file=sys.stderr)
+        return _cpu_single(cfg, variant)
+
+
+def _cpu_multi(cfg, variant="full", procs=None, chains_per_proc=24, frames=2000, sweeps=2):
+    """Times the float64 NumPy port (oracle/) of the same sweep on a bounded sample of the workload, on ALL host
+    cores: the port is bound by per-time-step interpreter overhead on one core, so the rows of the batch are
+    split over one process per core (the sharding the sweep has anyway: chains are independent, the parameter
+    draws are replicated) with BLAS pinned to one thread each.  Returns (frame_sweeps_per_sec, cores, sample)."""
+    import multiprocessing as mp
+    from keypoint_moseq_b200.synth import sample_dataset
+    procs = int(os.environ.get("KPMS_BENCH_CPU_PROCS", procs or min(os.cpu_count() or 1, 32)))
+    chains = procs * chains_per_proc
+    data, _, model = sample_dataset(recordings=chains, frames=frames, k=cfg["k"], D=cfg["D"], d=cfg["d"],
+                                    L=cfg["L"], K=cfg["K"], seed=123, seg_length=frames)
+    N, T, k, D = data["Y"].shape
+    per = N // procs
+    dims = {"d": cfg["d"], "L": cfg["L"], "K": cfg["K"]}
+
+    def rows(tree, a, b):
+        return {key: np.ascontiguousarray(np.asarray(val)[a:b]) for key, val in tree.items()}
+
+    saved = {key: os.environ.get(key) for key in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for key in saved:
+        os.environ[key] = "1"
+    ctx = mp.get_context("spawn")
+    barrier, out_q = ctx.Barrier(procs + 1), ctx.Queue()
+    workers = []
+    try:
+        for i in range(procs):
+            a, b = i * per, (i + 1) * per if i < procs - 1 else N
+            shard = (rows(data, a, b), rows(model["states"], a, b), model["params"], model["hypparams"],
+                     np.ascontiguousarray(np.asarray(model["noise_prior"])[a:b]))
+            w = ctx.Process(target=_cpu_worker, args=(i, shard, dims, variant, sweeps, barrier, out_q), daemon=True)
+            w.start()
+            workers.append(w)
+        barrier.wait(timeout=600)
+        results = [out_q.get(timeout=1800) for _ in range(procs)]
+    finally:
+        for key, val in saved.items():
+            if val is None:
+                os.environ.pop(key, None)
+            else:
+                os.environ[key] = val
+        for w in workers:
+            w.join(timeout=30)
+            if w.is_alive():
+                w.terminate()
+    errors = [r[3] for r in results if r[3]]
+    if errors:
+        raise RuntimeError("CPU arm worker failed: " + errors[0])
+    wall = max(r[1] for r in results)
+    valid = sum(r[2] for r in results)
+    sample = (f"{sweeps} {variant} sweep(s) of the float64 NumPy port on {N} chains x {T} frames of the {k}-keypoint, "
+              f"latent_dim {cfg['d']}, {cfg['K']}-state workload ({int(valid)} valid frames), rows split over {procs} "
+              f"host processes (one per core, BLAS single-threaded), {wall / sweeps:.2f} s per sweep")
+    return float(valid * sweeps / wall), int(procs), sample
 
 
 def workload_text(name, cfg, variant="full"):
