@@ -156,6 +156,30 @@ def cpu_port_throughput(cfg, variant="full"):
         return _cpu_single(cfg, variant)
 
 
+def _usable_procs(cap=32, gb_per_proc=1.5):
+    """Host processes for the CPU arm: the cores this process may run on, capped, and no more than fit in half
+    of the memory that is free (cgroup limit included) at about 1 GB per 24-chain shard."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    free_gb = None
+    try:
+        import psutil
+        free_gb = psutil.virtual_memory().available / 2 ** 30
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        limit = open("/sys/fs/cgroup/memory.max").read().strip()
+        if limit != "max":
+            used = int(open("/sys/fs/cgroup/memory.current").read())
+            free_gb = min(free_gb if free_gb is not None else 1e9, (int(limit) - used) / 2 ** 30)
+    except Exception:  # noqa: BLE001
+        pass
+    by_mem = cap if free_gb is None else int(free_gb * 0.5 / gb_per_proc)
+    return max(1, min(cores, cap, by_mem))
+
+
 def _cpu_multi(cfg, variant="full", procs=None, chains_per_proc=24, frames=2000, sweeps=2):
     """Times the float64 NumPy port (oracle/) of the same sweep on a bounded sample of the workload, on ALL host
     cores: the port is bound by per-time-step interpreter overhead on one core, so the rows of the batch are
@@ -163,7 +187,7 @@ def _cpu_multi(cfg, variant="full", procs=None, chains_per_proc=24, frames=2000,
     draws are replicated) with BLAS pinned to one thread each.  Returns (frame_sweeps_per_sec, cores, sample)."""
     import multiprocessing as mp
     from keypoint_moseq_b200.synth import sample_dataset
-    procs = int(os.environ.get("KPMS_BENCH_CPU_PROCS", procs or min(os.cpu_count() or 1, 32)))
+    procs = int(os.environ.get("KPMS_BENCH_CPU_PROCS", procs or _usable_procs()))
     chains = procs * chains_per_proc
     data, _, model = sample_dataset(recordings=chains, frames=frames, k=cfg["k"], D=cfg["D"], d=cfg["d"],
                                     L=cfg["L"], K=cfg["K"], seed=123, seg_length=frames)
