@@ -238,3 +238,36 @@ def test_transition_resampler_is_a_distribution_and_counts():
     np.testing.assert_allclose(betas.sum(), 1)
     np.testing.assert_allclose(pi.sum(1), 1)
     assert np.all(np.diag(pi) > 0.5)
+
+
+def test_padding_content_does_not_reach_valid_frames_or_parameters():
+    """Rows are padded to a common length with mask 0 (util.batch).  Whatever sits in the padded frames - the
+    keypoints, the noise prior, the old states - must not change any parameter draw nor any state at a valid
+    frame (same draws): the likelihood terms, sufficient statistics and filters all gate on the mask."""
+    from helpers import oracle_sweep, small_problem, tape_for
+    data, _, model = small_problem(seed=3)
+    mask = np.asarray(data["mask"]) > 0
+    assert (~mask).any()
+    tape = tape_for(data, model, seed=5)
+    flags = dict(resample_global_noise_scale=True)
+    st0, pr0, lz0 = oracle_sweep(data, model, tape, **flags)
+
+    rng = np.random.default_rng(9)
+    data2 = {k_: np.array(v, copy=True) for k_, v in data.items()}
+    data2["Y"][~mask] = rng.standard_normal(data2["Y"][~mask].shape) * 50.0
+    model2 = {"states": {k_: np.array(v, copy=True) for k_, v in model["states"].items()},
+              "params": model["params"], "hypparams": model["hypparams"],
+              "noise_prior": np.array(model["noise_prior"], copy=True)}
+    model2["noise_prior"][~mask] = 7.0
+    for name in ("v", "h", "s"):
+        pad = model2["states"][name][~mask]
+        model2["states"][name][~mask] = np.abs(rng.standard_normal(pad.shape)) + 0.5
+    st1, pr1, lz1 = oracle_sweep(data2, model2, tape, **flags)
+
+    for name in ("Ab", "Q", "pi", "betas", "sigmasq"):
+        assert np.array_equal(pr0[name], pr1[name]), name
+    assert np.array_equal(lz0, lz1)
+    L = mask.shape[1] - st0["z"].shape[1]
+    assert np.array_equal(st0["z"][mask[:, L:]], st1["z"][mask[:, L:]])
+    for name in ("x", "v", "h", "s"):
+        assert np.array_equal(st0[name][mask], st1[name][mask]), name
