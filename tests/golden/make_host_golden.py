@@ -228,5 +228,69 @@ for case in app_cases:
     app_records.append({"case": case, "sweeps": len(calls), "kwargs_per_sweep": calls[0], "results": res,
                         "model_count": None if model_back is None else model_back["count"]})
 json.dump(app_records, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_apply_loop.json"), "w"), indent=1)
+# estimate_syllable_marginals' control flow (fitting.py:428-559): which sweeps are sampled, the averaging, the
+# nlags shift of the bounds and the edge padding; `unbatch` / `get_nlags` are this repo's (jax_moseq's are absent)
+from keypoint_moseq_b200.util import get_nlags as _get_nlags, unbatch as _unbatch  # noqa: E402
+
+MARG_N, MARG_TZ, MARG_K, MARG_L, MARG_D = 2, 7, 3, 2, 1
+
+
+def marg_pattern(count):
+    """Deterministic stand-in for the smoother marginals of the model after `count` sweeps."""
+    base = np.arange(MARG_N * MARG_TZ * MARG_K, dtype=np.float64).reshape(MARG_N, MARG_TZ, MARG_K)
+    return (base + 1.0) * (1.0 + 0.01 * count)
+
+
+def z_pattern(count):
+    return (np.arange(MARG_N * MARG_TZ).reshape(MARG_N, MARG_TZ) + count) % MARG_K
+
+
+def marg_model(count):
+    return {"count": count, "seed": 1,
+            "states": {"x": np.zeros((MARG_N, MARG_TZ + MARG_L, MARG_D)), "z": z_pattern(count)},
+            "params": {"Ab": np.zeros((MARG_K, MARG_D, MARG_D * MARG_L + 1)), "Q": np.zeros((MARG_K, MARG_D, MARG_D)),
+                       "pi": np.eye(MARG_K)},
+            "hypparams": {"trans_hypparams": {"num_states": MARG_K}}}
+
+
+marg_calls = []
+
+
+def _stub_resample3(data, count=0, **kw):
+    marg_calls.append(count + 1)
+    return marg_model(count + 1)
+
+
+sampled_at = []
+
+
+def _stub_marginals(x, mask, Ab=None, Q=None, pi=None, **kw):
+    sampled_at.append(marg_calls[-1])
+    return marg_pattern(marg_calls[-1])
+
+
+marg_ns = dict(app_ns)
+marg_ns.update({"init_model": lambda **kw: marg_model(0), "stateseq_marginals": _stub_marginals,
+                "keypoint_slds": types.SimpleNamespace(resample_model=_stub_resample3),
+                "get_nlags": _get_nlags, "unbatch": _unbatch})
+for node in ftree.body:
+    if isinstance(node, ast.FunctionDef) and node.name in ("_wrapped_resample", "estimate_syllable_marginals"):
+        exec(compile(ast.Module(body=[node], type_ignores=[]), "reference/fitting.py", "exec"), marg_ns)
+marg_meta = (["a", "b"], np.array([[0, MARG_TZ + MARG_L], [0, MARG_TZ + MARG_L - 2]]))
+marg_data = {"mask": np.ones((MARG_N, MARG_TZ + MARG_L))}
+marg_records = []
+for case in [dict(burn_in_iters=3, num_samples=2, steps_per_sample=4), dict(burn_in_iters=0, num_samples=3, steps_per_sample=1, return_samples=True),
+             dict(burn_in_iters=5, num_samples=1, steps_per_sample=2, return_samples=True)]:
+    marg_calls.clear()
+    sampled_at.clear()
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = marg_ns["estimate_syllable_marginals"](marg_model(0), marg_data, marg_meta, **case)
+    smp = None
+    if isinstance(res, tuple):
+        res, smp = res
+    marg_records.append({"case": case, "sweeps": len(marg_calls), "sampled_at": list(sampled_at),
+                         "marginals": {k_: v_.tolist() for k_, v_ in res.items()},
+                         "samples": None if smp is None else {k_: np.asarray(v_).tolist() for k_, v_ in smp.items()}})
+json.dump(marg_records, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_marginals_loop.json"), "w"), indent=1)
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host_helpers.npz"), **out)
 print("segment lengths:", segs, "update_hypparams cases:", len(records))

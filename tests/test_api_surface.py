@@ -229,6 +229,65 @@ def test_apply_model_loop_matches_the_reference_loop(monkeypatch):
         assert (None if back is None else back["count"]) == rec["model_count"]
 
 
+def test_estimate_syllable_marginals_loop_matches_the_reference_loop(monkeypatch):
+    """estimate_syllable_marginals' control flow against the reference's own (executed with stubs by
+    make_host_golden.py): burn-in, which sweeps are sampled, the average over samples, the nlags shift of the
+    bounds and the edge padding of marginals and label samples."""
+    import sys
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from keypoint_moseq_b200 import fitting
+    recs = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_marginals_loop.json")))
+    N, TZ, K, L, D = 2, 7, 3, 2, 1
+
+    def pattern(count):
+        base = np.arange(N * TZ * K, dtype=np.float64).reshape(N, TZ, K)
+        return (base + 1.0) * (1.0 + 0.01 * count)
+
+    def model_at(count):
+        z = (np.arange(N * TZ).reshape(N, TZ) + count) % K
+        return {"count": count, "seed": 1,
+                "states": {"x": torch.zeros(N, TZ + L, D), "z": torch.as_tensor(z)},
+                "params": {"Ab": torch.zeros(K, D, D * L + 1), "Q": torch.zeros(K, D, D), "pi": torch.eye(K)},
+                "hypparams": {"trans_hypparams": {"num_states": K}}}
+
+    calls, sampled_at = [], []
+
+    def stub_resample(data, count=0, **kw):
+        assert kw.get("states_only") is True and "jitter" not in kw
+        calls.append(count + 1)
+        return model_at(count + 1)
+
+    def stub_marginals(x, mask, Ab, Q, pi, **kw):
+        sampled_at.append(calls[-1])
+        return torch.as_tensor(pattern(calls[-1]))
+
+    monkeypatch.setattr(fitting.gibbs, "resample_model", stub_resample)
+    monkeypatch.setattr(fitting.gibbs, "stateseq_marginals", stub_marginals)
+    monkeypatch.setattr(fitting.gibbs, "to_device_data", lambda d, *a, **k: d)
+    monkeypatch.setattr(fitting.gibbs, "to_device_model", lambda m, *a, **k: m)
+    monkeypatch.setattr(fitting, "init_model", lambda **kw: model_at(0))
+    monkeypatch.setattr(fitting, "check_for_nans", lambda m: (False, [], []))
+    metadata = (["a", "b"], np.array([[0, TZ + L], [0, TZ + L - 2]]))
+    data = {"mask": torch.ones(N, TZ + L)}
+    for rec in recs:
+        calls.clear()
+        sampled_at.clear()
+        res = fitting.estimate_syllable_marginals(model_at(0), data, metadata, **rec["case"])
+        smp = None
+        if isinstance(res, tuple):
+            res, smp = res
+        assert len(calls) == rec["sweeps"] and sampled_at == rec["sampled_at"], rec["case"]
+        assert set(res) == set(rec["marginals"])
+        for key, val in rec["marginals"].items():
+            np.testing.assert_allclose(res[key], np.array(val), rtol=1e-13)
+        assert (smp is None) == (rec["samples"] is None)
+        if smp is not None:
+            for key, val in rec["samples"].items():
+                assert np.array_equal(np.asarray(smp[key]), np.array(val)), key
+
+
 # ---------------------------------------------------------------------------------------------------
 # HDF5 tree layout: our writer against the reference's `_savetree_hdf5`, each reader on the other's tree
 # ---------------------------------------------------------------------------------------------------
