@@ -292,5 +292,38 @@ for case in [dict(burn_in_iters=3, num_samples=2, steps_per_sample=4), dict(burn
                          "marginals": {k_: v_.tolist() for k_, v_ in res.items()},
                          "samples": None if smp is None else {k_: np.asarray(v_).tolist() for k_, v_ in smp.items()}})
 json.dump(marg_records, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_marginals_loop.json"), "w"), indent=1)
+# expected_marginal_likelihoods (fitting.py:615-678): which (parameters, trajectory) pairs are scored and how
+# the scores and standard errors are formed
+class _Scalar(float):
+    def item(self):
+        return float(self)
+
+
+def eml_score(mask, x, Ab, Q, pi):
+    return _Scalar(np.sin(float(np.asarray(Ab).sum()) * 1.3 + float(np.asarray(x).sum()) * 0.7) * 100.0 - 500.0)
+
+
+def eml_checkpoint(path):
+    i = int(os.path.basename(os.path.dirname(path))[1:])
+    return ({"states": {"x": np.full((2, 3), float(i))},
+             "params": {"Ab": np.full((2, 2), 10.0 + i), "Q": np.zeros(1), "pi": np.zeros(1)}},
+            {"mask": np.ones((2, 3))}, None, 0)
+
+
+eml_ns = dict(fit_ns)
+eml_ns.update({"jnp": types.SimpleNamespace(array=lambda a: a), "load_checkpoint": lambda path=None: eml_checkpoint(path),
+               "marginal_log_likelihood": eml_score, "os": os,
+               "tqdm": types.SimpleNamespace(trange=lambda n, **kw: range(n))})
+for node in ftree.body:
+    if isinstance(node, ast.FunctionDef) and node.name == "expected_marginal_likelihoods":
+        exec(compile(ast.Module(body=[node], type_ignores=[]), "reference/fitting.py", "exec"), eml_ns)
+eml_records = []
+for names in (["m0", "m1", "m2"], ["m3", "m1", "m4", "m0", "m2"]):
+    sc, se = eml_ns["expected_marginal_likelihoods"]("/proj", names)
+    eml_records.append({"model_names": names, "scores": np.asarray(sc).tolist(), "standard_errors": np.asarray(se).tolist()})
+sc, se = eml_ns["expected_marginal_likelihoods"](checkpoint_paths=["/a/m2/checkpoint.h5", "/b/m0/checkpoint.h5"])
+eml_records.append({"checkpoint_paths": ["/a/m2/checkpoint.h5", "/b/m0/checkpoint.h5"], "scores": np.asarray(sc).tolist(),
+                    "standard_errors": np.asarray(se).tolist()})
+json.dump(eml_records, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_eml.json"), "w"), indent=1)
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host_helpers.npz"), **out)
 print("segment lengths:", segs, "update_hypparams cases:", len(records))

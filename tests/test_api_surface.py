@@ -288,6 +288,39 @@ def test_estimate_syllable_marginals_loop_matches_the_reference_loop(monkeypatch
                 assert np.array_equal(np.asarray(smp[key]), np.array(val)), key
 
 
+def test_expected_marginal_likelihoods_matches_the_reference_function(monkeypatch):
+    """Which (parameters of model i, trajectory of model j) pairs are scored, and how scores and standard errors
+    are formed from them (fitting.py:615-678, executed from the reference source with a stub scorer)."""
+    import numpy as np
+    from keypoint_moseq_b200 import fitting
+    recs = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_eml.json")))
+
+    class Scalar(float):
+        def item(self):
+            return float(self)
+
+    def score(mask, x, Ab, Q, pi):
+        return Scalar(np.sin(float(np.asarray(Ab).sum()) * 1.3 + float(np.asarray(x).sum()) * 0.7) * 100.0 - 500.0)
+
+    def checkpoint(path=None):
+        i = int(os.path.basename(os.path.dirname(path))[1:])
+        return ({"states": {"x": np.full((2, 3), float(i))},
+                 "params": {"Ab": np.full((2, 2), 10.0 + i), "Q": np.zeros(1), "pi": np.zeros(1)}},
+                {"mask": np.ones((2, 3))}, None, 0)
+
+    monkeypatch.setattr(fitting, "load_checkpoint", checkpoint)
+    monkeypatch.setattr(fitting.gibbs, "marginal_log_likelihood", score)
+    for rec in recs:
+        if "model_names" in rec:
+            sc, se = fitting.expected_marginal_likelihoods("/proj", rec["model_names"])
+        else:
+            sc, se = fitting.expected_marginal_likelihoods(checkpoint_paths=rec["checkpoint_paths"])
+        np.testing.assert_allclose(sc, rec["scores"], rtol=1e-13)
+        np.testing.assert_allclose(se, rec["standard_errors"], rtol=1e-10)
+    with pytest.raises(AssertionError):
+        fitting.expected_marginal_likelihoods()
+
+
 # ---------------------------------------------------------------------------------------------------
 # HDF5 tree layout: our writer against the reference's `_savetree_hdf5`, each reader on the other's tree
 # ---------------------------------------------------------------------------------------------------
