@@ -104,23 +104,21 @@ VARIANT_TEXT = {"full": "full sweep (params, z, s, x, h, v)", "ar_only": "ar_onl
                 "states_only": "states_only sweep (z, s, x, h, v; no parameter updates, no all-reduce)"}
 
 
-def _cpu_worker(idx, shard, dims, variant, sweeps, barrier, out_q):
+def _cpu_worker(idx, shard, dims, variant, sweeps, ready_q, go, out_q):
     """One host process of the CPU arm: the float64 NumPy port on its own rows of the batch."""
     try:
         import oracle as orc
         data, states, params, hypparams, prior = shard
         N, T, k, D = data["Y"].shape
         tape = orc.make_tape(np.random.default_rng(idx + 1), N, T, k, D, dims["d"], dims["L"], dims["K"])
-        barrier.wait(timeout=600)
+        ready_q.put(idx)
+        if not go.wait(timeout=180):
+            raise RuntimeError("start signal never came")
         t0 = time.perf_counter()
         for _ in range(sweeps):
             orc.resample_model(data, states, params, hypparams, prior, tape, **VARIANT_OPTS[variant])
         out_q.put((idx, time.perf_counter() - t0, float(data["mask"].sum()), None))
     except Exception as e:  # noqa: BLE001
-        try:
-            barrier.abort()
-        except Exception:  # noqa: BLE001
-            pass
         out_q.put((idx, 0.0, 0.0, repr(e)))
 
 
@@ -202,18 +200,34 @@ def _cpu_multi(cfg, variant="full", procs=None, chains_per_proc=24, frames=2000,
     for key in saved:
         os.environ[key] = "1"
     ctx = mp.get_context("spawn")
-    barrier, out_q = ctx.Barrier(procs + 1), ctx.Queue()
+    ready_q, go, out_q = ctx.Queue(), ctx.Event(), ctx.Queue()
     workers = []
     try:
         for i in range(procs):
             a, b = i * per, (i + 1) * per if i < procs - 1 else N
             shard = (rows(data, a, b), rows(model["states"], a, b), model["params"], model["hypparams"],
                      np.ascontiguousarray(np.asarray(model["noise_prior"])[a:b]))
-            w = ctx.Process(target=_cpu_worker, args=(i, shard, dims, variant, sweeps, barrier, out_q), daemon=True)
+            w = ctx.Process(target=_cpu_worker, args=(i, shard, dims, variant, sweeps, ready_q, go, out_q), daemon=True)
             w.start()
             workers.append(w)
-        barrier.wait(timeout=600)
-        results = [out_q.get(timeout=1800) for _ in range(procs)]
+        import queue
+
+        def gather(q, count, seconds, what):
+            got, deadline = [], time.perf_counter() + seconds
+            while len(got) < count:
+                try:
+                    got.append(q.get(timeout=1))
+                except queue.Empty:
+                    dead = [i for i, w in enumerate(workers) if not w.is_alive() and w.exitcode not in (0, None)]
+                    if dead:
+                        raise RuntimeError(f"worker {dead[0]} died (exit code {workers[dead[0]].exitcode}) before {what}")
+                    if time.perf_counter() > deadline:
+                        raise RuntimeError(f"CPU arm timed out waiting for {what}")
+            return got
+
+        gather(ready_q, procs, 120, "start")             # every worker has imported and unpacked its rows
+        go.set()
+        results = gather(out_q, procs, 420, "results")
     finally:
         for key, val in saved.items():
             if val is None:
@@ -221,7 +235,7 @@ def _cpu_multi(cfg, variant="full", procs=None, chains_per_proc=24, frames=2000,
             else:
                 os.environ[key] = val
         for w in workers:
-            w.join(timeout=30)
+            w.join(timeout=0.5 if sys.exc_info()[0] else 30)
             if w.is_alive():
                 w.terminate()
     errors = [r[3] for r in results if r[3]]
