@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import gibbs
-from .io import delete_snapshots_after, extract_results, load_checkpoint, save_hdf5
+from .io import SnapshotWriter, delete_snapshots_after, extract_results, load_checkpoint, save_hdf5
 from .util import NanGuard, check_for_nans, get_nlags, to_numpy_tree, unbatch
 
 try:  # progress bars are optional
@@ -206,7 +206,10 @@ def fit_model(model, data, metadata, project_dir=None, model_name=None, num_iter
     (signature and checkpoint behaviour of fitting.py:109-287).  Returns (model, model_name).
 
     Extra keyword arguments understood here: `dtype` (torch.float32 / torch.float64 for the states and
-    the continuous-path kernels, default float64 like the reference's x64 mode), `hmm_dtype`, `group`.
+    the continuous-path kernels, default float64 like the reference's x64 mode), `hmm_dtype`, `group`,
+    `nan_check_lag`, and `async_checkpoints` (default False: snapshots are written before the next sweep is
+    launched, as in the reference; True: the snapshot is copied to the host and written by `io.SnapshotWriter`
+    on a background thread while the next sweeps run - all writes have finished when fit_model returns).
     """
     if location_aware:
         raise NotImplementedError("location_aware=True (allo_keypoint_slds) is not implemented by the B200 sweep")
@@ -242,6 +245,18 @@ def fit_model(model, data, metadata, project_dir=None, model_name=None, num_iter
     # returned after a NaN is the last one that was checked clean, as in fitting.py:30-44, :263-264
     guard = NanGuard(lag=int(kwargs.pop("nan_check_lag", NAN_CHECK_LAG)))
     guard.clean = model
+    writer = SnapshotWriter(save=save_hdf5) if kwargs.pop("async_checkpoints", False) and checkpoint_path else None
+    try:
+        model = _fit_loop(model, data_dev, resample_func, guard, writer, checkpoint_path, start_iter, num_iters,
+                          save_every_n_iters, ar_only, verbose, jitter, parallel_message_passing, extra)
+    finally:
+        if writer is not None:
+            writer.close()
+    return model, model_name
+
+
+def _fit_loop(model, data_dev, resample_func, guard, writer, checkpoint_path, start_iter, num_iters,
+              save_every_n_iters, ar_only, verbose, jitter, parallel_message_passing, extra):
     with _trange(start_iter, num_iters + 1, ncols=72) as pbar:
         for iteration in pbar:
             try:
@@ -256,12 +271,15 @@ def fit_model(model, data, metadata, project_dir=None, model_name=None, num_iter
                     if not _drain_guard(guard, pbar):           # never checkpoint an unchecked sweep
                         model = guard.clean
                         break
-                    save_hdf5(checkpoint_path, _host_model(model), f"model_snapshots/{iteration}", exist_ok=True)
+                    if writer is not None:
+                        writer.submit(checkpoint_path, _host_model(model), f"model_snapshots/{iteration}")
+                    else:
+                        save_hdf5(checkpoint_path, _host_model(model), f"model_snapshots/{iteration}", exist_ok=True)
                     # progress plots (viz.plot_progress) are outside the sweep's scope and are skipped
         else:
             if not _drain_guard(guard, pbar):
                 model = guard.clean
-    return model, model_name
+    return model
 
 
 def apply_model(model, data, metadata, project_dir=None, model_name=None, num_iters=500, ar_only=False,

@@ -24,7 +24,7 @@ except Exception:  # pragma: no cover
     HAVE_H5PY = False
 
 __all__ = ["save_hdf5", "load_hdf5", "load_checkpoint", "reindex_syllables_in_checkpoint", "extract_results", "load_results",
-           "delete_snapshots_after", "HAVE_H5PY"]
+           "delete_snapshots_after", "SnapshotWriter", "HAVE_H5PY"]
 
 _TYPES_KEY = "__tree_types__"
 _noticed = False
@@ -150,6 +150,67 @@ def save_hdf5(filepath, save_dict, datapath=None, exist_ok=False, overwrite=Fals
     old_leaves.update(leaves)
     old_types.update(types)
     _npz_write(filepath, old_leaves, old_types)
+
+
+class SnapshotWriter:
+    """Writes checkpoint snapshots on a background thread, in submission order (the per-save
+    stall of the reference, fitting.py:266-275, becomes visible once a sweep takes tens of milliseconds).
+
+    `submit(filepath, tree, datapath)` hands over a HOST tree (the caller has already copied it off the device,
+    so later sweeps cannot touch it) and returns at once; the thread calls `save(filepath, tree, datapath,
+    exist_ok=True)`.  At most `max_pending` snapshots wait in memory (submit blocks beyond that).  `close()`
+    waits for the queue to drain and raises the first write error; the error also surfaces at every later
+    `submit`, and snapshots submitted after it are dropped rather than written after a hole.  Only this thread touches the file while it is open, which is what h5py's threading model asks."""
+
+    def __init__(self, save=None, max_pending=2):
+        import queue
+        import threading
+        self._save = save if save is not None else save_hdf5
+        self._queue = queue.Queue(maxsize=max_pending)
+        self._error = None
+        self._thread = threading.Thread(target=self._run, name="kpms-snapshot-writer", daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        while True:
+            job = self._queue.get()
+            try:
+                if job is None:
+                    return
+                if self._error is None:                      # after a failure later snapshots are dropped, not written
+                    filepath, tree, datapath = job
+                    self._save(filepath, tree, datapath, exist_ok=True)
+            except BaseException as e:  # noqa: BLE001 - handed to the caller's thread
+                self._error = e
+            finally:
+                self._queue.task_done()
+
+    def _raise(self):
+        if self._error is not None:                          # sticky: a writer that failed stays failed
+            raise self._error
+
+    def submit(self, filepath, tree, datapath):
+        self._raise()
+        self._queue.put((filepath, tree, datapath))
+
+    def close(self):
+        if self._thread.is_alive():
+            self._queue.put(None)
+            self._thread.join()
+        self._raise()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is None:
+            self.close()
+        else:                                                # do not mask the caller's exception
+            try:
+                self.close()
+            except BaseException:  # noqa: BLE001
+                pass
+        return False
 
 
 def _h5_load(node):

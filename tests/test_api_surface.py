@@ -157,7 +157,8 @@ def test_extract_results_matches_the_reference_function():
             np.testing.assert_array_equal(np.asarray(res[rec][field]), g[f"er_out/{rec}/{field}"])
 
 
-def test_fit_model_loop_matches_the_reference_loop(tmp_path, monkeypatch):
+@pytest.mark.parametrize("async_checkpoints", [False, True])
+def test_fit_model_loop_matches_the_reference_loop(tmp_path, monkeypatch, async_checkpoints):
     """fit_model's control flow against the reference's own loop (fit_model + _wrapped_resample executed by
     make_host_golden.py with stubs below the boundary): the same snapshots are written, and after a NaN
     sweep the model from before it comes back - although the NaN check here trails the sweeps by
@@ -186,9 +187,9 @@ def test_fit_model_loop_matches_the_reference_loop(tmp_path, monkeypatch):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             model, name = fitting.fit_model({"count": 0, "nan_at": nan_at}, {}, ([], []), str(tmp_path / f"p{i}"), "m",
-                                            generate_progress_plots=False, **kw)
+                                            generate_progress_plots=False, async_checkpoints=async_checkpoints, **kw)
         assert name == "m"
-        assert saves == rec["saves"], rec["case"]
+        assert saves == rec["saves"], rec["case"]          # background writes are complete on return, in order
         assert model["count"] == rec["returned_count"], rec["case"]
 
 

@@ -300,3 +300,87 @@ def test_format_data_reindexes_bodyparts_and_interpolates_missing_points():
     out = interpolate_keypoints(np.full((4, 1, 2), np.nan), np.ones((4, 1), bool))
     assert (out == 0).all()
     assert reindex_by_bodyparts(np.arange(8.0).reshape(1, 4, 2), parts, ["paw"]).tolist() == [[[6.0, 7.0]]]
+
+
+def test_snapshot_writer_orders_bounds_and_reports():
+    """io.SnapshotWriter: snapshots reach the file in submission order while the caller keeps going, at most
+    `max_pending` wait in memory, everything is on disk after close(), and a failed write surfaces in the
+    caller's thread (later snapshots are dropped rather than written after a hole)."""
+    import threading
+    import time
+    from keypoint_moseq_b200.io import SnapshotWriter
+    written, gate = [], threading.Event()
+
+    def slow_save(path, tree, datapath, exist_ok=False):
+        gate.wait(5)
+        assert exist_ok is True
+        written.append((path, datapath, tree["k"]))
+
+    w = SnapshotWriter(save=slow_save, max_pending=2)
+    t0 = time.perf_counter()
+    for i in range(3):                                   # one in flight + two queued: none of these block
+        w.submit("f.h5", {"k": i}, f"model_snapshots/{i}")
+    assert time.perf_counter() - t0 < 1.0 and written == []
+    blocked = threading.Thread(target=lambda: w.submit("f.h5", {"k": 3}, "model_snapshots/3"))
+    blocked.start()
+    blocked.join(0.3)
+    assert blocked.is_alive()                            # the fourth waits for room
+    gate.set()
+    blocked.join(5)
+    w.close()
+    assert written == [("f.h5", f"model_snapshots/{i}", i) for i in range(4)]
+
+    def failing_save(path, tree, datapath, exist_ok=False):
+        if tree["k"] == 1:
+            raise OSError("disk full")
+        written.append(tree["k"])
+
+    written.clear()
+    w = SnapshotWriter(save=failing_save)
+    for i in range(3):
+        try:
+            w.submit("f.h5", {"k": i}, str(i))
+        except OSError:
+            break
+        time.sleep(0.05)
+    else:
+        raise AssertionError("the write error never reached the caller")
+    with pytest.raises(OSError):
+        w.submit("f.h5", {"k": 9}, "9")
+    with pytest.raises(OSError):
+        w.close()
+    assert written == [0]
+
+
+def test_snapshot_writer_writes_a_loadable_checkpoint(tmp_path):
+    from keypoint_moseq_b200.io import SnapshotWriter, load_hdf5, save_hdf5
+    path = str(tmp_path / "checkpoint.h5")
+    save_hdf5(path, {"model_snapshots": {"0": {"x": np.zeros(3)}}, "data": {"mask": np.ones(2)}})
+    with SnapshotWriter() as w:
+        for it in (25, 50):
+            w.submit(path, {"x": np.full(3, float(it))}, f"model_snapshots/{it}")
+    back = load_hdf5(path)
+    assert sorted(back["model_snapshots"], key=int) == ["0", "25", "50"]
+    assert np.array_equal(back["model_snapshots"]["50"]["x"], np.full(3, 50.0))
+
+
+def test_fit_model_async_checkpoint_failure_reaches_the_caller(tmp_path, monkeypatch):
+    """A background write that fails must not be lost: fit_model raises it (at the next snapshot or on return)."""
+    from keypoint_moseq_b200 import fitting
+    monkeypatch.setattr(fitting.gibbs, "resample_model", lambda data, count=0, **kw: {"count": count + 1, "x": np.zeros(1)})
+    monkeypatch.setattr(fitting.gibbs, "to_device_data", lambda d, *a, **k: d)
+    monkeypatch.setattr(fitting.gibbs, "to_device_model", lambda m, *a, **k: m)
+    monkeypatch.setattr(fitting, "_host_model", lambda m: m)
+    monkeypatch.setattr(fitting, "to_numpy_tree", lambda t: t)
+
+    def save(path, tree, datapath=None, **kw):
+        if datapath == "model_snapshots/4":
+            raise OSError("disk full")
+
+    monkeypatch.setattr(fitting, "save_hdf5", save)
+    with pytest.raises(OSError, match="disk full"):
+        fitting.fit_model({"count": 0}, {}, ([], []), str(tmp_path), "m", num_iters=6, save_every_n_iters=2,
+                          generate_progress_plots=False, async_checkpoints=True)
+    with pytest.raises(OSError, match="disk full"):                       # and the synchronous path as before
+        fitting.fit_model({"count": 0}, {}, ([], []), str(tmp_path), "m2", num_iters=6, save_every_n_iters=2,
+                          generate_progress_plots=False)
