@@ -384,3 +384,28 @@ def test_fit_model_async_checkpoint_failure_reaches_the_caller(tmp_path, monkeyp
     with pytest.raises(OSError, match="disk full"):                       # and the synchronous path as before
         fitting.fit_model({"count": 0}, {}, ([], []), str(tmp_path), "m2", num_iters=6, save_every_n_iters=2,
                           generate_progress_plots=False)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the CUDA arm): exactly one JSON line on
+    stdout with the contract's keys, the oracle port labelled as such, rows split over the requested processes."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, KPMS_BENCH_CPU_PROCS="2")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--variant", "ar_only"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "frame_sweeps_per_sec" and line["unit"] == "frame-sweeps/s"
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["dtype"] == "f64"
+    assert line["value"] > 0 and "ar_only" in line["config"]["workload"]
+    cpu = line["cpu_baseline"]
+    assert cpu["kind"] == "port" and cpu["cores"] == 2 and cpu["value"] == line["value"] and "2 host processes" in cpu["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
