@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import gibbs
+from .dist import gather_rows, shard_rows, shard_tree
 from .io import SnapshotWriter, delete_snapshots_after, extract_results, load_checkpoint, save_hdf5
 from .util import NanGuard, check_for_nans, get_nlags, to_numpy_tree, unbatch
 
@@ -109,6 +110,63 @@ def _host_model(model):
     out = to_numpy_tree(model)
     out["states"]["z"] = np.asarray(out["states"]["z"]).astype(np.int64)
     return out
+
+
+class _Shards:
+    """One fit spread over the ranks of a process group: every rank calls `fit_model` / `apply_model`
+    with the SAME full data and model plus `group=`; the rows are dealt out with `dist.shard_rows` (whole
+    recordings together, balanced by valid frames), each rank sweeps its own rows, the sufficient statistics are
+    all-reduced inside the sweep, and states are gathered only when a snapshot is due or the call returns.
+    Rank 0 alone touches the files.  Without a group (or with one rank) every method is the identity."""
+
+    def __init__(self, group, data, metadata):
+        self.group, self.world, self.rank, self.rows = group, 1, 0, None
+        if group is not None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 1:
+            self.rows_per_rank = shard_rows(data["mask"], self.world, list(metadata[0]))
+            self.rows = self.rows_per_rank[self.rank]
+            self.N = int(data["mask"].shape[0])
+
+    @property
+    def writes(self):
+        return self.rank == 0
+
+    def _per_row(self, leaf):
+        shape = getattr(leaf, "shape", ())
+        return self.rows is not None and len(shape) >= 1 and int(shape[0]) == self.N
+
+    def agree(self, obj):
+        """Rank 0's value of a small Python object on every rank (the timestamped model name)."""
+        if self.world == 1:
+            return obj
+        import torch.distributed as dist
+        box = [obj]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(self.group, 0), group=self.group)
+        return box[0]
+
+    def split_data(self, data):
+        return data if self.rows is None else shard_tree(dict(data), self.rows)
+
+    def split_model(self, model):
+        if self.rows is None:
+            return model
+        out = dict(model, states=shard_tree(dict(model["states"]), self.rows))
+        if self._per_row(model.get("noise_prior")):
+            out["noise_prior"] = shard_tree(model["noise_prior"], self.rows)
+        return out
+
+    def join_model(self, host_model):
+        """Collective: the full host model from every rank's rows (parameters are identical on all ranks)."""
+        if self.rows is None:
+            return host_model
+        out = dict(host_model, states={key: gather_rows(val, self.rows_per_rank, self.group)
+                                       for key, val in host_model["states"].items()})
+        prior = host_model.get("noise_prior")
+        if getattr(prior, "shape", ()) and int(prior.shape[0]) == len(self.rows):
+            out["noise_prior"] = gather_rows(prior, self.rows_per_rank, self.group)
+        return out
 
 
 def init_states(data, params, hypparams, seed, noise_prior=None, anterior_idxs=None, posterior_idxs=None,
@@ -217,20 +275,23 @@ def fit_model(model, data, metadata, project_dir=None, model_name=None, num_iter
         warnings.warn(fill("The `generate_progress_plots` option requires that `save_every_n_iters` be greater "
                            "than 0. Progress plots will not be generated."))
         generate_progress_plots = False
+    shards = _Shards(kwargs.get("group"), data, metadata)
     if model_name is None:
-        model_name = str(datetime.now().strftime("%Y_%m_%d-%H_%M_%S"))
+        model_name = shards.agree(str(datetime.now().strftime("%Y_%m_%d-%H_%M_%S")))
     checkpoint_path = None
     if save_every_n_iters is not None:
         savedir = os.path.join(project_dir, model_name)
-        os.makedirs(savedir, exist_ok=True)
-        print(fill(f"Outputs will be saved to {savedir}"))
         checkpoint_path = os.path.join(savedir, "checkpoint.h5")
-        if not os.path.exists(checkpoint_path):
-            save_hdf5(checkpoint_path, {"model_snapshots": {f"{start_iter}": _host_model(model)},
-                                        "metadata": (np.asarray(metadata[0]), np.asarray(metadata[1])),
-                                        "data": to_numpy_tree(data)})
-        else:
-            delete_snapshots_after(checkpoint_path, start_iter)
+        if shards.writes:
+            os.makedirs(savedir, exist_ok=True)
+            print(fill(f"Outputs will be saved to {savedir}"))
+            if not os.path.exists(checkpoint_path):
+                save_hdf5(checkpoint_path, {"model_snapshots": {f"{start_iter}": _host_model(model)},
+                                            "metadata": (np.asarray(metadata[0]), np.asarray(metadata[1])),
+                                            "data": to_numpy_tree(data)})
+            else:
+                delete_snapshots_after(checkpoint_path, start_iter)
+    data, model = shards.split_data(data), shards.split_model(model)
 
     parallel_message_passing = _set_parallel_flag(parallel_message_passing)
     dtype = kwargs.pop("dtype", torch.float64)
@@ -243,20 +304,23 @@ def fit_model(model, data, metadata, project_dir=None, model_name=None, num_iter
 
     # NaN check pipelined by one sweep (kwarg nan_check_lag, 0 = synchronous as in the reference): the model
     # returned after a NaN is the last one that was checked clean, as in fitting.py:30-44, :263-264
-    guard = NanGuard(lag=int(kwargs.pop("nan_check_lag", NAN_CHECK_LAG)))
+    guard = NanGuard(lag=int(kwargs.pop("nan_check_lag", NAN_CHECK_LAG)), group=shards.group if shards.world > 1 else None)
     guard.clean = model
-    writer = SnapshotWriter(save=save_hdf5) if kwargs.pop("async_checkpoints", False) and checkpoint_path else None
+    use_writer = kwargs.pop("async_checkpoints", False) and checkpoint_path and shards.writes
+    writer = SnapshotWriter(save=save_hdf5) if use_writer else None
     try:
         model = _fit_loop(model, data_dev, resample_func, guard, writer, checkpoint_path, start_iter, num_iters,
-                          save_every_n_iters, ar_only, verbose, jitter, parallel_message_passing, extra)
+                          save_every_n_iters, ar_only, verbose, jitter, parallel_message_passing, extra, shards)
     finally:
         if writer is not None:
             writer.close()
+    if shards.world > 1:                                  # every rank returns the whole model, as with one GPU
+        model = gibbs.to_device_model(shards.join_model(_host_model(model)), device, dtype)
     return model, model_name
 
 
 def _fit_loop(model, data_dev, resample_func, guard, writer, checkpoint_path, start_iter, num_iters,
-              save_every_n_iters, ar_only, verbose, jitter, parallel_message_passing, extra):
+              save_every_n_iters, ar_only, verbose, jitter, parallel_message_passing, extra, shards):
     with _trange(start_iter, num_iters + 1, ncols=72) as pbar:
         for iteration in pbar:
             try:
@@ -271,10 +335,11 @@ def _fit_loop(model, data_dev, resample_func, guard, writer, checkpoint_path, st
                     if not _drain_guard(guard, pbar):           # never checkpoint an unchecked sweep
                         model = guard.clean
                         break
+                    snapshot = shards.join_model(_host_model(model))      # collective when sharded
                     if writer is not None:
-                        writer.submit(checkpoint_path, _host_model(model), f"model_snapshots/{iteration}")
-                    else:
-                        save_hdf5(checkpoint_path, _host_model(model), f"model_snapshots/{iteration}", exist_ok=True)
+                        writer.submit(checkpoint_path, snapshot, f"model_snapshots/{iteration}")
+                    elif shards.writes:
+                        save_hdf5(checkpoint_path, snapshot, f"model_snapshots/{iteration}", exist_ok=True)
                     # progress plots (viz.plot_progress) are outside the sweep's scope and are skipped
         else:
             if not _drain_guard(guard, pbar):
@@ -294,12 +359,13 @@ def apply_model(model, data, metadata, project_dir=None, model_name=None, num_it
     dtype = kwargs.pop("dtype", torch.float64)
     device = kwargs.pop("device", "cuda")
     extra = {key: kwargs.pop(key) for key in ("hmm_dtype", "group", "fix_heading") if key in kwargs}
-    data_dev = gibbs.to_device_data(data, device, dtype)
+    shards = _Shards(extra.get("group"), data, metadata)
     if save_results and results_path is None:
         assert project_dir is not None and model_name is not None, fill(
             "The `save_results` option requires either a `results_path` or the `project_dir` and "
             "`model_name` arguments")
         results_path = os.path.join(project_dir, model_name, "results.h5")
+    data_dev = gibbs.to_device_data(shards.split_data(data), device, dtype)
     model = init_model(data=data_dev, seed=model["seed"], params=model["params"], hypparams=model["hypparams"],
                        dtype=dtype, device=device, **kwargs)
     model = gibbs.to_device_model(model, device, dtype)
@@ -311,7 +377,9 @@ def apply_model(model, data, metadata, project_dir=None, model_name=None, num_it
                                           parallel_message_passing=parallel_message_passing, **extra)
             except StopResampling:
                 break
-    results = extract_results(model, metadata, project_dir, model_name, save_results, results_path,
+    if shards.world > 1:          # states-only sweeps exchange nothing; the rows meet again here, rank 0 saves
+        model = gibbs.to_device_model(shards.join_model(_host_model(model)), device, dtype)
+    results = extract_results(model, metadata, project_dir, model_name, save_results and shards.writes, results_path,
                               overwrite=overwrite)
     return (results, model) if return_model else results
 

@@ -169,11 +169,21 @@ class NanGuard:
     the device and copied to pinned host memory asynchronously, and is read `lag` sweeps later, so the
     host can queue a whole sweep ahead of the GPU instead of draining it after every sweep.  A failed
     check is reported at most `lag` sweeps late; the caller keeps the last model known to be clean.
-    `lag = 0` is the synchronous check."""
+    `lag = 0` is the synchronous check.  `group`: ranks of a sharded fit agree on every verdict."""
 
-    def __init__(self, lag=1):
+    def __init__(self, lag=1, group=None):
         import collections
-        self.lag, self.pending, self.pool = int(lag), collections.deque(), []
+        self.lag, self.pending, self.pool, self.group = int(lag), collections.deque(), [], group
+
+    def _any_rank(self, flag):
+        """With a process group the verdict is shared (MAX over ranks): a rank that stopped alone would leave
+        the others waiting in the next sweep's all-reduce."""
+        if self.group is None:
+            return flag
+        import torch.distributed as dist
+        word = flag.to(torch.int32).reshape(1)
+        dist.all_reduce(word, op=dist.ReduceOp.MAX, group=self.group)
+        return word[0] > 0
 
     def submit(self, model):
         leaves = []
@@ -192,7 +202,7 @@ class NanGuard:
         if not leaves:
             self.pending.append((None, None, model))
             return
-        flag = torch.stack([torch.isnan(t).any() for t in leaves]).any()
+        flag = self._any_rank(torch.stack([torch.isnan(t).any() for t in leaves]).any())
         host = self.pool.pop() if self.pool else torch.empty((), dtype=torch.bool).pin_memory()
         host.copy_(flag, non_blocking=True)
         ev = torch.cuda.Event()
@@ -209,7 +219,7 @@ class NanGuard:
             host, ev, model = self.pending.popleft()
             bad = False
             if host is None:
-                bad = check_for_nans(model)[0]
+                bad = bool(self._any_rank(torch.tensor(bool(check_for_nans(model)[0]))))
             else:
                 ev.synchronize()
                 bad = bool(host.item())

@@ -409,3 +409,106 @@ def test_bench_reference_arm_prints_one_contract_line():
     cpu = line["cpu_baseline"]
     assert cpu["kind"] == "port" and cpu["cores"] == 2 and cpu["value"] == line["value"] and "2 host processes" in cpu["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def _sharded_fit_worker(rank, world, port, tmp):
+    """Two ranks run the SAME fit_model / apply_model call on the full cohort with group=WORLD; the sweep is a
+    stub (no GPU here) that adds one to x on the rows it is given and all-reduces the valid-frame count."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from keypoint_moseq_b200 import fitting, io
+    N, T = 5, 6
+    mask = np.ones((N, T))
+    mask[1, 4:] = 0
+    mask[4, 2:] = 0
+    keys = ["a", "a", "b", "c", "c"]
+    metadata = (keys, np.array([[0, 6], [6, 10], [0, 6], [0, 6], [6, 8]]))
+    x0 = np.arange(N, dtype=np.float64)[:, None, None] * np.ones((N, T, 2))
+
+    def fresh():
+        return {"seed": 0, "states": {"x": torch.tensor(x0), "z": torch.zeros(N, T - 1, dtype=torch.int64)},
+                "params": {"count": torch.zeros(1, dtype=torch.float64)}, "hypparams": {},
+                "noise_prior": torch.ones(N, T, 3, dtype=torch.float64)}
+
+    data = {"Y": torch.zeros(N, T, 3, 2, dtype=torch.float64), "mask": torch.tensor(mask)}
+    poison = {"at": None}
+    sweeps = {"n": 0}
+
+    def stub_sweep(d, seed, states, params, hypparams, noise_prior, group=None, **kw):
+        assert group is not None and states["x"].shape[0] == d["mask"].shape[0] == noise_prior.shape[0] < N
+        sweeps["n"] += 1
+        total = d["mask"].sum().reshape(1).clone()
+        dist.all_reduce(total, group=group)                 # stands for the statistics all-reduce of the real sweep
+        x = states["x"] + 1.0
+        if poison["at"] == sweeps["n"] and rank == 1:
+            x = x.clone()
+            x[0, 0, 0] = float("nan")
+        return {"seed": seed + 1, "states": dict(states, x=x), "params": {"count": total}, "hypparams": hypparams,
+                "noise_prior": noise_prior}
+
+    fitting.gibbs.resample_model = stub_sweep
+    fitting.gibbs.to_device_data = lambda d, *a, **k: d
+    fitting.gibbs.to_device_model = lambda m, *a, **k: m
+    out = {}
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model, name = fitting.fit_model(fresh(), data, metadata, tmp, None, num_iters=4, save_every_n_iters=2,
+                                        generate_progress_plots=False, group=dist.group.WORLD, device="cpu")
+        out["name"] = name
+        out["x"] = np.asarray(model["states"]["x"])
+        out["count"] = float(np.asarray(model["params"]["count"])[0])
+        out["prior_rows"] = int(np.asarray(model["noise_prior"]).shape[0])
+        # a NaN on rank 1 alone stops every rank at the same sweep (synchronous check for a deterministic count)
+        sweeps["n"], poison["at"] = 0, 3
+        model2, _ = fitting.fit_model(fresh(), data, metadata, tmp, "nan_run", num_iters=6, save_every_n_iters=None,
+                                      generate_progress_plots=False, group=dist.group.WORLD, device="cpu", nan_check_lag=0)
+        out["x_nan"] = np.asarray(model2["states"]["x"])
+        out["sweeps_nan"] = sweeps["n"]
+        poison["at"] = None
+        # apply_model: rows meet again for extract_results, rank 0 alone saves
+        fitting.init_model = lambda data=None, **kw: {"seed": 0, "states": {"x": torch.zeros(data["mask"].shape[0], T, 2, dtype=torch.float64),
+                                                                           "z": torch.zeros(data["mask"].shape[0], T - 1, dtype=torch.int64),
+                                                                           "v": torch.zeros(data["mask"].shape[0], T, 2, dtype=torch.float64),
+                                                                           "h": torch.zeros(data["mask"].shape[0], T, dtype=torch.float64)},
+                                                      "params": {"count": torch.zeros(1)}, "hypparams": {},
+                                                      "noise_prior": torch.ones(data["mask"].shape[0], T, 3, dtype=torch.float64)}
+        res = fitting.apply_model({"seed": 0, "params": {}, "hypparams": {}}, data, metadata, tmp, name, num_iters=3,
+                                  group=dist.group.WORLD, device="cpu")
+        out["results_keys"] = sorted(res)
+        out["latent_a"] = np.asarray(res["a"]["latent_state"])
+    np.save(os.path.join(tmp, f"sharded_fit_{rank}.npy"), np.array([out], dtype=object), allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_fit_and_apply_write_on_rank_zero_and_return_whole_models(tmp_path):
+    """rows are sharded inside fit_model / apply_model, snapshots are gathered and written by rank 0 only,
+    every rank returns the whole model, and a NaN seen by one rank stops all of them together."""
+    import torch.multiprocessing as mp
+    from keypoint_moseq_b200 import io
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_sharded_fit_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    outs = [np.load(tmp_path / f"sharded_fit_{r}.npy", allow_pickle=True)[0] for r in range(2)]
+    N, T = 5, 6
+    x0 = np.arange(N, dtype=np.float64)[:, None, None] * np.ones((N, T, 2))
+    assert outs[0]["name"] == outs[1]["name"]                          # the timestamped name is rank 0's
+    for o in outs:
+        np.testing.assert_array_equal(o["x"], x0 + 5.0)               # sweeps 0..4, every row, original order
+        assert o["count"] == 24.0 and o["prior_rows"] == N            # 30 frames - 6 masked, summed over ranks
+        np.testing.assert_array_equal(o["x_nan"], x0 + 2.0)           # last clean model, whole, on every rank
+        assert o["sweeps_nan"] == 3
+        assert o["results_keys"] == ["a", "b", "c"]
+        assert o["latent_a"].shape == (10, 2) and np.all(o["latent_a"] == 3.0)
+    ckpt = os.path.join(str(tmp_path), outs[0]["name"], "checkpoint.h5")
+    saved = io.load_hdf5(ckpt)
+    assert sorted(saved["model_snapshots"], key=int) == ["0", "2", "4"]
+    np.testing.assert_array_equal(saved["model_snapshots"]["2"]["states"]["x"], x0 + 3.0)
+    np.testing.assert_array_equal(saved["model_snapshots"]["4"]["states"]["x"], x0 + 5.0)
+    assert saved["model_snapshots"]["4"]["noise_prior"].shape == (N, T, 3)
+    assert saved["data"]["mask"].shape == (N, T)
+    results = io.load_results(str(tmp_path), outs[0]["name"])
+    assert sorted(results) == ["a", "b", "c"] and results["c"]["latent_state"].shape == (8, 2)
