@@ -268,6 +268,9 @@ def fit_model(model, data, metadata, project_dir=None, model_name=None, num_iter
     `nan_check_lag`, and `async_checkpoints` (default False: snapshots are written before the next sweep is
     launched, as in the reference; True: the snapshot is copied to the host and written by `io.SnapshotWriter`
     on a background thread while the next sweeps run - all writes have finished when fit_model returns).
+    With `group` (a torch.distributed process group, one rank per GPU) every rank passes the same full data and
+    model; rows are sharded inside, rank 0 writes the gathered snapshots and every rank returns the whole model
+    (see `_Shards`).
     """
     if location_aware:
         raise NotImplementedError("location_aware=True (allo_keypoint_slds) is not implemented by the B200 sweep")
