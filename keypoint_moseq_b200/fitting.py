@@ -398,7 +398,9 @@ def estimate_syllable_marginals(model, data, metadata, burn_in_iters=200, num_sa
     parallel_message_passing = _set_parallel_flag(parallel_message_passing)
     dtype = kwargs.pop("dtype", torch.float64)
     device = kwargs.pop("device", "cuda")
-    data_dev = gibbs.to_device_data(data, device, dtype)
+    extra = {key: kwargs.pop(key) for key in ("hmm_dtype", "group") if key in kwargs}
+    shards = _Shards(extra.get("group"), data, metadata)          # rows sharded over the ranks, joined at the end
+    data_dev = gibbs.to_device_data(shards.split_data(data), device, dtype)
     model = init_model(data=data_dev, seed=model["seed"], params=model["params"], hypparams=model["hypparams"],
                        dtype=dtype, device=device, **kwargs)
     model = gibbs.to_device_model(model, device, dtype)
@@ -408,7 +410,7 @@ def estimate_syllable_marginals(model, data, metadata, burn_in_iters=200, num_sa
         for it in pbar:
             try:
                 model = _wrapped_resample(gibbs.resample_model, data_dev, model, pbar=pbar, states_only=True,
-                                          verbose=verbose, parallel_message_passing=parallel_message_passing)
+                                          verbose=verbose, parallel_message_passing=parallel_message_passing, **extra)
             except StopResampling:
                 break
             if it >= burn_in_iters and (it - burn_in_iters) % steps_per_sample == 0:
@@ -420,6 +422,9 @@ def estimate_syllable_marginals(model, data, metadata, burn_in_iters=200, num_sa
     nlags = get_nlags(model["params"]["Ab"])
     keys, bounds = list(metadata[0]), np.asarray(metadata[1]) + np.array([nlags, 0])
     est = (acc / num_samples).cpu().numpy()
+    if shards.world > 1:
+        est = gather_rows(est, shards.rows_per_rank, shards.group)
+        samples = [gather_rows(z, shards.rows_per_rank, shards.group) for z in samples]
     marginals = unbatch(est, keys, bounds)
     marginals = {k_: np.pad(v[nlags:], ((nlags, 0), (0, 0)), mode="edge") for k_, v in marginals.items()}
     if return_samples:

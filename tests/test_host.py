@@ -433,7 +433,11 @@ def _sharded_fit_worker(rank, world, port, tmp):
                 "params": {"count": torch.zeros(1, dtype=torch.float64)}, "hypparams": {},
                 "noise_prior": torch.ones(N, T, 3, dtype=torch.float64)}
 
-    data = {"Y": torch.zeros(N, T, 3, 2, dtype=torch.float64), "mask": torch.tensor(mask)}
+    data = {"Y": torch.zeros(N, T, 3, 2, dtype=torch.float64), "mask": torch.tensor(mask), "row": torch.arange(N, dtype=torch.float64)}
+
+    def shard_x(d):       # x = 10 * global row index, so the joined marginals show which row went where
+        return (10.0 * d["row"])[:, None, None] * torch.ones(d["mask"].shape[0], T, 2, dtype=torch.float64)
+
     poison = {"at": None}
     sweeps = {"n": 0}
 
@@ -446,7 +450,7 @@ def _sharded_fit_worker(rank, world, port, tmp):
         if poison["at"] == sweeps["n"] and rank == 1:
             x = x.clone()
             x[0, 0, 0] = float("nan")
-        return {"seed": seed + 1, "states": dict(states, x=x), "params": {"count": total}, "hypparams": hypparams,
+        return {"seed": seed + 1, "states": dict(states, x=x), "params": dict(params, count=total), "hypparams": hypparams,
                 "noise_prior": noise_prior}
 
     fitting.gibbs.resample_model = stub_sweep
@@ -480,6 +484,17 @@ def _sharded_fit_worker(rank, world, port, tmp):
                                   group=dist.group.WORLD, device="cpu")
         out["results_keys"] = sorted(res)
         out["latent_a"] = np.asarray(res["a"]["latent_state"])
+        # estimate_syllable_marginals: local smoother marginals, rows joined before unbatching
+        fitting.gibbs.stateseq_marginals = lambda x, mask, Ab, Q, pi: x[:, 1:, :1].repeat(1, 1, 3) * 0 + x[:, 1:, :1]
+        fitting.get_nlags = lambda Ab: 1
+        fitting.init_model = lambda data=None, **kw: {
+            "seed": 0, "states": {"x": shard_x(data), "z": torch.zeros(data["mask"].shape[0], T - 1, dtype=torch.int64)},
+            "params": {"Ab": None, "Q": None, "pi": None}, "hypparams": {}, "noise_prior": torch.ones(data["mask"].shape[0], T, 3, dtype=torch.float64)}
+        marg, smp = fitting.estimate_syllable_marginals({"seed": 0, "params": {}, "hypparams": {}}, data, metadata,
+                                                        burn_in_iters=1, num_samples=2, steps_per_sample=1,
+                                                        return_samples=True, group=dist.group.WORLD, device="cpu")
+        out["marg_c"] = np.asarray(marg["c"])
+        out["smp_a"] = np.asarray(smp["a"]).shape
     np.save(os.path.join(tmp, f"sharded_fit_{rank}.npy"), np.array([out], dtype=object), allow_pickle=True)
     dist.barrier()
     dist.destroy_process_group()
@@ -503,6 +518,11 @@ def test_two_rank_fit_and_apply_write_on_rank_zero_and_return_whole_models(tmp_p
         assert o["sweeps_nan"] == 3
         assert o["results_keys"] == ["a", "b", "c"]
         assert o["latent_a"].shape == (10, 2) and np.all(o["latent_a"] == 3.0)
+        # recording c = rows 3 and 4 (6 + 2 frames): sweeps add 1 per iteration, samples after sweeps 2 and 3
+        # (frame 6 is the first frame of row 4, cut by the nlags shift; real rows overlap their predecessor there)
+        np.testing.assert_allclose(o["marg_c"][:6, 0], 30.0 + 2.5)
+        np.testing.assert_allclose(o["marg_c"][7, 0], 40.0 + 2.5)
+        assert o["marg_c"].shape == (8, 3) and o["smp_a"] == (10, 2)
     ckpt = os.path.join(str(tmp_path), outs[0]["name"], "checkpoint.h5")
     saved = io.load_hdf5(ckpt)
     assert sorted(saved["model_snapshots"], key=int) == ["0", "2", "4"]
