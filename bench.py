@@ -303,6 +303,23 @@ def kernel_bytes_per_frame(name, cfg, esz, hmm_esz):
     return table.get(name)
 
 
+MEASURED_FP32_TFLOPS = 71.6   # FFMA peak measured on this pool's B200 (profiles/r01_dmma_peak.txt, 32 warps/SM)
+
+
+def kernel_flops_per_frame(name, cfg):
+    """Algorithmic floating-point operations per (chain, frame) of the factorisation kernels:
+    backward preparation = A S, A S A' + Q, two Cholesky, two triangular solves, one symmetric rank-n update
+    = 13/6 n^3 multiply-adds; filter step = rank-d measurement update of the n x n covariance, companion-form
+    prediction, d x d factorisation.  Other kernels are memory-shaped and return None."""
+    d, L = cfg["d"], cfg["L"]
+    n = d * L
+    table = {
+        "kalman_backprep": 2.0 * (13.0 / 6.0) * n ** 3,
+        "kalman_forward": 2.0 * (3.0 * n * n * d + n * d * d + d ** 3),
+    }
+    return table.get(name)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -510,6 +527,16 @@ def main():
                             "shared-memory operand traffic (ncu: issue slots 41 % busy, FMA pipe 28 %, DRAM traffic = "
                             "0.96 x algorithmic bytes); the HBM fraction is reported as the contract requires "
                             "(DESIGN.md section 4.1)"}
+
+    try:        # the dominant kernels are arithmetic-shaped: say what fraction of the FP32 SIMT peak they reach
+        fpf = kernel_flops_per_frame(roofline["kernel"], cfg) if roofline else None
+        if fpf:
+            tf = fpf * frames_rank / (roofline["launch_ms"] * 1e-3) / 1e12
+            roofline["compute"] = {"achieved": tf, "peak": MEASURED_FP32_TFLOPS, "unit": "TFLOP/s",
+                                   "frac": tf / MEASURED_FP32_TFLOPS, "flops_per_frame": fpf,
+                                   "peak_source": "FFMA micro-benchmark, profiles/r01_dmma_peak.txt"}
+    except Exception as e:  # noqa: BLE001 - never lose the bench line over a derived figure
+        print(f"bench: compute roofline skipped ({e!r})", file=sys.stderr)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
