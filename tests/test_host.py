@@ -532,3 +532,38 @@ def test_two_rank_fit_and_apply_write_on_rank_zero_and_return_whole_models(tmp_p
     assert saved["data"]["mask"].shape == (N, T)
     results = io.load_results(str(tmp_path), outs[0]["name"])
     assert sorted(results) == ["a", "b", "c"] and results["c"]["latent_state"].shape == (8, 2)
+
+
+def test_batch_unbatch_and_sharding_properties_hold_for_ragged_cohorts():
+    """Property test over ragged cohorts (empty-ish, tiny and long recordings, any segment length): unbatch
+    inverts batch exactly, the mask counts every frame once plus the overlap, and shard_rows is a partition whose
+    shards reassemble (as gather_rows does) to the original rows."""
+    from hypothesis import given, settings, strategies as st
+    from keypoint_moseq_b200.dist import shard_rows, shard_tree
+    from keypoint_moseq_b200.util import batch, unbatch
+
+    @settings(max_examples=60, deadline=None)
+    @given(lengths=st.lists(st.integers(min_value=1, max_value=90), min_size=1, max_size=6),
+           seg=st.integers(min_value=5, max_value=60), overlap=st.integers(min_value=0, max_value=8),
+           world=st.integers(min_value=1, max_value=4), seed=st.integers(min_value=0, max_value=10 ** 6))
+    def check(lengths, seg, overlap, world, seed):
+        rng = np.random.default_rng(seed)
+        recs = {f"r{i}": rng.standard_normal((n, 2)) for i, n in enumerate(lengths)}
+        stack, mask, (keys, bounds) = batch(recs, seg_length=seg, seg_overlap=overlap)
+        assert stack.shape[:2] == mask.shape and stack.shape[1] == seg + overlap
+        back = unbatch(stack, keys, bounds)
+        assert set(back) == set(recs)
+        for name, arr in recs.items():
+            np.testing.assert_array_equal(back[name], arr)
+        bounds = np.asarray(bounds)
+        np.testing.assert_array_equal(mask.sum(1), bounds[:, 1] - bounds[:, 0])      # valid frames per row
+        shards = shard_rows(mask, world, keys)
+        flat = np.sort(np.concatenate(shards))
+        np.testing.assert_array_equal(flat, np.arange(mask.shape[0]))                # a partition of the rows
+        joined = np.empty_like(stack)
+        for rows in shards:
+            if len(rows):
+                joined[rows] = shard_tree({"Y": stack}, rows)["Y"]
+        np.testing.assert_array_equal(joined, stack)
+
+    check()
