@@ -18,7 +18,8 @@ def shard_rows(mask, world_size, keys=None):
     """Greedy balanced assignment of rows to ranks by valid-frame count.
 
     Rows of one recording (equal `keys`) are kept on one rank when that does not unbalance the
-    load by more than one row.  Returns a list of index arrays, one per rank, each sorted.
+    load by more than one row; otherwise (few long recordings, many ranks) single rows are dealt out.
+    Returns a list of index arrays, one per rank, each sorted.
     """
     mask = np.asarray(mask.cpu() if isinstance(mask, torch.Tensor) else mask)
     load = mask.sum(1).astype(np.int64)
@@ -30,13 +31,21 @@ def shard_rows(mask, world_size, keys=None):
         for i, key in enumerate(keys):
             order.setdefault(key, []).append(i)
         groups = list(order.values())
-    groups.sort(key=lambda g: (-int(load[g].sum()), g[0]))
-    totals = np.zeros(world_size, dtype=np.int64)
-    out = [[] for _ in range(world_size)]
-    for g in groups:
-        r = int(np.argmin(totals))
-        out[r].extend(g)
-        totals[r] += int(load[g].sum())
+
+    def deal(groups):
+        groups = sorted(groups, key=lambda g: (-int(load[g].sum()), g[0]))
+        totals = np.zeros(world_size, dtype=np.int64)
+        out = [[] for _ in range(world_size)]
+        for g in groups:
+            r = int(np.argmin(totals))
+            out[r].extend(g)
+            totals[r] += int(load[g].sum())
+        return out, totals
+
+    out, totals = deal(groups)
+    if keys is not None and N and int(totals.max() - totals.min()) > int(load.max()):
+        # few long recordings on many ranks: whole recordings cannot be balanced, deal single rows instead
+        out, totals = deal([[i] for i in range(N)])
     return [np.array(sorted(rows), dtype=np.int64) for rows in out]
 
 

@@ -151,6 +151,10 @@ def test_shard_rows_balances_and_keeps_recordings_together():
         assert len(owners) == 1
     sub = shard_tree({"Y": np.arange(7)[:, None] * np.ones((7, 3)), "m": torch.arange(7)}, shards[0])
     assert sub["Y"].shape[0] == len(shards[0]) and sub["m"].tolist() == shards[0].tolist()
+    # one long recording on four ranks: whole recordings cannot balance, single rows are dealt out instead
+    shards = shard_rows(np.ones((8, 50), dtype=int), 4, ["a"] * 8)
+    assert sorted(len(s) for s in shards) == [2, 2, 2, 2]
+    assert sorted(np.concatenate(shards).tolist()) == list(range(8))
 
 
 def _gloo_worker(rank, world, port, tmp):
