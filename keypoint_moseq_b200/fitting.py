@@ -125,12 +125,12 @@ class _Shards:
             import torch.distributed as dist
             self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > 1:
+            self.N = int(data["mask"].shape[0])
             self.rows_per_rank = shard_rows(data["mask"], self.world, list(metadata[0]))
             if min(len(rows) for rows in self.rows_per_rank) == 0:
-                raise ValueError(f"{self.world} ranks but only {self.N if hasattr(self, 'N') else data['mask'].shape[0]} row(s): "
-                                 "every rank needs at least one row; use fewer GPUs or a shorter segment length")
+                raise ValueError(f"{self.world} ranks but only {self.N} row(s): every rank needs at least one row; "
+                                 "use fewer GPUs or a shorter segment length")
             self.rows = self.rows_per_rank[self.rank]
-            self.N = int(data["mask"].shape[0])
 
     @property
     def writes(self):
