@@ -206,12 +206,69 @@ __device__ inline HmmTask hmm_task(long long id, int pass, int N, int Tp, int C,
         const int b = vb[nn] + k * HMM_TL;
         if (b >= Tp) return t;
         t.on = true; t.given = true; t.nn = nn; t.begin = t.start = b; t.end = min(b + HMM_TL, Tp); t.slot = k;
+    } else if (pass == 3) {
+        // refinement: the prefix chunks of the chains still flagged, restarted (no warm-up) from the end
+        // state their predecessor produced in the previous pass; chains with mask holes stay sequential
+        const int nn = (int)(id / C), ck = (int)(id % C);
+        if (nn >= N || dirty[nn] == 0 || vb[N + nn] != 0) return t;
+        const int v = vb[nn];
+        const ChunkRange cr = chunk_range(v, v, C, Wm, ck, 8);
+        if (cr.empty || cr.begin >= cr.end) return t;
+        t.on = true; t.given = ck > 0; t.nn = nn; t.begin = t.start = cr.begin; t.end = cr.end; t.slot = ck;
     } else {
         const int nn = (int)id;
         if (nn >= N || (dirty && dirty[nn] == 0)) return t;
         t.on = true; t.nn = nn; t.begin = t.start = 0; t.end = Tp; t.slot = 0;
     }
     return t;
+}
+
+// After a refinement pass: boundary c of a refined chain compares the start chunk c used (`cur`, the end state
+// chunk c-1 had produced one pass earlier) with the end state chunk c-1 produced in this pass (`fresh`),
+// component by component (see boundary_check_kernel<COMPONENTWISE>), then makes the fresh state current.
+// When every boundary of a chain agrees, its chunks all started from what their predecessors now end in, so
+// the concatenation IS the sequential filter to that tolerance.  Grid (C, N); boundary C feeds the padded tail.
+template <typename R>
+__global__ void __launch_bounds__(128)
+hmm_refine_check_kernel(R* __restrict__ cur, const R* __restrict__ fresh, const int* __restrict__ vb, int N, int Tp,
+                        int C, int Wm, int K, R tol, const int* __restrict__ dirty_in, int* __restrict__ dirty_out,
+                        unsigned* __restrict__ left) {
+    __shared__ R red[4];
+    const int nn = blockIdx.y, c = blockIdx.x + 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (dirty_in[nn] == 0) return;
+    if (vb[N + nn] != 0) {                                   // mask holes: sequential re-run, as before
+        if (c == 1 && threadIdx.x == 0 && atomicExch(&dirty_out[nn], 1) == 0) atomicAdd(left, 1u);
+        return;
+    }
+    const int v = vb[nn];
+    const ChunkRange prev = chunk_range(v, v, C, Wm, c - 1, 8);
+    if (prev.empty || prev.begin >= prev.end || prev.end >= Tp) return;       // no end state was written
+    bool compare = false;
+    if (c < C) {
+        const ChunkRange me = chunk_range(v, v, C, Wm, c, 8);
+        compare = !me.empty && me.begin < me.end;
+    }
+    R* a = cur + ((size_t)nn * C + c) * K;
+    const R* b = fresh + ((size_t)nn * C + c) * K;
+    R worst = 0;
+    int bad = 0;
+    for (int e = threadIdx.x; e < K; e += blockDim.x) {
+        const R x = a[e], y = b[e];
+        if (compare) {
+            R dd = fabs(x - y);
+            if (!(dd < (R)INFINITY)) bad = 1;
+            const R big = fmax(fabs(x), fabs(y));
+            worst = fmax(worst, big > (R)0 ? dd / big : (R)0);
+        }
+        a[e] = y;
+    }
+    worst = warp_max(worst);
+    if (lane == 0) red[warp] = worst;
+    const int any_bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0 && compare) {
+        worst = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+        if ((any_bad || !(worst <= tol)) && atomicExch(&dirty_out[nn], 1) == 0) atomicAdd(left, 1u);
+    }
 }
 
 // ROWW: the weights are (N, Tp, ldW) state-contiguous (float64 path) instead of (N, K, ldT).
@@ -369,7 +426,7 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
         if (tid == 4 * m) {
             const double val = lz[m] + log(lzp[m]) + 0.6931471805599453094 * (double)lze[m] + msum[m];
             if (pass == 2) logZ[tk[m].nn] = val;
-            else logZ_part[(size_t)tk[m].nn * (C + CT) + (pass == 0 ? tk[m].slot : C + tk[m].slot)] = val;
+            else logZ_part[(size_t)tk[m].nn * (C + CT) + (pass == 1 ? C + tk[m].slot : tk[m].slot)] = val;
         }
     }
 }
@@ -793,7 +850,7 @@ static void hmm_ws_layout(int N, int T, int K, int d, int L, size_t off[HW_END +
                          (size_t)state_tiles(K) * (d * ((d * L + d + 3) / 4) * 32 + d * 8 + 8) * sizeof(double),
                          (size_t)K * sizeof(R),
                          (size_t)N * 8,
-                         (size_t)N * 4,
+                         (size_t)N * 8,
                          (size_t)N * (C + 1) * K * sizeof(R),
                          (size_t)N * (C + 1) * K * sizeof(R),
                          (size_t)N * (C + CT) * sizeof(double),
@@ -888,6 +945,11 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
     R* tstart = reinterpret_cast<R*>(base + off[HW_TS]);
     R* pw = reinterpret_cast<R*>(base + off[HW_PW]);
     const ChunkConfig cfg = chunk_config();
+    static const int cfg_refine = [] {
+        const char* e = getenv("KPMS_HMM_REFINE");
+        const int v = e ? atoi(e) : 3;                           // default: three passes (0 switches them off)
+        return v < 0 ? 0 : v > 8 ? 8 : v;
+    }();
     const int C = hmm_chunks(N, Tp, sizeof(R) == 8), CT = (Tp + HMM_TL - 1) / HMM_TL, Wm = (cfg.warmup + 7) / 8 * 8;
     const dim3 block(4 * Kpad);
 #define FWD(RPT, GRID, PASS, VB, DIRTY)                                                                       \
@@ -902,7 +964,8 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
 #define FWD64(KT_, GRID, PASS, VB, DIRTY)                                                                     \
     hmm_forward_dmma_kernel<KT_, HMM_MT><<<GRID, 32 * KT_, 0, st>>>(                                          \
         (const double*)W, (const double*)mx, (const double*)pi, N, K, Tp, ldT, ldK, (double*)filt, logZ, lzp, \
-        PASS, C, CT, Wm, VB, DIRTY, (double*)bw, (double*)be, (const double*)tstart);
+        PASS, C, CT, Wm, VB, DIRTY, (double*)bw, (PASS) == 3 ? (double*)nullptr : (double*)be,                \
+        (PASS) == 3 ? (const double*)be : (const double*)tstart);
 #define FWD_K(GRID, PASS, VB, DIRTY)                                             \
     if (sizeof(R) == 8) {                                                        \
         if (K <= 32) FWD64(4, GRID, PASS, VB, DIRTY)                             \
@@ -926,6 +989,26 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
     { KPMS_LAUNCH("hmm_forward_check", st);
       cudaMemsetAsync(dirty, 0, (size_t)N * sizeof(int), st);
       boundary_check_kernel<R, true><<<dim3(C - 1, N), 128, 0, st>>>(bw, be, vb, Tp, C, Wm, 8, K, K, tol, dirty, diag, holes); }
+    if (sizeof(R) == 8 && cfg_refine > 0) {
+        // Refinement passes (KPMS_HMM_REFINE=<passes>, default 3): chains whose warm-up did not forget are not
+        // handed to the sequential kernel at once; their chunks restart from the predecessor's last end state,
+        // the boundary error contracts by the chunk-long forgetting factor per pass, and the same
+        // component-wise check certifies convergence.  Chains still flagged afterwards fall back as before.
+        int* dirty2 = dirty + N;
+        int* din = dirty;
+        int* dout = dirty2;
+        cudaMemsetAsync(diag + 4, cfg_refine, 1, st);            // low byte of word 4 = passes enabled
+        for (int r = 0; r < cfg_refine; ++r) {
+            cudaMemsetAsync(dout, 0, (size_t)N * sizeof(int), st);
+            cudaMemsetAsync(diag + 5, 0, sizeof(unsigned), st);
+            { KPMS_LAUNCH("hmm_forward_refine", st);
+              FWD_K((int)(((long long)N * C + M - 1) / M), 3, vb, din) }
+            { KPMS_LAUNCH("hmm_forward_check", st);
+              hmm_refine_check_kernel<R><<<dim3(C, N), 128, 0, st>>>(be, bw, vb, N, Tp, C, Wm, K, tol, din, dout, diag + 5); }
+            int* tmp = din; din = dout; dout = tmp;
+        }
+        dirty = din;
+    }
     // pi^TL by repeated squaring, then the starting predictions of the padded-tail chunks
     {
         const R* src = (const R*)pi;

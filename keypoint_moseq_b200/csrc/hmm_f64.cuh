@@ -152,7 +152,9 @@ ar_loglik_dmma_kernel(const double* __restrict__ x, const int* __restrict__ mask
 // fragments; the filtered vectors of the 8 tasks of a tile are the A operand, exchanged through a
 // double-buffered shared tile; one barrier per step.  Scaled filter (same recursion as the
 // float kernel):  q_t = pred_t * w_t,  s_t = sum q_t,  filt_t = q_t / s_t,  pred_{t+1} = pi' filt_t.
-// Task scheme (prefix chunks / padded-tail chunks / sequential re-run) as in hmm_forward_kernel.
+// Task scheme (prefix chunks / padded-tail chunks / sequential re-run) as in hmm_forward_kernel, plus pass 3:
+// refinement of flagged chains (prefix chunks restarted from `tail_start` = the current end states, fresh end
+// states written to `bnd_warm`; see hmm_refine_check_kernel).
 // ---------------------------------------------------------------------------
 template <int KT, int MT>
 __global__ void __launch_bounds__(32 * KT, 1)
@@ -201,7 +203,9 @@ hmm_forward_dmma_kernel(const double* __restrict__ W, const double* __restrict__
         pr[mt][0] = c0 < K ? 1.0 / (double)K : 0.0;
         pr[mt][1] = c0 + 1 < K ? 1.0 / (double)K : 0.0;
         if (tk[mt].on && tk[mt].given) {
-            const double* ts = tail_start + ((size_t)tk[mt].nn * CT + tk[mt].slot) * K;
+            // padded-tail chunks start from pi-power predictions; refinement chunks (pass 3) from the end
+            // state of their predecessor, kept per (chain, chunk) like the boundary records
+            const double* ts = tail_start + ((size_t)tk[mt].nn * (pass == 3 ? C : CT) + tk[mt].slot) * K;
             pr[mt][0] = c0 < K ? ts[c0] : 0.0;
             pr[mt][1] = c0 + 1 < K ? ts[c0 + 1] : 0.0;
         }
@@ -283,15 +287,15 @@ hmm_forward_dmma_kernel(const double* __restrict__ W, const double* __restrict__
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         if (!tk[mt].on) continue;
-        if (pass == 0 && tk[mt].end < Tp) {                   // handed to the next chunk / to the padded tail
-            double* be = bnd_end + ((size_t)tk[mt].nn * C + tk[mt].slot + 1) * K;
+        if ((pass == 0 || pass == 3) && tk[mt].end < Tp) {    // handed to the next chunk / to the padded tail
+            double* be = (pass == 3 ? bnd_warm : bnd_end) + ((size_t)tk[mt].nn * C + tk[mt].slot + 1) * K;
             if (c0 < K) be[c0] = pr[mt][0];
             if (c0 + 1 < K) be[c0 + 1] = pr[mt][1];
         }
         if (warp == 0 && p == 0) {
             const double val = lz[mt] + log(lzp[mt]) + 0.6931471805599453094 * (double)lze[mt] + msum_s[mt * 8 + g];
             if (pass == 2) logZ[tk[mt].nn] = val;
-            else logZ_part[(size_t)tk[mt].nn * (C + CT) + (pass == 0 ? tk[mt].slot : C + tk[mt].slot)] = val;
+            else logZ_part[(size_t)tk[mt].nn * (C + CT) + (pass == 1 ? C + tk[mt].slot : tk[mt].slot)] = val;
         }
     }
 }

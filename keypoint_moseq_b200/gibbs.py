@@ -44,12 +44,15 @@ def chunk_diagnostics(tag="kalman_ws", device="cuda"):
                 buf = b
     if buf is None:
         return None
-    raw = buf[:16].cpu().numpy()
+    raw = buf[:32].cpu().numpy()
     u = raw.view(np.uint32)
     f = raw.view(np.float32)
     if tag == "hmm_ws":     # backward sampler: exact merge-and-repair, counts instead of a tolerance
-        return {"forward_max_err": float(f[0]), "forward_rerun": int(u[1]),
-                "backward_mismatches": int(u[2]), "backward_rewalked": int(u[3])}
+        out = {"forward_max_err": float(f[0]), "forward_rerun": int(u[1]),
+               "backward_mismatches": int(u[2]), "backward_rewalked": int(u[3])}
+        if int(u[4]) > 0:   # refinement passes enabled (KPMS_HMM_REFINE): chains flagged first / still flagged after
+            out.update(forward_refine_passes=int(u[4]), forward_flagged_first=int(u[1]), forward_rerun=int(u[5]))
+        return out
     return {"forward_max_err": float(f[0]), "forward_rerun": int(u[1]),
             "backward_max_err": float(f[2]), "backward_rerun": int(u[3])}
 

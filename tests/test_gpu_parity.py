@@ -123,8 +123,8 @@ def test_scales_heading_location(dtype, tol, D):
     h, v = g.resample_heading_location(dd["Y"], dd["mask"], s_["x"], s_["v"], s_["h"], s_["s"], p_["Cd"],
                                        p_["sigmasq"], 0.5, u_h=torch.as_tensor(tape["u_h"]),
                                        w_v=torch.as_tensor(tape["w_v"]))
-    dh = np.angle(np.exp(1j * (_np(h) - h_ref)))
-    assert np.abs(dh).max() < (1e-6 if dtype == torch.float64 else 2e-3)
+    dh = np.angle(np.exp(1j * (_np(h).astype(np.float64) - h_ref)))
+    assert np.abs(dh).max() < (1e-6 if dtype == torch.float64 else F32_TOL), np.abs(dh).max()
     # location is conditioned on the heading just drawn: feed the oracle the kernel's heading
     v_ref = orc.resample_location(data["Y"], data["mask"], st["x"], _np(h).astype(np.float64), st["s"], pr["Cd"],
                                   pr["sigmasq"], 0.5, tape["w_v"])
@@ -186,10 +186,9 @@ def test_full_sweep(dtype, tol, flags):
     if not flags.get("ar_only"):
         assert np.abs(_np(out["states"]["s"]) / st_ref["s"] - 1).max() < tol * 10
         assert rel_err(_np(out["states"]["x"]), st_ref["x"]) < tol
-        if dtype == torch.float64:
-            dh = np.angle(np.exp(1j * (_np(out["states"]["h"]) - st_ref["h"])))
-            assert np.abs(dh).max() < 1e-6
-            assert rel_err(_np(out["states"]["v"]), st_ref["v"]) < tol
+        dh = np.angle(np.exp(1j * (_np(out["states"]["h"]).astype(np.float64) - st_ref["h"])))
+        assert np.abs(dh).max() < (1e-6 if dtype == torch.float64 else F32_TOL)
+        assert rel_err(_np(out["states"]["v"]), st_ref["v"]) < tol
 
 
 def test_philox_sweeps_are_finite_and_reproducible():
@@ -301,7 +300,8 @@ def test_discrete_stateseqs_time_chunks(mode, shape, chunking):
     if mode == "chunked":
         assert diag["forward_rerun"] == 0 and diag["forward_max_err"] < 1e-12, diag
     elif mode == "fallback":
-        assert diag["forward_rerun"] > 0, diag
+        # the boundary check flagged chains; refinement passes (default 3) or the sequential re-run repaired them
+        assert diag.get("forward_flagged_first", diag["forward_rerun"]) > 0, diag
     marg = g.stateseq_marginals(dm["states"]["x"], dd["mask"], dm["params"]["Ab"], dm["params"]["Q"], dm["params"]["pi"])
     ref = orc.stateseq_marginals(st["x"], data["mask"].astype(float), pr["Ab"], pr["Q"], pr["pi"])
     assert np.abs(_np(marg) - ref).max() < 1e-9
@@ -327,3 +327,35 @@ def test_host_operands_are_staged_and_streamed_back():
         assert torch.equal(sink[key], ref["states"][key].cpu()), key
     for key in ("Ab", "Q", "pi", "betas"):
         assert torch.equal(out["params"][key], ref["params"][key]), key
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_padding_content_does_not_reach_valid_frames_or_parameters(dtype):
+    """Size-independent property (oracle counterpart in test_oracle.py): whatever sits in the masked frames of
+    the keypoints, the noise prior and the old states must not change any parameter nor any state at a valid
+    frame - bit for bit, Philox draws included, since every kernel gates on the mask and not on the values."""
+    g = _gibbs()
+    data, _, model = small_problem(seed=3, recordings=3, frames=900, seg_length=500, d=4, L=3, K=12, k=5, D=2)
+    mask = np.asarray(data["mask"]) > 0
+    assert (~mask).any()
+    rng = np.random.default_rng(9)
+    data2 = {key: np.array(val, copy=True) for key, val in data.items()}
+    data2["Y"][~mask] = rng.standard_normal(data2["Y"][~mask].shape) * 50.0
+    st2 = {key: np.array(val, copy=True) for key, val in model["states"].items()}
+    for name in ("v", "h", "s"):
+        st2[name][~mask] = np.abs(rng.standard_normal(st2[name][~mask].shape)) + 0.5
+    prior2 = np.array(model["noise_prior"], copy=True)
+    prior2[~mask] = 7.0
+    model2 = dict(model, states=st2, noise_prior=prior2)
+    outs = []
+    for dta, mdl in ((data, model), (data2, model2)):
+        dd, dm = _to_dev(dta, mdl, dtype)
+        outs.append(g.resample_model(dd, **dm, resample_global_noise_scale=True))
+    a, b = outs
+    for key in ("Ab", "Q", "betas", "pi", "sigmasq"):
+        assert torch.equal(a["params"][key], b["params"][key]), key
+    m = torch.as_tensor(mask, device="cuda")
+    L = mask.shape[1] - a["states"]["z"].shape[1]
+    assert torch.equal(a["states"]["z"][m[:, L:]], b["states"]["z"][m[:, L:]])
+    for key in ("x", "v", "h", "s"):
+        assert torch.equal(a["states"][key][m], b["states"][key][m]), key
