@@ -468,7 +468,7 @@ def main():
     if rank == 0:
         time.sleep(0.25)          # let the sampler finish its start-up and first query outside the timed region
         clocks.mark()
-    launches0 = _lib.launch_count()
+    launches0 = _lib.launch_count() + gibbs.graph_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -484,7 +484,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     step_ms = [round(([e0] + marks)[i_].elapsed_time(marks[i_]), 3) for i_ in range(args.steps)]
-    launches = _lib.launch_count() - launches0
+    launches = _lib.launch_count() + gibbs.graph_kernel_launches() - launches0
     clk = clocks.stop() if rank == 0 else None
     if world > 1:
         tmax = torch.tensor([ms], dtype=torch.float64, device=dev)

@@ -15,6 +15,9 @@
  *   - no allocation happens inside: scratch comes from the caller (`*_workspace_bytes`);
  *   - `*_tape` arguments are nullable: non-null = verification mode (injected standard
  *     normals / uniforms, layouts in DESIGN.md), null = Philox4x32-10 keyed by `seed`;
+ *   - every sampler takes its key as `uint64_t seed, const uint64_t* seed_dev`: with seed_dev == NULL the key is
+ *     `seed`; otherwise it is `*seed_dev XOR seed`, read on the device at run time, so that a sweep captured in a
+ *     CUDA graph draws fresh numbers at every replay (kpms_advance_seed steps the device-resident key);
  *   - N chains (segments), T frames per chain, k keypoints, Dk in {2,3}, d = latent_dim,
  *     L = nlags, n = d*L, K = num_states, Tp = T - L, Tx = T - L + 1.
  */
@@ -33,6 +36,9 @@ extern "C" {
 #define KPMS_VONMISES_ATTEMPTS 8 /* taped Best-Fisher attempts; tape row = 8*3 uniforms */
 
 int kpms_version(void);
+/* *seed_dev <- splitmix64 step of *seed_dev (one thread; the per-sweep key schedule of resample_model, which the
+ * reference drives with jax.random.split on model["seed"], fitting.py:25). */
+int kpms_advance_seed(uint64_t* seed_dev, void* stream);
 const char* kpms_last_error(void);
 /* launch accounting: number of kernels launched by this library so far; optional per-kernel
  * CUDA-event timing (enable, run, then report "name total_ms count" lines; report synchronises). */
@@ -73,8 +79,8 @@ int kpms_hmm_forward(int dtype, const void* W, const void* mx, const void* pi, i
  * the label actually produced above it and un-merged stretches are re-walked (workspace words 2, 3 =
  * mismatched boundaries, re-walked steps).  `ws` must be the workspace kpms_ar_loglik ran on. */
 int kpms_hmm_backward_sample(int dtype, const void* filt, const void* pi, const void* u_tape, void* u_scratch,
-                             uint64_t seed, int N, int K, int Tp, int32_t* z, void* ws, int d, int L,
-                             void* stream);
+                             uint64_t seed, const uint64_t* seed_dev, int N, int K, int Tp, int32_t* z, void* ws,
+                             int d, int L, void* stream);
 /* marg (N,Tp,K) smoothed marginals from the stored filter. */
 int kpms_hmm_smooth(int dtype, const void* filt, const void* pi, int N, int K, int Tp, void* marg,
                     void* stream);
@@ -86,14 +92,14 @@ size_t kpms_kalman_workspace_bytes(int dtype, int N, int T, int d, int L);
 int kpms_kalman_sample(int dtype, const void* Y, const int32_t* mask, const void* v, const void* h,
                        const void* s, const int32_t* z, const void* Ct, const void* sigmasq,
                        const void* Ab, const void* Q, double jitter, const void* w_tape, uint64_t seed,
-                       int N, int T, int k, int Dk, int d, int L, void* x, void* ws, void* stream);
+                       const uint64_t* seed_dev, int N, int T, int k, int Dk, int d, int L, void* x, void* ws, void* stream);
 
 /* ---- per-keypoint noise scales: jax_moseq.models.keypoint_slds.resample_scales.
  *      g_tape (N,T,k,13) gamma tape or NULL; noise_prior, s_out (N,T,k). */
 int kpms_resample_scales(int dtype, const void* Y, const void* x, const void* v, const void* h,
                          const void* Ct, const void* sigmasq, const void* noise_prior, double nu_s,
-                         const void* g_tape, uint64_t seed, int N, int T, int k, int Dk, int d, void* s_out,
-                         void* stream);
+                         const void* g_tape, uint64_t seed, const uint64_t* seed_dev, int N, int T, int k, int Dk,
+                         int d, void* s_out, void* stream);
 
 /* ---- heading + centroid: keypoint_slds.resample_heading followed by keypoint_slds.resample_location
  *      (which reuses utils.kalman.kalman_sample with identity dynamics).  h_out (N,T), v_out (N,T,Dk);
@@ -102,8 +108,8 @@ size_t kpms_heading_location_workspace_bytes(int dtype, int N, int T, int Dk);
 int kpms_resample_heading_location(int dtype, const void* Y, const int32_t* mask, const void* x,
                                    const void* v_in, const void* h_in, const void* s, const void* Ct,
                                    const void* sigmasq, double sigmasq_loc, int fix_heading,
-                                   const void* u_tape, const void* w_tape, uint64_t seed, int N, int T, int k,
-                                   int Dk, int d, void* h_out, void* v_out, void* ws, void* stream);
+                                   const void* u_tape, const void* w_tape, uint64_t seed,
+                                   const uint64_t* seed_dev, int N, int T, int k, int Dk, int d, void* h_out, void* v_out, void* ws, void* stream);
 
 /* ---- sufficient statistics (the only data that crosses GPUs; all-reduce these)
  *      counts (K,K) int32: utils.transitions.count_transitions;
@@ -128,14 +134,16 @@ int kpms_obsvar_suffstats(int dtype, const void* Y, const int32_t* mask, const v
  *      keypoint_slds.resample_obs_variance: g_sig (k,13). */
 int kpms_resample_ar_params(const double* gram, const double* K_0, const double* M_0, const double* S_0,
                             double nu_0, const double* w_G, const double* w_B, const double* g_chi,
-                            uint64_t seed, int K, int d, int L, double* Ab, double* Q, void* stream);
+                            uint64_t seed, const uint64_t* seed_dev, int K, int d, int L, double* Ab, double* Q,
+                            void* stream);
 size_t kpms_transitions_workspace_bytes(int K);
 int kpms_resample_hdp_transitions(const int32_t* counts, const double* betas_in, double alpha, double kappa,
                                   double gamma, const double* u_crp, const double* u_bin, const double* g_beta,
-                                  const double* g_pi, uint64_t seed, int K, double* betas_out, double* pi,
-                                  void* ws, void* stream);
+                                  const double* g_pi, uint64_t seed, const uint64_t* seed_dev, int K, double* betas_out,
+                                  double* pi, void* ws, void* stream);
 int kpms_resample_obs_variance(const double* stats, double nu_sigma, double sigmasq_0, int Dk,
-                               const double* g_sig, uint64_t seed, int k, double* sigmasq, void* stream);
+                               const double* g_sig, uint64_t seed, const uint64_t* seed_dev, int k, double* sigmasq,
+                               void* stream);
 
 #ifdef __cplusplus
 }

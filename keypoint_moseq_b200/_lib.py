@@ -29,26 +29,27 @@ SIGNATURES = {
     "kpms_hmm_weights_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "kpms_ar_loglik": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kpms_hmm_forward": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
-    "kpms_hmm_backward_sample": (_i, [_i, _vp, _vp, _vp, _vp, _u64, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "kpms_advance_seed": (_i, [_vp, _vp]),
+    "kpms_hmm_backward_sample": (_i, [_i, _vp, _vp, _vp, _vp, _u64, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "kpms_hmm_smooth": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "kpms_kalman_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "kpms_kalman_sample": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _u64,
+    "kpms_kalman_sample": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _u64, _vp,
                                 _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "kpms_resample_scales": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _u64, _i, _i, _i, _i, _i,
+    "kpms_resample_scales": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _u64, _vp, _i, _i, _i, _i, _i,
                                   _vp, _vp]),
     "kpms_heading_location_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "kpms_resample_heading_location": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _u64,
+    "kpms_resample_heading_location": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _u64, _vp,
                                             _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kpms_transition_counts": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "kpms_ar_suffstats_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "kpms_ar_suffstats": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "kpms_obsvar_workspace_bytes": (_sz, [_i, _i, _i]),
     "kpms_obsvar_suffstats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "kpms_resample_ar_params": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _u64, _i, _i, _i, _vp, _vp, _vp]),
+    "kpms_resample_ar_params": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _u64, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "kpms_transitions_workspace_bytes": (_sz, [_i]),
-    "kpms_resample_hdp_transitions": (_i, [_vp, _vp, _d, _d, _d, _vp, _vp, _vp, _vp, _u64, _i, _vp, _vp, _vp,
+    "kpms_resample_hdp_transitions": (_i, [_vp, _vp, _d, _d, _d, _vp, _vp, _vp, _vp, _u64, _vp, _i, _vp, _vp, _vp,
                                            _vp]),
-    "kpms_resample_obs_variance": (_i, [_vp, _d, _d, _i, _vp, _u64, _i, _vp, _vp]),
+    "kpms_resample_obs_variance": (_i, [_vp, _d, _d, _i, _vp, _u64, _vp, _i, _vp, _vp]),
 }
 
 _lib = None
@@ -122,8 +123,17 @@ def launch_count():
     return int(load().kpms_launch_count())
 
 
+_PROFILING = [False]
+
+
 def profile(enable):
+    _PROFILING[0] = bool(enable)
     load().kpms_profile_enable(1 if enable else 0)
+
+
+def profiling():
+    """True while per-kernel event timing is on (event records cannot go into a graph capture)."""
+    return _PROFILING[0]
 
 
 def profile_report():

@@ -108,6 +108,23 @@ int kpms_profile_report(char* buf, size_t cap) {
     return 0;
 }
 
-int kpms_version(void) { return 100; }
+// splitmix64 step on the device-resident sweep key (same map as gibbs.advance_seed on the host)
+static __global__ void advance_seed_kernel(uint64_t* seed) {
+    uint64_t v = seed[0] + 0x9E3779B97F4A7C15ull;
+    v ^= v >> 30;
+    v *= 0xBF58476D1CE4E5B9ull;
+    v ^= v >> 27;
+    v *= 0x94D049BB133111EBull;
+    v ^= v >> 31;
+    seed[0] = v;
+}
+
+int kpms_advance_seed(uint64_t* seed_dev, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    { KPMS_LAUNCH("advance_seed", st); advance_seed_kernel<<<1, 1, 0, st>>>(seed_dev); }
+    return kpms::check_launch("advance_seed");
+}
+
+int kpms_version(void) { return 101; }
 const char* kpms_last_error(void) { return kpms::g_err; }
 }

@@ -64,6 +64,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
+// Philox key of a sampler call: `salt` by value, optionally XORed with a 64-bit key read from device memory.
+// A captured CUDA graph freezes by-value arguments, so a replayed sweep takes its per-sweep key from `dev`
+// (advanced on the device by kpms_advance_seed) and keeps only the constant salt (e.g. the rank mix) by value.
+struct SeedArg {
+    uint64_t salt;
+    const uint64_t* dev;
+    __host__ __device__ SeedArg(uint64_t s = 0, const uint64_t* d = nullptr) : salt(s), dev(d) {}
+    __device__ __forceinline__ operator uint64_t() const { return dev ? (__ldg(dev) ^ salt) : salt; }
+};
+
 // One logical generator per (seed, stream, element); `draw` advances inside it.
 struct Philox {
     uint2 key;

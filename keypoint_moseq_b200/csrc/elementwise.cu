@@ -16,7 +16,7 @@ template <typename R, int DK>
 __global__ void __launch_bounds__(256)
 scales_kernel(const R* __restrict__ Y, const R* __restrict__ x, const R* __restrict__ v,
               const R* __restrict__ h, const R* __restrict__ Ct, const R* __restrict__ sigmasq,
-              const R* __restrict__ prior, double nu_s, const R* __restrict__ g_tape, uint64_t seed,
+              const R* __restrict__ prior, double nu_s, const R* __restrict__ g_tape, SeedArg seed,
               long long frames, int k, int d, R* __restrict__ s_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R* Cs = reinterpret_cast<R*>(smem_raw);
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128)
 heading_location_kernel(const R* __restrict__ Y, const R* __restrict__ x, const R* __restrict__ v,
                         const R* __restrict__ h_in, const R* __restrict__ s, const R* __restrict__ Ct,
                         const R* __restrict__ sigmasq, int fix_heading, const R* __restrict__ u_tape,
-                        uint64_t seed, long long frames, int k, int d, R* __restrict__ h_out,
+                        SeedArg seed, long long frames, int k, int d, R* __restrict__ h_out,
                         R* __restrict__ mu, R* __restrict__ gsq, R* __restrict__ wbuf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R* Cs = reinterpret_cast<R*>(smem_raw);
@@ -382,7 +382,7 @@ location_ffbs_kernel(const R* __restrict__ mu, const R* __restrict__ gsq, const 
 // ---------------------------------------------------------------------------
 template <typename R>
 static int scales_impl(const void* Y, const void* x, const void* v, const void* h, const void* Ct,
-                       const void* sigmasq, const void* prior, double nu_s, const void* g_tape, uint64_t seed,
+                       const void* sigmasq, const void* prior, double nu_s, const void* g_tape, SeedArg seed,
                        int N, int T, int k, int Dk, int d, void* s_out, cudaStream_t st) {
     const long long frames = (long long)N * T;
     const long long elems = frames * k;
@@ -425,7 +425,7 @@ static int obsvar_impl(const void* Y, const int* mask, const void* x, const void
 template <typename R>
 static int headloc_impl(const void* Y, const int* mask, const void* x, const void* v_in, const void* h_in,
                         const void* s, const void* Ct, const void* sigmasq, double sigmasq_loc, int fix_heading,
-                        const void* u_tape, const void* w_tape, uint64_t seed, int N, int T, int k, int Dk, int d,
+                        const void* u_tape, const void* w_tape, SeedArg seed, int N, int T, int k, int Dk, int d,
                         void* h_out, void* v_out, void* ws, cudaStream_t st) {
     const long long frames = (long long)N * T;
     size_t smem = ((size_t)k * Dk * (d + 1) + k) * sizeof(R);
@@ -459,8 +459,9 @@ extern "C" {
 
 int kpms_resample_scales(int dtype, const void* Y, const void* x, const void* v, const void* h, const void* Ct,
                          const void* sigmasq, const void* noise_prior, double nu_s, const void* g_tape,
-                         uint64_t seed, int N, int T, int k, int Dk, int d, void* s_out, void* stream) {
-    return KPMS_DISPATCH_DTYPE(dtype, scales_impl, Y, x, v, h, Ct, sigmasq, noise_prior, nu_s, g_tape, seed, N, T,
+                         uint64_t seed, const uint64_t* seed_dev, int N, int T, int k, int Dk, int d, void* s_out,
+                         void* stream) {
+    return KPMS_DISPATCH_DTYPE(dtype, scales_impl, Y, x, v, h, Ct, sigmasq, noise_prior, nu_s, g_tape, SeedArg(seed, seed_dev), N, T,
                                k, Dk, d, s_out, (cudaStream_t)stream);
 }
 
@@ -484,10 +485,10 @@ size_t kpms_heading_location_workspace_bytes(int dtype, int N, int T, int Dk) {
 int kpms_resample_heading_location(int dtype, const void* Y, const int32_t* mask, const void* x, const void* v_in,
                                    const void* h_in, const void* s, const void* Ct, const void* sigmasq,
                                    double sigmasq_loc, int fix_heading, const void* u_tape, const void* w_tape,
-                                   uint64_t seed, int N, int T, int k, int Dk, int d, void* h_out, void* v_out,
+                                   uint64_t seed, const uint64_t* seed_dev, int N, int T, int k, int Dk, int d, void* h_out, void* v_out,
                                    void* ws, void* stream) {
     return KPMS_DISPATCH_DTYPE(dtype, headloc_impl, Y, mask, x, v_in, h_in, s, Ct, sigmasq, sigmasq_loc,
-                               fix_heading, u_tape, w_tape, seed, N, T, k, Dk, d, h_out, v_out, ws,
+                               fix_heading, u_tape, w_tape, SeedArg(seed, seed_dev), N, T, k, Dk, d, h_out, v_out, ws,
                                (cudaStream_t)stream);
 }
 

@@ -510,7 +510,7 @@ hmm_tail_starts_kernel(const R* __restrict__ PTL, const R* __restrict__ bnd_end,
 // and the uniforms (tape or pre-generated Philox draws) are fetched 32 steps at a time.
 // ---------------------------------------------------------------------------
 template <typename R>
-__global__ void fill_uniform_kernel(R* __restrict__ u, long long count, uint64_t seed, uint32_t stream) {
+__global__ void fill_uniform_kernel(R* __restrict__ u, long long count, SeedArg seed, uint32_t stream) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= count) return;
     Philox g(seed, stream, (uint64_t)e);
@@ -1058,7 +1058,7 @@ static int hmm_backward_chunks(int N, int Tp) {
 }
 
 template <typename R>
-static int hmm_backward_impl(const void* filt, const void* pi, const void* u, void* u_scratch, uint64_t seed, int N,
+static int hmm_backward_impl(const void* filt, const void* pi, const void* u, void* u_scratch, SeedArg seed, int N,
                              int K, int Tp, int* z, void* ws, int d, int L, cudaStream_t st) {
     const int ldK = (K + 3) / 4 * 4;
     if (K > 128) return set_error(-3, "hmm_backward: num_states %d > 128 not supported", K);
@@ -1148,8 +1148,9 @@ int kpms_hmm_forward(int dtype, const void* W, const void* mx, const void* pi, i
 }
 
 int kpms_hmm_backward_sample(int dtype, const void* filt, const void* pi, const void* u_tape, void* u_scratch,
-                             uint64_t seed, int N, int K, int Tp, int* z, void* ws, int d, int L, void* stream) {
-    return KPMS_DISPATCH_DTYPE(dtype, hmm_backward_impl, filt, pi, u_tape, u_scratch, seed, N, K, Tp, z, ws, d, L,
+                             uint64_t seed, const uint64_t* seed_dev, int N, int K, int Tp, int* z, void* ws, int d, int L,
+                             void* stream) {
+    return KPMS_DISPATCH_DTYPE(dtype, hmm_backward_impl, filt, pi, u_tape, u_scratch, SeedArg(seed, seed_dev), N, K, Tp, z, ws, d, L,
                                (cudaStream_t)stream);
 }
 

@@ -955,7 +955,7 @@ template <typename R, int D_, int L_, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS)
 kalman_backprep_kernel(const R* __restrict__ stash_m, const R* __restrict__ stash_S,
                        const int* __restrict__ mask, const int* __restrict__ z, const R* __restrict__ Ab,
-                       const R* __restrict__ Q, R jitter, const R* __restrict__ w_tape, uint64_t seed, int N,
+                       const R* __restrict__ Q, R jitter, const R* __restrict__ w_tape, SeedArg seed, int N,
                        int T, R* __restrict__ GH) {
     typedef PrepSmem<R, D_, L_> SM;
     constexpr int n = SM::n, LD = SM::LD, NP2 = n * (n + 1) / 2, NO = n - D_, NA1 = n + 1;
@@ -1158,7 +1158,7 @@ template <typename R, int D_, int L_, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__ stash_S,
                             const int* __restrict__ mask, const int* __restrict__ z, const R* __restrict__ Ab,
-                            const R* __restrict__ Q, R jitter, const R* __restrict__ w_tape, uint64_t seed,
+                            const R* __restrict__ Q, R jitter, const R* __restrict__ w_tape, SeedArg seed,
                             int N, int T, R* __restrict__ GH) {
     typedef PrepRowsSmem<R, D_, L_> SM;
     typedef typename Vec16<R>::type VecT;
@@ -1555,7 +1555,7 @@ static int kalman_chunks(int N, int T, int d, int L, bool backward) {
 template <typename R, int D_, int L_>
 static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, const R* s, const int* z,
                          const R* Ct, const R* sigmasq, const R* Ab, const R* Q, double jitter,
-                         const R* w_tape, uint64_t seed, int N, int T, int k, int Dk, R* x, void* ws,
+                         const R* w_tape, SeedArg seed, int N, int T, int k, int Dk, R* x, void* ws,
                          cudaStream_t st) {
     constexpr int n = D_ * L_;
     const int Tx = T - L_ + 1;
@@ -1716,7 +1716,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
 template <typename R>
 static int kalman_impl(const void* Y, const int* mask, const void* v, const void* h, const void* s, const int* z,
                        const void* Ct, const void* sigmasq, const void* Ab, const void* Q, double jitter,
-                       const void* w_tape, uint64_t seed, int N, int T, int k, int Dk, int d, int L, void* x,
+                       const void* w_tape, SeedArg seed, int N, int T, int k, int Dk, int d, int L, void* x,
                        void* ws, cudaStream_t st) {
     if (Dk != 2 && Dk != 3) return set_error(-3, "kalman_sample: keypoint dimension must be 2 or 3, got %d", Dk);
     if (T < L) return set_error(-3, "kalman_sample: T (%d) < nlags (%d)", T, L);
@@ -1746,10 +1746,10 @@ size_t kpms_kalman_workspace_bytes(int dtype, int N, int T, int d, int L) {
 
 int kpms_kalman_sample(int dtype, const void* Y, const int* mask, const void* v, const void* h, const void* s,
                        const int* z, const void* Ct, const void* sigmasq, const void* Ab, const void* Q,
-                       double jitter, const void* w_tape, uint64_t seed, int N, int T, int k, int Dk, int d,
+                       double jitter, const void* w_tape, uint64_t seed, const uint64_t* seed_dev, int N, int T, int k, int Dk, int d,
                        int L, void* x, void* ws, void* stream) {
     return KPMS_DISPATCH_DTYPE(dtype, kalman_impl, Y, mask, v, h, s, z, Ct, sigmasq, Ab, Q, jitter, w_tape,
-                               seed, N, T, k, Dk, d, L, x, ws, (cudaStream_t)stream);
+                               SeedArg(seed, seed_dev), N, T, k, Dk, d, L, x, ws, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -93,7 +93,7 @@ template <typename R, int D_, int L_, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 kalman_backprep_rows2_kernel(const R* __restrict__ stash_m, const R* __restrict__ stash_S,
                              const int* __restrict__ mask, const int* __restrict__ z, const R* __restrict__ Ab,
-                             const R* __restrict__ Q, R jitter, const R* __restrict__ w_tape, uint64_t seed,
+                             const R* __restrict__ Q, R jitter, const R* __restrict__ w_tape, SeedArg seed,
                              int N, int T, R* __restrict__ GH) {
     typedef PrepRows2<R, D_, L_> SM;
     typedef typename Vec16<R>::type VecT;

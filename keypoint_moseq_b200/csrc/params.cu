@@ -57,7 +57,7 @@ __device__ inline void w_matmul(const double* A, int ars, int acs, const double*
 __global__ void __launch_bounds__(32)
 ar_params_kernel(const double* __restrict__ gram, const double* __restrict__ K_0, const double* __restrict__ M_0,
                  const double* __restrict__ S_0, double nu_0, const double* __restrict__ w_G,
-                 const double* __restrict__ w_B, const double* __restrict__ g_chi, uint64_t seed, int d, int L,
+                 const double* __restrict__ w_B, const double* __restrict__ g_chi, SeedArg seed, int d, int L,
                  double* __restrict__ Ab, double* __restrict__ Q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = d * L, p = n + 1, F = n + d + 1;
@@ -203,7 +203,7 @@ count_prefix_kernel(const int* __restrict__ counts, int K, long long* __restrict
 // CRP table counts: one block per row, one warp per column (strided)
 __global__ void __launch_bounds__(256)
 crp_tables_kernel(const int* __restrict__ counts, const double* __restrict__ betas, double alpha, double kappa,
-                  const long long* __restrict__ starts, const double* __restrict__ u_crp, uint64_t seed, int K,
+                  const long long* __restrict__ starts, const double* __restrict__ u_crp, SeedArg seed, int K,
                   int* __restrict__ m) {
     const int i = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     constexpr int BIG = 4096;                  // entries with more customers than this are drawn by the whole CTA
@@ -239,7 +239,7 @@ crp_tables_kernel(const int* __restrict__ counts, const double* __restrict__ bet
 // overrides w_i ~ Bin(m_ii, rho / (rho + beta_i (1 - rho))): one warp per state, written into m's diagonal
 __global__ void __launch_bounds__(32)
 overrides_kernel(int* __restrict__ m, const double* __restrict__ betas_in, double alpha, double kappa,
-                 const long long* __restrict__ dstarts, const double* __restrict__ u_bin, uint64_t seed, int K,
+                 const long long* __restrict__ dstarts, const double* __restrict__ u_bin, SeedArg seed, int K,
                  int* __restrict__ wov) {
     const int i = blockIdx.x, lane = threadIdx.x;
     const double rho = kappa / (alpha + kappa);
@@ -258,7 +258,7 @@ overrides_kernel(int* __restrict__ m, const double* __restrict__ betas_in, doubl
 
 // betas ~ Dir(gamma/K + colsum(m) - w); single block of >= K threads
 __global__ void betas_kernel(const int* __restrict__ m, const int* __restrict__ wov, double gamma,
-                             const double* __restrict__ g_beta, uint64_t seed, int K,
+                             const double* __restrict__ g_beta, SeedArg seed, int K,
                              double* __restrict__ betas_out) {
     extern __shared__ double sh[];
     double* gb = sh;             // K gammas
@@ -279,7 +279,7 @@ __global__ void betas_kernel(const int* __restrict__ m, const int* __restrict__ 
 
 // pi_i ~ Dir(alpha betas + kappa e_i + N_i.); one block per row
 __global__ void pi_rows_kernel(const int* __restrict__ counts, const double* __restrict__ betas, double alpha,
-                               double kappa, const double* __restrict__ g_pi, uint64_t seed, int K,
+                               double kappa, const double* __restrict__ g_pi, SeedArg seed, int K,
                                double* __restrict__ pi) {
     __shared__ double red[32];
     const int i = blockIdx.x, j = threadIdx.x;
@@ -294,7 +294,7 @@ __global__ void pi_rows_kernel(const int* __restrict__ counts, const double* __r
 }
 
 __global__ void sigmasq_kernel(const double* __restrict__ stats, double nu_sigma, double sigmasq_0, int Dk,
-                               const double* __restrict__ g_sig, uint64_t seed, int k, double* __restrict__ sigmasq) {
+                               const double* __restrict__ g_sig, SeedArg seed, int k, double* __restrict__ sigmasq) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= k) return;
     const double degs = nu_sigma + Dk * stats[k];
@@ -311,8 +311,9 @@ using namespace kpms;
 extern "C" {
 
 int kpms_resample_ar_params(const double* gram, const double* K_0, const double* M_0, const double* S_0, double nu_0,
-                            const double* w_G, const double* w_B, const double* g_chi, uint64_t seed, int K, int d,
-                            int L, double* Ab, double* Q, void* stream) {
+                            const double* w_G, const double* w_B, const double* g_chi, uint64_t seed_, const uint64_t* seed_dev, int K,
+                            int d, int L, double* Ab, double* Q, void* stream) {
+    const SeedArg seed(seed_, seed_dev);
     const int n = d * L, p = n + 1;
     size_t smem = ((size_t)4 * p * p + 3 * d * p + 4 * d * d) * sizeof(double);
     if (smem > 220 * 1024) return set_error(-3, "resample_ar_params: (latent_dim, nlags) = (%d, %d) too large", d, L);
@@ -329,8 +330,9 @@ size_t kpms_transitions_workspace_bytes(int K) {
 
 int kpms_resample_hdp_transitions(const int32_t* counts, const double* betas_in, double alpha, double kappa,
                                   double gamma, const double* u_crp, const double* u_bin, const double* g_beta,
-                                  const double* g_pi, uint64_t seed, int K, double* betas_out, double* pi, void* ws,
-                                  void* stream) {
+                                  const double* g_pi, uint64_t seed_, const uint64_t* seed_dev, int K, double* betas_out, double* pi,
+                                  void* ws, void* stream) {
+    const SeedArg seed(seed_, seed_dev);
     cudaStream_t st = (cudaStream_t)stream;
     if (K > 1024) return set_error(-3, "resample_hdp_transitions: num_states %d > 1024", K);
     char* base = reinterpret_cast<char*>(ws);
@@ -350,7 +352,8 @@ int kpms_resample_hdp_transitions(const int32_t* counts, const double* betas_in,
 }
 
 int kpms_resample_obs_variance(const double* stats, double nu_sigma, double sigmasq_0, int Dk, const double* g_sig,
-                               uint64_t seed, int k, double* sigmasq, void* stream) {
+                               uint64_t seed_, const uint64_t* seed_dev, int k, double* sigmasq, void* stream) {
+    const SeedArg seed(seed_, seed_dev);
     { cudaStream_t st = (cudaStream_t)stream; KPMS_LAUNCH("obs_variance", st);
     sigmasq_kernel<<<(k + 63) / 64, 64, 0, st>>>(stats, nu_sigma, sigmasq_0, Dk, g_sig, seed, k, sigmasq); }
     return check_launch("resample_obs_variance");

@@ -365,6 +365,8 @@ def apply_model(model, data, metadata, project_dir=None, model_name=None, num_it
     dtype = kwargs.pop("dtype", torch.float64)
     device = kwargs.pop("device", "cuda")
     extra = {key: kwargs.pop(key) for key in ("hmm_dtype", "group", "fix_heading") if key in kwargs}
+    if "fix_heading" in extra:                # the flag shapes the initial heading (0) AND freezes it in every sweep
+        kwargs["fix_heading"] = extra["fix_heading"]
     shards = _Shards(extra.get("group"), data, metadata)
     if save_results and results_path is None:
         assert project_dir is not None and model_name is not None, fill(
@@ -375,14 +377,22 @@ def apply_model(model, data, metadata, project_dir=None, model_name=None, num_it
     model = init_model(data=data_dev, seed=model["seed"], params=model["params"], hypparams=model["hypparams"],
                        dtype=dtype, device=device, **kwargs)
     model = gibbs.to_device_model(model, device, dtype)
+    # pipelined NaN check, verdict shared by the ranks of a sharded call (a rank stopping alone would desert its
+    # peers in the collectives below)
+    guard = NanGuard(lag=int(kwargs.pop("nan_check_lag", NAN_CHECK_LAG)), group=shards.group if shards.world > 1 else None)
+    guard.clean = model
     with _trange(num_iters, ncols=72) as pbar:
         for _ in pbar:
             try:
-                model = _wrapped_resample(gibbs.resample_model, data_dev, model, pbar=pbar, ar_only=ar_only,
+                model = _wrapped_resample(gibbs.resample_model, data_dev, model, pbar=pbar, guard=guard, ar_only=ar_only,
                                           states_only=True, verbose=verbose,
                                           parallel_message_passing=parallel_message_passing, **extra)
             except StopResampling:
+                model = guard.clean
                 break
+        else:
+            if not _drain_guard(guard, pbar):
+                model = guard.clean
     if shards.world > 1:          # states-only sweeps exchange nothing; the rows meet again here, rank 0 saves
         model = gibbs.to_device_model(shards.join_model(_host_model(model)), device, dtype)
     results = extract_results(model, metadata, project_dir, model_name, save_results and shards.writes, results_path,
@@ -402,32 +412,44 @@ def estimate_syllable_marginals(model, data, metadata, burn_in_iters=200, num_sa
     dtype = kwargs.pop("dtype", torch.float64)
     device = kwargs.pop("device", "cuda")
     extra = {key: kwargs.pop(key) for key in ("hmm_dtype", "group") if key in kwargs}
+    if "fix_heading" in kwargs:               # initial heading 0 (init_model) and frozen in every sweep
+        extra["fix_heading"] = kwargs["fix_heading"]
     shards = _Shards(extra.get("group"), data, metadata)          # rows sharded over the ranks, joined at the end
     data_dev = gibbs.to_device_data(shards.split_data(data), device, dtype)
     model = init_model(data=data_dev, seed=model["seed"], params=model["params"], hypparams=model["hypparams"],
                        dtype=dtype, device=device, **kwargs)
     model = gibbs.to_device_model(model, device, dtype)
     total = burn_in_iters + num_samples * steps_per_sample
-    acc, samples = None, []
+    acc, n_acc, samples = None, 0, []
+    guard = NanGuard(lag=int(kwargs.pop("nan_check_lag", NAN_CHECK_LAG)), group=shards.group if shards.world > 1 else None)
+    guard.clean = model
     with _trange(total, ncols=72) as pbar:
         for it in pbar:
             try:
-                model = _wrapped_resample(gibbs.resample_model, data_dev, model, pbar=pbar, states_only=True,
+                model = _wrapped_resample(gibbs.resample_model, data_dev, model, pbar=pbar, guard=guard, states_only=True,
                                           verbose=verbose, parallel_message_passing=parallel_message_passing, **extra)
             except StopResampling:
                 break
             if it >= burn_in_iters and (it - burn_in_iters) % steps_per_sample == 0:
+                if not _drain_guard(guard, pbar):               # only sweeps checked clean are sampled (all ranks agree)
+                    break
                 p = model["params"]
                 marg = gibbs.stateseq_marginals(model["states"]["x"], data_dev["mask"], p["Ab"], p["Q"], p["pi"])
                 acc = marg.clone() if acc is None else acc + marg
+                n_acc += 1
                 if return_samples:
                     samples.append(model["states"]["z"].cpu().numpy())
     nlags = get_nlags(model["params"]["Ab"])
     keys, bounds = list(metadata[0]), np.asarray(metadata[1]) + np.array([nlags, 0])
-    est = (acc / num_samples).cpu().numpy()
+    if acc is None:
+        raise RuntimeError("estimate_syllable_marginals: the sweeps stopped (NaNs or interruption) before the first "
+                           "sample was taken")
+    est = (acc / n_acc).cpu().numpy()          # n_acc == num_samples unless the sweeps stopped early
     if shards.world > 1:
         est = gather_rows(est, shards.rows_per_rank, shards.group)
-        samples = [gather_rows(z, shards.rows_per_rank, shards.group) for z in samples]
+        if samples:                                             # one collective for all samples (same count on every rank)
+            stacked = gather_rows(np.moveaxis(np.asarray(samples), 0, 1), shards.rows_per_rank, shards.group)
+            samples = list(np.moveaxis(stacked, 1, 0))
     marginals = unbatch(est, keys, bounds)
     marginals = {k_: np.pad(v[nlags:], ((nlags, 0), (0, 0)), mode="edge") for k_, v in marginals.items()}
     if return_samples:

@@ -198,11 +198,14 @@ class NanGuard:
             elif isinstance(node, torch.Tensor) and node.is_cuda and node.is_floating_point():
                 leaves.append(node)
 
-        collect(model)
-        if not leaves:
-            self.pending.append((None, None, model))
-            return
-        flag = self._any_rank(torch.stack([torch.isnan(t).any() for t in leaves]).any())
+        ready = getattr(model, "nan_flag", None)        # reduced on the device as part of the sweep (gibbs.SweepResult)
+        if ready is None:
+            collect(model)
+            if not leaves:
+                self.pending.append((None, None, model))
+                return
+            ready = torch.stack([torch.isnan(t).any() for t in leaves]).any()
+        flag = self._any_rank(ready)
         host = self.pool.pop() if self.pool else torch.empty((), dtype=torch.bool).pin_memory()
         host.copy_(flag, non_blocking=True)
         ev = torch.cuda.Event()

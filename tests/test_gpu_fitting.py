@@ -178,3 +178,14 @@ def test_two_gpu_sharded_sweep_matches_single_gpu(tmp_path):
                           os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "dist_check ok" in out.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_fit_and_apply(tmp_path):
+    """`fit_model` / `apply_model` with group=WORLD on two real GPUs (checkpoint cadence, whole model on every rank,
+    per-recording results); the host logic alone is covered on the CPU by tests/test_host.py with a stub sweep."""
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631",
+                          os.path.join(ROOT, "tools", "dist_fit_check.py")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "dist_fit_check ok" in out.stdout

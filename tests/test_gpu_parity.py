@@ -359,3 +359,64 @@ def test_padding_content_does_not_reach_valid_frames_or_parameters(dtype):
     assert torch.equal(a["states"]["z"][m[:, L:]], b["states"]["z"][m[:, L:]])
     for key in ("x", "v", "h", "s"):
         assert torch.equal(a["states"][key][m], b["states"][key][m]), key
+
+
+# ----------------------------------------------------------------------------
+# the sweep as one CUDA graph: same numbers as the kernels launched one by one
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [dict(), dict(ar_only=True), dict(states_only=True),
+                                   dict(resample_global_noise_scale=True)], ids=["full", "ar_only", "states_only", "global_noise"])
+def test_graph_replay_equals_eager_launches(flags):
+    """Philox sweeps through the captured graph (device-resident key, advanced on the device) reproduce the eager
+    path bit for bit over several consecutive sweeps, and a model handed back out of order is picked up again."""
+    g = _gibbs()
+    data, _, model = small_problem(seed=21, d=4, L=3, K=12, k=5, D=2, kappa=1e2, frames=700, seg_length=400)
+    dd, dm = _to_dev(data, model, torch.float32)
+    eager, graphed = [dm], [dm]
+    for _ in range(4):
+        eager.append(g.resample_model(dd, **eager[-1], graph=False, **flags))
+        graphed.append(g.resample_model(dd, **graphed[-1], graph=True, **flags))
+    assert getattr(graphed[-1], "nan_flag", None) is not None, "the graph path did not run"
+    for a, b in zip(eager[1:], graphed[1:]):
+        assert np.array_equal(a["seed"], b["seed"])
+        for key in ("x", "v", "h", "s", "z"):
+            assert torch.equal(a["states"][key], b["states"][key]), key
+        for key in ("Ab", "Q", "betas", "pi", "sigmasq", "Cd"):
+            assert torch.equal(a["params"][key], b["params"][key]), key
+        assert not bool(b.nan_flag)
+    # restart from an older model (what fit_model does after a NaN sweep): the device key is re-uploaded
+    again = g.resample_model(dd, **graphed[2], graph=True, **flags)
+    for key in ("x", "v", "h", "s", "z"):
+        assert torch.equal(again["states"][key], eager[3]["states"][key]), key
+    # models returned earlier are untouched by later replays (fresh tensors every sweep)
+    for key in ("x", "z"):
+        assert torch.equal(graphed[1]["states"][key], eager[1]["states"][key]), key
+
+
+def test_graph_sweep_reports_nans():
+    g = _gibbs()
+    data, _, model = small_problem(seed=22, d=4, L=3, K=12, k=5, D=2, kappa=1e2)
+    dd, dm = _to_dev(data, model, torch.float32)
+    ok = g.resample_model(dd, **dm, graph=True)
+    assert not bool(ok.nan_flag)
+    bad_states = dict(dm["states"], x=dm["states"]["x"].clone())
+    bad_states["x"][0, 40, 1] = float("nan")
+    bad = g.resample_model(dd, **dict(dm, states=bad_states), graph=True)
+    assert bool(bad.nan_flag)
+
+
+def test_shape_mismatches_are_rejected_before_any_kernel_reads_them():
+    """Raw pointers cross the C-ABI: a scalar noise_prior (checkpoints written without an error estimator) is
+    broadcast, anything else with the wrong shape raises instead of being read out of bounds."""
+    g = _gibbs()
+    data, _, model = small_problem(seed=23, d=4, L=3, K=12, k=5, D=2)
+    dd, dm = _to_dev(data, model, torch.float32)
+    ones = dict(model, noise_prior=np.ones_like(model["noise_prior"]))
+    scalar = dict(model, noise_prior=np.float64(1.0))
+    a = g.resample_model(dd, **g.to_device_model(ones, "cuda", torch.float32))
+    b = g.resample_model(dd, **g.to_device_model(scalar, "cuda", torch.float32))
+    assert torch.equal(a["states"]["s"], b["states"]["s"])
+    with pytest.raises(ValueError, match="states\\['v'\\]"):
+        g.resample_model(dd, **dict(dm, states=dict(dm["states"], v=dm["states"]["v"][:, :-1].contiguous())))
+    with pytest.raises(ValueError, match="noise_prior"):
+        g.resample_model(dd, **dict(dm, noise_prior=dm["noise_prior"][..., :-1].contiguous()))

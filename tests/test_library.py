@@ -35,18 +35,3 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
-
-
-def test_prepared_patches_still_apply():
-    """tools/patches/ holds kernel work prepared without a GPU; it must keep applying to the tree it was cut from."""
-    import glob
-    import shutil
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    if shutil.which("git") is None or not os.path.isdir(os.path.join(root, ".git")):
-        pytest.skip("needs the git work tree")
-    patches = sorted(glob.glob(os.path.join(root, "tools", "patches", "*.patch")))
-    assert patches
-    for patch in patches:
-        out = subprocess.run(["git", "apply", "--check", patch], cwd=root, capture_output=True, text=True)
-        assert out.returncode == 0, f"{os.path.basename(patch)}: {out.stderr}"
