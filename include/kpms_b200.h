@@ -88,11 +88,12 @@ int kpms_hmm_smooth(int dtype, const void* filt, const void* pi, int N, int K, i
 /* ---- continuous states: jax_moseq.models.keypoint_slds.resample_continuous_stateseqs
  *      (-> slds.resample_continuous_stateseqs -> utils.kalman.kalman_sample).
  *      Ct (k*Dk, d+1) = (Gamma kron I) Cd; w_tape (N,Tx,n) normals or NULL; x (N,T,d) out. */
-size_t kpms_kalman_workspace_bytes(int dtype, int N, int T, int d, int L);
+size_t kpms_kalman_workspace_bytes(int dtype, int N, int T, int d, int L, int K);
 int kpms_kalman_sample(int dtype, const void* Y, const int32_t* mask, const void* v, const void* h,
                        const void* s, const int32_t* z, const void* Ct, const void* sigmasq,
                        const void* Ab, const void* Q, double jitter, const void* w_tape, uint64_t seed,
-                       const uint64_t* seed_dev, int N, int T, int k, int Dk, int d, int L, void* x, void* ws, void* stream);
+                       const uint64_t* seed_dev, int N, int T, int k, int Dk, int d, int L, int K, void* x,
+                       void* ws, void* stream);
 
 /* ---- per-keypoint noise scales: jax_moseq.models.keypoint_slds.resample_scales.
  *      g_tape (N,T,k,13) gamma tape or NULL; noise_prior, s_out (N,T,k). */
@@ -109,7 +110,8 @@ int kpms_resample_heading_location(int dtype, const void* Y, const int32_t* mask
                                    const void* v_in, const void* h_in, const void* s, const void* Ct,
                                    const void* sigmasq, double sigmasq_loc, int fix_heading,
                                    const void* u_tape, const void* w_tape, uint64_t seed,
-                                   const uint64_t* seed_dev, int N, int T, int k, int Dk, int d, void* h_out, void* v_out, void* ws, void* stream);
+                                   const uint64_t* seed_dev, int N, int T, int k, int Dk, int d, void* h_out,
+                                   void* v_out, void* ws, void* stream);
 
 /* ---- sufficient statistics (the only data that crosses GPUs; all-reduce these)
  *      counts (K,K) int32: utils.transitions.count_transitions;

@@ -32,9 +32,9 @@ SIGNATURES = {
     "kpms_advance_seed": (_i, [_vp, _vp]),
     "kpms_hmm_backward_sample": (_i, [_i, _vp, _vp, _vp, _vp, _u64, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "kpms_hmm_smooth": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp]),
-    "kpms_kalman_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "kpms_kalman_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "kpms_kalman_sample": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _u64, _vp,
-                                _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+                                _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "kpms_resample_scales": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _u64, _vp, _i, _i, _i, _i, _i,
                                   _vp, _vp]),
     "kpms_heading_location_workspace_bytes": (_sz, [_i, _i, _i, _i]),

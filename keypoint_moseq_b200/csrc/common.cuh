@@ -237,7 +237,11 @@ template <> __device__ __forceinline__ double rsqrt_fast<double>(double x) { ret
 
 // reciprocal to ~1 ulp without the IEEE division sequence
 template <typename R> __device__ __forceinline__ R rcp_fast(R x);
-template <> __device__ __forceinline__ float rcp_fast<float>(float x) { return __frcp_rn(x); }
+template <> __device__ __forceinline__ float rcp_fast<float>(float x) {
+    float y;                                   // MUFU.RCP + one Newton step: < 1 ulp, no slow-path branch
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return fmaf(y, fmaf(-x, y, 1.0f), y);
+}
 template <> __device__ __forceinline__ double rcp_fast<double>(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));

@@ -1399,6 +1399,7 @@ kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__
 }
 
 #include "kalman_rows2.cuh"
+#include "kalman_split.cuh"
 
 // ---------------------------------------------------------------------------
 // K1d: serial affine recursion, one warp per chain, operands streamed through a
@@ -1532,17 +1533,19 @@ kalman_affine_kernel(const R* __restrict__ GH, const int* __restrict__ mask, int
 //             boundary records of the forward filter (warm, end) and of the backward recursion (warm, exact)]
 // diagnostics (unsigned[4]): max forward boundary discrepancy (float bits), forward chains re-run
 // sequentially, max backward discrepancy (float bits), backward chains re-run.
-enum { KW_DIAG, KW_VLEN, KW_DIRTY_F, KW_DIRTY_B, KW_INFO, KW_SM, KW_SS, KW_GH, KW_BFW, KW_BFE, KW_BBW, KW_BBE, KW_END };
+enum { KW_DIAG, KW_VLEN, KW_DIRTY_F, KW_DIRTY_B, KW_INFO, KW_SM, KW_SS, KW_GH, KW_BFW, KW_BFE, KW_BBW, KW_BBE, KW_OPS, KW_WN, KW_END };
 
 template <typename R>
-static void kalman_ws_layout(int N, int T, int d, int L, int C, int Cb, size_t off[KW_END + 1]) {
+static void kalman_ws_layout(int N, int T, int d, int L, int K, int C, int Cb, size_t off[KW_END + 1]) {
     const size_t n = (size_t)d * L, Tx = T - L + 1, fr = (size_t)N * Tx;
     const size_t rec = info_stride(d);
     const size_t recs = ((n * n + n) * sizeof(R) + 15) / 16 * 16 / sizeof(R);
     const size_t brec = n + n * n, nb = (size_t)N * (C + 1), nbb = (size_t)N * (Cb + 1);
+    const size_t vec = 16 / sizeof(R), dp = (d + vec - 1) / vec * vec;
+    const size_t ops = n * dp + dp + d * dp;             // PrepSplit::OPS: per-state operator block of the backward preparation
     size_t sz[KW_END] = {256, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4, fr * rec * sizeof(R), fr * stash_m_stride((int)n) * sizeof(R),
                          fr * stash_S_stride((int)n) * sizeof(R), fr * recs * sizeof(R), nb * brec * sizeof(R), nb * brec * sizeof(R),
-                         nbb * n * sizeof(R), nbb * n * sizeof(R)};
+                         nbb * n * sizeof(R), nbb * n * sizeof(R), (size_t)K * ops * sizeof(R), (fr * n + 4) * sizeof(R)};
     off[0] = 0;
     for (int i = 0; i < KW_END; ++i) off[i + 1] = off[i] + align_up(sz[i], 256);
 }
@@ -1555,7 +1558,7 @@ static int kalman_chunks(int N, int T, int d, int L, bool backward) {
 template <typename R, int D_, int L_>
 static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, const R* s, const int* z,
                          const R* Ct, const R* sigmasq, const R* Ab, const R* Q, double jitter,
-                         const R* w_tape, SeedArg seed, int N, int T, int k, int Dk, R* x, void* ws,
+                         const R* w_tape, SeedArg seed, int N, int T, int k, int Dk, int K, R* x, void* ws,
                          cudaStream_t st) {
     constexpr int n = D_ * L_;
     const int Tx = T - L_ + 1;
@@ -1563,7 +1566,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
     const int C = kalman_chunks(N, T, D_, L_, false), Cb = kalman_chunks(N, T, D_, L_, true), W = cfg.warmup;
     const R tol = (R)(sizeof(R) == 4 ? cfg.tol32 : cfg.tol64);
     size_t off[KW_END + 1];
-    kalman_ws_layout<R>(N, T, D_, L_, C, Cb, off);
+    kalman_ws_layout<R>(N, T, D_, L_, K, C, Cb, off);
     char* base = reinterpret_cast<char*>(ws);
     unsigned* diag = reinterpret_cast<unsigned*>(base + off[KW_DIAG]);
     int* vlen = reinterpret_cast<int*>(base + off[KW_VLEN]);
@@ -1577,6 +1580,8 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
     R* bfe = reinterpret_cast<R*>(base + off[KW_BFE]);
     R* bbw = reinterpret_cast<R*>(base + off[KW_BBW]);
     R* bbe = reinterpret_cast<R*>(base + off[KW_BBE]);
+    R* ops = reinterpret_cast<R*>(base + off[KW_OPS]);
+    R* wbuf = reinterpret_cast<R*>(base + off[KW_WN]);
     const long long frames = (long long)N * Tx;
     cudaMemsetAsync(diag, 0, 256, st);
     if (C > 1 || Cb > 1) {
@@ -1638,7 +1643,53 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         int rc = check_launch("kalman forward");
         if (rc) return rc;
     }
-    static const bool rows1 = [] { const char* e = getenv("KPMS_BACKPREP"); return e && std::string(e) == "rows1"; }();
+    // standard normals of the backward draw: the tape in verification mode, else one Philox pass (four per call)
+    if (!w_tape) {
+        const long long count = frames * n;
+        KPMS_LAUNCH("kalman_normals", st);
+        fill_normal_kernel<R><<<(int)((count / 4 + 256) / 256), 256, 0, st>>>(wbuf, count, seed, KPMS_STREAM_X);
+        w_tape = wbuf;
+    }
+    bool backprep_done = false;
+    static const std::string bp_mode = [] { const char* e = getenv("KPMS_BACKPREP"); return std::string(e ? e : "split"); }();
+    static const bool rows1 = bp_mode == "rows1";
+    if constexpr (L_ >= 2 && D_ <= 32) {
+      if (bp_mode == "split") {
+        // two-stage backward preparation (kalman_split.cuh): d lanes per frame, 32/d frames per warp
+        typedef PrepSplit<R, D_, L_> PS;
+        { KPMS_LAUNCH("kalman_backprep_ops", st);
+          backprep_ops_kernel<R, D_, L_><<<K, 128, 0, st>>>(Ab, Q, (R)jitter, ops); }
+        { KPMS_LAUNCH("kalman_backprep_special", st);
+          backprep_special_kernel<R, D_, L_, (n > 32)><<<N, 128, 0, st>>>(stash_m, stash_S, mask, w_tape, N, T, GH); }
+        auto launch = [&](auto kern, int warps, int minb) {
+            const size_t smem = (size_t)warps * PS::FPW * PS::frame_bytes + warps * sizeof(uint64_t);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const long long tiles = (frames + warps * PS::FPW - 1) / (warps * PS::FPW);
+            const int blocks = (int)std::min<long long>(tiles, (long long)KPMS_SM_COUNT * minb);
+            KPMS_LAUNCH("kalman_backprep", st);
+            kern<<<blocks, 32 * warps, smem, st>>>(stash_m, stash_S, mask, z, ops, (R)(KPMS_EPS_SHIFT + jitter), w_tape, N, T, GH);
+        };
+        constexpr int FIT4 = (int)((220 * 1024) / (4 * PS::FPW * PS::frame_bytes + 64));
+        constexpr int MINB = sizeof(R) == 8 ? 1 : (FIT4 >= 3 ? 3 : (FIT4 >= 1 ? FIT4 : 1));
+        static_assert(FIT4 >= 1, "one CTA of the two-stage backward preparation must fit in shared memory");
+        bool done = false;
+        if constexpr (sizeof(R) == 4 && D_ == 10 && L_ == 3) {      // launch-shape experiments (KPMS_BP_CFG), C2 shape only
+            static const std::string cfg = [] { const char* e = getenv("KPMS_BP_CFG"); return std::string(e ? e : ""); }();
+            done = true;
+            if (cfg == "4x3") launch(kalman_backprep_split_kernel<R, D_, L_, 4, 3, false>, 4, 3);
+            else if (cfg == "6x2") launch(kalman_backprep_split_kernel<R, D_, L_, 6, 2, false>, 6, 2);
+            else if (cfg == "6x2L") launch(kalman_backprep_split_kernel<R, D_, L_, 6, 2, true>, 6, 2);
+            else if (cfg == "12x1L") launch(kalman_backprep_split_kernel<R, D_, L_, 12, 1, true>, 12, 1);
+            else if (cfg == "5x2L") launch(kalman_backprep_split_kernel<R, D_, L_, 5, 2, true>, 5, 2);
+            else done = false;
+        }
+        if (!done) launch(kalman_backprep_split_kernel<R, D_, L_, 4, MINB, true>, 4, MINB);
+        int rc = check_launch("kalman backprep (two-stage)");
+        if (rc) return rc;
+        backprep_done = true;
+      }
+    }
+    if (!backprep_done) {
     auto launch_generic = [&]() -> int {
         // generic shared-memory kernel, one warp per frame; as many warps per CTA as shared memory allows
         constexpr int WARPS_MAX = (int)(220 * 1024 / (PrepSmem<R, D_, L_>::per_warp * sizeof(R)));
@@ -1690,6 +1741,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         int rc = launch_generic();
         if (rc) return rc;
     }
+    }
     {
         constexpr int STAGES = 4;
         auto kern = kalman_affine_kernel<R, D_, L_, STAGES>;
@@ -1716,7 +1768,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
 template <typename R>
 static int kalman_impl(const void* Y, const int* mask, const void* v, const void* h, const void* s, const int* z,
                        const void* Ct, const void* sigmasq, const void* Ab, const void* Q, double jitter,
-                       const void* w_tape, SeedArg seed, int N, int T, int k, int Dk, int d, int L, void* x,
+                       const void* w_tape, SeedArg seed, int N, int T, int k, int Dk, int d, int L, int K, void* x,
                        void* ws, cudaStream_t st) {
     if (Dk != 2 && Dk != 3) return set_error(-3, "kalman_sample: keypoint dimension must be 2 or 3, got %d", Dk);
     if (T < L) return set_error(-3, "kalman_sample: T (%d) < nlags (%d)", T, L);
@@ -1724,7 +1776,7 @@ static int kalman_impl(const void* Y, const int* mask, const void* v, const void
     if (d == DD && L == LL)                                                                                  \
         return kalman_launch<R, DD, LL>((const R*)Y, mask, (const R*)v, (const R*)h, (const R*)s, z,         \
                                         (const R*)Ct, (const R*)sigmasq, (const R*)Ab, (const R*)Q, jitter,  \
-                                        (const R*)w_tape, seed, N, T, k, Dk, (R*)x, ws, st);
+                                        (const R*)w_tape, seed, N, T, k, Dk, K, (R*)x, ws, st);
     KPMS_FOR_EACH_DL(X)
 #undef X
     return set_error(-3, "kalman_sample: unsupported (latent_dim, nlags) = (%d, %d)", d, L);
@@ -1736,20 +1788,21 @@ using namespace kpms;
 
 extern "C" {
 
-size_t kpms_kalman_workspace_bytes(int dtype, int N, int T, int d, int L) {
+size_t kpms_kalman_workspace_bytes(int dtype, int N, int T, int d, int L, int K) {
     size_t off[KW_END + 1];
     const int C = kalman_chunks(N, T, d, L, false), Cb = kalman_chunks(N, T, d, L, true);
-    if (dtype == 0) kalman_ws_layout<float>(N, T, d, L, C, Cb, off);
-    else kalman_ws_layout<double>(N, T, d, L, C, Cb, off);
+    if (dtype == 0) kalman_ws_layout<float>(N, T, d, L, K, C, Cb, off);
+    else kalman_ws_layout<double>(N, T, d, L, K, C, Cb, off);
     return off[KW_END];
 }
 
 int kpms_kalman_sample(int dtype, const void* Y, const int* mask, const void* v, const void* h, const void* s,
                        const int* z, const void* Ct, const void* sigmasq, const void* Ab, const void* Q,
                        double jitter, const void* w_tape, uint64_t seed, const uint64_t* seed_dev, int N, int T, int k, int Dk, int d,
-                       int L, void* x, void* ws, void* stream) {
+                       int L, int K, void* x, void* ws, void* stream) {
+    if (K < 1) return set_error(-3, "kalman_sample: num_states must be positive, got %d", K);
     return KPMS_DISPATCH_DTYPE(dtype, kalman_impl, Y, mask, v, h, s, z, Ct, sigmasq, Ab, Q, jitter, w_tape,
-                               SeedArg(seed, seed_dev), N, T, k, Dk, d, L, x, ws, (cudaStream_t)stream);
+                               SeedArg(seed, seed_dev), N, T, k, Dk, d, L, K, x, ws, (cudaStream_t)stream);
 }
 
 }  // extern "C"

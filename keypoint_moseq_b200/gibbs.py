@@ -312,12 +312,13 @@ def resample_continuous_stateseqs(Y, mask, v, h, s, z, Cd, sigmasq, Ab, Q, jitte
     if Ct is None:
         Ct = lifted_obs_matrix(Cd, k, D)
     Ctd, sg, AA, QQ = (_dev(t, dt, dev) for t in (Ct, sigmasq, Ab, Q))
-    ws = _scratch("kalman_ws", _lib.query("kpms_kalman_workspace_bytes", code, N, T, d, L), dev)
+    K = Ab.shape[0]
+    ws = _scratch("kalman_ws", _lib.query("kpms_kalman_workspace_bytes", code, N, T, d, L, K), dev)
     x = torch.empty((N, T, d), dtype=dt, device=dev)
     w = _dev(w_x, dt, dev)
     _lib.call("kpms_kalman_sample", code, _lib.ptr(Y), _lib.ptr(mask), _lib.ptr(v), _lib.ptr(h), _lib.ptr(s),
               _lib.ptr(z), _lib.ptr(Ctd), _lib.ptr(sg), _lib.ptr(AA), _lib.ptr(QQ), float(jitter), _lib.ptr(w),
-              seed64, _lib.ptr(seed_dev), N, T, k, D, d, L, _lib.ptr(x), _lib.ptr(ws), _lib.stream_ptr())
+              seed64, _lib.ptr(seed_dev), N, T, k, D, d, L, K, _lib.ptr(x), _lib.ptr(ws), _lib.stream_ptr())
     return x
 
 
