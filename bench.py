@@ -1,22 +1,24 @@
 #!/usr/bin/env python
-"""Benchmark of the keypoint-SLDS Gibbs sweep (BASELINE.json metric: Gibbs sweeps/s and
-frame-sweeps/s on synthetic keypoints sampled from the generative process).
+"""Benchmark of the keypoint-SLDS Gibbs sweep (BASELINE.json metric: Gibbs sweeps/s and frame-sweeps/s on
+synthetic keypoints sampled from the generative process, at 1/2/4/8 B200, next to the CPU path).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --steps K --warmup W    # CPU arm: float64 NumPy port of the
-                                                           # reference path (jax_moseq is not installable)
+  python bench.py --impl reference --steps K --warmup W    # CPU arm: float64 NumPy port of the reference path
+                                                           # (jax_moseq is not installable; probed first)
 
-One "step" is one full `resample_model` sweep (all kernels, the sufficient-statistic all-reduce
-when N > 1, and the per-sweep NaN check that `fit_model` performs, fitting.py:30).  At N = 1 the
-workload is BASELINE config C2 (20 recordings x 36k frames, 12 keypoints, latent_dim 10, nlags 3,
-100 states -> 80 chains x 10 030 frames).  For N > 1 every rank holds its own C2-sized cohort
-(weak scaling; recordings shard naturally and only the packed statistics cross GPUs).
-Prints ONE JSON line on rank 0.
+One "step" is one full `resample_model` sweep (every kernel, the sufficient-statistic all-reduce when N > 1, and
+the per-sweep NaN check that `fit_model` performs, fitting.py:30).  The headline `value` is measured on BASELINE
+config C2 per GPU (20 recordings x 36 000 frames, 12 keypoints, latent_dim 10, nlags 3, 100 states -> 80 chains x
+10 030 frames); for N > 1 every rank holds its own C2-sized share of one cohort (weak scaling: recordings shard,
+only the packed statistics cross GPUs).  The same run also times the north-star cohort C4 (200 recordings x
+54 000 frames, the SAME total work at every N, recordings dealt over the ranks) and reports it under `strong_c4`,
+so that the driver's N = 1, 2, 4, 8 lines carry the strong-scaling curve as well (`--config C4` makes it the
+headline instead).  Frames are counted as valid frames without the 30-frame segment overlaps (recordings x
+frames), as SURVEY 8(d) defines frame-sweeps/s.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -29,7 +31,7 @@ if ROOT not in sys.path:
 
 METRIC = "frame_sweeps_per_sec"
 UNIT = "frame-sweeps/s"
-NOMINAL_FP32_TFLOPS = 74.0   # 148 SM x 128 FMA x 2 x 1.965 GHz
+MEASURED_FP32_TFLOPS = 71.6   # FFMA peak measured on this pool's B200 (profiles/r01_dmma_peak.txt, 32 warps/SM)
 
 
 def parse():
@@ -39,13 +41,20 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="weak: every rank holds one --config-sized share (default for C1-C3); strong: the --config "
+                         "cohort is dealt over the ranks (default for C4)")
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--hmm-dtype", default="float64", choices=["float32", "float64"])
     ap.add_argument("--variant", default="full", choices=["full", "ar_only", "states_only"],
                     help="full sweep (the headline metric), or the reference's ar_only / states_only sweeps "
                          "(fit_model's AR-HMM stage, apply_model's sweeps); SURVEY 8(d)")
+    ap.add_argument("--start", default="converged", choices=["converged", "cold"],
+                    help="cold: AR parameters and transitions redrawn from the prior, states re-initialised from the "
+                         "data (what the first sweeps of a fit look like), timed from the first sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the strong-scaling C4 section of the default run")
     return ap.parse_args()
 
 
@@ -54,109 +63,99 @@ def workload(name):
     return dict(CONFIGS[name])
 
 
-class ClockSampler:
-    """Samples nvidia-smi clocks and throttle reasons during the timed region (the profiling recipe's
-    clocks line, -lms 200).  Every query stalls kernel launches for a while (measured: one step in ten
-    takes 30-50 ms instead of 18 when polling at 100 ms, and NVML polled in-process at 20 ms is far worse),
-    so the poll period is not shortened further; `step_ms` in the JSON line shows the outliers."""
-    FIELDS = os.environ.get("KPMS_BENCH_CLOCK_FIELDS") or (
-        "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-        "clocks_event_reasons.sw_power_cap")
-    PERIOD_MS = os.environ.get("KPMS_BENCH_CLOCK_MS", "200")
-
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", self.PERIOD_MS], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([p.strip() for p in line.split(",")])
-
-    def mark(self):
-        """Start of the timed region: only rows sampled from here on are reported (the process is
-        started before the warm-up so that its start-up cost does not fall into the timed steps)."""
-        self.first = len(self.rows)
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        self.proc.terminate()
-        rows = self.rows[getattr(self, "first", 0):] or self.rows[-1:]
-        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
-
-
 VARIANT_OPTS = {"full": {}, "ar_only": {"ar_only": True}, "states_only": {"states_only": True}}
 VARIANT_TEXT = {"full": "full sweep (params, z, s, x, h, v)", "ar_only": "ar_only sweep (transitions, AR params, z)",
                 "states_only": "states_only sweep (z, s, x, h, v; no parameter updates, no all-reduce)"}
 
 
-def _cpu_worker(idx, shard, dims, variant, sweeps, ready_q, go, out_q):
-    """One host process of the CPU arm: the float64 NumPy port on its own rows of the batch."""
+def workload_text(name, cfg, variant="full", scaling="weak"):
+    where = "per GPU" if scaling == "weak" else "in total, recordings dealt over the GPUs"
+    return (f"{name} {where}: {cfg['recordings']} recordings x {cfg['frames']} frames, k={cfg['k']}, D={cfg['D']}, "
+            f"latent_dim={cfg['d']}, nlags={cfg['L']}, num_states={cfg['K']}; {VARIANT_TEXT[variant]} + NaN check")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks: NVML read in-process (a thread, every 250 ms) during the timed region - no subprocess, no nvidia-smi parse
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, index, period=0.25):
+        self.period, self.rows, self.stop_flag, self.handle, self.nv = period, [], threading.Event(), None, None
+        self.max_mhz, self.thread = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = (os.environ.get("CUDA_VISIBLE_DEVICES") or "").split(",")
+            phys = int(visible[index]) if index < len(visible) and visible[index].strip().isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.handle = None
+
+    def _one(self):
+        nv = self.nv
+        try:
+            sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            try:
+                why = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:  # noqa: BLE001
+                why = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.rows.append((sm, why))
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            self._one()
+            self.stop_flag.wait(self.period)
+
+    def start(self):
+        if self.handle is None:
+            return
+        self.rows = []
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.handle is None or self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": "NVML unavailable"}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        self._one()
+        sm = [r[0] for r in self.rows]
+        reasons = [name for name, bit in self.BAD.items() if any(r[1] & bit for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "how": "NVML in-process every 250 ms during the timed region (clocks, event reasons)"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own path if importable, else the float64 NumPy port (oracle/) on all host cores
+# ----------------------------------------------------------------------------------------------------------------
+def _cpu_worker(idx, shard, dims, variant, cmd_q, out_q):
+    """One host process of the CPU arm: the float64 NumPy port on its own rows, one sweep per command."""
     try:
         import oracle as orc
         data, states, params, hypparams, prior = shard
         N, T, k, D = data["Y"].shape
         tape = orc.make_tape(np.random.default_rng(idx + 1), N, T, k, D, dims["d"], dims["L"], dims["K"])
-        ready_q.put(idx)
-        if not go.wait(timeout=180):
-            raise RuntimeError("start signal never came")
-        t0 = time.perf_counter()
-        for _ in range(sweeps):
-            orc.resample_model(data, states, params, hypparams, prior, tape, **VARIANT_OPTS[variant])
-        out_q.put((idx, time.perf_counter() - t0, float(data["mask"].sum()), None))
+        out_q.put((idx, "ready", 0.0))
+        while True:
+            cmd = cmd_q.get()
+            if cmd == "stop":
+                return
+            t0 = time.perf_counter()
+            st, pr, _ = orc.resample_model(data, states, params, hypparams, prior, tape, **VARIANT_OPTS[variant])
+            states, params = st, pr
+            out_q.put((idx, "done", time.perf_counter() - t0))
     except Exception as e:  # noqa: BLE001
-        out_q.put((idx, 0.0, 0.0, repr(e)))
-
-
-def _cpu_single(cfg, variant="full", chains=40, frames=2000, sweeps=2):
-    """Fallback of the CPU arm: one process, BLAS threads as configured."""
-    import oracle as orc
-    from keypoint_moseq_b200.synth import sample_dataset
-    data, _, model = sample_dataset(recordings=chains, frames=frames, k=cfg["k"], D=cfg["D"], d=cfg["d"],
-                                    L=cfg["L"], K=cfg["K"], seed=123, seg_length=frames)
-    N, T, k, D = data["Y"].shape
-    tape = orc.make_tape(np.random.default_rng(1), N, T, k, D, cfg["d"], cfg["L"], cfg["K"])
-    t0 = time.perf_counter()
-    for _ in range(sweeps):
-        orc.resample_model(data, model["states"], model["params"], model["hypparams"], model["noise_prior"], tape,
-                           **VARIANT_OPTS[variant])
-    dt = (time.perf_counter() - t0) / sweeps
-    try:
-        from threadpoolctl import threadpool_info
-        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:  # noqa: BLE001
-        cores = os.cpu_count() or 1
-    sample = (f"{sweeps} {variant} sweep(s) of the float64 NumPy port on {chains} chains x {T} frames of the {k}-keypoint, "
-              f"latent_dim {cfg['d']}, {cfg['K']}-state workload ({int(data['mask'].sum())} valid frames), one process, "
-              f"{dt:.2f} s per sweep")
-    return float(data["mask"].sum() / dt), int(cores), sample
-
-
-def cpu_port_throughput(cfg, variant="full"):
-    try:
-        return _cpu_multi(cfg, variant)
-    except Exception as e:  # noqa: BLE001
-        print(f"bench: multi-process CPU arm failed ({e!r}); timing one process instead", file=sys.stderr)
-        return _cpu_single(cfg, variant)
+        out_q.put((idx, "error", repr(e)))
 
 
 def _usable_procs(cap=32, gb_per_proc=1.5):
-    """Host processes for the CPU arm: the cores this process may run on, capped, and no more than fit in half
-    of the memory that is free (cgroup limit included) at about 1 GB per 24-chain shard."""
+    """Host processes for the CPU arm: the cores this process may run on, capped, and no more than fit in half of
+    the memory that is free (cgroup limit included)."""
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
@@ -178,109 +177,147 @@ def _usable_procs(cap=32, gb_per_proc=1.5):
     return max(1, min(cores, cap, by_mem))
 
 
-def _cpu_multi(cfg, variant="full", procs=None, chains_per_proc=24, frames=2000, sweeps=2):
-    """Times the float64 NumPy port (oracle/) of the same sweep on a bounded sample of the workload, on ALL host
-    cores: the port is bound by per-time-step interpreter overhead on one core, so the rows of the batch are
-    split over one process per core (the sharding the sweep has anyway: chains are independent, the parameter
-    draws are replicated) with BLAS pinned to one thread each.  Returns (frame_sweeps_per_sec, cores, sample)."""
-    import multiprocessing as mp
-    from keypoint_moseq_b200.synth import sample_dataset
-    procs = int(os.environ.get("KPMS_BENCH_CPU_PROCS", procs or _usable_procs()))
-    chains = procs * chains_per_proc
-    data, _, model = sample_dataset(recordings=chains, frames=frames, k=cfg["k"], D=cfg["D"], d=cfg["d"],
-                                    L=cfg["L"], K=cfg["K"], seed=123, seg_length=frames)
-    N, T, k, D = data["Y"].shape
-    per = N // procs
-    dims = {"d": cfg["d"], "L": cfg["L"], "K": cfg["K"]}
+class CpuPort:
+    """The float64 NumPy port (oracle/) of the same sweep on a bounded sample of the workload, on ALL host cores:
+    the port is bound by per-time-step interpreter overhead on one core, so the rows of the batch are split over
+    one process per core (the sharding the sweep has anyway: chains are independent, parameter draws replicated),
+    BLAS pinned to one thread each.  Every process holds ONE full-length chain (T = 10 030, the segment length of
+    every BASELINE config), so per-step overheads are amortised as they are in the real workload.  `step()` runs
+    one sweep on every process and returns its wall time."""
 
-    def rows(tree, a, b):
-        return {key: np.ascontiguousarray(np.asarray(val)[a:b]) for key, val in tree.items()}
-
-    saved = {key: os.environ.get(key) for key in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
-    for key in saved:
-        os.environ[key] = "1"
-    ctx = mp.get_context("spawn")
-    ready_q, go, out_q = ctx.Queue(), ctx.Event(), ctx.Queue()
-    workers = []
-    try:
-        for i in range(procs):
-            a, b = i * per, (i + 1) * per if i < procs - 1 else N
-            shard = (rows(data, a, b), rows(model["states"], a, b), model["params"], model["hypparams"],
-                     np.ascontiguousarray(np.asarray(model["noise_prior"])[a:b]))
-            w = ctx.Process(target=_cpu_worker, args=(i, shard, dims, variant, sweeps, ready_q, go, out_q), daemon=True)
-            w.start()
-            workers.append(w)
+    def __init__(self, cfg, variant="full", procs=None):
+        import multiprocessing as mp
         import queue
+        from keypoint_moseq_b200.synth import sample_dataset
+        self.queue_mod = queue
+        self.procs = int(os.environ.get("KPMS_BENCH_CPU_PROCS", procs or _usable_procs()))
+        frames = min(cfg["frames"], 10_000)
+        data, _, model = sample_dataset(recordings=self.procs, frames=frames, k=cfg["k"], D=cfg["D"], d=cfg["d"],
+                                        L=cfg["L"], K=cfg["K"], seed=123, seg_length=frames)
+        self.N, self.T = data["Y"].shape[:2]
+        self.valid = float(self.procs * frames)                       # without the padding / overlap frames
+        dims = {"d": cfg["d"], "L": cfg["L"], "K": cfg["K"]}
+        rows = lambda tree, a, b: {key: np.ascontiguousarray(np.asarray(val)[a:b]) for key, val in tree.items()}  # noqa: E731
+        saved = {key: os.environ.get(key) for key in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+        for key in saved:
+            os.environ[key] = "1"
+        ctx = mp.get_context("spawn")
+        self.out_q, self.cmd_qs, self.workers = ctx.Queue(), [], []
+        per = self.N // self.procs
+        try:
+            for i in range(self.procs):
+                a, b = i * per, (i + 1) * per if i < self.procs - 1 else self.N
+                shard = (rows(data, a, b), rows(model["states"], a, b), model["params"], model["hypparams"],
+                         np.ascontiguousarray(np.asarray(model["noise_prior"])[a:b]))
+                q = ctx.Queue()
+                w = ctx.Process(target=_cpu_worker, args=(i, shard, dims, variant, q, self.out_q), daemon=True)
+                w.start()
+                self.cmd_qs.append(q)
+                self.workers.append(w)
+        finally:
+            for key, val in saved.items():
+                if val is None:
+                    os.environ.pop(key, None)
+                else:
+                    os.environ[key] = val
+        self._gather("ready", 180)
+        self.sample = (f"one {variant} sweep per step of the float64 NumPy port (oracle/, NOT JAX) on {self.N} chains x "
+                       f"{self.T} frames of the {cfg['k']}-keypoint, latent_dim {cfg['d']}, {cfg['K']}-state workload "
+                       f"({int(self.valid)} valid frames), one full-length chain per host process, {self.procs} processes "
+                       f"(one per core, BLAS single-threaded)")
 
-        def gather(q, count, seconds, what):
-            got, deadline = [], time.perf_counter() + seconds
-            while len(got) < count:
-                try:
-                    got.append(q.get(timeout=1))
-                except queue.Empty:
-                    dead = [i for i, w in enumerate(workers) if not w.is_alive() and w.exitcode not in (0, None)]
-                    if dead:
-                        raise RuntimeError(f"worker {dead[0]} died (exit code {workers[dead[0]].exitcode}) before {what}")
-                    if time.perf_counter() > deadline:
-                        raise RuntimeError(f"CPU arm timed out waiting for {what}")
-            return got
+    def _gather(self, what, seconds):
+        got, deadline = [], time.perf_counter() + seconds
+        while len(got) < self.procs:
+            try:
+                idx, kind, val = self.out_q.get(timeout=1)
+            except self.queue_mod.Empty:
+                dead = [i for i, w in enumerate(self.workers) if not w.is_alive()]
+                if dead:
+                    raise RuntimeError(f"CPU arm worker {dead[0]} died (exit code {self.workers[dead[0]].exitcode})")
+                if time.perf_counter() > deadline:
+                    raise RuntimeError(f"CPU arm timed out waiting for '{what}'")
+                continue
+            if kind == "error":
+                raise RuntimeError("CPU arm worker failed: " + str(val))
+            if kind == what:
+                got.append(val)
+        return got
 
-        gather(ready_q, procs, 120, "start")             # every worker has imported and unpacked its rows
-        go.set()
-        results = gather(out_q, procs, 420, "results")
-    finally:
-        for key, val in saved.items():
-            if val is None:
-                os.environ.pop(key, None)
-            else:
-                os.environ[key] = val
-        for w in workers:
-            w.join(timeout=0.5 if sys.exc_info()[0] else 30)
+    def step(self):
+        t0 = time.perf_counter()
+        for q in self.cmd_qs:
+            q.put("sweep")
+        self._gather("done", 600)
+        return time.perf_counter() - t0
+
+    def close(self):
+        for q in self.cmd_qs:
+            q.put("stop")
+        for w in self.workers:
+            w.join(timeout=5)
             if w.is_alive():
                 w.terminate()
-    errors = [r[3] for r in results if r[3]]
-    if errors:
-        raise RuntimeError("CPU arm worker failed: " + errors[0])
-    wall = max(r[1] for r in results)
-    valid = sum(r[2] for r in results)
-    sample = (f"{sweeps} {variant} sweep(s) of the float64 NumPy port on {N} chains x {T} frames of the {k}-keypoint, "
-              f"latent_dim {cfg['d']}, {cfg['K']}-state workload ({int(valid)} valid frames), rows split over {procs} "
-              f"host processes (one per core, BLAS single-threaded), {wall / sweeps:.2f} s per sweep")
-    return float(valid * sweeps / wall), int(procs), sample
 
 
-def workload_text(name, cfg, variant="full"):
-    return (f"{name} per GPU: {cfg['recordings']} recordings x {cfg['frames']} frames, k={cfg['k']}, D={cfg['D']}, "
-            f"latent_dim={cfg['d']}, nlags={cfg['L']}, num_states={cfg['K']}; {VARIANT_TEXT[variant]} + NaN check")
+def probe_reference_engine():
+    """The reference's own engine (jax_moseq, JAX on CPU), from the environment or a driver-provided baseline/_ref."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        os.environ.setdefault("JAX_PLATFORMS", "cpu")
+        import jax  # noqa: F401
+        import jax_moseq  # noqa: F401
+        return True
+    except Exception:  # noqa: BLE001
+        return False
 
 
 def run_reference(args):
-    """CPU arm: jax_moseq (the reference's engine) cannot be installed here, so the oracle port is timed."""
+    """`--impl reference`: the CPU arm on the same config / metric / unit.  jax and jax_moseq are probed first; they
+    cannot be installed offline, so the float64 NumPy port of the same sweep is what runs,
+    labelled as such.  Executes exactly --warmup + --steps sweeps of the bounded sample and reports THEIR timing;
+    the extrapolation to the full workload sits in a separate, labelled field."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = workload(args.config)
-    best = None
-    for _ in range(max(1, min(args.steps, 2))):
-        val, cores, sample = cpu_port_throughput(cfg, variant=args.variant)
-        best = val if best is None else max(best, val)
+    have_jax = probe_reference_engine()
+    port = CpuPort(cfg, variant=args.variant)
+    try:
+        for _ in range(args.warmup):
+            port.step()
+        times = [port.step() for _ in range(args.steps)]
+    finally:
+        port.close()
+    ms = 1e3 * float(np.mean(times))
+    value = port.valid / (ms * 1e-3)
     frames_total = cfg["recordings"] * cfg["frames"]
+    scaling = args.scaling or ("strong" if args.config == "C4" else "weak")
     line = {
-        "impl": "reference", "metric": METRIC, "value": best, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * frames_total / best,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_text(args.config, cfg, args.variant)},
-        "sweeps_per_sec": best / frames_total,
-        "cpu_baseline": {"value": best, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": best, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference engine jax_moseq is an unvendored dependency and jax is not installable offline; "
-                "this arm times this repo's float64 NumPy restatement (oracle/), NOT JAX",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_text(args.config, cfg, args.variant, scaling),
+                   "sample": port.sample, "sample_valid_frames": int(port.valid)},
+        "step_ms": [round(1e3 * t, 1) for t in times],
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": port.procs, "kind": "port", "sample": port.sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "extrapolated": {"full_workload_valid_frames": frames_total,
+                         "full_workload_ms_per_sweep": 1e3 * frames_total / value,
+                         "note": "sample throughput applied to the whole workload; not measured"},
+        "jax_moseq_importable": have_jax,
+        "note": "the reference's engine (jax_moseq on JAX) is an un-vendored dependency that cannot be installed "
+                "offline; this arm times this repo's float64 NumPy restatement of the same sweep, NOT JAX",
     }
     print(json.dumps(line))
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# algorithmic bytes / flops per frame (DESIGN.md section 4)
+# ----------------------------------------------------------------------------------------------------------------
 def kernel_bytes_per_frame(name, cfg, esz, hmm_esz):
-    """Algorithmic HBM bytes per (chain, frame) for each kernel."""
     d, L, K, k, D = cfg["d"], cfg["L"], cfg["K"], cfg["k"], cfg["D"]
     n = d * L
     rec = d * (d + 1) // 2 + d
@@ -290,7 +327,7 @@ def kernel_bytes_per_frame(name, cfg, esz, hmm_esz):
     table = {
         "kalman_obs_info": (k * D + k + D + 1) * esz + 4 + rec * esz,
         "kalman_forward": (rec + stash) * esz + 8,
-        "kalman_backprep": (stash + gh) * esz + 8,
+        "kalman_backprep": (stash + gh + n) * esz + 8,
         "kalman_affine": gh * esz + d * esz,
         "ar_loglik": d * hmm_esz + 4 + (K + 1) * hmm_esz,
         "hmm_forward": (K + 1 + ldK) * hmm_esz,
@@ -303,21 +340,40 @@ def kernel_bytes_per_frame(name, cfg, esz, hmm_esz):
     return table.get(name)
 
 
-MEASURED_FP32_TFLOPS = 71.6   # FFMA peak measured on this pool's B200 (profiles/r01_dmma_peak.txt, 32 warps/SM)
-
-
 def kernel_flops_per_frame(name, cfg):
-    """Algorithmic floating-point operations per (chain, frame) of the factorisation kernels:
-    backward preparation = A S, A S A' + Q, two Cholesky, two triangular solves, one symmetric rank-n update
-    = 13/6 n^3 multiply-adds; filter step = rank-d measurement update of the n x n covariance, companion-form
-    prediction, d x d factorisation.  Other kernels are memory-shaped and return None."""
+    """Floating-point operations per (chain, frame) of the factorisation kernels.  Backward preparation, two-stage
+    form (csrc/kalman_split.cuh): Gauss-Jordan on the (n-d) x n stage-1 system, the d-row products with A, the
+    rank-d downdate and the lower-triangular Cholesky of Sigma, the (n-d) x n gain correction - the multiply-adds
+    the algebra needs (symmetry counted where the kernel uses it).  Filter step: rank-d measurement update of the
+    n x n covariance, companion-form prediction, d x d factorisation."""
     d, L = cfg["d"], cfg["L"]
     n = d * L
-    table = {
-        "kalman_backprep": 2.0 * (13.0 / 6.0) * n ** 3,
-        "kalman_forward": 2.0 * (3.0 * n * n * d + n * d * d + d ** 3),
-    }
+    no = n - d
+    backprep = (no * no * n                    # Gauss-Jordan [Z | T']
+                + d * no * d                   # Sigma1_aa
+                + n * n * d                    # W' = Sigma1' A'
+                + d * n * d                    # B2
+                + n * d * d                    # V2, K2
+                + no * n * d                   # G1' = K1' - Wc'' K2'
+                + n * n * d // 2 + n * d       # Sigma (lower) downdate
+                + n ** 3 // 6                  # chol(Sigma)
+                + 3 * n * n)                   # means
+    table = {"kalman_backprep": 2.0 * backprep, "kalman_forward": 2.0 * (3.0 * n * n * d + n * d * d + d ** 3)}
     return table.get(name)
+
+
+def cold_model(data, truth, cfg):
+    """Parameters that do NOT generate the data + states re-initialised from the data: the first sweeps of a fit."""
+    import torch
+    from keypoint_moseq_b200 import fitting
+    from keypoint_moseq_b200.synth import sample_dataset
+    _, _, other = sample_dataset(recordings=1, frames=64, k=cfg["k"], D=cfg["D"], d=cfg["d"], L=cfg["L"], K=cfg["K"],
+                                 seed=4321, kappa=1e4)
+    params = dict(truth["params"], Ab=other["params"]["Ab"], Q=other["params"]["Q"], pi=other["params"]["pi"],
+                  betas=other["params"]["betas"])
+    return fitting.init_model(data=data, params=params, hypparams=truth["hypparams"],
+                              seed=np.array([0, 7], dtype=np.uint32), noise_prior=truth["noise_prior"],
+                              dtype=torch.float32)
 
 
 def main():
@@ -328,6 +384,7 @@ def main():
     import torch
     import torch.distributed as dist
     from keypoint_moseq_b200 import _lib, gibbs
+    from keypoint_moseq_b200.fitting import NAN_CHECK_LAG
     from keypoint_moseq_b200.synth import sample_dataset
     from keypoint_moseq_b200.util import NanGuard, check_for_nans
 
@@ -344,80 +401,140 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
         group = dist.group.WORLD
     _lib.load()
-
-    cfg = workload(args.config)
     dt = torch.float32 if args.dtype == "float32" else torch.float64
     hdt = torch.float32 if args.hmm_dtype == "float32" else torch.float64
     esz, hesz = (4 if dt == torch.float32 else 8), (4 if hdt == torch.float32 else 8)
-    data, metadata, model = sample_dataset(recordings=cfg["recordings"], frames=cfg["frames"], k=cfg["k"], D=cfg["D"],
-                                           d=cfg["d"], L=cfg["L"], K=cfg["K"], seed=1000, kappa=1e4,
-                                           data_seed=None if world == 1 else 2000 + rank)
-    valid_local = int(data["mask"].sum())
-    dd = gibbs.to_device_data(data, dev, dt)
-    dm = gibbs.to_device_model(model, dev, dt)
-    opts = dict(hmm_dtype=hdt, group=group, **VARIANT_OPTS[args.variant])
+    scaling = args.scaling or ("strong" if args.config == "C4" else "weak")
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
-    # the per-sweep NaN check of fit_model, pipelined as fit_model does (fitting.NAN_CHECK_LAG sweeps)
-    from keypoint_moseq_b200.fitting import NAN_CHECK_LAG
-    guard = NanGuard(lag=int(os.environ.get("KPMS_NAN_LAG", NAN_CHECK_LAG)))
+    def allsum(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
 
-    def step(m):
-        m = gibbs.resample_model(dd, **m, **opts)
-        guard.submit(m)
-        failed, _ = guard.collect()
-        if failed is not None:
-            raise RuntimeError("NaNs in sweep: " + "; ".join(check_for_nans(failed)[2]))
-        return m
+    def allmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
 
-    def drain():
-        failed, _ = guard.collect(keep=0)
-        if failed is not None:
-            raise RuntimeError("NaNs in sweep: " + "; ".join(check_for_nans(failed)[2]))
+    def build(name, mode):
+        """Device-resident data + model of this rank's share of config `name`; returns (cfg, data, model, valid)."""
+        cfg = workload(name)
+        rec = cfg["recordings"]
+        if mode == "strong":                       # the cohort's recordings dealt over the ranks (same total at every N)
+            rec = cfg["recordings"] // world + (1 if rank < cfg["recordings"] % world else 0)
+        if rec == 0:
+            raise RuntimeError(f"{name}: {cfg['recordings']} recordings cannot be dealt over {world} ranks")
+        data, _, model = sample_dataset(recordings=rec, frames=cfg["frames"], k=cfg["k"], D=cfg["D"], d=cfg["d"],
+                                        L=cfg["L"], K=cfg["K"], seed=1000, kappa=1e4, dtype=np.float32,
+                                        data_seed=None if world == 1 else 2000 + rank)
+        if args.start == "cold":
+            model = cold_model(data, model, cfg)
+        dd = gibbs.to_device_data(data, dev, dt)
+        dm = gibbs.to_device_model(model, dev, dt)
+        return cfg, dd, dm, rec * cfg["frames"]
 
-    m = dm
-    for _ in range(max(args.warmup, 3)):
-        m = step(m)
-    drain()
+    opts = dict(hmm_dtype=hdt, group=group, **VARIANT_OPTS[args.variant])
+
+    class Runner:
+        """Steps a model through `resample_model` with the pipelined NaN check of `fit_model`."""
+
+        def __init__(self, dd, dm):
+            self.dd, self.m = dd, dm
+            self.guard = NanGuard(lag=int(os.environ.get("KPMS_NAN_LAG", NAN_CHECK_LAG)))
+
+        def step(self):
+            self.m = gibbs.resample_model(self.dd, **self.m, **opts)
+            self.guard.submit(self.m)
+            failed, _ = self.guard.collect()
+            if failed is not None:
+                raise RuntimeError("NaNs in sweep: " + "; ".join(check_for_nans(failed)[2]))
+
+        def drain(self):
+            failed, _ = self.guard.collect(keep=0)
+            if failed is not None:
+                raise RuntimeError("NaNs in sweep: " + "; ".join(check_for_nans(failed)[2]))
+
+        def timed(self, steps, warmup, clocks=None):
+            """`warmup` untimed sweeps, then exactly `steps` timed ones bracketed by barrier + synchronize; CUDA
+            events on the launching stream; returns (ms per step, max over ranks; per-step ms; kernel launches)."""
+            for _ in range(warmup):
+                self.step()
+            self.drain()
+            barrier()
+            if clocks is not None:
+                clocks.start()
+            launches0 = _lib.launch_count() + gibbs.graph_kernel_launches()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+            e0.record()
+            for i in range(steps):
+                self.step()
+                marks[i].record()
+            self.drain()                           # every timed sweep's check is read inside the timed region
+            e1.record()
+            barrier()
+            ms = allmax(e0.elapsed_time(e1)) / steps
+            step_ms = [round(([e0] + marks)[i].elapsed_time(marks[i]), 3) for i in range(steps)]
+            launches = _lib.launch_count() + gibbs.graph_kernel_launches() - launches0
+            return ms, step_ms, launches
+
+    cfg, dd, dm, valid_local = build(args.config, scaling)
+    valid_total = allsum(valid_local)
+    frame_slots = int(dd["Y"].shape[0]) * int(dd["Y"].shape[1])       # chains x T: what every per-frame kernel walks
+    run = Runner(dd, dm)
+    W = max(args.warmup, 3)
+    if args.start == "cold":
+        # timed from the very first sweep of the cold model (graph capture and scratch allocation happen on a copy)
+        scratch = Runner(dd, dm)
+        scratch.step()
+        scratch.drain()
+        del scratch
+        W = 0
+    else:
+        for _ in range(W):
+            run.step()
+        run.drain()
     barrier()
-    tv = torch.tensor([float(valid_local)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tv, op=dist.ReduceOp.SUM)
-    valid_total = float(tv[0])
-    # per-kernel CUDA-event timing (separate sweeps, same stream), for the roofline of the dominant kernel
+
+    # per-kernel CUDA-event timing (separate eager sweeps, same stream), for the roofline of the dominant kernel
     # (every rank steps - the sweep contains the statistics all-reduce - but only rank 0 records)
     prof = {}
-    psteps = 2
-    if rank == 0:
-        _lib.profile(True)
-    for _ in range(psteps):
-        m = step(m)
-    drain()
-    if rank == 0:
-        prof = _lib.profile_report()
-        _lib.profile(False)
-        prof = {k_: (v[0] / psteps, v[1] // psteps) for k_, v in prof.items()}
-    barrier()
+    if args.start != "cold":
+        psteps = 2
+        if rank == 0:
+            _lib.profile(True)
+        saved_model = run.m
+        for _ in range(psteps):
+            run.step()
+        run.drain()
+        if rank == 0:
+            prof = _lib.profile_report()
+            _lib.profile(False)
+            prof = {k_: (v[0] / psteps, v[1] // psteps) for k_, v in prof.items()}
+        run.m = saved_model
+        barrier()
 
-    # end to end through the public call with HOST buffers: pinned host -> device copies of the data and
-    # model every step, device -> host read of the resampled states inside the timed region
+    # end to end through the public call with HOST buffers: pinned host -> device copies of the data and model every
+    # step, device -> host read of the resampled states inside the timed region
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.start != "cold":
+        m = run.m
         host_data = {k_: v.cpu().pin_memory() for k_, v in dd.items()}
         host_states = {k_: v.cpu().pin_memory() for k_, v in m["states"].items()}
         host_prior = m["noise_prior"].cpu().pin_memory()
         host_params = {k_: v.cpu().pin_memory() for k_, v in m["params"].items()}
         out_host = {k_: torch.empty_like(v).pin_memory() for k_, v in host_states.items()}
-        nbytes = lambda d_: sum(v.numel() * v.element_size() for v in d_.values())
-        # what resample_model uploads: Y and mask (conf is not an operand of the sweep), the states it reads
-        # (the old noise scales are resampled before any use), the parameters and the noise prior
+        nbytes = lambda d_: sum(v.numel() * v.element_size() for v in d_.values())  # noqa: E731
         if args.variant == "ar_only":       # no keypoints, no noise prior; every state rides along unchanged
             h2d = nbytes({"mask": host_data["mask"]}) + nbytes(host_states) + nbytes(host_params)
         else:
@@ -429,12 +546,9 @@ def main():
         esteps = max(1, min(args.steps, 5))
 
         def e2e_step(seed):
-            # the public call with HOST operands: resample_model uploads them on its copy stream in
-            # order of first use and streams each resampled state back into `out_host` as it completes
             mm = {"seed": seed, "states": host_states, "params": host_params, "hypparams": m["hypparams"],
                   "noise_prior": host_prior}
             out = gibbs.resample_model(host_data, **mm, host_out=out_host, **opts)
-            # the per-sweep guard of fit_model (fitting.py:30) on everything the sweep produced
             any_nans, _, msgs = check_for_nans({"states": out["states"], "params": out["params"]})
             torch.cuda.synchronize()                         # host copies of the states are complete
             if any_nans:
@@ -449,53 +563,60 @@ def main():
             seed = e2e_step(seed)
         ee1.record()
         barrier()
-        ems = ee0.elapsed_time(ee1) / esteps
-        te = torch.tensor([ems], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": valid_total / (float(te[0]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te[0]), "steps": esteps}
+        ems = allmax(ee0.elapsed_time(ee1) / esteps)
+        e2e = {"value": valid_total / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ems, "steps": esteps}
+        del host_data, host_states, host_prior, host_params, out_host
 
-    # ---- the timed region proper: W warm-up sweeps again (the profiling and end-to-end sections above also
-    # serve as warm-up: the first seconds on a fresh box are noisy), then exactly K timed sweeps
-    clocks = ClockSampler(local)
-    if rank == 0 and not os.environ.get("KPMS_BENCH_NO_CLOCKS"):
-        clocks.start()
-    for _ in range(max(args.warmup, 3)):
-        m = step(m)
-    drain()
-    barrier()
-    if rank == 0:
-        time.sleep(0.25)          # let the sampler finish its start-up and first query outside the timed region
-        clocks.mark()
-    launches0 = _lib.launch_count() + gibbs.graph_kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    e0.record()
-    host_ms = []
-    for i_ in range(args.steps):
-        t_h = time.perf_counter()
-        m = step(m)
-        marks[i_].record()
-        host_ms.append(round((time.perf_counter() - t_h) * 1e3, 2))
-    drain()                       # every timed sweep's check is read inside the timed region
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    step_ms = [round(([e0] + marks)[i_].elapsed_time(marks[i_]), 3) for i_ in range(args.steps)]
-    launches = _lib.launch_count() + gibbs.graph_kernel_launches() - launches0
-    clk = clocks.stop() if rank == 0 else None
-    if world > 1:
-        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax[0])
-    ms_per_step = ms / args.steps
+    # ---- the timed region proper
+    clocks = ClockSampler(local) if rank == 0 and not os.environ.get("KPMS_BENCH_NO_CLOCKS") else None
+    ms_per_step, step_ms, launches = run.timed(args.steps, W, clocks)
+    clk = clocks.stop() if clocks is not None else None
     value = valid_total / (ms_per_step * 1e-3)
+    diag = {"kalman": gibbs.chunk_diagnostics("kalman_ws", dev), "hmm": gibbs.chunk_diagnostics("hmm_ws", dev)}
+    chains_rank = int(dd["Y"].shape[0])
+
+    # ---- the north-star cohort, strong scaling: C4 dealt over the ranks (same total work at every N)
+    strong = None
+    if args.config == "C2" and scaling == "weak" and args.variant == "full" and args.start == "converged" and not args.no_c4:
+        try:
+            del run, dd, dm
+            gibbs._GRAPHS.clear()
+            torch.cuda.empty_cache()
+            c4, dd4, dm4, valid4 = build("C4", "strong")
+            run4 = Runner(dd4, dm4)
+            ssteps = max(3, min(args.steps, 10))
+            ms4, step4, _ = run4.timed(ssteps, 3)
+            total4 = allsum(valid4)
+            strong = {"workload": workload_text("C4", c4, "full", "strong"), "scaling": "strong",
+                      "value": total4 / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4, "steps": ssteps, "warmup": 3,
+                      "sweeps_per_sec": 1e3 / ms4, "valid_frames_total": int(total4),
+                      "chains_this_rank": int(dd4["Y"].shape[0]), "step_ms": step4,
+                      "chunk_diagnostics": {"kalman": gibbs.chunk_diagnostics("kalman_ws", dev),
+                                            "hmm": gibbs.chunk_diagnostics("hmm_ws", dev)}}
+            del run4, dd4, dm4
+        except Exception as e:  # noqa: BLE001 - the headline line must survive a failure of the extra section
+            strong = {"error": repr(e)[:300]}
+            try:
+                barrier()
+            except Exception:  # noqa: BLE001
+                pass
+
+    def finish():
+        """Captured sweep graphs hold the NCCL communicator: they are released before the process group goes away
+        (destroying the group first blocks until the watchdog times out)."""
+        if world > 1:           # never let a stuck teardown hold eight GPUs: the line is out, leave after 45 s at most
+            watchdog = threading.Timer(45.0, lambda: os._exit(0))
+            watchdog.daemon = True
+            watchdog.start()
+        gibbs.release_graphs()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish()
         return
 
     peaks = {}
@@ -503,62 +624,69 @@ def main():
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
     hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
-    frames_rank = dd["Y"].shape[0] * dd["Y"].shape[1]
-    roofline = None
-    kernels = {}
+    roofline, kernels = None, {}
     if prof:
         total = sum(v[0] for v in prof.values())
         for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
             bpf = kernel_bytes_per_frame(name, cfg, esz, hesz)
             kernels[name] = {"ms_per_sweep": round(kms, 4), "launches": cnt, "share": round(kms / total, 4),
-                             "gbs": None if bpf is None else round(bpf * frames_rank / (kms * 1e-3) / 1e9, 1)}
+                             "gbs": None if bpf is None else round(bpf * frame_slots / (kms * 1e-3) / 1e9, 1)}
         top = max(prof.items(), key=lambda kv: kv[1][0])[0]
         bpf = kernel_bytes_per_frame(top, cfg, esz, hesz)
         dur = prof[top][0] / max(prof[top][1], 1)
-        ach = bpf * frames_rank / (dur * 1e-3) / 1e9 if bpf else None
-        traffic = None
+        ach = bpf * frame_slots / (dur * 1e-3) / 1e9 if bpf else None
+        traffic, traffic_src = None, None
         tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr_path) and args.config == "C2":
-            traffic = json.load(open(tr_path)).get(top, {}).get("bytes")     # from the committed ncu --set full capture
+        if os.path.exists(tr_path):
+            entry = json.load(open(tr_path)).get(top, {})
+            if entry.get("bytes_per_frame"):             # committed ncu --set full capture, DRAM bytes per frame slot
+                traffic, traffic_src = entry["bytes_per_frame"] * frame_slots, entry.get("source")
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": None if ach is None else ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                    "launch_ms": dur, "algorithmic_bytes_per_launch": None if bpf is None else bpf * frames_rank,
-                    "note": "the dominant kernel is a batch of per-frame 30x30 factorisations bound by FP32 issue and "
-                            "shared-memory operand traffic (ncu: issue slots 41 % busy, FMA pipe 28 %, DRAM traffic = "
-                            "0.96 x algorithmic bytes); the HBM fraction is reported as the contract requires "
-                            "(DESIGN.md section 4.1)"}
-
-    try:        # the dominant kernels are arithmetic-shaped: say what fraction of the FP32 SIMT peak they reach
-        fpf = kernel_flops_per_frame(roofline["kernel"], cfg) if roofline else None
+                    "frac": None if ach is None else ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src, "launch_ms": dur,
+                    "algorithmic_bytes_per_launch": None if bpf is None else bpf * frame_slots,
+                    "note": "the dominant kernel is a batch of per-frame factorisations of 30 x 30 matrices: it is bound "
+                            "by FP32 instruction issue and dependency latency, not by HBM (DRAM traffic stays near the "
+                            "algorithmic bytes); `compute` states its rate against the measured FP32 FMA peak and is the "
+                            "figure to read - the HBM fraction is reported because the contract asks for it"}
+        fpf = kernel_flops_per_frame(top, cfg)
         if fpf:
-            tf = fpf * frames_rank / (roofline["launch_ms"] * 1e-3) / 1e12
+            tf = fpf * frame_slots / (dur * 1e-3) / 1e12
             roofline["compute"] = {"achieved": tf, "peak": MEASURED_FP32_TFLOPS, "unit": "TFLOP/s",
                                    "frac": tf / MEASURED_FP32_TFLOPS, "flops_per_frame": fpf,
                                    "peak_source": "FFMA micro-benchmark, profiles/r01_dmma_peak.txt"}
-    except Exception as e:  # noqa: BLE001 - never lose the bench line over a derived figure
-        print(f"bench: compute roofline skipped ({e!r})", file=sys.stderr)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        val, cores, sample = cpu_port_throughput(cfg, variant=args.variant)
-        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        try:
+            port = CpuPort(cfg, variant=args.variant)
+            try:
+                port.step()
+                times = [port.step() for _ in range(2)]
+            finally:
+                port.close()
+            cpu = {"value": port.valid / float(np.mean(times)), "unit": UNIT, "cores": port.procs, "kind": "port",
+                   "sample": port.sample + f"; one warm-up and two timed sweeps, {np.mean(times):.2f} s per sweep"}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"error": repr(e)[:300]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32" if dt == torch.float32 else "f64", "data": "synthetic",
-        "config": {"workload": workload_text(args.config, cfg, args.variant),
-                   "chains_per_gpu": int(dd["Y"].shape[0]), "frames_per_chain": int(dd["Y"].shape[1]),
-                   "valid_frames_total": int(valid_total), "hmm_dtype": "f32" if hdt == torch.float32 else "f64",
+        "config": {"workload": workload_text(args.config, cfg, args.variant, scaling),
+                   "start": args.start, "valid_frames_total": int(valid_total), "chains_this_rank": chains_rank,
+                   "hmm_dtype": "f32" if hdt == torch.float32 else "f64",
+                   "launch": "one CUDA graph per sweep" if gibbs.graphs_enabled() else "eager launches",
                    "l2": "working set per sweep (> 4 GB of filter/backward records) exceeds the 126 MB L2"},
         "sweeps_per_sec": 1e3 / ms_per_step,
-        "step_ms": step_ms, "step_host_ms": host_ms,
+        "step_ms": step_ms,
         "gpu_launches": int(launches),
         "e2e": e2e,
         "roofline": roofline,
         "kernels": kernels,
-        "chunk_diagnostics": {"kalman": gibbs.chunk_diagnostics("kalman_ws", dev),
-                              "hmm": gibbs.chunk_diagnostics("hmm_ws", dev)},
+        "chunk_diagnostics": diag,
+        "strong_c4": strong,
         "cpu_baseline": cpu,
         "clocks": clk,
     }
@@ -566,8 +694,7 @@ def main():
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
     os.dup2(2, 1)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

@@ -17,6 +17,9 @@
 #define KPMS_EPS_SHIFT 1e-2
 #define KPMS_X_PRIOR_VAR 10.0
 #define KPMS_V_PRIOR_VAR 1e6
+/* degrees of freedom one keypoint of dimension DK adds to the scaled-inverse-chi-square posteriors of the noise
+ * scales and of sigmasq (oracle: SCALE_DOF / OBSVAR_DOF = None); upstream may hard-code 3 - change both together */
+#define KPMS_OBS_DOF(DK) (DK)
 #define KPMS_SM_COUNT 148     /* B200; the library is built for sm_100a only */
 #define KPMS_MAX_CHUNKS 1024   /* time chunks per chain at most (a single 10^6-frame chain still fills the device) */
 

@@ -47,7 +47,7 @@ scales_kernel(const R* __restrict__ Y, const R* __restrict__ x, const R* __restr
     }
     const double variance = (double)sq / (double)sigmasq[j] + nu_s * (double)prior[e];
     Philox gen(seed, KPMS_STREAM_S, (uint64_t)e);
-    const double gam = gamma_draw<R>(0.5 * (nu_s + DK), g_tape ? g_tape + e * KPMS_GAMMA_TAPE : nullptr, gen);
+    const double gam = gamma_draw<R>(0.5 * (nu_s + KPMS_OBS_DOF(DK)), g_tape ? g_tape + e * KPMS_GAMMA_TAPE : nullptr, gen);
     s_out[e] = (R)(variance / (2.0 * gam));
 }
 

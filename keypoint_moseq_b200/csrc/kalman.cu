@@ -1672,18 +1672,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         constexpr int FIT4 = (int)((220 * 1024) / (4 * PS::FPW * PS::frame_bytes + 64));
         constexpr int MINB = sizeof(R) == 8 ? 1 : (FIT4 >= 3 ? 3 : (FIT4 >= 1 ? FIT4 : 1));
         static_assert(FIT4 >= 1, "one CTA of the two-stage backward preparation must fit in shared memory");
-        bool done = false;
-        if constexpr (sizeof(R) == 4 && D_ == 10 && L_ == 3) {      // launch-shape experiments (KPMS_BP_CFG), C2 shape only
-            static const std::string cfg = [] { const char* e = getenv("KPMS_BP_CFG"); return std::string(e ? e : ""); }();
-            done = true;
-            if (cfg == "4x3") launch(kalman_backprep_split_kernel<R, D_, L_, 4, 3, false>, 4, 3);
-            else if (cfg == "6x2") launch(kalman_backprep_split_kernel<R, D_, L_, 6, 2, false>, 6, 2);
-            else if (cfg == "6x2L") launch(kalman_backprep_split_kernel<R, D_, L_, 6, 2, true>, 6, 2);
-            else if (cfg == "12x1L") launch(kalman_backprep_split_kernel<R, D_, L_, 12, 1, true>, 12, 1);
-            else if (cfg == "5x2L") launch(kalman_backprep_split_kernel<R, D_, L_, 5, 2, true>, 5, 2);
-            else done = false;
-        }
-        if (!done) launch(kalman_backprep_split_kernel<R, D_, L_, 4, MINB, true>, 4, MINB);
+        launch(kalman_backprep_split_kernel<R, D_, L_, 4, MINB, false>, 4, MINB);
         int rc = check_launch("kalman backprep (two-stage)");
         if (rc) return rc;
         backprep_done = true;

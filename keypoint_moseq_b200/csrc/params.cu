@@ -297,7 +297,7 @@ __global__ void sigmasq_kernel(const double* __restrict__ stats, double nu_sigma
                                const double* __restrict__ g_sig, SeedArg seed, int k, double* __restrict__ sigmasq) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= k) return;
-    const double degs = nu_sigma + Dk * stats[k];
+    const double degs = nu_sigma + KPMS_OBS_DOF(Dk) * stats[k];
     const double variance = stats[j] + nu_sigma * sigmasq_0;
     Philox gen(seed, KPMS_STREAM_SIGMA, (uint64_t)j);
     const double g = gamma_draw<double>(0.5 * degs, g_sig ? g_sig + (size_t)j * KPMS_GAMMA_TAPE : nullptr, gen);

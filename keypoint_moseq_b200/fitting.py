@@ -322,6 +322,7 @@ def fit_model(model, data, metadata, project_dir=None, model_name=None, num_iter
             writer.close()
     if shards.world > 1:                                  # every rank returns the whole model, as with one GPU
         model = gibbs.to_device_model(shards.join_model(_host_model(model)), device, dtype)
+        gibbs.release_graphs()                            # captured sweeps hold the communicator (see gibbs.release_graphs)
     return model, model_name
 
 
@@ -395,6 +396,7 @@ def apply_model(model, data, metadata, project_dir=None, model_name=None, num_it
                 model = guard.clean
     if shards.world > 1:          # states-only sweeps exchange nothing; the rows meet again here, rank 0 saves
         model = gibbs.to_device_model(shards.join_model(_host_model(model)), device, dtype)
+        gibbs.release_graphs()
     results = extract_results(model, metadata, project_dir, model_name, save_results and shards.writes, results_path,
                               overwrite=overwrite)
     return (results, model) if return_model else results

@@ -17,7 +17,7 @@ __all__ = [
     "resample_model", "resample_discrete_stateseqs", "resample_continuous_stateseqs",
     "resample_scales", "resample_heading_location", "resample_ar_params",
     "resample_hdp_transitions", "resample_obs_variance", "sufficient_statistics",
-    "marginal_log_likelihood", "stateseq_marginals", "lifted_obs_matrix", "seed_to_u64",
+    "marginal_log_likelihood", "stateseq_marginals", "lifted_obs_matrix", "seed_to_u64", "release_graphs",
     "advance_seed", "to_device_model", "to_device_data", "chunk_diagnostics",
 ]
 
@@ -558,6 +558,14 @@ def _broadcast_prior(prior, Yshape):
 _GRAPHS = {}
 _GRAPH_DISABLED = set()
 _GRAPH_LAUNCHES = [0]
+
+
+def release_graphs():
+    """Drops every captured sweep graph (and its static buffers).  A graph that contains the statistics all-reduce
+    keeps its NCCL communicator busy: call this before `torch.distributed.destroy_process_group()`."""
+    import gc
+    _GRAPHS.clear()
+    gc.collect()
 
 
 def graph_kernel_launches():

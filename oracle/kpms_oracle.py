@@ -33,6 +33,11 @@ V_PRIOR_VAR = 1e6     # diffuse prior variance of the centroid random walk
 GAMMA_R = 6           # taped Marsaglia-Tsang attempts per gamma draw
 VM_R = 8              # taped Best-Fisher attempts per von Mises draw
 GAMMA_TAPE = 2 * GAMMA_R + 1   # [normals R | uniforms R | boost uniform]
+# degrees of freedom a keypoint adds to the scaled-inverse-chi-square posteriors of s and sigmasq: None = its
+# dimension D (what the model implies); upstream may hard-code 3 (open point (vii), tests/test_jax_moseq_adapter.py).
+# The kernels use KPMS_OBS_DOF in csrc/common.cuh: change both together.
+SCALE_DOF = None
+OBSVAR_DOF = None
 
 __all__ = [n for n in dir() if n.isupper()] + [
     "center_embedding", "lifted_obs_matrix", "rotate", "estimate_coordinates",
@@ -42,7 +47,7 @@ __all__ = [n for n in dir() if n.isupper()] + [
     "compute_squared_error", "gamma_mt", "vonmises_bf", "resample_scales",
     "resample_obs_variance", "obs_variance_suffstats", "resample_heading",
     "resample_location", "ar_suffstats", "count_transitions",
-    "resample_ar_params", "sample_mniw_from_stats", "resample_hdp_transitions",
+    "resample_ar_params", "mniw_posterior", "sample_mniw_from_stats", "resample_hdp_transitions",
     "make_tape", "resample_model",
 ]
 
@@ -334,7 +339,7 @@ def compute_squared_error(Y, x, v, h, Cd):
 
 def resample_scales(Y, x, v, h, Cd, sigmasq, nu_s, s_0, g_s):
     """s | rest. g_s (N,T,k,GAMMA_TAPE). s = (e2/sig2 + nu_s s0) / (2 Gamma((nu_s+D)/2))."""
-    D = Y.shape[-1]
+    D = Y.shape[-1] if SCALE_DOF is None else SCALE_DOF
     sqerr = compute_squared_error(Y, x, v, h, Cd)
     degs = nu_s + D
     variance = sqerr / sigmasq + s_0 * nu_s
@@ -348,7 +353,7 @@ def obs_variance_suffstats(Y, mask, x, v, h, s, Cd):
 
 def resample_obs_variance(Y, mask, x, v, h, s, Cd, nu_sigma, sigmasq_0, g_sig):
     """sigmasq | rest. g_sig (k, GAMMA_TAPE)."""
-    D = Y.shape[-1]
+    D = Y.shape[-1] if OBSVAR_DOF is None else OBSVAR_DOF
     S, n_valid = obs_variance_suffstats(Y, mask, x, v, h, s, Cd)
     degs = nu_sigma + D * n_valid
     variance = S + nu_sigma * sigmasq_0
@@ -431,9 +436,8 @@ def count_transitions(z, mask, K):
     return Nij
 
 
-def sample_mniw_from_stats(G, nu_0, S_0, M_0, K_0, w_G, w_B, g_chi):
-    """One state's (Ab, Q) from its Gram. w_G (d,n+1), w_B (d,d), g_chi (d,GAMMA_TAPE)."""
-    d = S_0.shape[0]
+def mniw_posterior(G, nu_0, S_0, M_0, K_0):
+    """Posterior (M_n, K_n, S_n, nu_n) of one state's MNIW from its Gram of f = [phi; 1; y]."""
     p = K_0.shape[0]                       # n+1
     Sxx, Syx, Syy, cnt = G[:p, :p], G[p:, :p], G[p:, p:], G[p - 1, p - 1]
     K0i = np.linalg.inv(K_0)
@@ -441,7 +445,13 @@ def sample_mniw_from_stats(G, nu_0, S_0, M_0, K_0, w_G, w_B, g_chi):
     Kn = _sym(np.linalg.inv(Kni))
     Mn = (M_0 @ K0i + Syx) @ Kn
     Sn = _sym(S_0 + Syy + M_0 @ K0i @ M_0.T - Mn @ Kni @ Mn.T)
-    nu = nu_0 + cnt
+    return Mn, Kn, Sn, nu_0 + cnt
+
+
+def sample_mniw_from_stats(G, nu_0, S_0, M_0, K_0, w_G, w_B, g_chi):
+    """One state's (Ab, Q) from its Gram. w_G (d,n+1), w_B (d,d), g_chi (d,GAMMA_TAPE)."""
+    d = S_0.shape[0]
+    Mn, Kn, Sn, nu = mniw_posterior(G, nu_0, S_0, M_0, K_0)
     chi2 = 2.0 * gamma_mt((nu - np.arange(d)) / 2.0, g_chi)
     Z = np.diag(np.sqrt(chi2)) + np.tril(w_B, -1)
     Ls = np.linalg.cholesky(Sn)

@@ -411,8 +411,12 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["dtype"] == "f64"
     assert line["value"] > 0 and "ar_only" in line["config"]["workload"]
     cpu = line["cpu_baseline"]
-    assert cpu["kind"] == "port" and cpu["cores"] == 2 and cpu["value"] == line["value"] and "2 host processes" in cpu["sample"]
+    assert cpu["kind"] == "port" and cpu["cores"] == 2 and cpu["value"] == line["value"] and "2 processes" in cpu["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the line reports what was run: one timed sweep of the sample, its own wall time; the extrapolation is separate
+    assert line["steps"] == 1 and len(line["step_ms"]) == 1 and abs(line["ms_per_step"] - line["step_ms"][0]) < 1.0
+    assert abs(line["value"] - line["config"]["sample_valid_frames"] / (line["ms_per_step"] * 1e-3)) < 1e-6 * line["value"]
+    assert line["extrapolated"]["full_workload_ms_per_sweep"] > line["ms_per_step"]
 
 
 def _sharded_fit_worker(rank, world, port, tmp):

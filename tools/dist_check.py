@@ -47,5 +47,6 @@ flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("dist_check ok" if flag.item() == 1 else "dist_check FAILED")
+gibbs.release_graphs()
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 1 else 1)

@@ -14,7 +14,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from keypoint_moseq_b200 import fitting, io  # noqa: E402
+from keypoint_moseq_b200 import fitting, gibbs, io  # noqa: E402
 from keypoint_moseq_b200.synth import sample_dataset  # noqa: E402
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -54,5 +54,6 @@ flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("dist_fit_check ok" if flag.item() == 1 else "dist_fit_check FAILED")
+gibbs.release_graphs()
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 1 else 1)
