@@ -89,11 +89,18 @@ int kpms_hmm_smooth(int dtype, const void* filt, const void* pi, int N, int K, i
  *      (-> slds.resample_continuous_stateseqs -> utils.kalman.kalman_sample).
  *      Ct (k*Dk, d+1) = (Gamma kron I) Cd; w_tape (N,Tx,n) normals or NULL; x (N,T,d) out. */
 size_t kpms_kalman_workspace_bytes(int dtype, int N, int T, int d, int L, int K);
+/* info_ready != 0: the per-frame observation records of this workspace were already computed by kpms_kalman_obs_info
+ * (same Y, v, h, s, Ct, sigmasq), e.g. on another stream beside the discrete-state kernels. */
 int kpms_kalman_sample(int dtype, const void* Y, const int32_t* mask, const void* v, const void* h,
                        const void* s, const int32_t* z, const void* Ct, const void* sigmasq,
                        const void* Ab, const void* Q, double jitter, const void* w_tape, uint64_t seed,
-                       const uint64_t* seed_dev, int N, int T, int k, int Dk, int d, int L, int K, void* x,
-                       void* ws, void* stream);
+                       const uint64_t* seed_dev, int N, int T, int k, int Dk, int d, int L, int K, int info_ready,
+                       void* x, void* ws, void* stream);
+/* first stage of the sampler alone: un-rotated, centred keypoints -> chol(C' R_t^-1 C) and C' R_t^-1 (y_t - d) per
+ * frame, written into the workspace (it depends on s, v, h but not on z or the AR parameters). */
+int kpms_kalman_obs_info(int dtype, const void* Y, const int32_t* mask, const void* v, const void* h, const void* s,
+                         const void* Ct, const void* sigmasq, int N, int T, int k, int Dk, int d, int L, int K,
+                         void* ws, void* stream);
 
 /* ---- per-keypoint noise scales: jax_moseq.models.keypoint_slds.resample_scales.
  *      g_tape (N,T,k,13) gamma tape or NULL; noise_prior, s_out (N,T,k). */

@@ -34,7 +34,8 @@ SIGNATURES = {
     "kpms_hmm_smooth": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "kpms_kalman_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "kpms_kalman_sample": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _u64, _vp,
-                                _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+                                _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "kpms_kalman_obs_info": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "kpms_resample_scales": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _u64, _vp, _i, _i, _i, _i, _i,
                                   _vp, _vp]),
     "kpms_heading_location_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -272,6 +272,21 @@ __device__ __forceinline__ void fma2<float>(float& c0, float& c1, float a0, floa
     asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(c));
 }
 
+// Two independent products in one issue slot: c0 = a0*b, c1 = a1*b (mul.rn.f32x2, sm_100+).
+template <typename R>
+__device__ __forceinline__ void mul2(R& c0, R& c1, R a0, R a1, R b) {
+    c0 = a0 * b;
+    c1 = a1 * b;
+}
+template <>
+__device__ __forceinline__ void mul2<float>(float& c0, float& c1, float a0, float a1, float b) {
+    unsigned long long a, bb, c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(c));
+}
+
 // asynchronous global -> shared copies (one element, or one 16-byte chunk)
 template <typename R>
 __device__ __forceinline__ void cp_async_elem(R* dst, const R* src) {

@@ -1559,7 +1559,9 @@ template <typename R, int D_, int L_>
 static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, const R* s, const int* z,
                          const R* Ct, const R* sigmasq, const R* Ab, const R* Q, double jitter,
                          const R* w_tape, SeedArg seed, int N, int T, int k, int Dk, int K, R* x, void* ws,
-                         cudaStream_t st) {
+                         cudaStream_t st, int stage) {
+    // stage 0: the whole sampler; 1: only the per-frame observation records (kpms_kalman_obs_info, which may run on
+    // another stream beside the discrete-state kernels); 2: everything but those records
     constexpr int n = D_ * L_;
     const int Tx = T - L_ + 1;
     const ChunkConfig cfg = chunk_config();
@@ -1583,12 +1585,14 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
     R* ops = reinterpret_cast<R*>(base + off[KW_OPS]);
     R* wbuf = reinterpret_cast<R*>(base + off[KW_WN]);
     const long long frames = (long long)N * Tx;
-    cudaMemsetAsync(diag, 0, 256, st);
-    if (C > 1 || Cb > 1) {
-        KPMS_LAUNCH("valid_len", st);
-        valid_len_kernel<<<N, 256, 0, st>>>(mask, T, L_ - 1, Tx, vlen);
+    if (stage != 1) {
+        cudaMemsetAsync(diag, 0, 256, st);
+        if (C > 1 || Cb > 1) {
+            KPMS_LAUNCH("valid_len", st);
+            valid_len_kernel<<<N, 256, 0, st>>>(mask, T, L_ - 1, Tx, vlen);
+        }
     }
-    {
+    if (stage != 2) {
         size_t smem = ((size_t)k * Dk * (D_ + 1) + k) * sizeof(R);
         int blocks = (int)((frames + 127) / 128);
         KPMS_LAUNCH("kalman_obs_info", st);
@@ -1599,6 +1603,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         int rc = check_launch("kalman obs_info");
         if (rc) return rc;
     }
+    if (stage == 1) return 0;
     if constexpr (n <= 32) {
         constexpr int WARPS = 8;
         auto kern = kalman_forward_rows_kernel<R, D_, L_, WARPS>;
@@ -1653,6 +1658,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
     bool backprep_done = false;
     static const std::string bp_mode = [] { const char* e = getenv("KPMS_BACKPREP"); return std::string(e ? e : "split"); }();
     static const bool rows1 = bp_mode == "rows1";
+    if (frames >= (1LL << 31)) return set_error(-3, "kalman_sample: %lld frame slots on one device exceed 2^31", frames);
     if constexpr (L_ >= 2 && D_ <= 32) {
       if (bp_mode == "split") {
         // two-stage backward preparation (kalman_split.cuh): d lanes per frame, 32/d frames per warp
@@ -1662,7 +1668,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         { KPMS_LAUNCH("kalman_backprep_special", st);
           backprep_special_kernel<R, D_, L_, (n > 32)><<<N, 128, 0, st>>>(stash_m, stash_S, mask, w_tape, N, T, GH); }
         auto launch = [&](auto kern, int warps, int minb) {
-            const size_t smem = (size_t)warps * PS::FPW * PS::frame_bytes + warps * sizeof(uint64_t);
+            const size_t smem = (size_t)warps * PS::FPW * PS::frame_bytes + warps * 2 * sizeof(uint64_t);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             const long long tiles = (frames + warps * PS::FPW - 1) / (warps * PS::FPW);
             const int blocks = (int)std::min<long long>(tiles, (long long)KPMS_SM_COUNT * minb);
@@ -1672,7 +1678,12 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         constexpr int FIT4 = (int)((220 * 1024) / (4 * PS::FPW * PS::frame_bytes + 64));
         constexpr int MINB = sizeof(R) == 8 ? 1 : (FIT4 >= 3 ? 3 : (FIT4 >= 1 ? FIT4 : 1));
         static_assert(FIT4 >= 1, "one CTA of the two-stage backward preparation must fit in shared memory");
-        launch(kalman_backprep_split_kernel<R, D_, L_, 4, MINB, false>, 4, MINB);
+        bool done = false;
+        if constexpr (sizeof(R) == 4 && D_ == 10 && L_ == 3) {      // occupancy experiment (KPMS_BP_CFG=4x2: 255 registers, 8 warps per SM)
+            static const std::string cfg = [] { const char* e = getenv("KPMS_BP_CFG"); return std::string(e ? e : ""); }();
+            if (cfg == "4x2") { launch(kalman_backprep_split_kernel<R, D_, L_, 4, 2>, 4, 2); done = true; }
+        }
+        if (!done) launch(kalman_backprep_split_kernel<R, D_, L_, 4, MINB>, 4, MINB);
         int rc = check_launch("kalman backprep (two-stage)");
         if (rc) return rc;
         backprep_done = true;
@@ -1758,14 +1769,14 @@ template <typename R>
 static int kalman_impl(const void* Y, const int* mask, const void* v, const void* h, const void* s, const int* z,
                        const void* Ct, const void* sigmasq, const void* Ab, const void* Q, double jitter,
                        const void* w_tape, SeedArg seed, int N, int T, int k, int Dk, int d, int L, int K, void* x,
-                       void* ws, cudaStream_t st) {
+                       void* ws, cudaStream_t st, int stage) {
     if (Dk != 2 && Dk != 3) return set_error(-3, "kalman_sample: keypoint dimension must be 2 or 3, got %d", Dk);
     if (T < L) return set_error(-3, "kalman_sample: T (%d) < nlags (%d)", T, L);
 #define X(DD, LL)                                                                                            \
     if (d == DD && L == LL)                                                                                  \
         return kalman_launch<R, DD, LL>((const R*)Y, mask, (const R*)v, (const R*)h, (const R*)s, z,         \
                                         (const R*)Ct, (const R*)sigmasq, (const R*)Ab, (const R*)Q, jitter,  \
-                                        (const R*)w_tape, seed, N, T, k, Dk, K, (R*)x, ws, st);
+                                        (const R*)w_tape, seed, N, T, k, Dk, K, (R*)x, ws, st, stage);
     KPMS_FOR_EACH_DL(X)
 #undef X
     return set_error(-3, "kalman_sample: unsupported (latent_dim, nlags) = (%d, %d)", d, L);
@@ -1788,10 +1799,19 @@ size_t kpms_kalman_workspace_bytes(int dtype, int N, int T, int d, int L, int K)
 int kpms_kalman_sample(int dtype, const void* Y, const int* mask, const void* v, const void* h, const void* s,
                        const int* z, const void* Ct, const void* sigmasq, const void* Ab, const void* Q,
                        double jitter, const void* w_tape, uint64_t seed, const uint64_t* seed_dev, int N, int T, int k, int Dk, int d,
-                       int L, int K, void* x, void* ws, void* stream) {
+                       int L, int K, int info_ready, void* x, void* ws, void* stream) {
     if (K < 1) return set_error(-3, "kalman_sample: num_states must be positive, got %d", K);
     return KPMS_DISPATCH_DTYPE(dtype, kalman_impl, Y, mask, v, h, s, z, Ct, sigmasq, Ab, Q, jitter, w_tape,
-                               SeedArg(seed, seed_dev), N, T, k, Dk, d, L, K, x, ws, (cudaStream_t)stream);
+                               SeedArg(seed, seed_dev), N, T, k, Dk, d, L, K, x, ws, (cudaStream_t)stream, info_ready ? 2 : 0);
+}
+
+int kpms_kalman_obs_info(int dtype, const void* Y, const int* mask, const void* v, const void* h, const void* s,
+                         const void* Ct, const void* sigmasq, int N, int T, int k, int Dk, int d, int L, int K, void* ws,
+                         void* stream) {
+    if (K < 1) return set_error(-3, "kalman_obs_info: num_states must be positive, got %d", K);
+    return KPMS_DISPATCH_DTYPE(dtype, kalman_impl, Y, mask, v, h, s, (const int*)nullptr, Ct, sigmasq, (const void*)nullptr,
+                               (const void*)nullptr, 0.0, (const void*)nullptr, SeedArg(), N, T, k, Dk, d, L, K, (void*)nullptr,
+                               ws, (cudaStream_t)stream, 1);
 }
 
 }  // extern "C"

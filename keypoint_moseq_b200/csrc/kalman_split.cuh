@@ -49,11 +49,11 @@ struct PrepSplit {
     static constexpr int XA = X_PIV + 2 * NP, XB = X_B2 + D_ * DP;
     static constexpr int X_END = (XA > XB ? XA : XB);
     static_assert(n * DP <= SB + NO * DP, "W' rows must not reach the pivot rows");
-    static constexpr int O_OPS = X_END, O_M = O_OPS + OPS, O_W = O_M + SMS, O_T = O_W + NP, RAW = O_T + DP;
+    static constexpr int O_OPS = X_END, O_M = O_OPS + OPS, O_W = O_M + 2 * SMS, O_T = O_W + 2 * NP, RAW = O_T + DP;   // mean, normals: ping-pong
     // frames of one warp sit 8 banks apart (mod 32) so that broadcasts with FPW distinct addresses do not collide
     static constexpr int PER_FRAME = FPW > 1 ? (RAW + 31) / 32 * 32 + 8 : RAW;
     static constexpr size_t frame_bytes = (size_t)PER_FRAME * sizeof(R);
-    static constexpr unsigned TX = (unsigned)((SB + SMS + OPS) * sizeof(R));      // bytes of one frame's bulk copies
+    static constexpr unsigned TX_S = (unsigned)((SB + SMS) * sizeof(R)), TX_A = (unsigned)(OPS * sizeof(R));   // bytes per frame
 };
 
 // ---- mbarrier / bulk-copy primitives (sm_90+; SASS: SYNCS / UBLKCP) ----
@@ -175,7 +175,7 @@ backprep_special_kernel(const R* __restrict__ stash_m, const R* __restrict__ sta
     }
 }
 
-template <typename R, int D_, int L_, int WARPS, int MINB, bool LOCK>
+template <typename R, int D_, int L_, int WARPS, int MINB>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict__ stash_S, const int* __restrict__ mask,
                              const int* __restrict__ z, const R* __restrict__ ops, R eps1, const R* __restrict__ wbuf,
@@ -195,7 +195,8 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
     const int gl = live ? lane - grp0 * D_ : D_ - 1;  // spare lanes shadow the last lane of the last group
     const int gbase = grp * D_;
     R* fb = reinterpret_cast<R*>(smem_raw) + (size_t)(warp * FPW + grp) * P::PER_FRAME;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<R*>(smem_raw) + (size_t)WARPS * FPW * P::PER_FRAME) + warp;
+    uint64_t* barS = reinterpret_cast<uint64_t*>(reinterpret_cast<R*>(smem_raw) + (size_t)WARPS * FPW * P::PER_FRAME) + 2 * warp;
+    uint64_t* barA = barS + 1;
     R* Sb = fb;
     R* TTs = fb + P::X_TT;
     R* piv = fb + P::X_PIV;
@@ -205,8 +206,8 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
     R* Ats = fb + P::O_OPS;
     R* bvec = Ats + n * DP;
     R* Qs = bvec + DP;
-    R* mv = fb + P::O_M;
-    R* wv = fb + P::O_W;
+    R* mvb = fb + P::O_M;                         // 2 x SMS
+    R* wvb = fb + P::O_W;                         // 2 x NP
     R* tv = fb + P::O_T;
     const int Tx = T - L_ + 1;
     const long long frames = (long long)N * Tx;
@@ -216,70 +217,107 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
     // accessors of the packed covariance for the rows this lane owns: S[r][c] = c <= r ? pL[offL(c)] : pU[offU(c)]
     auto offL = [](int c) { return ROWPACK ? c : col_start(n, c) - c; };
     auto offU = [](int c) { return ROWPACK ? c * (c + 1) / 2 : c; };
-    const R* pL0 = ROWPACK ? Sb + gl * (gl + 1) / 2 : Sb + gl;
-    const R* pU0 = ROWPACK ? Sb + gl : Sb + col_start(n, gl) - gl;
-    const R* pLs[LA];
-    const R* pUs[LA];
-#pragma unroll
-    for (int s = 0; s < LA; ++s) {
-        const int r = D_ + gl + s * D_;
-        pLs[s] = ROWPACK ? Sb + r * (r + 1) / 2 : Sb + r;
-        pUs[s] = ROWPACK ? Sb + r : Sb + col_start(n, r) - r;
+    if (lane == 0) {
+        mbar_init(barS, 1);
+        mbar_init(barA, 1);
     }
-
-    if (lane == 0) mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     __syncwarp();
-    unsigned parity = 0;
+    unsigned parS = 0, parA = 0;
 
-    // LOCK: the warps of a CTA walk their frames in lockstep phases (one barrier per phase).  The unrolled body is
-    // far larger than the instruction caches; warps that run the same phase share its instruction fetches.
-    for (long long cbase = (long long)blockIdx.x * WARPS * FPW; cbase < frames; cbase += stride) {
-        const long long base = cbase + (long long)warp * FPW;
-        if (!LOCK && base >= frames) break;
-        const long long g = base + grp;
-        bool on = false;
-        int zi = 0;
-        if (g < frames) {
-            const int nn = (int)(g / Tx), i = (int)(g % Tx);
-            on = (i < Tx - 1) && mask[(size_t)nn * T + (L_ - 1) + i] != 0;
-            if (on) zi = z[(size_t)nn * (Tx - 1) + i];
-        }
-        const unsigned onmask = __ballot_sync(FULL, on && live && gl == 0);
-        if (!LOCK && onmask == 0) continue;
-        // ---- phase A: three bulk copies per frame; the previous iteration's generic-proxy accesses are fenced first
+    // Frame of this lane group in the iteration that starts at frame cb: its index and the raw words that decide
+    // whether it is a regular frame.  Plain loads with clamped addresses and no branch on their values, so that they
+    // can be issued at the top of an iteration and consumed much later (the host guarantees frames < 2^31).
+    const unsigned uframes = (unsigned)frames, ustride = (unsigned)stride, uTx = (unsigned)Tx;
+    auto peek = [&](unsigned cb, unsigned& g, int& i, int& mk, int& zr) {
+        g = cb + (unsigned)(warp * FPW + grp);
+        const unsigned gc = (cb < uframes && g < uframes) ? g : 0u;
+        const unsigned nn = gc / uTx;
+        i = (int)(gc - nn * uTx);
+        mk = mask[(size_t)nn * T + (L_ - 1) + i];
+        zr = Tx > 1 ? z[(size_t)nn * (Tx - 1) + min(i, Tx - 2)] : 0;
+        if (!(cb < uframes && g < uframes)) i = Tx;                   // out of range: never a regular frame
+    };
+    // Bulk copies of a frame's inputs (every lane calls; generic-proxy accesses of the target are fenced first).
+    // The covariance lands in the place the W' / V2 rows used, the operator block in its own, the mean in buffer `buf`.
+    auto request_S = [&](unsigned g, bool on, unsigned onmask, int buf) {
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && onmask != 0) mbar_expect_tx(bar, (unsigned)__popc(onmask) * P::TX);
+        if (onmask == 0) return;
+        if (lane == 0) mbar_expect_tx(barS, (unsigned)__popc(onmask) * P::TX_S);
         __syncwarp();
         if (on && live && gl == 0) {
-            bulk_g2s(Sb, stash_S + (size_t)g * P::SB, P::SB * (unsigned)sizeof(R), bar);
-            bulk_g2s(mv, stash_m + (size_t)g * P::SMS, P::SMS * (unsigned)sizeof(R), bar);
-            bulk_g2s(Ats, ops + (size_t)zi * P::OPS, P::OPS * (unsigned)sizeof(R), bar);
+            bulk_g2s(Sb, stash_S + (size_t)g * P::SB, P::SB * (unsigned)sizeof(R), barS);
+            bulk_g2s(mvb + buf * P::SMS, stash_m + (size_t)g * P::SMS, P::SMS * (unsigned)sizeof(R), barS);
         }
-        if (on) {
-            for (int c = gl; c < n; c += D_) wv[c] = wbuf[(size_t)g * n + c];
-        }
-        if (onmask != 0) {
-            mbar_wait(bar, parity);
-            parity ^= 1;
-        }
+    };
+    auto request_A = [&](int zi, bool on, unsigned onmask) {
+        fence_proxy_async();
         __syncwarp();
-        R* Gout = GH + (size_t)(on ? g : 0) * RECS;
+        if (onmask == 0) return;
+        if (lane == 0) mbar_expect_tx(barA, (unsigned)__popc(onmask) * P::TX_A);
+        __syncwarp();
+        if (on && live && gl == 0) bulk_g2s(Ats, ops + (size_t)zi * P::OPS, P::OPS * (unsigned)sizeof(R), barA);
+    };
 
-        if (LOCK) __syncthreads();
+    unsigned g, cbase = (unsigned)blockIdx.x * WARPS * FPW;
+    int zi, buf = 0;
+    bool on;
+    {
+        int i0, mk0;
+        peek(cbase, g, i0, mk0, zi);
+        on = i0 < Tx - 1 && mk0 != 0;
+    }
+    unsigned onmask = __ballot_sync(FULL, on && live && gl == 0);
+    request_S(g, on, onmask, 0);
+    request_A(zi, on, onmask);
+    if (on) {
+#pragma unroll
+        for (int s = 0; s < L_; ++s) wvb[gl + s * D_] = wbuf[(size_t)g * n + gl + s * D_];
+    }
+    // Every iteration requests the NEXT frame's inputs while the current one is factored: the operator block as soon
+    // as phase G has consumed it, covariance and mean once the V2 rows are consumed (before the Cholesky of Sigma).
+    // The words that describe the next frame (mask, state label, normals) are loaded here and first used there.
+    for (; cbase < uframes; cbase += ustride, buf ^= 1) {
+        unsigned gN;
+        int iN, mkN, ziN;
+        peek(cbase + ustride, gN, iN, mkN, ziN);
+        R wN[L_];
+        auto load_wN = [&]() {                        // normals of the next frame (stored into the other buffer at the end)
+            const size_t gw = (size_t)(iN < Tx ? gN : 0u) * n;
+#pragma unroll
+            for (int s = 0; s < L_; ++s) wN[s] = wbuf[gw + gl + s * D_];
+        };
+        bool onN;
+        unsigned onmaskN;
+        if (onmask == 0) {
+            load_wN();
+            onN = iN < Tx - 1 && mkN != 0;
+            onmaskN = __ballot_sync(FULL, onN && live && gl == 0);
+            request_A(ziN, onN, onmaskN);
+            request_S(gN, onN, onmaskN, buf ^ 1);
+        } else {
+        const R* mv = mvb + buf * P::SMS;
+        const R* wv = wvb + buf * NP;
+        mbar_wait(barS, parS);
+        parS ^= 1;
+        __syncwarp();
+        R* Gout = GH + (size_t)(on ? g : 0u) * RECS;
+
         // ---- phase B: Gauss-Jordan on [S_cc + eps1 I | S_ca], rows rc = gl + s d  ->  [Z | T']
         R m[LA][n];                                   // m[s][e] e < NO: c columns; m[s][NO + a]: a columns
 #pragma unroll
         for (int s = 0; s < LA; ++s) {
             const int rmin = D_ + s * D_, rmax = rmin + D_ - 1, r = rmin + gl;
+            const R* pLs_ = ROWPACK ? Sb + r * (r + 1) / 2 : Sb + r;
+            const R* pUs_ = ROWPACK ? Sb + r : Sb + col_start(n, r) - r;
 #pragma unroll
             for (int e = 0; e < n; ++e) {
                 const int c = e < NO ? D_ + e : e - NO;             // column of S
                 R val;
-                if (c <= rmin) val = pLs[s][offL(c)];
-                else if (c > rmax) val = pUs[s][offU(c)];
-                else val = (c <= r) ? pLs[s][offL(c)] : pUs[s][offU(c)];
+                if (c <= rmin) val = pLs_[offL(c)];
+                else if (c > rmax) val = pUs_[offU(c)];
+                else val = (c <= r) ? pLs_[offL(c)] : pUs_[offU(c)];
                 if (c >= rmin && c <= rmax) val += (c == r) ? eps1 : (R)0;
                 m[s][e] = val;
             }
@@ -309,33 +347,27 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
                 for (int q = 0; q < VEC; ++q) prow[cv * VEC + q] = le[q];
             }
             const R ip = rcp_fast<R>(prow[j]);
-            const bool is_piv = (gl == oj);
 #pragma unroll
             for (int s = 0; s < LA; ++s) {
-                const R f = m[s][j];
-                const bool pv = (s == sj) && is_piv;
-                // ordinary row: m -= (f ip) prow;  pivot row: m = ip prow  (written as 0 - (-ip) prow)
-                const R coef = pv ? -ip : f * ip;
+                const R coef = m[s][j] * ip;              // ordinary row: m -= (f ip) prow, m[j] = -f ip
                 const R ncoef = -coef;
 #pragma unroll
                 for (int c = 0; c + 1 < n; c += 2) {
                     if (c == j || c + 1 == j) {
-#pragma unroll
-                        for (int t = 0; t < 2; ++t)
-                            if (c + t != j) m[s][c + t] = fma(ncoef, prow[c + t], (s == sj && pv) ? (R)0 : m[s][c + t]);
+                        if (c != j) m[s][c] = fma(ncoef, prow[c], m[s][c]);
+                        if (c + 1 != j) m[s][c + 1] = fma(ncoef, prow[c + 1], m[s][c + 1]);
                     } else {
-                        R b0 = m[s][c], b1 = m[s][c + 1];
-                        if (s == sj) { b0 = pv ? (R)0 : b0; b1 = pv ? (R)0 : b1; }
-                        fma2<R>(b0, b1, ncoef, ncoef, prow[c], prow[c + 1]);
-                        m[s][c] = b0;
-                        m[s][c + 1] = b1;
+                        fma2<R>(m[s][c], m[s][c + 1], ncoef, ncoef, prow[c], prow[c + 1]);
                     }
                 }
-                if (n & 1) {
-                    constexpr int c = n - 1;
-                    if (c != j) m[s][c] = fma(ncoef, prow[c], (s == sj && pv) ? (R)0 : m[s][c]);
-                }
-                m[s][j] = pv ? ip : -coef;
+                if ((n & 1) && n - 1 != j) m[s][n - 1] = fma(ncoef, prow[n - 1], m[s][n - 1]);
+                m[s][j] = ncoef;
+            }
+            if (gl == oj) {                               // the pivot row itself: prow / pivot, 1 / pivot on the diagonal
+#pragma unroll
+                for (int c = 0; c + 1 < n; c += 2) mul2<R>(m[sj][c], m[sj][c + 1], prow[c], prow[c + 1], ip);
+                if (n & 1) m[sj][n - 1] = prow[n - 1] * ip;
+                m[sj][j] = ip;
             }
         }
         // m[s] = [Z row | T' row]; turn the Z part into F = I - eps1 Z
@@ -363,9 +395,10 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
         }
         __syncwarp();
 
-        if (LOCK) __syncthreads();
         // ---- phase D: a-row of Sigma1: [S_aa - S_ac T' | eps1 T row]; u1 = K1 m_c for the owned rows
-        R s1a[D_], s1c[NO], u1[L_];
+        R s1a[D_], u1[L_];
+        const R* pL0 = ROWPACK ? Sb + gl * (gl + 1) / 2 : Sb + gl;
+        const R* pU0 = ROWPACK ? Sb + gl : Sb + col_start(n, gl) - gl;
 #pragma unroll
         for (int a = 0; a < D_; ++a) s1a[a] = (a <= gl) ? pL0[offL(a)] : pU0[offU(a)];
         u1[0] = (R)0;
@@ -373,7 +406,6 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
         for (int e = 0; e < NO; ++e) {
             const R sac = pU0[offU(D_ + e)];                        // S[gl][d + e], always above the diagonal
             const R tg = TTs[e * DP + gl];                          // T[gl][e]
-            s1c[e] = eps1 * tg;
             u1[0] = fma(tg, mv[D_ + e], u1[0]);
             const R nsac = -sac;
 #pragma unroll
@@ -381,20 +413,17 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
                 const VecT lv = *reinterpret_cast<const VecT*>(TTs + e * DP + cv * VEC);
                 const R* le = reinterpret_cast<const R*>(&lv);
 #pragma unroll
-                for (int q = 0; q < VEC; ++q)
-                    if (cv * VEC + q < D_) s1a[cv * VEC + q] = fma(nsac, le[q], s1a[cv * VEC + q]);
+                for (int q = 0; q < VEC; q += 2) {
+                    const int a = cv * VEC + q;
+                    if (a + 1 < D_) fma2<R>(s1a[a], s1a[a + 1], nsac, nsac, le[q], le[q + 1]);
+                    else if (a < D_) s1a[a] = fma(nsac, le[q], s1a[a]);
+                }
             }
-        }
-#pragma unroll
-        for (int s = 0; s < LA; ++s) {
-            R acc = 0;
-#pragma unroll
-            for (int e = 0; e < NO; ++e) acc = fma(m[s][e], mv[D_ + e], acc);
-            u1[s + 1] = acc;
         }
         __syncwarp();                                 // every lane is done with the packed covariance
 
-        if (LOCK) __syncthreads();
+        mbar_wait(barA, parA);
+        parA ^= 1;
         // ---- phase E: W' rows = [Sigma1 a-row ; K1' rows] x A'   (wt[0] = Wa' row, wt[s+1] = Wc'' rows)
         R wt[L_][D_];
 #pragma unroll
@@ -414,7 +443,8 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
 #pragma unroll
             for (int s = 0; s < L_; ++s) {
                 // coefficient Sigma1'[row][e] in the column order [a | c]
-                const R cf = (s == 0) ? (e < D_ ? s1a[e < D_ ? e : 0] : s1c[e >= D_ ? e - D_ : 0])
+                // (the c part of the a-row, eps1 T[gl][:], is read back from the T' rows instead of being kept)
+                const R cf = (s == 0) ? (e < D_ ? s1a[e < D_ ? e : 0] : eps1 * TTs[(e >= D_ ? e - D_ : 0) * DP + gl])
                                       : (e < D_ ? m[s > 0 ? s - 1 : 0][NO + (e < D_ ? e : 0)] : m[s > 0 ? s - 1 : 0][e >= D_ ? e - D_ : 0]);
 #pragma unroll
                 for (int a = 0; a + 1 < D_; a += 2) fma2<R>(wt[s][a], wt[s][a + 1], cf, cf, arow[a], arow[a + 1]);
@@ -435,7 +465,6 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
         }
         __syncwarp();
 
-        if (LOCK) __syncthreads();
         // ---- phase G: B2 row gl = Q'[gl] + sum_r W[gl][r] A'[r];  t[gl] = (A m + b)[gl] - (Wc' m_c)[gl]
         R b2[D_];
 #pragma unroll
@@ -459,13 +488,15 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
                 const VecT lv = *reinterpret_cast<const VecT*>(Ats + r * DP + cv * VEC);
                 const R* le = reinterpret_cast<const R*>(&lv);
 #pragma unroll
-                for (int q = 0; q < VEC; ++q)
-                    if (cv * VEC + q < D_) b2[cv * VEC + q] = fma(wv_, le[q], b2[cv * VEC + q]);
+                for (int q = 0; q < VEC; q += 2) {
+                    const int a = cv * VEC + q;
+                    if (a + 1 < D_) fma2<R>(b2[a], b2[a + 1], wv_, wv_, le[q], le[q + 1]);
+                    else if (a < D_) b2[a] = fma(wv_, le[q], b2[a]);
+                }
             }
         }
         tv[gl] = tacc;
 
-        if (LOCK) __syncthreads();
         // ---- phase H: L2 = chol(B2) across the d lanes of the frame (row gl per lane), inverse pivots in every lane
         R invd[D_];
 #pragma unroll
@@ -493,36 +524,60 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
             }
         }
         __syncwarp();                                 // L2 rows, t and every lane's reads of the W' columns are complete
+        load_wN();
+        onN = iN < Tx - 1 && mkN != 0;               // first use of the words loaded at the top of the iteration
+        onmaskN = __ballot_sync(FULL, onN && live && gl == 0);
+        request_A(ziN, onN, onmaskN);                 // the operator block is consumed: fetch the next frame's
         // V2 rows = W rows L2^-T (forward substitution), K2 rows = V2 rows L2^-1 (back substitution); the K2 rows go
         // straight to K2', to the last d rows of G' and into the offset of the mean
-        R v2[L_][D_], hk[L_];
+        R hk[L_];
+        {
+        R v2[L_][D_];
 #pragma unroll
-        for (int s = 0; s < L_; ++s) {
-            const R sc = (s == 0) ? (R)1 : eps1;
+        for (int c = 0; c < D_; ++c) {                // forward substitution, every owned row at once
+            R acc[L_];
 #pragma unroll
-            for (int c = 0; c < D_; ++c) {
-                R acc = sc * wt[s][c];
+            for (int s = 0; s < L_; ++s) acc[s] = (s == 0) ? wt[s][c] : eps1 * wt[s][c];
 #pragma unroll
-                for (int p2 = 0; p2 < c; ++p2) acc = fma(-B2s[c * DP + p2], v2[s][p2], acc);
-                v2[s][c] = acc * invd[c];
+            for (int p2 = 0; p2 < c; ++p2) {
+                const R nl = -B2s[c * DP + p2];
+#pragma unroll
+                for (int s = 0; s + 1 < L_; s += 2) fma2<R>(acc[s], acc[s + 1], nl, nl, v2[s][p2], v2[s + 1][p2]);
+                if (L_ & 1) acc[L_ - 1] = fma(nl, v2[L_ - 1][p2], acc[L_ - 1]);
             }
-            R k2[D_];
+#pragma unroll
+            for (int s = 0; s < L_; ++s) v2[s][c] = acc[s] * invd[c];
+        }
+#pragma unroll
+        for (int s0 = 0; s0 < L_; s0 += 2) {          // back substitution, two owned rows at a time (packed)
+            constexpr int dummy2 = 0; (void)dummy2;
+            const bool two = s0 + 1 < L_;
+            R k2[2][D_];
 #pragma unroll
             for (int c = D_ - 1; c >= 0; --c) {
-                R acc = v2[s][c];
+                R a0 = v2[s0][c], a1 = two ? v2[two ? s0 + 1 : s0][c] : (R)0;
 #pragma unroll
-                for (int p2 = c + 1; p2 < D_; ++p2) acc = fma(-B2s[p2 * DP + c], k2[p2], acc);
-                k2[c] = acc * invd[c];
+                for (int p2 = c + 1; p2 < D_; ++p2) {
+                    const R nl = -B2s[p2 * DP + c];
+                    if (two) fma2<R>(a0, a1, nl, nl, k2[0][p2], k2[1][p2]);
+                    else a0 = fma(nl, k2[0][p2], a0);
+                }
+                k2[0][c] = a0 * invd[c];
+                k2[1][c] = a1 * invd[c];
             }
-            const int r = gl + s * D_;
-            R acc = 0;
 #pragma unroll
-            for (int e = 0; e < D_; ++e) {
-                K2T[e * NP + r] = k2[e];
-                acc = fma(k2[e], tv[e], acc);
-                if (on && live) Gout[(size_t)(NO + e) * n + r] = k2[e];
+            for (int t = 0; t < 2; ++t) {
+                if (t == 1 && !two) continue;
+                const int sidx = s0 + t, r = gl + sidx * D_;
+                R acc = 0;
+#pragma unroll
+                for (int e = 0; e < D_; ++e) {
+                    K2T[e * NP + r] = k2[t][e];
+                    acc = fma(k2[t][e], tv[e], acc);
+                    if (on && live) Gout[(size_t)(NO + e) * n + r] = k2[t][e];
+                }
+                hk[sidx] = acc;
             }
-            hk[s] = acc;
         }
         // V2 rows over the W' rows (their columns were consumed before the barrier above)
 #pragma unroll
@@ -537,9 +592,9 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
                 *reinterpret_cast<VecT*>(dst + cv * VEC) = ov;
             }
         }
+        }                                             // v2 leaves the registers here: phase I reads the owned rows back
         __syncwarp();
 
-        if (LOCK) __syncthreads();
         // ---- phase J: G1' rows rc: K1'[rc][:] - Wc''[rc][:] K2'  (column chunks, straight to global memory)
         {
             constexpr int CH = 2 * VEC;               // columns per chunk
@@ -587,7 +642,13 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
             }
         }
 
-        if (LOCK) __syncthreads();
+#pragma unroll
+        for (int s = 0; s < LA; ++s) {                // u1 = F m_c for the owned c rows (F still unscaled)
+            R acc = 0;
+#pragma unroll
+            for (int e = 0; e < NO; ++e) acc = fma(m[s][e], mv[D_ + e], acc);
+            u1[s + 1] = acc;
+        }
         // ---- phase I: Sigma rows (lower triangle only: slot s needs columns < (s+1) d), natural column order [a | c]
         R sg[L_][n];
 #pragma unroll
@@ -596,6 +657,17 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
         for (int s = 1; s < L_; ++s)
 #pragma unroll
             for (int c = 0; c < (s + 1) * D_; ++c) sg[s][c] = eps1 * (c < D_ ? m[s - 1][NO + (c < D_ ? c : 0)] : m[s - 1][c >= D_ ? c - D_ : 0]);
+        R v2[L_][D_];                                 // owned V2 rows, back from shared memory
+#pragma unroll
+        for (int s = 0; s < L_; ++s)
+#pragma unroll
+            for (int cv = 0; cv < DV; ++cv) {
+                const VecT lv = *reinterpret_cast<const VecT*>(WTs + (gl + s * D_) * DP + cv * VEC);
+                const R* le = reinterpret_cast<const R*>(&lv);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q)
+                    if (cv * VEC + q < D_) v2[s][cv * VEC + q] = le[q];
+            }
 #pragma unroll
         for (int c = 0; c < n; ++c) {
             R vrow[DP];
@@ -618,7 +690,7 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
             }
         }
         __syncwarp();                                 // V2 rows consumed: the ring below reuses the pivot rows' place
-        if (LOCK) __syncthreads();
+        request_S(gN, onN, onmaskN, buf ^ 1);         // ... and the next frame's covariance takes theirs
         // ---- Ls = chol(Sigma), right-looking; column j is published in a two-row ring and read back by every lane
 #pragma unroll
         for (int j = 0; j < n; ++j) {
@@ -638,24 +710,29 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
                 }
             }
             if (j + 1 < n) {
+                R nl[L_];
+#pragma unroll
+                for (int s = 0; s < L_; ++s) nl[s] = -l[s];
                 __syncwarp();
 #pragma unroll
                 for (int cv = (j + 1) / VEC; cv < NV; ++cv) {
                     const VecT lv = *reinterpret_cast<const VecT*>(ring + cv * VEC);
                     const R* le = reinterpret_cast<const R*>(&lv);
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) {
+                    for (int q = 0; q < VEC; q += 2) {
                         const int c = cv * VEC + q;
-                        if (c > j && c < n) {
 #pragma unroll
-                            for (int s = 0; s < L_; ++s)
-                                if (s >= sj && c < (s + 1) * D_) sg[s][c] = fma(-l[s], le[q], sg[s][c]);
+                        for (int s = 0; s < L_; ++s) {
+                            if (s < sj) continue;
+                            const bool ok0 = c > j && c < (s + 1) * D_, ok1 = c + 1 > j && c + 1 < (s + 1) * D_;
+                            if (ok0 && ok1) fma2<R>(sg[s][c], sg[s][c + 1], nl[s], nl[s], le[q], le[q + 1]);
+                            else if (ok0) sg[s][c] = fma(nl[s], le[q], sg[s][c]);
+                            else if (ok1) sg[s][c + 1] = fma(nl[s], le[q + 1], sg[s][c + 1]);
                         }
                     }
                 }
             }
         }
-        if (LOCK) __syncthreads();
         // ---- h = m - K1 m_c - K2 t + Ls w
 #pragma unroll
         for (int s = 0; s < L_; ++s) {
@@ -665,6 +742,15 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
             for (int c = 0; c < (s + 1) * D_; ++c) acc = fma((c <= r) ? sg[s][c] : (R)0, wv[c], acc);
             if (on && live) Gout[(size_t)n * n + r] = mv[r] - u1[s] - hk[s] + acc;
         }
+        }                                             // onmask != 0
+        if (onN) {
+#pragma unroll
+            for (int s = 0; s < L_; ++s) wvb[(buf ^ 1) * NP + gl + s * D_] = wN[s];
+        }
         __syncwarp();
+        g = gN;
+        on = onN;
+        zi = ziN;
+        onmask = onmaskN;
     }
 }

@@ -297,8 +297,24 @@ def _dims(Y, x):
     return N, T, k, D, x.shape[-1]
 
 
+def kalman_observation_records(Y, mask, v, h, s, Cd, sigmasq, d, L, K, Ct=None):
+    """First stage of `resample_continuous_stateseqs` alone (C-ABI kpms_kalman_obs_info): the per-frame observation
+    information, written into the sampler's workspace.  It needs the new noise scales but neither z nor the AR
+    parameters, so the sweep runs it on a second stream beside the discrete-state kernels."""
+    dev, dt = Y.device, Y.dtype
+    N, T, k, D = Y.shape
+    code = _lib.dtype_code(dt)
+    if Ct is None:
+        Ct = lifted_obs_matrix(Cd, k, D)
+    Ctd, sg = _dev(Ct, dt, dev), _dev(sigmasq, dt, dev)
+    ws = _scratch("kalman_ws", _lib.query("kpms_kalman_workspace_bytes", code, N, T, d, L, K), dev)
+    _lib.call("kpms_kalman_obs_info", code, _lib.ptr(Y), _lib.ptr(mask), _lib.ptr(v), _lib.ptr(h), _lib.ptr(s),
+              _lib.ptr(Ctd), _lib.ptr(sg), N, T, k, D, d, L, K, _lib.ptr(ws), _lib.stream_ptr())
+    return Ctd, sg           # kept alive by the caller until the launch has been enqueued
+
+
 def resample_continuous_stateseqs(Y, mask, v, h, s, z, Cd, sigmasq, Ab, Q, jitter=1e-3, seed64=0, w_x=None,
-                                  Ct=None, seed_dev=None, **kwargs):
+                                  Ct=None, seed_dev=None, info_ready=False, **kwargs):
     """x | rest by Kalman forward filtering / backward sampling over the lag-augmented state.
 
     Mirrors jax_moseq.models.keypoint_slds.resample_continuous_stateseqs; dtype follows Y.
@@ -318,7 +334,8 @@ def resample_continuous_stateseqs(Y, mask, v, h, s, z, Cd, sigmasq, Ab, Q, jitte
     w = _dev(w_x, dt, dev)
     _lib.call("kpms_kalman_sample", code, _lib.ptr(Y), _lib.ptr(mask), _lib.ptr(v), _lib.ptr(h), _lib.ptr(s),
               _lib.ptr(z), _lib.ptr(Ctd), _lib.ptr(sg), _lib.ptr(AA), _lib.ptr(QQ), float(jitter), _lib.ptr(w),
-              seed64, _lib.ptr(seed_dev), N, T, k, D, d, L, K, _lib.ptr(x), _lib.ptr(ws), _lib.stream_ptr())
+              seed64, _lib.ptr(seed_dev), N, T, k, D, d, L, K, int(bool(info_ready)), _lib.ptr(x), _lib.ptr(ws),
+              _lib.stream_ptr())
     return x
 
 
@@ -475,6 +492,25 @@ def _sweep_device(Y, mask, prior, st, pr, hypparams, seed64, seed_loc, seed_dev,
     L = T - st["z"].shape[1]
     get = late if late is not None else (lambda key: {"Y": Y, "prior": prior}.get(key, st.get(key)))
     Ct = None if ar_only else lifted_obs_matrix(pr["Cd"], kD[0], kD[1])
+    # Device-resident sweeps fork here: the noise scales and the observation records of the Kalman sampler depend on
+    # neither the parameters drawn below nor z, so they run on a second stream beside the statistics / parameter /
+    # HMM kernels (which leave most FP32 and memory capacity idle) and join before the filter starts.
+    forked = None
+    if (late is None and sink is None and not ar_only and resample_local_noise_scale and not tp
+            and not (resample_global_noise_scale and not states_only) and _overlap_enabled()):
+        main = torch.cuda.current_stream()
+        side = _side_stream(st["x"].device, "prep")
+        fork_ev = torch.cuda.Event()
+        fork_ev.record(main)
+        side.wait_event(fork_ev)
+        with torch.cuda.stream(side):
+            s_new = resample_scales(Y, st["x"], st["v"], st["h"], pr["Cd"], pr["sigmasq"], oh["nu_s"], prior,
+                                    seed_loc, None, Ct=Ct, seed_dev=seed_dev)
+            keep = kalman_observation_records(Y, mask, st["v"], st["h"], s_new, pr["Cd"], pr["sigmasq"], d, L, K, Ct=Ct)
+            join_ev = torch.cuda.Event()
+            join_ev.record(side)
+        s_new.record_stream(main)
+        forked = (s_new, join_ev, keep)
     if not states_only:
         obs = None
         if resample_global_noise_scale and not ar_only:
@@ -503,14 +539,17 @@ def _sweep_device(Y, mask, prior, st, pr, hypparams, seed64, seed_loc, seed_dev,
                 st[key] = val
     if not ar_only:
         Yd, pri = get("Y"), get("prior")
-        if resample_local_noise_scale:
+        if forked is not None:
+            torch.cuda.current_stream().wait_event(forked[1])
+            st["s"] = forked[0]
+        elif resample_local_noise_scale:
             st["s"] = resample_scales(Yd, st["x"], st["v"], st["h"], pr["Cd"], pr["sigmasq"], oh["nu_s"], pri,
                                       seed_loc, tp.get("g_s"), Ct=Ct, seed_dev=seed_dev)
         if sink is not None:
             sink.emit("s", st["s"])
         st["x"] = resample_continuous_stateseqs(Yd, mask, st["v"], st["h"], st["s"], st["z"], pr["Cd"],
                                                 pr["sigmasq"], pr["Ab"], pr["Q"], jitter, seed_loc, tp.get("w_x"),
-                                                Ct=Ct, seed_dev=seed_dev)
+                                                Ct=Ct, seed_dev=seed_dev, info_ready=forked is not None)
         if sink is not None:
             sink.emit("x", st["x"])
         st["h"], st["v"] = resample_heading_location(Yd, mask, st["x"], st["v"], st["h"], st["s"], pr["Cd"],
@@ -576,6 +615,11 @@ def graph_kernel_launches():
 def graphs_enabled():
     import os
     return os.environ.get("KPMS_GRAPH", "1") != "0"
+
+
+def _overlap_enabled():
+    import os
+    return os.environ.get("KPMS_OVERLAP", "0") == "1"      # measured at C2: 16.00 ms with, 15.95 ms without - off by default
 
 
 def _hyp_key(hypparams):
