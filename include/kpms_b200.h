@@ -101,6 +101,10 @@ int kpms_kalman_sample(int dtype, const void* Y, const int32_t* mask, const void
 int kpms_kalman_obs_info(int dtype, const void* Y, const int32_t* mask, const void* v, const void* h, const void* s,
                          const void* Ct, const void* sigmasq, int N, int T, int k, int Dk, int d, int L, int K,
                          void* ws, void* stream);
+/* (latent_dim, nlags) pairs the kernels were compiled for (io.py:72-83 leaves both to the user's config): writes up
+ * to `cap` pairs as d0, L0, d1, L1, ... and returns how many exist.  Any other pair fails with status -3 in
+ * kpms_ar_loglik / kpms_ar_suffstats / kpms_kalman_sample. */
+int kpms_supported_dims(int* pairs, int cap);
 
 /* ---- per-keypoint noise scales: jax_moseq.models.keypoint_slds.resample_scales.
  *      g_tape (N,T,k,13) gamma tape or NULL; noise_prior, s_out (N,T,k). */

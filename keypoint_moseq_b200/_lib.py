@@ -36,6 +36,7 @@ SIGNATURES = {
     "kpms_kalman_sample": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _u64, _vp,
                                 _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "kpms_kalman_obs_info": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "kpms_supported_dims": (_i, [_vp, _i]),
     "kpms_resample_scales": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _u64, _vp, _i, _i, _i, _i, _i,
                                   _vp, _vp]),
     "kpms_heading_location_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -112,6 +113,37 @@ def call(name, *args):
 def query(name, *args):
     """Invoke a size query."""
     return int(getattr(load(), name)(*args))
+
+
+def supported_dims():
+    """[(latent_dim, nlags), ...] the library was compiled for (no device needed)."""
+    if not _DIMS:
+        lib = load()
+        count = lib.kpms_supported_dims(None, 0)
+        buf = (C.c_int * (2 * count))()
+        lib.kpms_supported_dims(C.cast(buf, C.c_void_p), count)
+        _DIMS.extend((buf[2 * i], buf[2 * i + 1]) for i in range(count))
+    return list(_DIMS)
+
+
+_DIMS = []
+
+
+MAX_STATES = 128        # the HMM kernels keep pi slices in registers / shared memory (csrc/hmm.cu)
+
+
+def check_model_dims(latent_dim, nlags, num_states):
+    """Fail before the first sweep, with the supported set in the message, instead of inside a kernel launch."""
+    pairs = supported_dims()
+    if (int(latent_dim), int(nlags)) not in pairs:
+        by_lag = {}
+        for d, L in sorted(pairs):
+            by_lag.setdefault(L, []).append(d)
+        table = "; ".join(f"nlags={L}: latent_dim in {ds}" for L, ds in sorted(by_lag.items()))
+        raise KpmsError(f"(latent_dim, nlags) = ({latent_dim}, {nlags}) is not compiled into libkpms_b200.so. "
+                        f"Supported: {table}. Add the pair to KPMS_DL_GROUP_* in csrc/common.cuh and rebuild.")
+    if not 1 <= int(num_states) <= MAX_STATES:
+        raise KpmsError(f"num_states = {num_states} is outside 1..{MAX_STATES}")
 
 
 def set_time_chunking(chunks=-1, warmup=-1, tol32=-1.0, tol64=-1.0):

@@ -421,5 +421,25 @@ int chunks_for(int N, int slots, int len, int warmup);
                   : ((dtype) == 1 ? FN<double>(__VA_ARGS__)                            \
                                   : kpms::set_error(-2, "dtype must be 0 (f32) or 1 (f64), got %d", (int)(dtype))))
 
-// compile-time (latent_dim, nlags) instantiations
-#define KPMS_FOR_EACH_DL(X) X(2, 2) X(4, 3) X(10, 3) X(16, 3)
+// compile-time (latent_dim, nlags) instantiations.  The unrolled Kalman and likelihood kernels cost 20 - 60 s of
+// nvcc time per pair, so the pairs are dealt into KPMS_DL_GROUPS groups and kalman.cu / ar_loglik.cu are compiled
+// once per group (-DKPMS_DL_GROUP=g, build.py) in parallel; KPMS_FOR_EACH_DL lists them all for the cheap kernels
+// and for the host-side table (kpms_supported_dims).  latent_dim 2..16 at the reference's default nlags = 3, the
+// even dimensions at nlags 2, and 4..10 at nlags 1, 4 (and 4, 6 at nlags 5).
+#define KPMS_DL_GROUPS 8
+#define KPMS_DL_GROUP_0(X) X(10, 3) X(2, 2) X(2, 3) X(4, 1)
+#define KPMS_DL_GROUP_1(X) X(16, 3) X(3, 3) X(4, 2) X(6, 1)
+#define KPMS_DL_GROUP_2(X) X(15, 3) X(4, 3) X(6, 2) X(8, 1) X(4, 4)
+#define KPMS_DL_GROUP_3(X) X(14, 3) X(5, 3) X(8, 2) X(10, 1) X(4, 5)
+#define KPMS_DL_GROUP_4(X) X(13, 3) X(6, 3) X(10, 2) X(6, 4)
+#define KPMS_DL_GROUP_5(X) X(12, 3) X(7, 3) X(12, 2) X(6, 5)
+#define KPMS_DL_GROUP_6(X) X(11, 3) X(8, 3) X(16, 2) X(8, 4)
+#define KPMS_DL_GROUP_7(X) X(9, 3) X(10, 4)
+#define KPMS_FOR_EACH_DL(X)                                                                                       \
+    KPMS_DL_GROUP_0(X) KPMS_DL_GROUP_1(X) KPMS_DL_GROUP_2(X) KPMS_DL_GROUP_3(X) KPMS_DL_GROUP_4(X) KPMS_DL_GROUP_5(X) \
+    KPMS_DL_GROUP_6(X) KPMS_DL_GROUP_7(X)
+#ifdef KPMS_DL_GROUP
+#define KPMS_FOR_GROUP_DL(X) KPMS_CAT(KPMS_DL_GROUP_, KPMS_DL_GROUP)(X)
+#endif
+// return code of a group's dispatcher for a pair that belongs to another group
+#define KPMS_NOT_IN_GROUP (-1000)

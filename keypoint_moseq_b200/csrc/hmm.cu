@@ -12,6 +12,9 @@
 //   filt  (N, T', ldK)         filtered state probabilities
 //   z     (N, T') int32
 #include <algorithm>
+#ifndef KPMS_DL_GROUP
+#define KPMS_DL_GROUP 0
+#endif
 #include "common.cuh"
 #include "../../include/kpms_b200.h"
 
@@ -433,6 +436,7 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
 
 #include "hmm_f64.cuh"
 
+#if KPMS_DL_GROUP == 0
 // logZ[nn] = ordered sum of the chunks' parts (zero-initialised; chains flagged dirty are
 // overwritten by the sequential pass afterwards)
 __global__ void logz_sum_kernel(const double* __restrict__ part, int N, int parts, double* __restrict__ logZ) {
@@ -442,10 +446,11 @@ __global__ void logz_sum_kernel(const double* __restrict__ part, int N, int part
     for (int c = 0; c < parts; ++c) acc += part[(size_t)nn * parts + c];
     logZ[nn] = acc;
 }
+#endif
 
 // vb[nn] = length of the leading unmasked run of steps, rounded up to 8 (capped at Tp);
 // holes[nn] = 1 when a valid frame follows a masked one (such chains run sequentially)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 hmm_prefix_kernel(const int* __restrict__ mask, int T, int L, int Tp, int* __restrict__ vb, int* __restrict__ holes) {
     __shared__ int first, late;
     const int nn = blockIdx.x;
@@ -553,7 +558,7 @@ __global__ void transpose_pi_kernel(const R* __restrict__ pi, int K, int ldK, R*
 }
 
 constexpr int HMM_BW_WARPS = 4;      // warps per CTA (one CTA per SM: pi^T and the rings fill shared memory)
-constexpr int HMM_BW_RING = 32;      // ring slots per warp = four groups of 8 steps
+[[maybe_unused]] constexpr int HMM_BW_RING = 32;      // ring slots per warp = four groups of 8 steps
 
 // NPC = 16-byte pieces of a row per lane of a 4-lane group: ceil(ldK * sizeof(R) / 64)
 template <typename R, int NPC>
@@ -911,18 +916,50 @@ static int ar_loglik_launch(const R* x, const int* mask, const R* Ab, const R* Q
     return check_launch("ar_loglik");
 }
 
+// (latent_dim, nlags) pairs of this translation unit's group (common.cuh: KPMS_DL_GROUP_g, -DKPMS_DL_GROUP=g)
 template <typename R>
-static int ar_loglik_impl(const void* x, const int* mask, const void* Ab, const void* Q, int N, int T, int d,
-                          int L, int K, int ldT, void* W, void* mx, void* ws, cudaStream_t st) {
-    if (T <= L) return set_error(-3, "ar_loglik: T (%d) must exceed nlags (%d)", T, L);
-    if (ldT < T - L || ldT % 8) return set_error(-3, "ar_loglik: ldT (%d) must be a multiple of 8 and >= T-L", ldT);
+static int ar_loglik_group_impl(const void* x, const int* mask, const void* Ab, const void* Q, int N, int T, int d,
+                                int L, int K, int ldT, void* W, void* mx, void* ws, cudaStream_t st) {
 #define X(DD, LL)                                                                                         \
     if (d == DD && L == LL)                                                                               \
         return ar_loglik_launch<R, DD, LL>((const R*)x, mask, (const R*)Ab, (const R*)Q, N, T, K, ldT,    \
                                            (R*)W, (R*)mx, ws, st);
-    KPMS_FOR_EACH_DL(X)
+    KPMS_FOR_GROUP_DL(X)
 #undef X
-    return set_error(-3, "ar_loglik: unsupported (latent_dim, nlags) = (%d, %d)", d, L);
+    return KPMS_NOT_IN_GROUP;
+}
+
+#define KPMS_ARLL_GROUP_ARGS                                                                                      \
+    int dtype, const void *x, const int *mask, const void *Ab, const void *Q, int N, int T, int d, int L, int K,  \
+        int ldT, void *W, void *mx, void *ws, cudaStream_t st
+
+int KPMS_CAT(ar_loglik_group_, KPMS_DL_GROUP)(KPMS_ARLL_GROUP_ARGS) {
+    return KPMS_DISPATCH_DTYPE(dtype, ar_loglik_group_impl, x, mask, Ab, Q, N, T, d, L, K, ldT, W, mx, ws, st);
+}
+
+#if KPMS_DL_GROUP == 0
+int ar_loglik_group_1(KPMS_ARLL_GROUP_ARGS);
+int ar_loglik_group_2(KPMS_ARLL_GROUP_ARGS);
+int ar_loglik_group_3(KPMS_ARLL_GROUP_ARGS);
+int ar_loglik_group_4(KPMS_ARLL_GROUP_ARGS);
+int ar_loglik_group_5(KPMS_ARLL_GROUP_ARGS);
+int ar_loglik_group_6(KPMS_ARLL_GROUP_ARGS);
+int ar_loglik_group_7(KPMS_ARLL_GROUP_ARGS);
+static_assert(KPMS_DL_GROUPS == 8, "one dispatcher per group");
+
+static int ar_loglik_dispatch(KPMS_ARLL_GROUP_ARGS) {
+    if (dtype != 0 && dtype != 1) return set_error(-2, "dtype must be 0 (f32) or 1 (f64), got %d", dtype);
+    if (T <= L) return set_error(-3, "ar_loglik: T (%d) must exceed nlags (%d)", T, L);
+    if (ldT < T - L || ldT % 8) return set_error(-3, "ar_loglik: ldT (%d) must be a multiple of 8 and >= T-L", ldT);
+    typedef int (*GroupFn)(KPMS_ARLL_GROUP_ARGS);
+    static const GroupFn groups[KPMS_DL_GROUPS] = {ar_loglik_group_0, ar_loglik_group_1, ar_loglik_group_2,
+                                                   ar_loglik_group_3, ar_loglik_group_4, ar_loglik_group_5,
+                                                   ar_loglik_group_6, ar_loglik_group_7};
+    for (int g = 0; g < KPMS_DL_GROUPS; ++g) {
+        const int rc = groups[g](dtype, x, mask, Ab, Q, N, T, d, L, K, ldT, W, mx, ws, st);
+        if (rc != KPMS_NOT_IN_GROUP) return rc;
+    }
+    return set_error(-3, "ar_loglik: unsupported (latent_dim, nlags) = (%d, %d); see kpms_supported_dims", d, L);
 }
 
 template <typename R>
@@ -1116,8 +1153,11 @@ static int hmm_smooth_impl(const void* filt, const void* pi, int N, int K, int T
     return check_launch("hmm_smooth");
 }
 
+#endif  // KPMS_DL_GROUP == 0
+
 }  // namespace kpms
 
+#if KPMS_DL_GROUP == 0
 using namespace kpms;
 
 extern "C" {
@@ -1137,8 +1177,7 @@ size_t kpms_hmm_weights_bytes(int dtype, int N, int T, int K, int L) {
 
 int kpms_ar_loglik(int dtype, const void* x, const int* mask, const void* Ab, const void* Q, int N, int T,
                    int d, int L, int K, int ldT, void* W, void* mx, void* ws, void* stream) {
-    return KPMS_DISPATCH_DTYPE(dtype, ar_loglik_impl, x, mask, Ab, Q, N, T, d, L, K, ldT, W, mx, ws,
-                               (cudaStream_t)stream);
+    return ar_loglik_dispatch(dtype, x, mask, Ab, Q, N, T, d, L, K, ldT, W, mx, ws, (cudaStream_t)stream);
 }
 
 int kpms_hmm_forward(int dtype, const void* W, const void* mx, const void* pi, int N, int K, int Tp, int ldT,
@@ -1159,3 +1198,4 @@ int kpms_hmm_smooth(int dtype, const void* filt, const void* pi, int N, int K, i
 }
 
 }  // extern "C"
+#endif

@@ -17,6 +17,9 @@
 #include <type_traits>
 #include <cstdlib>
 #include <string>
+#ifndef KPMS_DL_GROUP
+#define KPMS_DL_GROUP 0
+#endif
 #include "common.cuh"
 #include "../../include/kpms_b200.h"
 
@@ -941,462 +944,14 @@ __device__ inline void warp_cholesky(R* A, R* invdiag, int lane) {
 }
 
 // ---------------------------------------------------------------------------
-// K1c: backward preparation, one warp per frame
+// K1c: backward preparation (kalman_split.cuh; nlags = 1: kalman_rows2.cuh)
 // ---------------------------------------------------------------------------
 template <typename R, int D_, int L_>
 struct PrepSmem {
     static constexpr int n = D_ * L_, LD = n | 1;
-    static constexpr size_t per_warp = 3 * n * LD + 5 * n;
     // one backward record per frame: [GT | h | pad] in 16-byte units
     static constexpr int RECS = ((n * n + n) * (int)sizeof(R) + 15) / 16 * 16 / (int)sizeof(R);
 };
-
-template <typename R, int D_, int L_, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS)
-kalman_backprep_kernel(const R* __restrict__ stash_m, const R* __restrict__ stash_S,
-                       const int* __restrict__ mask, const int* __restrict__ z, const R* __restrict__ Ab,
-                       const R* __restrict__ Q, R jitter, const R* __restrict__ w_tape, SeedArg seed, int N,
-                       int T, R* __restrict__ GH) {
-    typedef PrepSmem<R, D_, L_> SM;
-    constexpr int n = SM::n, LD = SM::LD, NP2 = n * (n + 1) / 2, NO = n - D_, NA1 = n + 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    R* S = reinterpret_cast<R*>(smem_raw) + (size_t)warp * SM::per_warp;
-    R* Pp = S + n * LD;
-    R* Wt = Pp + n * LD;
-    R* mv = Wt + n * LD;
-    R* mp = mv + n;
-    R* wv = mp + n;
-    R* idP = wv + n;
-    R* idS = idP + n;
-    const int Tx = T - L_ + 1;
-    const long long g = (long long)blockIdx.x * WARPS + warp;
-    if (g >= (long long)N * Tx) return;
-    const int nn = (int)(g / Tx), i = (int)(g % Tx);
-    const bool last = (i == Tx - 1);
-    R* Gout = GH + (size_t)g * SM::RECS;
-    R* hout = Gout + n * n;
-    if (!last && mask[(size_t)nn * T + (L_ - 1) + i] == 0) {
-        for (int w = lane; w < n * n; w += 32) Gout[w] = ((w / n) == (w % n)) ? (R)1 : (R)0;
-        for (int w = lane; w < n; w += 32) hout[w] = (R)0;
-        return;
-    }
-    // operands
-    const R* Sg = stash_S + (size_t)g * stash_S_stride(n);
-    for (int q = lane; q < NP2; q += 32) {
-        int r, c;
-        tri_unpack(q, r, c);
-        R val = Sg[q];
-        S[r * LD + c] = val;
-        S[c * LD + r] = val;
-    }
-    for (int w = lane; w < n; w += 32) {
-        mv[w] = stash_m[(size_t)g * stash_m_stride(n) + w];
-        R wn;
-        if (w_tape) wn = w_tape[(size_t)g * n + w];
-        else {
-            Philox gen(seed, KPMS_STREAM_X, (uint64_t)g * n + w);
-            double a0, a1;
-            philox_normal2(gen, a0, a1);
-            wn = (R)a0;
-        }
-        wv[w] = wn;
-    }
-    __syncwarp();
-    if (last) {
-        warp_cholesky<R, n, LD>(S, idS, lane);
-        for (int r = lane; r < n; r += 32) {
-            R acc = mv[r];
-            for (int c = 0; c <= r; ++c) acc = fma(S[r * LD + c], wv[c], acc);
-            hout[r] = acc;
-        }
-        return;
-    }
-    const int zi = z[(size_t)nn * (Tx - 1) + i];
-    const R* A = Ab + (size_t)zi * D_ * NA1;
-    const R* Qk = Q + (size_t)zi * D_ * D_;
-    const R eps = (R)KPMS_EPS_SHIFT + jitter;
-    // Wt = Aaug S   (lane <-> column)
-    for (int c = lane; c < n; c += 32) {
-        for (int r = 0; r < NO; ++r) Wt[r * LD + c] = S[(r + D_) * LD + c];
-        for (int a = 0; a < D_; ++a) {
-            R acc = 0;
-            for (int e = 0; e < n; ++e) acc = fma(__ldg(A + a * NA1 + e), S[e * LD + c], acc);
-            Wt[(NO + a) * LD + c] = acc;
-        }
-    }
-    // mp = Aaug m + b
-    for (int r = lane; r < n; r += 32) {
-        if (r < NO) mp[r] = mv[r + D_];
-        else {
-            int a = r - NO;
-            R acc = __ldg(A + a * NA1 + n);
-            for (int e = 0; e < n; ++e) acc = fma(__ldg(A + a * NA1 + e), mv[e], acc);
-            mp[r] = acc;
-        }
-    }
-    __syncwarp();
-    // Pp = Wt Aaug' + Qaug   (lane <-> row)
-    for (int r = lane; r < n; r += 32) {
-        for (int c = 0; c < NO; ++c) Pp[r * LD + c] = Wt[r * LD + c + D_] + ((r == c) ? eps : (R)0);
-        for (int a = 0; a < D_; ++a) {
-            R acc = (r >= NO) ? (__ldg(Qk + (r - NO) * D_ + a) + ((r - NO == a) ? jitter : (R)0)) : (R)0;
-            for (int e = 0; e < n; ++e) acc = fma(Wt[r * LD + e], __ldg(A + a * NA1 + e), acc);
-            Pp[r * LD + NO + a] = acc;
-        }
-    }
-    __syncwarp();
-    warp_cholesky<R, n, LD>(Pp, idP, lane);
-    // V = Lp^-1 Wt  (forward substitution, lane <-> column, in place)
-    for (int c = lane; c < n; c += 32) {
-        R col[n];
-#pragma unroll
-        for (int r = 0; r < n; ++r) {
-            R acc = Wt[r * LD + c];
-#pragma unroll
-            for (int e = 0; e < r; ++e) acc = fma(-Pp[r * LD + e], col[e], acc);
-            col[r] = acc * idP[r];
-            Wt[r * LD + c] = col[r];
-        }
-    }
-    __syncwarp();
-    // Sigma = S - V'V (lower, in place over S; lane <-> column b, rows a >= b)
-    for (int bcol = lane; bcol < n; bcol += 32) {
-        R col[n];
-#pragma unroll
-        for (int e = 0; e < n; ++e) col[e] = Wt[e * LD + bcol];
-        for (int a = bcol; a < n; ++a) {
-            R acc = S[a * LD + bcol];
-#pragma unroll
-            for (int e = 0; e < n; ++e) acc = fma(-Wt[e * LD + a], col[e], acc);
-            S[a * LD + bcol] = acc;
-        }
-    }
-    __syncwarp();
-    warp_cholesky<R, n, LD>(S, idS, lane);
-    // X = Lp^-T V  (back substitution, lane <-> column, in place); GT[c][r] = X[c][r]
-    for (int c = lane; c < n; c += 32) {
-        R col[n];
-#pragma unroll
-        for (int r = n - 1; r >= 0; --r) {
-            R acc = Wt[r * LD + c];
-#pragma unroll
-            for (int e = r + 1; e < n; ++e) acc = fma(-Pp[e * LD + r], col[e], acc);
-            col[r] = acc * idP[r];
-            Wt[r * LD + c] = col[r];
-        }
-    }
-    __syncwarp();
-    for (int w = lane; w < n * n; w += 32) Gout[w] = Wt[(w / n) * LD + (w % n)];
-    // h = m - G mp + Ls w,  G[r][c] = X[c][r]
-    for (int r = lane; r < n; r += 32) {
-        R acc = mv[r];
-        for (int c = 0; c < n; ++c) acc = fma(-Wt[c * LD + r], mp[c], acc);
-        for (int c = 0; c <= r; ++c) acc = fma(S[r * LD + c], wv[c], acc);
-        hout[r] = acc;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// K1c (n <= 32): backward preparation with one warp per frame and one matrix row (= column, the
-// matrices are symmetric) per lane held in registers.  Shared memory only carries what other lanes
-// must see, always as whole rows read back as 16-byte broadcasts:
-//   Wt = Aaug S          lane c: column c from its own column of S; transposed through T2
-//   Pp = Wt Aaug' + Q    lane r: row r
-//   Lp = chol(Pp)        right-looking; column j is published as row j of T1 (= Lp') and the same
-//                        broadcast drives the forward substitution V = Lp^-1 Wt on every lane's column
-//   Sigma = S - V'V      lane b: row b, V' rows published in T2
-//   Ls = chol(Sigma)     as above, Ls' rows in T2
-//   X = Lp^-T V          row-oriented back substitution against the rows of T1;  GT = X
-//   h = m - X' mp + Ls w
-// ---------------------------------------------------------------------------
-template <typename R, int D_, int L_>
-struct PrepRowsSmem {
-    static constexpr int n = D_ * L_, LS = 36, NP2 = n * (n + 1) / 2;
-    static constexpr int SB = stash_S_stride(n);
-    static constexpr size_t per_warp = 2 * 32 * LS + D_ * LS + SB + 6 * 32;
-};
-
-// Right-looking Cholesky of the matrix whose row `lane` is in a[]; column j is published as row j
-// of LT.  On return a[c] (c <= lane) holds L[lane][c].  With SOLVE, `col` is forward-substituted in
-// the same sweep (col <- L^-1 col) and the inverse pivots are kept in invd.
-template <typename R, int n, int LS, bool SOLVE>
-__device__ __forceinline__ void chol_rows(R (&a)[n], R* LT, R (&col)[n], R* invd, int lane) {
-    typedef typename Vec16<R>::type VecT;
-    constexpr int VEC = 16 / (int)sizeof(R), NV = (n + VEC - 1) / VEC;
-#pragma unroll
-    for (int j = 0; j < n; ++j) {
-        const R dj = __shfl_sync(0xffffffffu, a[j], j);
-        const R inv = rsqrt_fast<R>(dj);
-        const R l = (lane >= j) ? a[j] * inv : (R)0;
-        a[j] = l;
-        LT[j * LS + lane] = l;
-        R vj = 0;
-        if (SOLVE) {
-            invd[j] = inv;
-            vj = col[j] * inv;
-            col[j] = vj;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int cv = (j + 1) / VEC; cv < NV; ++cv) {
-            const VecT lv = *reinterpret_cast<const VecT*>(LT + j * LS + cv * VEC);
-            const R* le = reinterpret_cast<const R*>(&lv);
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) {
-                const int c = cv * VEC + q;
-                if (c > j && c < n) {
-                    a[c] = fma(-l, le[q], a[c]);
-                    if (SOLVE) col[c] = fma(-le[q], vj, col[c]);
-                }
-            }
-        }
-    }
-}
-
-template <typename R, int D_, int L_, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 1)
-kalman_backprep_rows_kernel(const R* __restrict__ stash_m, const R* __restrict__ stash_S,
-                            const int* __restrict__ mask, const int* __restrict__ z, const R* __restrict__ Ab,
-                            const R* __restrict__ Q, R jitter, const R* __restrict__ w_tape, SeedArg seed,
-                            int N, int T, R* __restrict__ GH) {
-    typedef PrepRowsSmem<R, D_, L_> SM;
-    typedef typename Vec16<R>::type VecT;
-    constexpr int n = SM::n, LS = SM::LS, NO = n - D_, NA1 = n + 1;
-    constexpr int VEC = 16 / (int)sizeof(R), NV = (n + VEC - 1) / VEC;
-    constexpr int SMS = stash_m_stride(n), SSS = stash_S_stride(n);
-    static_assert(n <= 32, "one matrix row per lane");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    R* T1 = reinterpret_cast<R*>(smem_raw) + (size_t)warp * SM::per_warp;   // Lp' rows (32 x LS)
-    R* T2 = T1 + 32 * LS;                                                  // Wt' / V' / Ls' rows (32 x LS)
-    R* As = T2 + 32 * LS;                                                  // D_ rows [A | b]
-    R* Sb = As + D_ * LS;                                                  // packed lower triangle of S
-    R* mvb = Sb + SM::SB;                                                  // 2 x 32 filtered means (ping-pong)
-    R* wvb = mvb + 64;                                                     // 2 x 32 normals (ping-pong)
-    R* mp = wvb + 64;
-    R* invd = mp + 32;
-    const int Tx = T - L_ + 1;
-    const long long frames = (long long)N * Tx;
-    const long long stride = (long long)gridDim.x * WARPS;
-    const bool act = lane < n;
-    const int row = act ? lane : n - 1;              // idle lanes shadow the last row; their stores land in padding
-    // S is the lower triangle packed by columns: S[row][c] = c <= row ? pB[col_start(c) - c] : pA[c]
-    const R* pA = Sb + col_start(n, row) - row;
-    const R* pB = Sb + row;
-    const R eps = (R)KPMS_EPS_SHIFT + jitter;
-
-    // frame status: 0 = masked (identity record), 1 = regular, 2 = last frame of its chain
-    auto status = [&](long long g) {
-        const int nn = (int)(g / Tx), i = (int)(g % Tx);
-        if (i == Tx - 1) return 2;
-        return mask[(size_t)nn * T + (L_ - 1) + i] != 0 ? 1 : 0;
-    };
-    // The inputs of the next frame are requested while the current one is still being factored:
-    // A once Pp is formed, S / m / w once Sigma is formed.
-    auto issue_A = [&](long long g) {
-        if (g < frames && status(g) == 1) {
-            const int nn = (int)(g / Tx), i = (int)(g % Tx);
-            const R* A = Ab + (size_t)z[(size_t)nn * (Tx - 1) + i] * D_ * NA1;
-            for (int w = lane; w < D_ * NA1; w += 32) cp_async_elem(As + (w / NA1) * LS + (w % NA1), A + w);
-        }
-        asm volatile("cp.async.commit_group;\n" ::);
-    };
-    auto issue_S = [&](long long g, int buf) {
-        if (g < frames && status(g) != 0) {
-            const char* Sg = reinterpret_cast<const char*>(stash_S + (size_t)g * SSS);
-            for (int c = lane; c < SSS * (int)sizeof(R) / 16; c += 32) cp_async_16(reinterpret_cast<char*>(Sb) + 16 * c, Sg + 16 * c);
-            const char* mg = reinterpret_cast<const char*>(stash_m + (size_t)g * SMS);
-            for (int c = lane; c < SMS * (int)sizeof(R) / 16; c += 32) cp_async_16(reinterpret_cast<char*>(mvb + 32 * buf) + 16 * c, mg + 16 * c);
-            if (w_tape && act) cp_async_elem(wvb + 32 * buf + lane, w_tape + (size_t)g * n + lane);
-        }
-        asm volatile("cp.async.commit_group;\n" ::);
-    };
-    auto publish_row = [&](R* dst, const R (&v)[n]) {       // row `lane` of a 32 x LS buffer
-#pragma unroll
-        for (int cv = 0; cv < NV; ++cv) {
-            VecT ov;
-            R* oe = reinterpret_cast<R*>(&ov);
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) oe[q] = (cv * VEC + q < n) ? v[cv * VEC + q] : (R)0;
-            *reinterpret_cast<VecT*>(dst + lane * LS + cv * VEC) = ov;
-        }
-    };
-
-    // All warps of the CTA walk their frames in lockstep (one barrier per phase): the unrolled
-    // body is far larger than the instruction caches, and warps that share a scheduler then share
-    // its instruction fetches.
-    int buf = 0;
-    {
-        const long long g0 = (long long)blockIdx.x * WARPS + warp;
-        issue_A(g0);
-        issue_S(g0, buf);
-    }
-    for (long long base = (long long)blockIdx.x * WARPS; base < frames; base += stride, buf ^= 1) {
-        const long long g = base + warp, gn = g + stride;
-        const int stat = (g < frames) ? status(g) : -1;
-        const int nn = (int)(g / Tx), i = (int)(g % Tx);
-        R* Gout = GH + (size_t)g * PrepSmem<R, D_, L_>::RECS;
-        R* hout = Gout + n * n;
-        asm volatile("cp.async.wait_all;\n" ::);
-        __syncwarp();
-        const R* mv = mvb + 32 * buf;
-        R* wv = wvb + 32 * buf;
-        if (stat > 0 && !w_tape && act) {
-            Philox gen(seed, KPMS_STREAM_X, (uint64_t)g * n + lane);
-            double a0, a1;
-            philox_normal2(gen, a0, a1);
-            wv[lane] = (R)a0;
-        }
-        if (stat == 0) {
-            for (int w = lane; w < n * n; w += 32) Gout[w] = ((w / n) == (w % n)) ? (R)1 : (R)0;
-            for (int w = lane; w < n; w += 32) hout[w] = (R)0;
-        }
-        if (stat == 2) {                             // terminal frame: draw from the filter marginal
-            R a[n], dummy[n];
-#pragma unroll
-            for (int c = 0; c < n; ++c) a[c] = (c <= row) ? pB[col_start(n, c) - c] : pA[c];
-            __syncwarp();
-            chol_rows<R, n, LS, false>(a, T1, dummy, invd, lane);
-            R acc = mv[row];
-#pragma unroll
-            for (int c = 0; c < n; ++c) acc = fma((c <= row) ? a[c] : (R)0, wv[c], acc);
-            if (act) hout[lane] = acc;
-            __syncwarp();
-        }
-        if (stat != 1) {
-            issue_A(gn);
-            issue_S(gn, buf ^ 1);
-        }
-        const bool on = (stat == 1);
-        const int zi = on ? z[(size_t)nn * (Tx - 1) + i] : 0;
-        R wt[n], pp[n], sig[n];
-        // ---- phase 1: Wt column `row` = Aaug S[:, row]; mp = Aaug m + b
-        if (on) {
-            R sc[n];
-#pragma unroll
-            for (int c = 0; c < n; ++c) sc[c] = (c <= row) ? pB[col_start(n, c) - c] : pA[c];
-#pragma unroll
-            for (int r = 0; r < NO; ++r) wt[r] = sc[r + D_];
-#pragma unroll
-            for (int a = 0; a < D_; ++a) {
-                R acc0 = 0, acc1 = 0;
-#pragma unroll
-                for (int cv = 0; cv < NV; ++cv) {
-                    const VecT av = *reinterpret_cast<const VecT*>(As + a * LS + cv * VEC);
-                    const R* ae = reinterpret_cast<const R*>(&av);
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q) {
-                        const int e = cv * VEC + q;
-                        if (e < n) { if (e & 1) acc1 = fma(ae[q], sc[e], acc1); else acc0 = fma(ae[q], sc[e], acc0); }
-                    }
-                }
-                wt[NO + a] = acc0 + acc1;
-            }
-            R mpv;
-            if (row < NO) mpv = mv[row + D_];
-            else {
-                const R* arow = As + (row - NO) * LS;
-                mpv = arow[n];
-#pragma unroll 6
-                for (int e = 0; e < n; ++e) mpv = fma(arow[e], mv[e], mpv);
-            }
-            mp[lane] = mpv;
-            publish_row(T2, wt);                     // T2 = Wt'
-        }
-        __syncthreads();
-        // ---- phase 2: Pp row `row` = Wt[row, :] Aaug' + Qaug
-        if (on) {
-            R wr[n];
-#pragma unroll
-            for (int e = 0; e < n; ++e) wr[e] = T2[e * LS + row];
-#pragma unroll
-            for (int c = 0; c < NO; ++c) pp[c] = wr[c + D_] + ((row == c) ? eps : (R)0);
-            const R* Qk = Q + (size_t)zi * D_ * D_;
-#pragma unroll
-            for (int a = 0; a < D_; ++a) {
-                R acc0 = (row >= NO) ? (__ldg(Qk + (row - NO) * D_ + a) + ((row - NO == a) ? jitter : (R)0)) : (R)0;
-                R acc1 = 0;
-#pragma unroll
-                for (int cv = 0; cv < NV; ++cv) {
-                    const VecT av = *reinterpret_cast<const VecT*>(As + a * LS + cv * VEC);
-                    const R* ae = reinterpret_cast<const R*>(&av);
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q) {
-                        const int e = cv * VEC + q;
-                        if (e < n) { if (e & 1) acc1 = fma(ae[q], wr[e], acc1); else acc0 = fma(ae[q], wr[e], acc0); }
-                    }
-                }
-                pp[NO + a] = acc0 + acc1;
-            }
-            __syncwarp();                            // As and T2 (Wt') fully consumed
-            issue_A(gn);
-        }
-        __syncthreads();
-        // ---- phase 3: Lp = chol(Pp), V = Lp^-1 Wt
-        if (on) {
-            chol_rows<R, n, LS, true>(pp, T1, wt, invd, lane);   // T1 = Lp', wt = V[:, row]
-            publish_row(T2, wt);                     // T2 = V'
-        }
-        __syncthreads();
-        // ---- phase 4: Sigma row `row` = S[row, :] - V[:, row]' V
-        if (on) {
-#pragma unroll
-            for (int a = 0; a < n; ++a) {
-                R acc0 = (a <= row) ? pB[col_start(n, a) - a] : pA[a], acc1 = 0;
-#pragma unroll
-                for (int cv = 0; cv < NV; ++cv) {
-                    const VecT vv = *reinterpret_cast<const VecT*>(T2 + a * LS + cv * VEC);
-                    const R* ve = reinterpret_cast<const R*>(&vv);
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q) {
-                        const int e = cv * VEC + q;
-                        if (e < n) { if (e & 1) acc1 = fma(-ve[q], wt[e], acc1); else acc0 = fma(-ve[q], wt[e], acc0); }
-                    }
-                }
-                sig[a] = acc0 + acc1;
-            }
-            __syncwarp();                            // Sb and T2 (V') fully consumed
-            issue_S(gn, buf ^ 1);
-        }
-        __syncthreads();
-        // ---- phase 5: Ls = chol(Sigma)
-        if (on) chol_rows<R, n, LS, false>(sig, T2, pp, invd, lane);   // sig[c <= row] = Ls[row][c]
-        __syncthreads();
-        // ---- phase 6: X = Lp^-T V (column `row`, in place over wt), records out
-        if (on) {
-#pragma unroll
-            for (int r = n - 1; r >= 0; --r) {
-                R acc0 = wt[r], acc1 = 0;
-#pragma unroll
-                for (int cv = (r + 1) / VEC; cv < NV; ++cv) {
-                    const VecT lv = *reinterpret_cast<const VecT*>(T1 + r * LS + cv * VEC);
-                    const R* le = reinterpret_cast<const R*>(&lv);
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q) {
-                        const int e = cv * VEC + q;
-                        if (e > r && e < n) { if (e & 1) acc1 = fma(-le[q], wt[e], acc1); else acc0 = fma(-le[q], wt[e], acc0); }
-                    }
-                }
-                wt[r] = (acc0 + acc1) * invd[r];
-            }
-            if (act) {
-#pragma unroll
-                for (int r = 0; r < n; ++r) Gout[r * n + lane] = wt[r];
-            }
-            // h = m - X' mp + Ls w
-            R acc = mv[row], acc2 = 0;
-#pragma unroll
-            for (int c = 0; c < n; ++c) {
-                acc = fma(-wt[c], mp[c], acc);
-                acc2 = fma((c <= row) ? sig[c] : (R)0, wv[c], acc2);
-            }
-            if (act) hout[lane] = acc + acc2;
-        }
-        __syncthreads();                             // also orders this frame's shared-memory reads before the next one's writes
-    }
-    asm volatile("cp.async.wait_all;\n" ::);
-}
 
 #include "kalman_rows2.cuh"
 #include "kalman_split.cuh"
@@ -1655,68 +1210,30 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         fill_normal_kernel<R><<<(int)((count / 4 + 256) / 256), 256, 0, st>>>(wbuf, count, seed, KPMS_STREAM_X);
         w_tape = wbuf;
     }
-    bool backprep_done = false;
-    static const std::string bp_mode = [] { const char* e = getenv("KPMS_BACKPREP"); return std::string(e ? e : "split"); }();
-    static const bool rows1 = bp_mode == "rows1";
     if (frames >= (1LL << 31)) return set_error(-3, "kalman_sample: %lld frame slots on one device exceed 2^31", frames);
-    if constexpr (L_ >= 2 && D_ <= 32) {
-      if (bp_mode == "split") {
+    if constexpr (L_ >= 2) {
         // two-stage backward preparation (kalman_split.cuh): d lanes per frame, 32/d frames per warp
         typedef PrepSplit<R, D_, L_> PS;
         { KPMS_LAUNCH("kalman_backprep_ops", st);
           backprep_ops_kernel<R, D_, L_><<<K, 128, 0, st>>>(Ab, Q, (R)jitter, ops); }
         { KPMS_LAUNCH("kalman_backprep_special", st);
           backprep_special_kernel<R, D_, L_, (n > 32)><<<N, 128, 0, st>>>(stash_m, stash_S, mask, w_tape, N, T, GH); }
-        auto launch = [&](auto kern, int warps, int minb) {
-            const size_t smem = (size_t)warps * PS::FPW * PS::frame_bytes + warps * 2 * sizeof(uint64_t);
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            const long long tiles = (frames + warps * PS::FPW - 1) / (warps * PS::FPW);
-            const int blocks = (int)std::min<long long>(tiles, (long long)KPMS_SM_COUNT * minb);
-            KPMS_LAUNCH("kalman_backprep", st);
-            kern<<<blocks, 32 * warps, smem, st>>>(stash_m, stash_S, mask, z, ops, (R)(KPMS_EPS_SHIFT + jitter), w_tape, N, T, GH);
-        };
         constexpr int FIT4 = (int)((220 * 1024) / (4 * PS::FPW * PS::frame_bytes + 64));
         constexpr int MINB = sizeof(R) == 8 ? 1 : (FIT4 >= 3 ? 3 : (FIT4 >= 1 ? FIT4 : 1));
         static_assert(FIT4 >= 1, "one CTA of the two-stage backward preparation must fit in shared memory");
-        bool done = false;
-        if constexpr (sizeof(R) == 4 && D_ == 10 && L_ == 3) {      // occupancy experiment (KPMS_BP_CFG=4x2: 255 registers, 8 warps per SM)
-            static const std::string cfg = [] { const char* e = getenv("KPMS_BP_CFG"); return std::string(e ? e : ""); }();
-            if (cfg == "4x2") { launch(kalman_backprep_split_kernel<R, D_, L_, 4, 2>, 4, 2); done = true; }
-        }
-        if (!done) launch(kalman_backprep_split_kernel<R, D_, L_, 4, MINB>, 4, MINB);
+        constexpr int WARPS = 4;
+        auto kern = kalman_backprep_split_kernel<R, D_, L_, WARPS, MINB>;
+        const size_t smem = (size_t)WARPS * PS::FPW * PS::frame_bytes + WARPS * 2 * sizeof(uint64_t);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const long long tiles = (frames + WARPS * PS::FPW - 1) / (WARPS * PS::FPW);
+        const int blocks = (int)std::min<long long>(tiles, (long long)KPMS_SM_COUNT * MINB);
+        { KPMS_LAUNCH("kalman_backprep", st);
+          kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, ops, (R)(KPMS_EPS_SHIFT + jitter), w_tape, N, T, GH); }
         int rc = check_launch("kalman backprep (two-stage)");
         if (rc) return rc;
-        backprep_done = true;
-      }
-    }
-    if (!backprep_done) {
-    auto launch_generic = [&]() -> int {
-        // generic shared-memory kernel, one warp per frame; as many warps per CTA as shared memory allows
-        constexpr int WARPS_MAX = (int)(220 * 1024 / (PrepSmem<R, D_, L_>::per_warp * sizeof(R)));
-        constexpr int WARPS = WARPS_MAX >= 4 ? 4 : (WARPS_MAX >= 1 ? WARPS_MAX : 1);
-        auto kern = kalman_backprep_kernel<R, D_, L_, WARPS>;
-        size_t smem = PrepSmem<R, D_, L_>::per_warp * WARPS * sizeof(R);
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int blocks = (int)((frames + WARPS - 1) / WARPS);
-        { KPMS_LAUNCH("kalman_backprep", st); kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH); }
-        return check_launch("kalman backprep");
-    };
-    if constexpr (n > 32 && n <= 64 && sizeof(R) == 4) {
-      if (rows1) { int rc = launch_generic(); if (rc) return rc; } else {
-        // latent_dim 16: one frame per warp, two rows per lane (the generic shared-memory kernel is ~50x slower)
-        typedef PrepRows2<R, D_, L_> P2;
-        constexpr int WARPS = (int)(200 * 1024 / (P2::per_group * P2::FPW * sizeof(R)));
-        auto kern = kalman_backprep_rows2_kernel<R, D_, L_, WARPS>;
-        size_t smem = (size_t)P2::per_group * P2::FPW * WARPS * sizeof(R);
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int blocks = (int)std::min<long long>((frames + WARPS * P2::FPW - 1) / (WARPS * P2::FPW), (long long)KPMS_SM_COUNT);
-        { KPMS_LAUNCH("kalman_backprep", st); kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH); }
-        int rc = check_launch("kalman backprep");
-        if (rc) return rc;
-      }
-    } else if constexpr (n <= 32) {
-      if (!rows1) {
-        // two rows per lane, FPW frames per warp (kalman_rows2.cuh); one CTA per SM
+    } else {
+        // nlags = 1 has no shifted block to condition on first: one-stage form, two rows per lane (kalman_rows2.cuh)
+        static_assert(n <= 32, "the one-stage backward preparation holds one frame per half warp");
         typedef PrepRows2<R, D_, L_> P2;
         constexpr int WARPS = sizeof(R) == 4 ? 8 : 4;
         auto kern = kalman_backprep_rows2_kernel<R, D_, L_, WARPS>;
@@ -1726,21 +1243,6 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         { KPMS_LAUNCH("kalman_backprep", st); kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH); }
         int rc = check_launch("kalman backprep");
         if (rc) return rc;
-      } else {
-        constexpr int WARPS = sizeof(R) == 4 ? 16 : 8;      // one CTA per SM
-        auto kern = kalman_backprep_rows_kernel<R, D_, L_, WARPS>;
-        size_t smem = PrepRowsSmem<R, D_, L_>::per_warp * WARPS * sizeof(R);
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        // persistent warps: every warp walks frames g, g + stride, ... and prefetches the next one
-        int blocks = (int)std::min<long long>((frames + WARPS - 1) / WARPS, (long long)KPMS_SM_COUNT);
-        { KPMS_LAUNCH("kalman_backprep", st); kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, Ab, Q, (R)jitter, w_tape, seed, N, T, GH); }
-        int rc = check_launch("kalman backprep");
-        if (rc) return rc;
-      }
-    } else {
-        int rc = launch_generic();
-        if (rc) return rc;
-    }
     }
     {
         constexpr int STAGES = 4;
@@ -1765,25 +1267,62 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
     return 0;
 }
 
+// (latent_dim, nlags) pairs of this translation unit's group (common.cuh: KPMS_DL_GROUP_g, -DKPMS_DL_GROUP=g)
 template <typename R>
-static int kalman_impl(const void* Y, const int* mask, const void* v, const void* h, const void* s, const int* z,
-                       const void* Ct, const void* sigmasq, const void* Ab, const void* Q, double jitter,
-                       const void* w_tape, SeedArg seed, int N, int T, int k, int Dk, int d, int L, int K, void* x,
-                       void* ws, cudaStream_t st, int stage) {
-    if (Dk != 2 && Dk != 3) return set_error(-3, "kalman_sample: keypoint dimension must be 2 or 3, got %d", Dk);
-    if (T < L) return set_error(-3, "kalman_sample: T (%d) < nlags (%d)", T, L);
+static int kalman_group_impl(const void* Y, const int* mask, const void* v, const void* h, const void* s, const int* z,
+                             const void* Ct, const void* sigmasq, const void* Ab, const void* Q, double jitter,
+                             const void* w_tape, SeedArg seed, int N, int T, int k, int Dk, int d, int L, int K, void* x,
+                             void* ws, cudaStream_t st, int stage) {
 #define X(DD, LL)                                                                                            \
     if (d == DD && L == LL)                                                                                  \
         return kalman_launch<R, DD, LL>((const R*)Y, mask, (const R*)v, (const R*)h, (const R*)s, z,         \
                                         (const R*)Ct, (const R*)sigmasq, (const R*)Ab, (const R*)Q, jitter,  \
                                         (const R*)w_tape, seed, N, T, k, Dk, K, (R*)x, ws, st, stage);
-    KPMS_FOR_EACH_DL(X)
+    KPMS_FOR_GROUP_DL(X)
 #undef X
-    return set_error(-3, "kalman_sample: unsupported (latent_dim, nlags) = (%d, %d)", d, L);
+    return KPMS_NOT_IN_GROUP;
 }
+
+#define KPMS_KALMAN_GROUP_ARGS                                                                                    \
+    int dtype, const void *Y, const int *mask, const void *v, const void *h, const void *s, const int *z,         \
+        const void *Ct, const void *sigmasq, const void *Ab, const void *Q, double jitter, const void *w_tape,    \
+        SeedArg seed, int N, int T, int k, int Dk, int d, int L, int K, void *x, void *ws, cudaStream_t st, int stage
+
+int KPMS_CAT(kalman_group_, KPMS_DL_GROUP)(KPMS_KALMAN_GROUP_ARGS) {
+    return KPMS_DISPATCH_DTYPE(dtype, kalman_group_impl, Y, mask, v, h, s, z, Ct, sigmasq, Ab, Q, jitter, w_tape, seed, N, T,
+                               k, Dk, d, L, K, x, ws, st, stage);
+}
+
+#if KPMS_DL_GROUP == 0
+int kalman_group_1(KPMS_KALMAN_GROUP_ARGS);
+int kalman_group_2(KPMS_KALMAN_GROUP_ARGS);
+int kalman_group_3(KPMS_KALMAN_GROUP_ARGS);
+int kalman_group_4(KPMS_KALMAN_GROUP_ARGS);
+int kalman_group_5(KPMS_KALMAN_GROUP_ARGS);
+int kalman_group_6(KPMS_KALMAN_GROUP_ARGS);
+int kalman_group_7(KPMS_KALMAN_GROUP_ARGS);
+static_assert(KPMS_DL_GROUPS == 8, "one dispatcher per group");
+
+static int kalman_dispatch(KPMS_KALMAN_GROUP_ARGS) {
+    if (dtype != 0 && dtype != 1) return set_error(-2, "dtype must be 0 (f32) or 1 (f64), got %d", dtype);
+    if (K < 1) return set_error(-3, "kalman_sample: num_states must be positive, got %d", K);
+    if (Dk != 2 && Dk != 3) return set_error(-3, "kalman_sample: keypoint dimension must be 2 or 3, got %d", Dk);
+    if (T < L) return set_error(-3, "kalman_sample: T (%d) < nlags (%d)", T, L);
+    typedef int (*GroupFn)(KPMS_KALMAN_GROUP_ARGS);
+    static const GroupFn groups[KPMS_DL_GROUPS] = {kalman_group_0, kalman_group_1, kalman_group_2, kalman_group_3,
+                                                   kalman_group_4, kalman_group_5, kalman_group_6, kalman_group_7};
+    for (int g = 0; g < KPMS_DL_GROUPS; ++g) {
+        const int rc = groups[g](dtype, Y, mask, v, h, s, z, Ct, sigmasq, Ab, Q, jitter, w_tape, seed, N, T, k, Dk, d, L, K,
+                                 x, ws, st, stage);
+        if (rc != KPMS_NOT_IN_GROUP) return rc;
+    }
+    return set_error(-3, "kalman_sample: unsupported (latent_dim, nlags) = (%d, %d); see kpms_supported_dims", d, L);
+}
+#endif
 
 }  // namespace kpms
 
+#if KPMS_DL_GROUP == 0
 using namespace kpms;
 
 extern "C" {
@@ -1800,18 +1339,29 @@ int kpms_kalman_sample(int dtype, const void* Y, const int* mask, const void* v,
                        const int* z, const void* Ct, const void* sigmasq, const void* Ab, const void* Q,
                        double jitter, const void* w_tape, uint64_t seed, const uint64_t* seed_dev, int N, int T, int k, int Dk, int d,
                        int L, int K, int info_ready, void* x, void* ws, void* stream) {
-    if (K < 1) return set_error(-3, "kalman_sample: num_states must be positive, got %d", K);
-    return KPMS_DISPATCH_DTYPE(dtype, kalman_impl, Y, mask, v, h, s, z, Ct, sigmasq, Ab, Q, jitter, w_tape,
-                               SeedArg(seed, seed_dev), N, T, k, Dk, d, L, K, x, ws, (cudaStream_t)stream, info_ready ? 2 : 0);
+    return kalman_dispatch(dtype, Y, mask, v, h, s, z, Ct, sigmasq, Ab, Q, jitter, w_tape, SeedArg(seed, seed_dev), N, T, k,
+                           Dk, d, L, K, x, ws, (cudaStream_t)stream, info_ready ? 2 : 0);
 }
 
 int kpms_kalman_obs_info(int dtype, const void* Y, const int* mask, const void* v, const void* h, const void* s,
                          const void* Ct, const void* sigmasq, int N, int T, int k, int Dk, int d, int L, int K, void* ws,
                          void* stream) {
-    if (K < 1) return set_error(-3, "kalman_obs_info: num_states must be positive, got %d", K);
-    return KPMS_DISPATCH_DTYPE(dtype, kalman_impl, Y, mask, v, h, s, (const int*)nullptr, Ct, sigmasq, (const void*)nullptr,
-                               (const void*)nullptr, 0.0, (const void*)nullptr, SeedArg(), N, T, k, Dk, d, L, K, (void*)nullptr,
-                               ws, (cudaStream_t)stream, 1);
+    return kalman_dispatch(dtype, Y, mask, v, h, s, nullptr, Ct, sigmasq, nullptr, nullptr, 0.0, nullptr, SeedArg(), N, T, k,
+                           Dk, d, L, K, nullptr, ws, (cudaStream_t)stream, 1);
+}
+
+/* (latent_dim, nlags) pairs the library was built for: writes up to `cap` pairs as d0, L0, d1, L1, ... and returns
+ * how many pairs exist. */
+int kpms_supported_dims(int* pairs, int cap) {
+    static const int table[][2] = {
+#define X(DD, LL) {DD, LL},
+        KPMS_FOR_EACH_DL(X)
+#undef X
+    };
+    const int count = (int)(sizeof(table) / sizeof(table[0]));
+    for (int i = 0; i < count && i < cap; ++i) { pairs[2 * i] = table[i][0]; pairs[2 * i + 1] = table[i][1]; }
+    return count;
 }
 
 }  // extern "C"
+#endif

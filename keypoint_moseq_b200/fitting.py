@@ -13,7 +13,7 @@ from textwrap import fill
 import numpy as np
 import torch
 
-from . import gibbs
+from . import _lib, gibbs
 from .dist import gather_rows, shard_rows, shard_tree
 from .io import SnapshotWriter, delete_snapshots_after, extract_results, load_checkpoint, save_hdf5
 from .util import NanGuard, check_for_nans, get_nlags, to_numpy_tree, unbatch
@@ -234,6 +234,9 @@ def init_model(data=None, states=None, params=None, hypparams=None, noise_prior=
         if missing:
             raise ValueError(f"init_model needs `hypparams` or the config entries {missing}")
         hypparams = initialize.init_hyperparams(trans_hypparams, ar_hypparams, obs_hypparams, cen_hypparams)
+    arh = hypparams["ar_hypparams"]
+    _lib.check_model_dims(arh["latent_dim"], arh["nlags"],
+                          arh.get("num_states", hypparams["trans_hypparams"].get("num_states", 1)))
     # (a model's own `hypparams` win over the config groups, as when apply_model re-initialises the states of a
     # fitted model with `**config()` in the call, fitting.py:387-394)
     if params is None:

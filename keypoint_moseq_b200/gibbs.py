@@ -755,6 +755,7 @@ def resample_model(data, seed, states, params, hypparams, noise_prior, ar_only=F
     noise_prior = _broadcast_prior(noise_prior, Yshape) if not ar_only else noise_prior
     prior_stable = noise_prior is noise_prior_in         # a broadcast copy has a new address every call
     _check_shapes(Yshape, data["mask"], states, noise_prior, ar_only)
+    _lib.check_model_dims(x.shape[-1], Yshape[1] - states["z"].shape[1], params["pi"].shape[0])
     rank = 0
     if group is not None:
         import torch.distributed as dist

@@ -125,10 +125,14 @@ def test_location_aware_is_rejected():
 
 def test_unsupported_shape_fails_loudly():
     from keypoint_moseq_b200 import _lib, gibbs
-    data, meta, model = small_problem(seed=16, d=3, L=3, K=6, k=5, D=2)
+    data, meta, model = small_problem(seed=16, d=3, L=2, K=6, k=5, D=2)
     dd, dm = gibbs.to_device_data(data), gibbs.to_device_model(model)
-    with pytest.raises(_lib.KpmsError, match="unsupported"):
+    with pytest.raises(_lib.KpmsError, match="not compiled"):
         gibbs.resample_model(dd, **dm)
+    # the raw entry point refuses as well (status -3, message from the library)
+    x, z = dm["states"]["x"], dm["states"]["z"]
+    with pytest.raises(_lib.KpmsError, match="unsupported"):
+        gibbs.sufficient_statistics(x, z, dd["mask"], 6)
 
 
 def test_full_size_properties_c2():

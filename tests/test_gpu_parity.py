@@ -191,6 +191,35 @@ def test_full_sweep(dtype, tol, flags):
         assert rel_err(_np(out["states"]["v"]), st_ref["v"]) < tol
 
 
+def _compiled_pairs():
+    from keypoint_moseq_b200 import _lib
+    return sorted(_lib.supported_dims())
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, F64_TOL), (torch.float32, F32_TOL)])
+@pytest.mark.parametrize("pair", _compiled_pairs(), ids=lambda p: f"d{p[0]}L{p[1]}")
+def test_full_sweep_every_compiled_pair(pair, dtype, tol):
+    """latent_dim and nlags are user configuration (keypoint_moseq/io.py:72-83): one full sweep against the oracle
+    on the same tape for every (latent_dim, nlags) pair compiled into the library (kpms_supported_dims)."""
+    g = _gibbs()
+    d, L = pair
+    data, _, model = small_problem(seed=21, d=d, L=L, K=8, k=max(5, (d + 1) // 2 + 1), D=2, kappa=1e2, frames=200,
+                                   seg_length=120)
+    tape = tape_for(data, model)
+    data, model, tape = _cast_problem(data, model, tape, dtype)
+    st_ref, pr_ref, _ = oracle_sweep(data, model, tape)
+    dd, dm = _to_dev(data, model, dtype)
+    out = g.resample_model(dd, **dm, draws=tape)
+    assert np.array_equal(_np(out["states"]["z"]), st_ref["z"])
+    for key in ("Ab", "Q", "betas", "pi"):
+        assert rel_err(_np(out["params"][key]), pr_ref[key]) < max(tol, 1e-7), key
+    assert np.abs(_np(out["states"]["s"]) / st_ref["s"] - 1).max() < tol * 10
+    assert rel_err(_np(out["states"]["x"]), st_ref["x"]) < tol
+    dh = np.angle(np.exp(1j * (_np(out["states"]["h"]).astype(np.float64) - st_ref["h"])))
+    assert np.abs(dh).max() < (1e-6 if dtype == torch.float64 else F32_TOL)
+    assert rel_err(_np(out["states"]["v"]), st_ref["v"]) < tol
+
+
 def test_philox_sweeps_are_finite_and_reproducible():
     g = _gibbs()
     data, _, model = small_problem(seed=9, d=4, L=3, K=12, k=5, D=2, kappa=1e2, frames=600, seg_length=300)
