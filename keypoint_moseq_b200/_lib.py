@@ -129,7 +129,7 @@ def supported_dims():
 _DIMS = []
 
 
-MAX_STATES = 128        # the HMM kernels keep pi slices in registers / shared memory (csrc/hmm.cu)
+MAX_STATES = 512        # csrc/hmm.cu for num_states <= 128, csrc/hmm_wide.cuh (float64 only) up to 512
 
 
 def check_model_dims(latent_dim, nlags, num_states):

@@ -435,6 +435,7 @@ hmm_forward_kernel(const R* __restrict__ W, const R* __restrict__ mx, const R* _
 }
 
 #include "hmm_f64.cuh"
+#include "hmm_wide.cuh"
 
 #if KPMS_DL_GROUP == 0
 // logZ[nn] = ordered sum of the chunks' parts (zero-initialised; chains flagged dirty are
@@ -836,7 +837,17 @@ static inline int fp_of(int n, int d, size_t esz) { int F = n + d + 1; int v = 1
 enum { HW_DIAG, HW_G, HW_GF, HW_CST, HW_VLEN, HW_DIRTY, HW_BW, HW_BE, HW_LZP, HW_TS, HW_PW, HW_PIT, HW_ZB, HW_END };
 
 // float64 path: state tiles of 8 columns (one warp each) for the tensor-pipe kernels; 0 = unsupported
-static inline int state_tiles(int K) { return K <= 32 ? 4 : K <= 56 ? 7 : K <= 104 ? 13 : K <= 128 ? 16 : 0; }
+// (K <= 128: one of four compiled tile counts; up to 512 states: run-time tile count of the wide kernels, hmm_wide.cuh)
+static inline int state_tiles(int K) {
+    return K <= 32 ? 4 : K <= 56 ? 7 : K <= 104 ? 13 : K <= 128 ? 16 : K <= 512 ? (K + 7) / 8 : 0;
+}
+static inline bool hmm_wide(int K) { return K > 128; }
+static int hmm_check_states(const char* who, int K, size_t esz) {
+    if (K < 1 || K > 512) return set_error(-3, "%s: num_states %d outside 1..512", who, K);
+    if (hmm_wide(K) && esz != 8)
+        return set_error(-3, "%s: num_states %d > 128 needs the float64 discrete-state path (hmm_dtype=float64)", who, K);
+    return 0;
+}
 constexpr int HMM_MT = 1;           // 8-task tiles per CTA of the float64 forward kernel
 
 static int hmm_chunks(int N, int Tp, bool f64) {
@@ -873,6 +884,7 @@ static int ar_loglik_launch(const R* x, const int* mask, const R* Ab, const R* Q
     constexpr int n = D_ * L_;
     constexpr int FPT = sizeof(R) == 4 ? 2 : 1;
     constexpr int KC = sizeof(R) == 4 ? 32 : 16;
+    if (int rc = hmm_check_states("ar_loglik", K, sizeof(R))) return rc;
     int Fp = fp_of(n, D_, sizeof(R));
     size_t off[HW_END + 1];
     hmm_ws_layout<R>(N, T, K, D_, L_, off);
@@ -889,7 +901,6 @@ static int ar_loglik_launch(const R* x, const int* mask, const R* Ab, const R* Q
         // tensor-pipe path: operators repacked in fragment order, W (N, Tp, 8*KT) states-contiguous
         typedef ArFrag<D_, L_> AF;
         const int KT = state_tiles(K);
-        if (KT == 0) return set_error(-3, "ar_loglik: num_states %d > 128 not supported", K);
         double* Gf = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + off[HW_GF]);
         { KPMS_LAUNCH("ar_pack_frag", st);
           ar_pack_frag_kernel<D_, L_><<<ceil_div(KT * AF::CHUNK, 256), 256, 0, st>>>((const double*)G, (const double*)cst, K, Fp, KT, Gf); }
@@ -903,7 +914,13 @@ static int ar_loglik_launch(const R* x, const int* mask, const R* Ab, const R* Q
             KPMS_LAUNCH("ar_loglik", st);                                                                     \
             kern<<<grid, 32 * AR_WARPS, smem, st>>>((const double*)x, mask, Gf, N, T, K, ldT, (double*)W, (double*)mx); \
         }
-        if (KT == 4) ARL(4) else if (KT == 7) ARL(7) else if (KT == 13) ARL(13) else ARL(16)
+        if (hmm_wide(K)) {
+            auto kern = ar_loglik_dmma_wide_kernel<D_, L_>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            KPMS_LAUNCH("ar_loglik", st);
+            kern<<<grid, 32 * AR_WARPS, smem, st>>>((const double*)x, mask, Gf, N, T, K, KT, ldT, (double*)W, (double*)mx);
+        }
+        else if (KT == 4) ARL(4) else if (KT == 7) ARL(7) else if (KT == 13) ARL(13) else ARL(16)
 #undef ARL
         return check_launch("ar_loglik");
     }
@@ -967,8 +984,14 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
                             void* filt, double* logZ, void* ws, int d, int L, cudaStream_t st) {
     const int ldK = (K + 3) / 4 * 4;
     const int Kpad = (K + 7) / 8 * 8;
-    if (K > 128) return set_error(-3, "hmm_forward: num_states %d > 128 not supported", K);
+    if (int rc = hmm_check_states("hmm_forward", K, sizeof(R))) return rc;
     constexpr int M = sizeof(R) == 8 ? 8 * HMM_MT : 4;       // tasks per CTA
+    static_assert(8 * HMM_MT == HMM_WIDE_M, "the wide filter shares the task grid of the tensor-pipe filter");
+    const bool wide = hmm_wide(K);
+    const int Kw = 8 * state_tiles(K);                       // row stride of W (float64 layout)
+    const int wide_threads = (K + 31) / 32 * 32;
+    const size_t wide_smem = ((size_t)2 * Kw * HMM_WIDE_M + (size_t)2 * HMM_WIDE_M * (wide_threads / 32)) * sizeof(double);
+    if (wide) cudaFuncSetAttribute(hmm_forward_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem);
     size_t off[HW_END + 1];
     hmm_ws_layout<R>(N, Tp + L, K, d, L, off);
     char* base = reinterpret_cast<char*>(ws);
@@ -1003,8 +1026,14 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
         (const double*)W, (const double*)mx, (const double*)pi, N, K, Tp, ldT, ldK, (double*)filt, logZ, lzp, \
         PASS, C, CT, Wm, VB, DIRTY, (double*)bw, (PASS) == 3 ? (double*)nullptr : (double*)be,                \
         (PASS) == 3 ? (const double*)be : (const double*)tstart);
+#define FWDW(GRID, PASS, VB, DIRTY)                                                                           \
+    hmm_forward_wide_kernel<<<GRID, wide_threads, wide_smem, st>>>(                                           \
+        (const double*)W, (const double*)mx, (const double*)pi, N, K, Kw, Tp, ldT, ldK, (double*)filt, logZ,  \
+        lzp, PASS, C, CT, Wm, VB, DIRTY, (double*)bw, (PASS) == 3 ? (double*)nullptr : (double*)be,           \
+        (PASS) == 3 ? (const double*)be : (const double*)tstart);
 #define FWD_K(GRID, PASS, VB, DIRTY)                                             \
-    if (sizeof(R) == 8) {                                                        \
+    if (wide) FWDW(GRID, PASS, VB, DIRTY)                                        \
+    else if (sizeof(R) == 8) {                                                   \
         if (K <= 32) FWD64(4, GRID, PASS, VB, DIRTY)                             \
         else if (K <= 56) FWD64(7, GRID, PASS, VB, DIRTY)                        \
         else if (K <= 104) FWD64(13, GRID, PASS, VB, DIRTY)                      \
@@ -1057,11 +1086,14 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
             which ^= 1;
         }
         KPMS_LAUNCH("hmm_tail_starts", st);
-        hmm_tail_starts_kernel<R><<<N, 128, 0, st>>>(src, be, vb, dirty, K, Tp, C, CT, Wm, tstart);
+        if (wide) hmm_tail_starts_wide_kernel<<<N, HMM_WIDE_MAX, 0, st>>>((const double*)src, (const double*)be, vb, dirty, K, Tp, C, CT, Wm, (double*)tstart);
+        else hmm_tail_starts_kernel<R><<<N, 128, 0, st>>>(src, be, vb, dirty, K, Tp, C, CT, Wm, tstart);
     }
     { KPMS_LAUNCH("hmm_forward_tail", st); FWD_K((int)(((long long)N * CT + M - 1) / M), 1, vb, dirty) }
     { KPMS_LAUNCH("hmm_logz_sum", st); logz_sum_kernel<<<ceil_div(N, 128), 128, 0, st>>>(lzp, N, C + CT, logZ); }
-    if (sizeof(R) == 8) {
+    if (wide) {
+        KPMS_LAUNCH("hmm_forward_rerun", st); FWDW((N + M - 1) / M, 2, (const int*)nullptr, dirty)
+    } else if (sizeof(R) == 8) {
         // Chains whose boundaries failed the check (slow forgetting: parameters far from the data) are
         // re-run sequentially, one chain per CTA on the latency-lean DFMA kernel (a DMMA step costs the
         // same pipe time for one task as for eight).
@@ -1084,6 +1116,7 @@ static int hmm_forward_impl(const void* W, const void* mx, const void* pi, int N
         KPMS_LAUNCH("hmm_forward_rerun", st); FWD_K((N + M - 1) / M, 2, (const int*)nullptr, dirty)
     }
 #undef FWD_K
+#undef FWDW
 #undef FWD64
 #undef FWD
     return check_launch("hmm_forward");
@@ -1098,7 +1131,7 @@ template <typename R>
 static int hmm_backward_impl(const void* filt, const void* pi, const void* u, void* u_scratch, SeedArg seed, int N,
                              int K, int Tp, int* z, void* ws, int d, int L, cudaStream_t st) {
     const int ldK = (K + 3) / 4 * 4;
-    if (K > 128) return set_error(-3, "hmm_backward: num_states %d > 128 not supported", K);
+    if (int rc = hmm_check_states("hmm_backward", K, sizeof(R))) return rc;
     size_t off[HW_END + 1];
     hmm_ws_layout<R>(N, Tp + L, K, d, L, off);
     char* base = reinterpret_cast<char*>(ws);
@@ -1118,6 +1151,23 @@ static int hmm_backward_impl(const void* filt, const void* pi, const void* u, vo
     { KPMS_LAUNCH("hmm_transpose_pi", st);
       transpose_pi_kernel<R><<<ceil_div(K * ldK, 256), 256, 0, st>>>((const R*)pi, K, ldK, piT); }
     cudaMemsetAsync(diag + 2, 0, 8, st);
+    if (hmm_wide(K)) {
+        constexpr int WPC = 4;
+#define BWDW(EPL_)                                                                                            \
+        {                                                                                                     \
+            { KPMS_LAUNCH("hmm_backward", st);                                                                \
+              hmm_backward_wide_kernel<EPL_><<<(int)(((long long)N * Cb + WPC - 1) / WPC), 32 * WPC, 0, st>>>( \
+                  (const double*)filt, (const double*)piT, (const double*)usrc, N, K, Tp, ldK, Cb, Wm, vb, 0, z, zwarm, diag); } \
+            if (Cb > 1) {                                                                                     \
+                KPMS_LAUNCH("hmm_backward_repair", st);                                                       \
+                hmm_backward_wide_kernel<EPL_><<<(N + WPC - 1) / WPC, 32 * WPC, 0, st>>>(                     \
+                    (const double*)filt, (const double*)piT, (const double*)usrc, N, K, Tp, ldK, Cb, Wm, vb, 1, z, zwarm, diag); \
+            }                                                                                                 \
+        }
+        if (ldK <= 256) BWDW(8) else BWDW(16)
+#undef BWDW
+        return check_launch("hmm_backward");
+    }
     const size_t warp_ring = (size_t)HMM_BW_RING * (ldK + 16 / sizeof(R)) * sizeof(R);
     const size_t pit_bytes = (size_t)K * ldK * sizeof(R);
     const int wpc = pit_bytes + HMM_BW_WARPS * warp_ring <= 220 * 1024 ? HMM_BW_WARPS : HMM_BW_WARPS / 2;   // warps per CTA
@@ -1145,6 +1195,12 @@ static int hmm_backward_impl(const void* filt, const void* pi, const void* u, vo
 template <typename R>
 static int hmm_smooth_impl(const void* filt, const void* pi, int N, int K, int Tp, void* marg, cudaStream_t st) {
     int ldK = (K + 3) / 4 * 4;
+    if (int rc = hmm_check_states("hmm_smooth", K, sizeof(R))) return rc;
+    if (hmm_wide(K)) {
+        KPMS_LAUNCH("hmm_smooth", st);
+        hmm_smooth_wide_kernel<<<N, (K + 31) / 32 * 32, 0, st>>>((const double*)filt, (const double*)pi, K, Tp, ldK, (double*)marg);
+        return check_launch("hmm_smooth");
+    }
     size_t smem = ((size_t)K * K + 3 * K) * sizeof(R);
     auto kern = hmm_smooth_kernel<R>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

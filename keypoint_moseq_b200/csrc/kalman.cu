@@ -1221,14 +1221,24 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         constexpr int FIT4 = (int)((220 * 1024) / (4 * PS::FPW * PS::frame_bytes + 64));
         constexpr int MINB = sizeof(R) == 8 ? 1 : (FIT4 >= 3 ? 3 : (FIT4 >= 1 ? FIT4 : 1));
         static_assert(FIT4 >= 1, "one CTA of the two-stage backward preparation must fit in shared memory");
-        constexpr int WARPS = 4;
-        auto kern = kalman_backprep_split_kernel<R, D_, L_, WARPS, MINB>;
-        const size_t smem = (size_t)WARPS * PS::FPW * PS::frame_bytes + WARPS * 2 * sizeof(uint64_t);
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const long long tiles = (frames + WARPS * PS::FPW - 1) / (WARPS * PS::FPW);
-        const int blocks = (int)std::min<long long>(tiles, (long long)KPMS_SM_COUNT * MINB);
-        { KPMS_LAUNCH("kalman_backprep", st);
-          kern<<<blocks, 32 * WARPS, smem, st>>>(stash_m, stash_S, mask, z, ops, (R)(KPMS_EPS_SHIFT + jitter), w_tape, N, T, GH); }
+        auto launch = [&](auto kern, int warps, int minb) {
+            const size_t smem = (size_t)warps * PS::FPW * PS::frame_bytes + warps * 2 * sizeof(uint64_t);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const long long tiles = (frames + warps * PS::FPW - 1) / (warps * PS::FPW);
+            const int blocks = (int)std::min<long long>(tiles, (long long)KPMS_SM_COUNT * minb);
+            KPMS_LAUNCH("kalman_backprep", st);
+            kern<<<blocks, 32 * warps, smem, st>>>(stash_m, stash_S, mask, z, ops, (R)(KPMS_EPS_SHIFT + jitter), w_tape, N, T, GH);
+        };
+        bool done = false;
+        if constexpr (sizeof(R) == 4 && D_ == 10 && L_ == 3) {
+            // instruction-cache experiment (KPMS_BP_CFG): warps x CTAs per SM, "s" = one CTA barrier per tile
+            static const std::string cfg = [] { const char* e = getenv("KPMS_BP_CFG"); return std::string(e ? e : ""); }();
+            if (cfg == "4x3s") { launch(kalman_backprep_split_kernel<R, D_, L_, 4, 3, true>, 4, 3); done = true; }
+            else if (cfg == "6x2s") { launch(kalman_backprep_split_kernel<R, D_, L_, 6, 2, true>, 6, 2); done = true; }
+            else if (cfg == "12x1s") { launch(kalman_backprep_split_kernel<R, D_, L_, 12, 1, true>, 12, 1); done = true; }
+            else if (cfg == "12x1") { launch(kalman_backprep_split_kernel<R, D_, L_, 12, 1, false>, 12, 1); done = true; }
+        }
+        if (!done) launch(kalman_backprep_split_kernel<R, D_, L_, 4, MINB>, 4, MINB);
         int rc = check_launch("kalman backprep (two-stage)");
         if (rc) return rc;
     } else {

@@ -175,7 +175,7 @@ backprep_special_kernel(const R* __restrict__ stash_m, const R* __restrict__ sta
     }
 }
 
-template <typename R, int D_, int L_, int WARPS, int MINB>
+template <typename R, int D_, int L_, int WARPS, int MINB, bool LOCKSTEP = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict__ stash_S, const int* __restrict__ mask,
                              const int* __restrict__ z, const R* __restrict__ ops, R eps1, const R* __restrict__ wbuf,
@@ -279,6 +279,9 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
     // as phase G has consumed it, covariance and mean once the V2 rows are consumed (before the Cholesky of Sigma).
     // The words that describe the next frame (mask, state label, normals) are loaded here and first used there.
     for (; cbase < uframes; cbase += ustride, buf ^= 1) {
+        // LOCKSTEP: the unrolled body is ~150 KB of code; warps of a CTA that start every tile together walk the same
+        // instruction-cache lines (the trip count is uniform over the CTA: cbase does not depend on the warp)
+        if (LOCKSTEP) __syncthreads();
         unsigned gN;
         int iN, mkN, ziN;
         peek(cbase + ustride, gN, iN, mkN, ziN);

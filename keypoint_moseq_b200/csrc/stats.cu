@@ -36,6 +36,21 @@ transition_count_kernel(const int* __restrict__ z, const int* __restrict__ mask,
         if (hist[i]) atomicAdd(&counts[i], hist[i]);
 }
 
+// num_states > 226: the K x K histogram no longer fits shared memory; transitions are sparse (sticky chains), so
+// global atomics on the L2-resident table are enough
+__global__ void __launch_bounds__(256)
+transition_count_global_kernel(const int* __restrict__ z, const int* __restrict__ mask, int N, int T, int L, int K,
+                               int* __restrict__ counts) {
+    const int Tp = T - L;
+    const long long total = (long long)N * (Tp - 1);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int nn = (int)(e / (Tp - 1)), t = (int)(e % (Tp - 1));
+        const int* mk = mask + (size_t)nn * T + L + t;
+        if (mk[0] != 0 && mk[1] != 0) atomicAdd(&counts[z[(size_t)nn * Tp + t] * K + z[(size_t)nn * Tp + t + 1]], 1);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 tile_hist_kernel(const int* __restrict__ z, const int* __restrict__ mask, int N, int T, int L, int K,
                  int* __restrict__ tile_hist) {
@@ -250,12 +265,17 @@ extern "C" {
 int kpms_transition_counts(const int32_t* z, const int32_t* mask, int N, int T, int L, int K, int32_t* counts,
                            void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if ((size_t)K * K * sizeof(int) > 200 * 1024) return set_error(-3, "transition_counts: num_states %d too large", K);
+    if (K < 1 || K > 512) return set_error(-3, "transition_counts: num_states %d outside 1..512", K);
     cudaMemsetAsync(counts, 0, (size_t)K * K * sizeof(int), st);
     if (T - L < 2) return 0;
     const long long total = (long long)N * (T - L - 1);
     int blocks = (int)max(1LL, min((long long)148 * 4, (total + 255) / 256));
     size_t smem = (size_t)K * K * sizeof(int);
+    if (smem > 200 * 1024) {
+        KPMS_LAUNCH("transition_counts", st);
+        transition_count_global_kernel<<<blocks, 256, 0, st>>>(z, mask, N, T, L, K, counts);
+        return check_launch("transition_counts");
+    }
     cudaFuncSetAttribute(transition_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     { KPMS_LAUNCH("transition_counts", st); transition_count_kernel<<<blocks, 256, smem, st>>>(z, mask, N, T, L, K, counts); }
     return check_launch("transition_counts");

@@ -46,7 +46,10 @@ def _cast_problem(data, model, tape, dtype):
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, F64_TOL), (torch.float32, F32_TOL)])
 @pytest.mark.parametrize("shape", [dict(d=4, L=3, K=12, k=5, D=2), dict(d=10, L=3, K=100, k=12, D=2),
                                    dict(d=4, L=3, K=30, k=6, D=3), dict(d=4, L=3, K=50, k=5, D=2),
-                                   dict(d=2, L=2, K=128, k=4, D=2), dict(d=16, L=3, K=25, k=12, D=2)])
+                                   dict(d=2, L=2, K=128, k=4, D=2), dict(d=16, L=3, K=25, k=12, D=2),
+                                   # wide-state kernels (hmm_wide.cuh): 128 < num_states <= 512
+                                   dict(d=4, L=3, K=129, k=5, D=2), dict(d=4, L=3, K=250, k=5, D=2),
+                                   dict(d=10, L=3, K=500, k=12, D=2), dict(d=2, L=2, K=512, k=4, D=2)])
 def test_discrete_stateseqs(dtype, tol, shape):
     g = _gibbs()
     data, _, model = small_problem(seed=3, **shape)
@@ -191,6 +194,23 @@ def test_full_sweep(dtype, tol, flags):
         assert rel_err(_np(out["states"]["v"]), st_ref["v"]) < tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, F64_TOL), (torch.float32, F32_TOL)])
+def test_full_sweep_wide_states(dtype, tol):
+    """num_states above 128 (BASELINE config 5 names up to 500): the whole sweep, including transition counts
+    without the shared-memory histogram and the CRP / beta / pi draws over 300 states."""
+    g = _gibbs()
+    data, _, model = small_problem(seed=23, d=4, L=3, K=300, k=5, D=2, kappa=1e2)
+    tape = tape_for(data, model)
+    data, model, tape = _cast_problem(data, model, tape, dtype)
+    st_ref, pr_ref, _ = oracle_sweep(data, model, tape)
+    dd, dm = _to_dev(data, model, dtype)
+    out = g.resample_model(dd, **dm, draws=tape)
+    assert np.array_equal(_np(out["states"]["z"]), st_ref["z"])
+    for key in ("Ab", "Q", "betas", "pi"):
+        assert rel_err(_np(out["params"][key]), pr_ref[key]) < max(tol, 1e-7), key
+    assert rel_err(_np(out["states"]["x"]), st_ref["x"]) < tol
+
+
 def _compiled_pairs():
     from keypoint_moseq_b200 import _lib
     return sorted(_lib.supported_dims())
@@ -303,7 +323,8 @@ def test_location_scan_long_chains(dtype, tol, frames, seg):
 
 
 @pytest.mark.parametrize("mode", ["chunked", "fallback", "sequential"])
-@pytest.mark.parametrize("shape", [dict(d=4, L=3, K=12, k=5, D=2), dict(d=10, L=3, K=100, k=12, D=2)])
+@pytest.mark.parametrize("shape", [dict(d=4, L=3, K=12, k=5, D=2), dict(d=10, L=3, K=100, k=12, D=2),
+                                   dict(d=4, L=3, K=200, k=5, D=2)])
 def test_discrete_stateseqs_time_chunks(mode, shape, chunking):
     """HMM FFBS on long ragged chains: forward filter in concurrent time chunks (prefix) and
     power-of-pi chunks (padded tail), backward sampling in time chunks that merge with the true path

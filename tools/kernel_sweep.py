@@ -5,8 +5,8 @@ dimension, time-chunked (default) against the sequential recursion (chunks = 1).
 
 One JSON line per (sampler, T, K, d, mode): median ms over `--reps` calls after one warm-up, frames/s and
 the chunk diagnostics.  Inputs are drawn from the generative model (synth.sample_dataset), N chosen so that
-N*T is about `--frames` frames.  num_states > 128 is outside the kernels' template range and is reported
-as unsupported."""
+N*T is about `--frames` frames.  `--new` runs only the rows added in round 2 (num_states 250 / 500 on the wide-state
+kernels, latent_dim 6 / 8 / 12)."""
 import argparse
 import json
 import os
@@ -24,6 +24,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=800_000)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--quick", action="store_true")
+ap.add_argument("--new", action="store_true")
 a = ap.parse_args()
 
 base = dict(T=10_000, K=100, d=10)
@@ -32,6 +33,8 @@ grid += [dict(base, K=K) for K in (25, 50, 128, 500)]
 grid += [dict(base, d=d) for d in (4, 16)]
 if a.quick:
     grid = [dict(base, T=1_000), base, dict(base, K=25), dict(base, d=4)]
+if a.new:
+    grid = [dict(base, K=K) for K in (250, 500)] + [dict(base, d=d) for d in (6, 8, 12)]
 
 
 def timed(fn, reps):
@@ -50,9 +53,6 @@ def timed(fn, reps):
 
 for g in grid:
     T, K, d = g["T"], g["K"], g["d"]
-    if K > 128:
-        print(json.dumps(dict(g, sampler="both", unsupported="num_states > 128 (kernel template range)")), flush=True)
-        continue
     N = max(1, a.frames // T)
     t0 = time.time()
     data, _, model = sample_dataset(recordings=N, frames=T, k=12, D=2, d=d, L=3, K=K, seed=5, seg_length=T,
