@@ -16,7 +16,7 @@ import torch
 from . import _lib, gibbs
 from .dist import gather_rows, shard_rows, shard_tree
 from .io import SnapshotWriter, delete_snapshots_after, extract_results, load_checkpoint, save_hdf5
-from .util import NanGuard, check_for_nans, get_nlags, to_numpy_tree, unbatch
+from .util import AsyncHostCopy, NanGuard, check_for_nans, get_nlags, to_numpy_tree, unbatch
 
 try:  # progress bars are optional
     import tqdm
@@ -106,10 +106,16 @@ def _set_parallel_flag(parallel_message_passing):
     return bool(parallel_message_passing)
 
 
-def _host_model(model):
-    out = to_numpy_tree(model)
-    out["states"]["z"] = np.asarray(out["states"]["z"]).astype(np.int64)
+def _widen_labels(out):
+    """int32 labels of the kernels -> the int64 the reference's checkpoints hold."""
+    states = out.get("states") if isinstance(out, dict) else None
+    if states is not None and "z" in states:
+        states["z"] = np.asarray(states["z"]).astype(np.int64)
     return out
+
+
+def _host_model(model):
+    return _widen_labels(to_numpy_tree(model))
 
 
 class _Shards:
@@ -345,6 +351,11 @@ def _fit_loop(model, data_dev, resample_func, guard, writer, checkpoint_path, st
                     if not _drain_guard(guard, pbar):           # never checkpoint an unchecked sweep
                         model = guard.clean
                         break
+                    if writer is not None and shards.world == 1:
+                        # copy on a side stream into pinned memory; the writer thread waits for it, the sweeps go on
+                        writer.submit(checkpoint_path, AsyncHostCopy(model, _widen_labels).result,
+                                      f"model_snapshots/{iteration}")
+                        continue
                     snapshot = shards.join_model(_host_model(model))      # collective when sharded
                     if writer is not None:
                         writer.submit(checkpoint_path, snapshot, f"model_snapshots/{iteration}")

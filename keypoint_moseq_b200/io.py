@@ -157,8 +157,9 @@ class SnapshotWriter:
     stall of the reference, fitting.py:266-275, becomes visible once a sweep takes tens of milliseconds).
 
     `submit(filepath, tree, datapath)` hands over a HOST tree (the caller has already copied it off the device,
-    so later sweeps cannot touch it) and returns at once; the thread calls `save(filepath, tree, datapath,
-    exist_ok=True)`.  At most `max_pending` snapshots wait in memory (submit blocks beyond that).  `close()`
+    so later sweeps cannot touch it) - or a callable that returns one, e.g. `util.AsyncHostCopy.result`, which waits
+    for a device->host copy that is still in flight on a side stream - and returns at once; the thread calls
+    `save(filepath, tree, datapath, exist_ok=True)`.  At most `max_pending` snapshots wait in memory (submit blocks beyond that).  `close()`
     waits for the queue to drain and raises the first write error; the error also surfaces at every later
     `submit`, and snapshots submitted after it are dropped rather than written after a hole.  Only this thread touches the file while it is open, which is what h5py's threading model asks."""
 
@@ -179,6 +180,8 @@ class SnapshotWriter:
                     return
                 if self._error is None:                      # after a failure later snapshots are dropped, not written
                     filepath, tree, datapath = job
+                    if callable(tree):                       # device->host copy still in flight: wait for it here
+                        tree = tree()
                     self._save(filepath, tree, datapath, exist_ok=True)
             except BaseException as e:  # noqa: BLE001 - handed to the caller's thread
                 self._error = e

@@ -113,6 +113,98 @@ def to_numpy_tree(tree):
     return tree
 
 
+class AsyncHostCopy:
+    """Device -> host copy of a tree of tensors that does not stall the sweeps (the reference's
+    blocking `device_get` before every checkpoint write is keypoint_moseq/fitting.py:266-275).
+
+    `AsyncHostCopy(tree)` enqueues, on a side stream that first waits for the work queued so far on the current
+    stream, one non-blocking copy per CUDA leaf into pinned host memory and records an event; the caller's stream
+    is never blocked and the host thread returns at once.  `result()` - typically called on the snapshot writer's
+    thread - waits for that event and returns the tree as NumPy arrays (copies, so the pinned buffers go back to
+    the pool).  The device tensors are kept alive and marked in use on the side stream until then; sweeps return
+    fresh tensors and never write into a state that was handed out, so the copy reads a consistent snapshot.
+    Host leaves pass through unchanged."""
+
+    _pool = {}          # (shape, dtype) -> [free pinned tensors]
+    _streams = {}
+
+    def __init__(self, tree, postprocess=None):
+        self._post = postprocess
+        self._pairs = []            # (pinned host tensor, device tensor kept alive)
+        dev = self._first_device(tree)
+        self._event = None
+        if dev is None:
+            self._tree = tree
+            return
+        side = self._streams.get(dev)
+        if side is None:
+            side = self._streams[dev] = torch.cuda.Stream(device=dev)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            self._tree = self._enqueue(tree, side)
+            self._event = torch.cuda.Event()
+            self._event.record(side)
+
+    @classmethod
+    def _first_device(cls, node):
+        if isinstance(node, torch.Tensor):
+            return node.device if node.is_cuda else None
+        if isinstance(node, dict):
+            node = list(node.values())
+        if isinstance(node, (list, tuple)):
+            for v in node:
+                d = cls._first_device(v)
+                if d is not None:
+                    return d
+        return None
+
+    def _enqueue(self, node, side):
+        if isinstance(node, torch.Tensor):
+            if not node.is_cuda:
+                return node
+            key = (tuple(node.shape), node.dtype)
+            free = self._pool.setdefault(key, [])
+            host = free.pop() if free else torch.empty(node.shape, dtype=node.dtype, pin_memory=True)
+            src = node.detach()
+            host.copy_(src, non_blocking=True)
+            src.record_stream(side)
+            self._pairs.append((key, host, src))
+            return host
+        if isinstance(node, dict):
+            return {k: self._enqueue(v, side) for k, v in node.items()}
+        if isinstance(node, (list, tuple)):
+            return type(node)(self._enqueue(v, side) for v in node)
+        return node
+
+    def result(self):
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = None
+        if self._pairs:
+            pinned = {id(h) for _, h, _ in self._pairs}
+
+            def settle(node):
+                if isinstance(node, torch.Tensor):
+                    arr = node.numpy()
+                    return arr.copy() if id(node) in pinned else arr
+                if isinstance(node, dict):
+                    return {k: settle(v) for k, v in node.items()}
+                if isinstance(node, (list, tuple)):
+                    return type(node)(settle(v) for v in node)
+                return node
+
+            self._tree = settle(self._tree)
+            for key, host, _ in self._pairs:
+                self._pool[key].append(host)
+            self._pairs = []
+        else:
+            self._tree = to_numpy_tree(self._tree)
+        out = self._tree
+        return self._post(out) if self._post is not None else out
+
+
 def check_for_nans(model):
     """(any_nans, nan_info, messages) over the leaves of a model dict (fitting.py:30).
 

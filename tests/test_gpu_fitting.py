@@ -39,6 +39,30 @@ def test_fit_model_checkpoints_and_resume(tmp_path):
     assert not np.array_equal(ck2["model_snapshots"]["5"]["states"]["x"], model["states"]["x"])
 
 
+def test_async_checkpoints_write_the_same_snapshots(tmp_path):
+    """async_checkpoints=True copies each snapshot to pinned memory on a side stream while the next sweeps are
+    already queued (util.AsyncHostCopy) and writes it on a background thread: every snapshot must equal the one
+    the synchronous path writes (the reference's blocking save, keypoint_moseq/fitting.py:266-275), i.e. later
+    sweeps must not leak into an earlier snapshot."""
+    from keypoint_moseq_b200 import fitting, io as kio
+    data, meta, model = small_problem(seed=14, d=4, L=3, K=12, k=5, D=2, kappa=1e2, frames=1200, seg_length=600)
+    proj = str(tmp_path)
+    for name, flag in (("sync", False), ("async", True)):
+        fitting.fit_model(model, data, meta, proj, name, num_iters=7, save_every_n_iters=1, dtype=torch.float32,
+                          async_checkpoints=flag)
+    a = kio.load_hdf5(os.path.join(proj, "sync", "checkpoint.h5"))["model_snapshots"]
+    b = kio.load_hdf5(os.path.join(proj, "async", "checkpoint.h5"))["model_snapshots"]
+    assert sorted(a, key=int) == sorted(b, key=int) == [str(i) for i in range(8)]
+    for it in a:
+        for key in ("x", "v", "h", "s", "z"):
+            np.testing.assert_array_equal(a[it]["states"][key], b[it]["states"][key], err_msg=f"{it}/{key}")
+            assert a[it]["states"][key].dtype == b[it]["states"][key].dtype
+        for key in ("Ab", "Q", "pi", "betas"):
+            np.testing.assert_array_equal(a[it]["params"][key], b[it]["params"][key], err_msg=f"{it}/{key}")
+        np.testing.assert_array_equal(a[it]["seed"], b[it]["seed"])
+    assert not np.array_equal(a["3"]["states"]["x"], a["4"]["states"]["x"])
+
+
 def test_fit_model_is_deterministic_and_float32_runs(tmp_path):
     from keypoint_moseq_b200 import fitting
     data, meta, model = small_problem(seed=12, d=4, L=3, K=12, k=5, D=2, kappa=1e2)
