@@ -594,10 +594,11 @@ kalman_forward_rows_kernel(const R* __restrict__ info, const int* __restrict__ m
     R* sm_g = stash_m + (size_t)nn * Tx * SMS;
     R* sS_g = stash_S + (size_t)nn * Tx * SSS;
     const R eps = (R)KPMS_EPS_SHIFT + jitter;
-    // entries of B (lower, packed by rows) computed by this lane
-    int ba[2], bc[2];
+    // entries of B (lower, packed by rows) computed by this lane: NQ = ceil(d(d+1)/2 / 32) per lane
+    constexpr int NQ = (NP + 31) / 32;
+    int ba[NQ], bc[NQ];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < NQ; ++q) {
         int a = 0, c = 0;
         const int idx = lane + 32 * q;
         if (idx < NP) tri_unpack(idx, a, c);
@@ -681,7 +682,7 @@ kalman_forward_rows_kernel(const R* __restrict__ info, const int* __restrict__ m
             __syncwarp();
             // ---- B = I + Lj' U[new,:] (lower) and nu = y~ - Lj' m_new, spread over the lanes
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < NQ; ++q) {
                 const int a = ba[q], c = bc[q];
                 R acc = (a == c) ? (R)1 : (R)0;
 #pragma unroll
@@ -1218,9 +1219,13 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
           backprep_ops_kernel<R, D_, L_><<<K, 128, 0, st>>>(Ab, Q, (R)jitter, ops); }
         { KPMS_LAUNCH("kalman_backprep_special", st);
           backprep_special_kernel<R, D_, L_, (n > 32)><<<N, 128, 0, st>>>(stash_m, stash_S, mask, w_tape, N, T, GH); }
-        constexpr int FIT4 = (int)((220 * 1024) / (4 * PS::FPW * PS::frame_bytes + 64));
-        constexpr int MINB = sizeof(R) == 8 ? 1 : (FIT4 >= 3 ? 3 : (FIT4 >= 1 ? FIT4 : 1));
-        static_assert(FIT4 >= 1, "one CTA of the two-stage backward preparation must fit in shared memory");
+        // warps x CTAs per SM: 12 warps per SM as 6 x 2 when shared memory allows (one barrier per tile keeps the
+        // six warps of a CTA on the same instruction-cache lines), else the largest CTA that fits
+        constexpr size_t per_warp = PS::FPW * PS::frame_bytes + 16;
+        constexpr int FITW = (int)((220 * 1024) / per_warp);                 // warps per SM by shared memory
+        static_assert(FITW >= 1, "one warp of the two-stage backward preparation must fit in shared memory");
+        constexpr int WARPS = FITW >= 12 ? 6 : (FITW >= 6 ? (FITW / 2 < 6 ? FITW / 2 : 6) : FITW);
+        constexpr int MINB = sizeof(R) == 8 ? 1 : (FITW / WARPS >= 2 ? 2 : 1);
         auto launch = [&](auto kern, int warps, int minb) {
             const size_t smem = (size_t)warps * PS::FPW * PS::frame_bytes + warps * 2 * sizeof(uint64_t);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1231,14 +1236,14 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         };
         bool done = false;
         if constexpr (sizeof(R) == 4 && D_ == 10 && L_ == 3) {
-            // instruction-cache experiment (KPMS_BP_CFG): warps x CTAs per SM, "s" = one CTA barrier per tile
+            // instruction-cache experiment (KPMS_BP_CFG): barriers per tile
             static const std::string cfg = [] { const char* e = getenv("KPMS_BP_CFG"); return std::string(e ? e : ""); }();
-            if (cfg == "4x3s") { launch(kalman_backprep_split_kernel<R, D_, L_, 4, 3, true>, 4, 3); done = true; }
-            else if (cfg == "6x2s") { launch(kalman_backprep_split_kernel<R, D_, L_, 6, 2, true>, 6, 2); done = true; }
-            else if (cfg == "12x1s") { launch(kalman_backprep_split_kernel<R, D_, L_, 12, 1, true>, 12, 1); done = true; }
-            else if (cfg == "12x1") { launch(kalman_backprep_split_kernel<R, D_, L_, 12, 1, false>, 12, 1); done = true; }
+            if (cfg == "6x2s2") { launch(kalman_backprep_split_kernel<R, D_, L_, 6, 2, 2>, 6, 2); done = true; }
+            else if (cfg == "6x2s3") { launch(kalman_backprep_split_kernel<R, D_, L_, 6, 2, 3>, 6, 2); done = true; }
+            else if (cfg == "4x3") { launch(kalman_backprep_split_kernel<R, D_, L_, 4, 3, 0>, 4, 3); done = true; }
+            else if (cfg == "5x2s") { launch(kalman_backprep_split_kernel<R, D_, L_, 5, 2, 1>, 5, 2); done = true; }   // 204 registers
         }
-        if (!done) launch(kalman_backprep_split_kernel<R, D_, L_, 4, MINB>, 4, MINB);
+        if (!done) launch(kalman_backprep_split_kernel<R, D_, L_, WARPS, MINB, 1>, WARPS, MINB);
         int rc = check_launch("kalman backprep (two-stage)");
         if (rc) return rc;
     } else {

@@ -175,7 +175,7 @@ backprep_special_kernel(const R* __restrict__ stash_m, const R* __restrict__ sta
     }
 }
 
-template <typename R, int D_, int L_, int WARPS, int MINB, bool LOCKSTEP = false>
+template <typename R, int D_, int L_, int WARPS, int MINB, int LOCKSTEP = 1>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict__ stash_S, const int* __restrict__ mask,
                              const int* __restrict__ z, const R* __restrict__ ops, R eps1, const R* __restrict__ wbuf,
@@ -279,9 +279,12 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
     // as phase G has consumed it, covariance and mean once the V2 rows are consumed (before the Cholesky of Sigma).
     // The words that describe the next frame (mask, state label, normals) are loaded here and first used there.
     for (; cbase < uframes; cbase += ustride, buf ^= 1) {
-        // LOCKSTEP: the unrolled body is ~150 KB of code; warps of a CTA that start every tile together walk the same
-        // instruction-cache lines (the trip count is uniform over the CTA: cbase does not depend on the warp)
-        if (LOCKSTEP) __syncthreads();
+        // LOCKSTEP: the unrolled body is ~150 KB of code, more than the instruction cache holds; warps of a CTA that
+        // start every tile together walk the same cache lines (measured at C2: 5.47 ms without, 4.57 ms with one
+        // barrier per tile, ncu `no_instruction` stall 2.3 -> see profiles/).  The trip count is uniform over the CTA
+        // (cbase does not depend on the warp); LOCKSTEP = 2, 3 add barriers after phases E and J, matched by the
+        // same number in the branch of a warp without regular frames.
+        if (LOCKSTEP >= 1) __syncthreads();
         unsigned gN;
         int iN, mkN, ziN;
         peek(cbase + ustride, gN, iN, mkN, ziN);
@@ -299,6 +302,8 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
             onmaskN = __ballot_sync(FULL, onN && live && gl == 0);
             request_A(ziN, onN, onmaskN);
             request_S(gN, onN, onmaskN, buf ^ 1);
+            if (LOCKSTEP >= 2) __syncthreads();
+            if (LOCKSTEP >= 3) __syncthreads();
         } else {
         const R* mv = mvb + buf * P::SMS;
         const R* wv = wvb + buf * NP;
@@ -467,6 +472,7 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
             }
         }
         __syncwarp();
+        if (LOCKSTEP >= 2) __syncthreads();
 
         // ---- phase G: B2 row gl = Q'[gl] + sum_r W[gl][r] A'[r];  t[gl] = (A m + b)[gl] - (Wc' m_c)[gl]
         R b2[D_];
@@ -645,6 +651,7 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
             }
         }
 
+        if (LOCKSTEP >= 3) __syncthreads();
 #pragma unroll
         for (int s = 0; s < LA; ++s) {                // u1 = F m_c for the owned c rows (F still unscaled)
             R acc = 0;

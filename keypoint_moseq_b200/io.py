@@ -88,13 +88,20 @@ def _unflatten(prefix, leaves, types):
     return vals if kind == "list" else tuple(vals)
 
 
-def _npz_read(filepath):
-    with zipfile.ZipFile(filepath) as zf:
-        names = zf.namelist()
+def _is_types_key(key):
+    return key == _TYPES_KEY or key.startswith(_TYPES_KEY + "#")
+
+
+def _npz_read(filepath, only=None):
+    """Leaves and group types of an archive; `only` = datapath prefix to load (the rest is not decompressed).
+    Group types live in one member per write (`__types__`, `__types__#1`, ...), merged in write order."""
     with np.load(filepath, allow_pickle=False) as f:
-        leaves = {k: f[k] for k in f.files if k != _TYPES_KEY}
-        types = json.loads(str(f[_TYPES_KEY])) if _TYPES_KEY in f.files else {}
-    del names
+        tkeys = sorted((k for k in f.files if _is_types_key(k)), key=lambda k: int(k.partition("#")[2] or 0))
+        types = {}
+        for k in tkeys:
+            types.update(json.loads(str(f[k])))
+        want = (lambda k: True) if only is None else (lambda k: k == only or k.startswith(only + "/"))
+        leaves = {k: f[k] for k in f.files if not _is_types_key(k) and want(k)}
     return leaves, types
 
 
@@ -103,6 +110,24 @@ def _npz_write(filepath, leaves, types):
     with open(tmp, "wb") as fh:
         np.savez(fh, **{_TYPES_KEY: np.asarray(json.dumps(types))}, **leaves)
     os.replace(tmp, filepath)
+
+
+def _npz_names(filepath):
+    """Member names (without .npy) from the central directory alone: no array is read."""
+    with zipfile.ZipFile(filepath) as zf:
+        return [n[:-4] if n.endswith(".npy") else n for n in zf.namelist()]
+
+
+def _npz_append(filepath, leaves, types, names):
+    """Add new members to an existing archive without rewriting what is there: a snapshot costs its own size,
+    not the size of the checkpoint (which holds the data and every earlier snapshot)."""
+    serial = 1 + max([int(n.partition("#")[2] or 0) for n in names if _is_types_key(n)], default=0)
+    with zipfile.ZipFile(filepath, "a", zipfile.ZIP_STORED, allowZip64=True) as zf:
+        members = dict(leaves)
+        members[f"{_TYPES_KEY}#{serial}"] = np.asarray(json.dumps(types))
+        for name, arr in members.items():
+            with zf.open(name + ".npy", "w", force_zip64=True) as fh:
+                np.lib.format.write_array(fh, np.asanyarray(arr), allow_pickle=False)
 
 
 def save_hdf5(filepath, save_dict, datapath=None, exist_ok=False, overwrite=False):
@@ -134,6 +159,21 @@ def save_hdf5(filepath, save_dict, datapath=None, exist_ok=False, overwrite=Fals
                     f.create_dataset(name, data=arr)
         return
     _notice()
+    # parents of a datapath are dict groups
+    for root in roots:
+        parts = root.split("/")
+        for i in range(1, len(parts)):
+            types.setdefault("/".join(parts[:i]), "dict")
+    if os.path.exists(filepath):
+        names = _npz_names(filepath)
+        clash = any(k == root or k.startswith(root + "/") for root in roots for k in names)
+        if not clash:                                        # the usual snapshot: append, nothing is rewritten
+            known = _npz_read(filepath, only="\0")[1]        # group types only
+            assert not (not overwrite and any(root in known for root in roots)), (
+                f"{roots} already exists in {filepath}. Set overwrite to True to overwrite data in an existing file.")
+            if not any(root in known for root in roots):
+                _npz_append(filepath, leaves, types, names)
+                return
     old_leaves, old_types = _npz_read(filepath) if os.path.exists(filepath) else ({}, {})
     for root in roots:
         exists = any(k == root or k.startswith(root + "/") for k in list(old_leaves) + list(old_types))
@@ -142,11 +182,6 @@ def save_hdf5(filepath, save_dict, datapath=None, exist_ok=False, overwrite=Fals
         for store in (old_leaves, old_types):
             for k in [k for k in store if k == root or k.startswith(root + "/")]:
                 del store[k]
-    # parents of a datapath are dict groups
-    for root in roots:
-        parts = root.split("/")
-        for i in range(1, len(parts)):
-            old_types.setdefault("/".join(parts[:i]), "dict")
     old_leaves.update(leaves)
     old_types.update(types)
     _npz_write(filepath, old_leaves, old_types)
@@ -245,7 +280,7 @@ def load_hdf5(filepath, datapath=None):
             if datapath is None:
                 return {k: _h5_load(f[k]) for k in f}
             return _h5_load(f[datapath])
-    leaves, types = _npz_read(filepath)
+    leaves, types = _npz_read(filepath, only=None if datapath is None else datapath.strip("/"))
     if datapath is not None:
         return _unflatten(datapath.strip("/"), leaves, types)
     roots = []

@@ -575,3 +575,40 @@ def test_batch_unbatch_and_sharding_properties_hold_for_ragged_cohorts():
         np.testing.assert_array_equal(joined, stack)
 
     check()
+
+
+def test_npz_checkpoint_snapshots_are_appended_not_rewritten(tmp_path, monkeypatch):
+    """Without h5py the checkpoint is a NumPy zip archive with the same group layout: a new snapshot is appended
+    as new members (cost = its own size, as with h5py's append mode, keypoint_moseq/io.py:1297-1329), collisions
+    are refused unless `overwrite`, deletes / overwrites fall back to a rewrite, and readers see one tree."""
+    from keypoint_moseq_b200 import io as kio
+    monkeypatch.setattr(kio, "HAVE_H5PY", False)
+    f = str(tmp_path / "checkpoint.h5")
+    snap = lambda it: {"states": {"x": np.full((3, 5, 2), float(it)), "z": np.arange(6).reshape(3, 2) + it},
+                       "params": {"pi": np.eye(2) * it}, "seed": np.array([1, it], np.uint32), "empty": {}}
+    kio.save_hdf5(f, {"model_snapshots": {"0": snap(0)}, "data": {"Y": np.ones((3, 5, 4, 2))},
+                      "metadata": (np.array(["a", "b"]), np.array([[0, 1], [2, 3]]))})
+    rewrites = []
+    real_write = kio._npz_write
+    monkeypatch.setattr(kio, "_npz_write", lambda *a, **k: (rewrites.append(1), real_write(*a, **k))[1])
+    for it in (5, 10):
+        kio.save_hdf5(f, snap(it), f"model_snapshots/{it}", exist_ok=True)
+    assert rewrites == []                                        # appended
+    ck = kio.load_hdf5(f)
+    assert sorted(ck["model_snapshots"], key=int) == ["0", "5", "10"]
+    assert isinstance(ck["metadata"], tuple) and list(ck["metadata"][0]) == ["a", "b"]
+    for it in (0, 5, 10):
+        got = kio.load_hdf5(f, f"model_snapshots/{it}")
+        assert got["empty"] == {} and got["seed"].dtype == np.uint32
+        np.testing.assert_array_equal(got["states"]["x"], snap(it)["states"]["x"])
+        np.testing.assert_array_equal(got["params"]["pi"], np.eye(2) * it)
+        np.testing.assert_array_equal(ck["model_snapshots"][str(it)]["states"]["z"], snap(it)["states"]["z"])
+    with pytest.raises(AssertionError, match="already exists"):
+        kio.save_hdf5(f, snap(11), "model_snapshots/10", exist_ok=True)
+    kio.save_hdf5(f, snap(11), "model_snapshots/10", exist_ok=True, overwrite=True)     # rewrite path
+    assert rewrites == [1]
+    np.testing.assert_array_equal(kio.load_hdf5(f, "model_snapshots/10")["params"]["pi"], np.eye(2) * 11)
+    kio.delete_snapshots_after(f, 5)
+    assert sorted(kio.load_hdf5(f)["model_snapshots"], key=int) == ["0", "5"]
+    kio.save_hdf5(f, snap(7), "model_snapshots/7", exist_ok=True)
+    assert sorted(kio.load_hdf5(f)["model_snapshots"], key=int) == ["0", "5", "7"]
