@@ -43,30 +43,44 @@ __host__ __device__ constexpr int info_stride(int d) { return (d * (d + 1) / 2 +
 // ---------------------------------------------------------------------------
 // K1a: per-frame observation information
 // ---------------------------------------------------------------------------
-template <typename R, int D_, int DK>
-__global__ void __launch_bounds__(128)
+// One thread per frame; the records (REC numbers per frame) are staged in shared memory with an odd stride and leave
+// the CTA as one contiguous, coalesced block: a thread writing its own 300-byte record word by word costs one
+// 32-byte sector transaction per word (measured: 0.38 ms at C2 for 244 MB of records).
+template <int D_>
+struct ObsInfoCfg {
+    static constexpr int REC = info_stride(D_), RS = REC | 1;          // padded record stride (odd: conflict-free)
+    template <typename R>
+    static constexpr int threads() { return (size_t)128 * RS * sizeof(R) <= 100 * 1024 ? 128 : 64; }
+};
+
+template <typename R, int D_, int DK, int TPB>
+__global__ void __launch_bounds__(TPB)
 obs_info_kernel(const R* __restrict__ Y, const int* __restrict__ mask, const R* __restrict__ v,
                 const R* __restrict__ h, const R* __restrict__ s, const R* __restrict__ sigmasq,
                 const R* __restrict__ Ct, int N, int T, int k, int L, R* __restrict__ info) {
-    constexpr int NP = D_ * (D_ + 1) / 2, REC = info_stride(D_);
+    constexpr int NP = D_ * (D_ + 1) / 2, REC = info_stride(D_), RS = ObsInfoCfg<D_>::RS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    R* Cs = reinterpret_cast<R*>(smem_raw);            // (k*DK) x (D_+1)
+    R* recs = reinterpret_cast<R*>(smem_raw);          // TPB x RS
+    R* Cs = recs + (size_t)TPB * RS;                   // (k*DK) x (D_+1)
     R* sg = Cs + (size_t)k * DK * (D_ + 1);            // k
-    for (int i = threadIdx.x; i < k * DK * (D_ + 1); i += blockDim.x) Cs[i] = Ct[i];
-    for (int i = threadIdx.x; i < k; i += blockDim.x) sg[i] = sigmasq[i];
+    for (int i = threadIdx.x; i < k * DK * (D_ + 1); i += TPB) Cs[i] = Ct[i];
+    for (int i = threadIdx.x; i < k; i += TPB) sg[i] = sigmasq[i];
     __syncthreads();
     const int Tx = T - L + 1;
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)N * Tx) return;
-    const int nn = (int)(g / Tx), i = (int)(g % Tx);
-    const int t = i + L - 1;
-    const size_t ft = (size_t)nn * T + t;
-    R* out = info + (size_t)g * REC;
-    if (mask[ft] == 0) {
+    const long long total = (long long)N * Tx, base = (long long)blockIdx.x * TPB;
+    const long long g = base + threadIdx.x;
+    R* out = recs + (size_t)threadIdx.x * RS;
+    bool on = false;
+    size_t ft = 0;
+    if (g < total) {
+        const int nn = (int)(g / Tx), i = (int)(g % Tx);
+        ft = (size_t)nn * T + (i + L - 1);
+        on = mask[ft] != 0;
+    }
+    if (!on) {
 #pragma unroll 1
         for (int q = 0; q < REC; ++q) out[q] = (R)0;
-        return;
-    }
+    } else {
     R J[NP], r[D_];
 #pragma unroll
     for (int q = 0; q < NP; ++q) J[q] = (R)0;
@@ -133,6 +147,14 @@ obs_info_kernel(const R* __restrict__ Y, const int* __restrict__ mask, const R* 
         r[c] = val * invp[c];
         out[NP + D_ + c] = r[c];
     }
+#pragma unroll
+    for (int q = NP + 2 * D_; q < REC; ++q) out[q] = (R)0;      // padding of the record
+    }
+    __syncthreads();
+    // the CTA's records are contiguous in global memory
+    const int count = (int)min((long long)TPB, total - base) * REC;
+    R* dst = info + (size_t)base * REC;
+    for (int w = threadIdx.x; w < count; w += TPB) dst[w] = recs[(w / REC) * RS + (w % REC)];
 }
 
 // ---------------------------------------------------------------------------
@@ -1149,13 +1171,20 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         }
     }
     if (stage != 2) {
-        size_t smem = ((size_t)k * Dk * (D_ + 1) + k) * sizeof(R);
-        int blocks = (int)((frames + 127) / 128);
+        constexpr int TPB = ObsInfoCfg<D_>::template threads<R>();
+        size_t smem = ((size_t)TPB * ObsInfoCfg<D_>::RS + (size_t)k * Dk * (D_ + 1) + k) * sizeof(R);
+        if (smem > 220 * 1024) return set_error(-3, "kalman_sample: %d keypoints exceed the shared-memory staging of the observation records", k);
+        int blocks = (int)((frames + TPB - 1) / TPB);
         KPMS_LAUNCH("kalman_obs_info", st);
-        if (Dk == 2)
-            obs_info_kernel<R, D_, 2><<<blocks, 128, smem, st>>>(Y, mask, v, h, s, sigmasq, Ct, N, T, k, L_, info);
-        else
-            obs_info_kernel<R, D_, 3><<<blocks, 128, smem, st>>>(Y, mask, v, h, s, sigmasq, Ct, N, T, k, L_, info);
+        if (Dk == 2) {
+            auto kern = obs_info_kernel<R, D_, 2, TPB>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<blocks, TPB, smem, st>>>(Y, mask, v, h, s, sigmasq, Ct, N, T, k, L_, info);
+        } else {
+            auto kern = obs_info_kernel<R, D_, 3, TPB>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<blocks, TPB, smem, st>>>(Y, mask, v, h, s, sigmasq, Ct, N, T, k, L_, info);
+        }
         int rc = check_launch("kalman obs_info");
         if (rc) return rc;
     }
@@ -1236,12 +1265,10 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         };
         bool done = false;
         if constexpr (sizeof(R) == 4 && D_ == 10 && L_ == 3) {
-            // instruction-cache experiment (KPMS_BP_CFG): barriers per tile
+            // A/B switch: KPMS_BP_CFG=4x3 is the round-2 layout without the barrier (5.47 ms at C2 against 4.56 ms; two
+            // or three barriers per tile: 4.66 / 4.64 ms; 5 warps x 2 CTAs with 204 registers: 5.23 ms)
             static const std::string cfg = [] { const char* e = getenv("KPMS_BP_CFG"); return std::string(e ? e : ""); }();
-            if (cfg == "6x2s2") { launch(kalman_backprep_split_kernel<R, D_, L_, 6, 2, 2>, 6, 2); done = true; }
-            else if (cfg == "6x2s3") { launch(kalman_backprep_split_kernel<R, D_, L_, 6, 2, 3>, 6, 2); done = true; }
-            else if (cfg == "4x3") { launch(kalman_backprep_split_kernel<R, D_, L_, 4, 3, 0>, 4, 3); done = true; }
-            else if (cfg == "5x2s") { launch(kalman_backprep_split_kernel<R, D_, L_, 5, 2, 1>, 5, 2); done = true; }   // 204 registers
+            if (cfg == "4x3") { launch(kalman_backprep_split_kernel<R, D_, L_, 4, 3, 0>, 4, 3); done = true; }
         }
         if (!done) launch(kalman_backprep_split_kernel<R, D_, L_, WARPS, MINB, 1>, WARPS, MINB);
         int rc = check_launch("kalman backprep (two-stage)");

@@ -277,9 +277,11 @@ def fit_model(model, data, metadata, project_dir=None, model_name=None, num_iter
 
     Extra keyword arguments understood here: `dtype` (torch.float32 / torch.float64 for the states and
     the continuous-path kernels, default float64 like the reference's x64 mode), `hmm_dtype`, `group`,
-    `nan_check_lag`, and `async_checkpoints` (default False: snapshots are written before the next sweep is
-    launched, as in the reference; True: the snapshot is copied to the host and written by `io.SnapshotWriter`
-    on a background thread while the next sweeps run - all writes have finished when fit_model returns).
+    `nan_check_lag`, and `async_checkpoints` (default True: the snapshot is copied to pinned host memory on a
+    side stream, `util.AsyncHostCopy`, and written by `io.SnapshotWriter` on a background thread while the next
+    sweeps run - all writes have finished, and any write error has been raised, when fit_model returns; measured at
+    C2: 87 ms per snapshot against 159 ms; False: snapshots are written before the next sweep is launched, as in
+    the reference).
     With `group` (a torch.distributed process group, one rank per GPU) every rank passes the same full data and
     model; rows are sharded inside, rank 0 writes the gathered snapshots and every rank returns the whole model
     (see `_Shards`).
@@ -321,7 +323,7 @@ def fit_model(model, data, metadata, project_dir=None, model_name=None, num_iter
     # returned after a NaN is the last one that was checked clean, as in fitting.py:30-44, :263-264
     guard = NanGuard(lag=int(kwargs.pop("nan_check_lag", NAN_CHECK_LAG)), group=shards.group if shards.world > 1 else None)
     guard.clean = model
-    use_writer = kwargs.pop("async_checkpoints", False) and checkpoint_path and shards.writes
+    use_writer = kwargs.pop("async_checkpoints", True) and checkpoint_path and shards.writes
     writer = SnapshotWriter(save=save_hdf5) if use_writer else None
     try:
         model = _fit_loop(model, data_dev, resample_func, guard, writer, checkpoint_path, start_iter, num_iters,
