@@ -138,6 +138,35 @@ def test_scales_heading_location(dtype, tol, D):
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_scales_philox_draws_have_the_posterior_moments(dtype):
+    """Production mode (no tape): s = variance / (2 G), G ~ Gamma((nu_s + D)/2, 1) drawn from Philox words (float32
+    states: float32 Box-Muller proposal, acceptance in double with the Marsaglia-Tsang squeeze).  With x = 0,
+    v = 0 and Y = 0 the residual vanishes and variance = nu_s * prior, so G = nu_s * prior / (2 s) is observable:
+    its first three moments over 1.2 M draws must match alpha, alpha (alpha + 1), alpha (alpha + 1)(alpha + 2)."""
+    g = _gibbs()
+    N, T, k, D, d, nu_s = 4, 50_000, 6, 2, 4, 5.0
+    dev = "cuda"
+    Y = torch.zeros((N, T, k, D), dtype=dtype, device=dev)
+    x = torch.zeros((N, T, d), dtype=dtype, device=dev)
+    v = torch.zeros((N, T, D), dtype=dtype, device=dev)
+    h = torch.zeros((N, T), dtype=dtype, device=dev)
+    prior = torch.full((N, T, k), 0.7, dtype=dtype, device=dev)
+    Cd = torch.zeros(((k - 1) * D, d + 1), dtype=torch.float64, device=dev)
+    sig = torch.ones(k, dtype=torch.float64, device=dev)
+    s = g.resample_scales(Y, x, v, h, Cd, sig, nu_s, prior, seed64=1234)
+    s2 = g.resample_scales(Y, x, v, h, Cd, sig, nu_s, prior, seed64=1234)
+    assert torch.equal(s, s2)
+    G = (nu_s * 0.7 / (2.0 * s.double())).flatten().cpu().numpy()
+    alpha, n = 0.5 * (nu_s + D), G.size
+    m1, m2, m3 = alpha, alpha * (alpha + 1), alpha * (alpha + 1) * (alpha + 2)
+    raw = lambda p: np.prod([alpha + i for i in range(p)])               # E[G^p]
+    for p, want in ((1, m1), (2, m2), (3, m3)):
+        sd = np.sqrt((raw(2 * p) - want ** 2) / n)
+        assert abs((G ** p).mean() - want) < 5 * sd, (p, (G ** p).mean(), want, sd)
+    assert G.min() > 0 and np.isfinite(G).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("shape", [dict(d=4, L=3, K=12, k=5, D=2), dict(d=10, L=3, K=100, k=12, D=2)])
 def test_sufficient_statistics_and_param_draws(dtype, shape):
     g = _gibbs()
