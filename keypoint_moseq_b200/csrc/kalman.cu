@@ -37,6 +37,9 @@ __host__ __device__ constexpr int stash_m_stride(int n) { return (n + 3) / 4 * 4
 __host__ __device__ constexpr int stash_S_stride(int n) { return (n * (n + 1) / 2 + 3) / 4 * 4; }
 // offset of column c in a lower triangle packed by columns (column c holds rows c..n-1)
 __host__ __device__ constexpr int col_start(int n, int c) { return c * n - c * (c - 1) / 2; }
+// packing of the filter's covariance record: by columns from the row-per-lane filters, by rows from the shared-memory one
+template <typename R, int n>
+constexpr bool stash_rowpack() { return n > 32 && !(sizeof(R) == 4 && n <= 64); }
 // per-frame observation record: [Lj packed lower (d(d+1)/2) | r (d) | Lj^-1 r (d) | pad]
 __host__ __device__ constexpr int info_stride(int d) { return (d * (d + 1) / 2 + 2 * d + 3) / 4 * 4; }
 
@@ -978,6 +981,7 @@ struct PrepSmem {
 
 #include "kalman_rows2.cuh"
 #include "kalman_split.cuh"
+#include "kalman_rows_wide.cuh"
 
 // ---------------------------------------------------------------------------
 // K1d: serial affine recursion, one warp per chain, operands streamed through a
@@ -1129,8 +1133,11 @@ static void kalman_ws_layout(int N, int T, int d, int L, int K, int C, int Cb, s
 }
 
 // chunks per chain for the Kalman recursions: enough chunk-CTAs to fill the device once
-static int kalman_chunks(int N, int T, int d, int L, bool backward) {
-    return chunks_for(N, KPMS_SM_COUNT * (backward ? 12 : (d * L <= 32 ? 16 : 3)), T - L + 1, chunk_config().warmup);
+// float32 filters: 16 chunk-warps per SM (n <= 32), 4 two-warp teams per SM (n <= 64); shared-memory filter: 3 CTAs
+static int kalman_chunks(int N, int T, int d, int L, bool backward, bool f32) {
+    const int n = d * L;
+    const int fwd = n <= 32 ? 16 : ((f32 && n <= 64) ? 4 : 3);
+    return chunks_for(N, KPMS_SM_COUNT * (backward ? 12 : fwd), T - L + 1, chunk_config().warmup);
 }
 
 template <typename R, int D_, int L_>
@@ -1143,7 +1150,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
     constexpr int n = D_ * L_;
     const int Tx = T - L_ + 1;
     const ChunkConfig cfg = chunk_config();
-    const int C = kalman_chunks(N, T, D_, L_, false), Cb = kalman_chunks(N, T, D_, L_, true), W = cfg.warmup;
+    const int C = kalman_chunks(N, T, D_, L_, false, sizeof(R) == 4), Cb = kalman_chunks(N, T, D_, L_, true, sizeof(R) == 4), W = cfg.warmup;
     const R tol = (R)(sizeof(R) == 4 ? cfg.tol32 : cfg.tol64);
     size_t off[KW_END + 1];
     kalman_ws_layout<R>(N, T, D_, L_, K, C, Cb, off);
@@ -1211,6 +1218,29 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         }
         int rc = check_launch("kalman forward");
         if (rc) return rc;
+    } else if constexpr (n <= 64 && sizeof(R) == 4) {
+        // two warps per (chain, chunk), one covariance row per lane (kalman_rows_wide.cuh)
+        constexpr int TEAMS = 4;
+        auto kern = kalman_forward_rows2w_kernel<R, D_, L_, TEAMS>;
+        size_t smem = FwdRows2wSmem<R, D_, L_>::per_team * TEAMS * sizeof(R);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (C > 1) {
+            { KPMS_LAUNCH("kalman_forward", st);
+              kern<<<(int)(((long long)N * C + TEAMS - 1) / TEAMS), 64 * TEAMS, smem, st>>>(
+                  info, mask, z, Ab, Q, (R)jitter, N, T, stash_m, stash_S, C, W, vlen, nullptr, bfw, bfe); }
+            { KPMS_LAUNCH("kalman_forward_check", st);
+              cudaMemsetAsync(dirty_f, 0, (size_t)N * sizeof(int), st);
+              boundary_check_kernel<R><<<dim3(C - 1, N), 128, 0, st>>>(bfw, bfe, vlen, Tx, C, W, 1, n, n + n * n, tol, dirty_f, diag); }
+            { KPMS_LAUNCH("kalman_forward_rerun", st);       // exits at once for chains whose boundaries agree
+              kern<<<(N + TEAMS - 1) / TEAMS, 64 * TEAMS, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, N, T, stash_m,
+                                                                    stash_S, 1, 0, nullptr, dirty_f, bfw, bfe); }
+        } else {
+            KPMS_LAUNCH("kalman_forward", st);
+            kern<<<(N + TEAMS - 1) / TEAMS, 64 * TEAMS, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, N, T, stash_m,
+                                                                  stash_S, 1, 0, nullptr, nullptr, bfw, bfe);
+        }
+        int rc = check_launch("kalman forward");
+        if (rc) return rc;
     } else {
         auto kern = kalman_forward_kernel<R, D_, L_>;
         size_t smem = FwdSmem<R, D_, L_>::bytes;
@@ -1247,7 +1277,7 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         { KPMS_LAUNCH("kalman_backprep_ops", st);
           backprep_ops_kernel<R, D_, L_><<<K, 128, 0, st>>>(Ab, Q, (R)jitter, ops); }
         { KPMS_LAUNCH("kalman_backprep_special", st);
-          backprep_special_kernel<R, D_, L_, (n > 32)><<<N, 128, 0, st>>>(stash_m, stash_S, mask, w_tape, N, T, GH); }
+          backprep_special_kernel<R, D_, L_, stash_rowpack<R, n>()><<<N, 128, 0, st>>>(stash_m, stash_S, mask, w_tape, N, T, GH); }
         // warps x CTAs per SM: 12 warps per SM as 6 x 2 when shared memory allows (one barrier per tile keeps the
         // six warps of a CTA on the same instruction-cache lines), else the largest CTA that fits
         constexpr size_t per_warp = PS::FPW * PS::frame_bytes + 16;
@@ -1371,7 +1401,7 @@ extern "C" {
 
 size_t kpms_kalman_workspace_bytes(int dtype, int N, int T, int d, int L, int K) {
     size_t off[KW_END + 1];
-    const int C = kalman_chunks(N, T, d, L, false), Cb = kalman_chunks(N, T, d, L, true);
+    const int C = kalman_chunks(N, T, d, L, false, dtype == 0), Cb = kalman_chunks(N, T, d, L, true, dtype == 0);
     if (dtype == 0) kalman_ws_layout<float>(N, T, d, L, K, C, Cb, off);
     else kalman_ws_layout<double>(N, T, d, L, K, C, Cb, off);
     return off[KW_END];

@@ -185,7 +185,7 @@ kalman_backprep_split_kernel(const R* __restrict__ stash_m, const R* __restrict_
     constexpr int n = P::n, NO = P::NO, LA = P::LA, FPW = P::FPW, VEC = P::VEC, DP = P::DP, NP = P::NP;
     constexpr int DV = DP / VEC, NV = NP / VEC;
     constexpr int RECS = PrepSmem<R, D_, L_>::RECS;
-    constexpr bool ROWPACK = n > 32;                  // packing of the filter's covariance record (see kalman_rows2.cuh)
+    constexpr bool ROWPACK = stash_rowpack<R, n>();   // packing of the filter's covariance record (see kalman_rows2.cuh)
     static_assert(L_ >= 2 && D_ <= 32, "two-stage form needs shifted blocks and one warp per frame group");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -25,6 +25,7 @@ ap.add_argument("--frames", type=int, default=800_000)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--quick", action="store_true")
 ap.add_argument("--new", action="store_true")
+ap.add_argument("--dims", default="", help="comma-separated latent dimensions: only those rows (K = 100, T = 10 000)")
 a = ap.parse_args()
 
 base = dict(T=10_000, K=100, d=10)
@@ -35,6 +36,8 @@ if a.quick:
     grid = [dict(base, T=1_000), base, dict(base, K=25), dict(base, d=4)]
 if a.new:
     grid = [dict(base, K=K) for K in (250, 500)] + [dict(base, d=d) for d in (6, 8, 12)]
+if a.dims:
+    grid = [dict(base, d=int(d)) for d in a.dims.split(",")]
 
 
 def timed(fn, reps):
