@@ -1,4 +1,5 @@
 // Error reporting and version for the C-ABI (include/kpms_b200.h).
+#include <cstdlib>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -57,7 +58,12 @@ LaunchScope::~LaunchScope() {
 }
 
 // ---- time-chunking configuration (common.cuh) ----
-static ChunkConfig g_chunk = {0, 64, 2e-5, 1e-10, 1e-12};
+// KPMS_WARMUP=<steps> overrides the default warm-up of the verified time chunks (experiments; kpms_set_time_chunking wins)
+static ChunkConfig g_chunk = [] {
+    ChunkConfig c = {0, 64, 2e-5, 1e-10, 1e-12};
+    if (const char* e = getenv("KPMS_WARMUP")) { const int w = atoi(e); if (w >= 0 && w <= 1024) c.warmup = w; }
+    return c;
+}();
 ChunkConfig chunk_config() { return g_chunk; }
 int chunks_for(int N, int slots, int len, int warmup) {
     int C = g_chunk.chunks > 0 ? g_chunk.chunks : slots / (N > 0 ? N : 1);

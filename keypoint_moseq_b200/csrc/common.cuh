@@ -350,18 +350,24 @@ __host__ __device__ inline ChunkRange chunk_range(int vlen, int len, int C, int 
     return r;
 }
 
-// vlen[nn] = number of leading steps i in [0, len) with mask[nn][off + i] != 0
+// vlen[nn] = number of leading steps i in [0, len) with mask[nn][off + i] != 0;
+// vlen[gridDim.x + nn] = one past the LAST unmasked step (= vlen for a chain whose only masked steps are its tail)
 static __global__ void __launch_bounds__(256)
 valid_len_kernel(const int* __restrict__ mask, int T, int off, int len, int* __restrict__ vlen) {
-    __shared__ int first;
+    __shared__ int first, last;
     const int nn = blockIdx.x;
-    if (threadIdx.x == 0) first = len;
+    if (threadIdx.x == 0) { first = len; last = 0; }
     __syncthreads();
     const int* mk = mask + (size_t)nn * T + off;
-    for (int i = threadIdx.x; i < len; i += blockDim.x)
-        if (mk[i] == 0) { atomicMin(&first, i); break; }
+    int mine_first = len, mine_last = 0;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        if (mk[i] == 0) { if (mine_first == len) mine_first = i; }
+        else mine_last = i + 1;
+    }
+    atomicMin(&first, mine_first);
+    atomicMax(&last, mine_last);
     __syncthreads();
-    if (threadIdx.x == 0) vlen[nn] = first;
+    if (threadIdx.x == 0) { vlen[nn] = first; vlen[gridDim.x + nn] = last; }
 }
 
 // Boundary check for real-valued states of `rec` numbers per boundary, in two blocks with their

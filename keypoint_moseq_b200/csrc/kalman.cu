@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(32 * WARPS, (sizeof(R) == 4 ? 2 : 1))
 kalman_forward_rows_kernel(const R* __restrict__ info, const int* __restrict__ mask, const int* __restrict__ z,
                            const R* __restrict__ Ab, const R* __restrict__ Q, R jitter, int N, int T,
                            R* __restrict__ stash_m, R* __restrict__ stash_S, int C, int W,
-                           const int* __restrict__ vlen, const int* __restrict__ dirty,
+                           const int* __restrict__ vlen, const int* __restrict__ vend, const int* __restrict__ dirty,
                            R* __restrict__ bnd_warm, R* __restrict__ bnd_end) {
     typedef FwdRowsSmem<R, D_, L_> SM;
     typedef typename Vec16<R>::type VecT;
@@ -630,9 +630,11 @@ kalman_forward_rows_kernel(const R* __restrict__ info, const int* __restrict__ m
         ba[q] = a;
         bc[q] = c;
     }
-    const int i0 = cr.start, i1 = cr.end;
+    // frames from vend[nn] on are all masked: they carry (m, P) unchanged, so the walk stops there and the state is
+    // stored once at the terminal frame (a short row's last chunk used to step through thousands of padded frames)
+    const int i0 = cr.start, i1 = cr.end, i_stop = min(i1, vend[nn]);
     auto issue_info = [&](int i) {
-        if (i < i1)
+        if (i < i_stop)
             for (int c = lane; c < RECI * (int)sizeof(R) / 16; c += 32)
                 cp_async_16(reinterpret_cast<char*>(ring + (i % STAGES) * RECI) + 16 * c,
                             reinterpret_cast<const char*>(inf_g + (size_t)i * RECI) + 16 * c);
@@ -656,7 +658,7 @@ kalman_forward_rows_kernel(const R* __restrict__ info, const int* __restrict__ m
     for (int s2 = 0; s2 < STAGES - 1; ++s2) issue_info(i0 + s2);
     int mk_cur = mk[i0];
     bool changed_prev = false;
-    for (int i = i0; i < i1; ++i) {
+    for (int i = i0; i < i_stop; ++i) {
         const bool last = (i == Tx - 1);
         const bool keep = (i >= cr.begin);
         const int mk_next = (i + 1 < Tx) ? mk[i + 1] : 0;
@@ -936,6 +938,13 @@ kalman_forward_rows_kernel(const R* __restrict__ info, const int* __restrict__ m
         __syncwarp();
     }
     asm volatile("cp.async.wait_all;\n" ::);
+    if (i1 == Tx && i_stop < Tx && act) {            // masked terminal frame: the carried state (Tx - 1 >= cr.begin)
+        sm_g[(size_t)(Tx - 1) * SMS + lane] = m;
+        R* so = sS_g + (size_t)(Tx - 1) * SSS + lane;
+#pragma unroll
+        for (int c = 0; c < n; ++c)
+            if (c <= lane) so[col_start(n, c) - c] = p[c];
+    }
     if (i1 < Tx && act) {                            // the state handed to the next chunk
         R* be = bnd_end + ((size_t)nn * C + ck + 1) * BREC;
         be[lane] = m;
@@ -1125,7 +1134,7 @@ static void kalman_ws_layout(int N, int T, int d, int L, int K, int C, int Cb, s
     const size_t brec = n + n * n, nb = (size_t)N * (C + 1), nbb = (size_t)N * (Cb + 1);
     const size_t vec = 16 / sizeof(R), dp = (d + vec - 1) / vec * vec;
     const size_t ops = n * dp + dp + d * dp;             // PrepSplit::OPS: per-state operator block of the backward preparation
-    size_t sz[KW_END] = {256, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4, fr * rec * sizeof(R), fr * stash_m_stride((int)n) * sizeof(R),
+    size_t sz[KW_END] = {256, (size_t)N * 8, (size_t)N * 4, (size_t)N * 4, fr * rec * sizeof(R), fr * stash_m_stride((int)n) * sizeof(R),
                          fr * stash_S_stride((int)n) * sizeof(R), fr * recs * sizeof(R), nb * brec * sizeof(R), nb * brec * sizeof(R),
                          nbb * n * sizeof(R), nbb * n * sizeof(R), (size_t)K * ops * sizeof(R), (fr * n + 4) * sizeof(R)};
     off[0] = 0;
@@ -1172,10 +1181,8 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
     const long long frames = (long long)N * Tx;
     if (stage != 1) {
         cudaMemsetAsync(diag, 0, 256, st);
-        if (C > 1 || Cb > 1) {
-            KPMS_LAUNCH("valid_len", st);
-            valid_len_kernel<<<N, 256, 0, st>>>(mask, T, L_ - 1, Tx, vlen);
-        }
+        { KPMS_LAUNCH("valid_len", st);
+          valid_len_kernel<<<N, 256, 0, st>>>(mask, T, L_ - 1, Tx, vlen); }
     }
     if (stage != 2) {
         constexpr int TPB = ObsInfoCfg<D_>::template threads<R>();
@@ -1204,17 +1211,17 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         if (C > 1) {
             { KPMS_LAUNCH("kalman_forward", st);
               kern<<<(int)(((long long)N * C + WARPS - 1) / WARPS), 32 * WARPS, smem, st>>>(
-                  info, mask, z, Ab, Q, (R)jitter, N, T, stash_m, stash_S, C, W, vlen, nullptr, bfw, bfe); }
+                  info, mask, z, Ab, Q, (R)jitter, N, T, stash_m, stash_S, C, W, vlen, vlen + N, nullptr, bfw, bfe); }
             { KPMS_LAUNCH("kalman_forward_check", st);
               cudaMemsetAsync(dirty_f, 0, (size_t)N * sizeof(int), st);
               boundary_check_kernel<R><<<dim3(C - 1, N), 128, 0, st>>>(bfw, bfe, vlen, Tx, C, W, 1, n, n + n * n, tol, dirty_f, diag); }
             { KPMS_LAUNCH("kalman_forward_rerun", st);       // exits at once for chains whose boundaries agree
               kern<<<(N + WARPS - 1) / WARPS, 32 * WARPS, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, N, T, stash_m,
-                                                                    stash_S, 1, 0, nullptr, dirty_f, bfw, bfe); }
+                                                                    stash_S, 1, 0, nullptr, vlen + N, dirty_f, bfw, bfe); }
         } else {
             KPMS_LAUNCH("kalman_forward", st);
             kern<<<(N + WARPS - 1) / WARPS, 32 * WARPS, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, N, T, stash_m,
-                                                                  stash_S, 1, 0, nullptr, nullptr, bfw, bfe);
+                                                                  stash_S, 1, 0, nullptr, vlen + N, nullptr, bfw, bfe);
         }
         int rc = check_launch("kalman forward");
         if (rc) return rc;
@@ -1227,17 +1234,17 @@ static int kalman_launch(const R* Y, const int* mask, const R* v, const R* h, co
         if (C > 1) {
             { KPMS_LAUNCH("kalman_forward", st);
               kern<<<(int)(((long long)N * C + TEAMS - 1) / TEAMS), 64 * TEAMS, smem, st>>>(
-                  info, mask, z, Ab, Q, (R)jitter, N, T, stash_m, stash_S, C, W, vlen, nullptr, bfw, bfe); }
+                  info, mask, z, Ab, Q, (R)jitter, N, T, stash_m, stash_S, C, W, vlen, vlen + N, nullptr, bfw, bfe); }
             { KPMS_LAUNCH("kalman_forward_check", st);
               cudaMemsetAsync(dirty_f, 0, (size_t)N * sizeof(int), st);
               boundary_check_kernel<R><<<dim3(C - 1, N), 128, 0, st>>>(bfw, bfe, vlen, Tx, C, W, 1, n, n + n * n, tol, dirty_f, diag); }
             { KPMS_LAUNCH("kalman_forward_rerun", st);       // exits at once for chains whose boundaries agree
               kern<<<(N + TEAMS - 1) / TEAMS, 64 * TEAMS, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, N, T, stash_m,
-                                                                    stash_S, 1, 0, nullptr, dirty_f, bfw, bfe); }
+                                                                    stash_S, 1, 0, nullptr, vlen + N, dirty_f, bfw, bfe); }
         } else {
             KPMS_LAUNCH("kalman_forward", st);
             kern<<<(N + TEAMS - 1) / TEAMS, 64 * TEAMS, smem, st>>>(info, mask, z, Ab, Q, (R)jitter, N, T, stash_m,
-                                                                  stash_S, 1, 0, nullptr, nullptr, bfw, bfe);
+                                                                  stash_S, 1, 0, nullptr, vlen + N, nullptr, bfw, bfe);
         }
         int rc = check_launch("kalman forward");
         if (rc) return rc;

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(64 * TEAMS, 1)
 kalman_forward_rows2w_kernel(const R* __restrict__ info, const int* __restrict__ mask, const int* __restrict__ z,
                              const R* __restrict__ Ab, const R* __restrict__ Q, R jitter, int N, int T,
                              R* __restrict__ stash_m, R* __restrict__ stash_S, int C, int W,
-                             const int* __restrict__ vlen, const int* __restrict__ dirty,
+                             const int* __restrict__ vlen, const int* __restrict__ vend, const int* __restrict__ dirty,
                              R* __restrict__ bnd_warm, R* __restrict__ bnd_end) {
     typedef FwdRows2wSmem<R, D_, L_> SM;
     typedef typename Vec16<R>::type VecT;
@@ -79,9 +79,11 @@ kalman_forward_rows2w_kernel(const R* __restrict__ info, const int* __restrict__
         ba[q] = a;
         bc[q] = c;
     }
-    const int i0 = cr.start, i1 = cr.end;
+    // frames from vend[nn] on are all masked: they carry (m, P) unchanged, so the walk stops there and the state is
+    // stored once at the terminal frame (a short row's last chunk used to step through thousands of padded frames)
+    const int i0 = cr.start, i1 = cr.end, i_stop = min(i1, vend[nn]);
     auto issue_info = [&](int i) {
-        if (i < i1)
+        if (i < i_stop)
             for (int c = tl; c < RECI * (int)sizeof(R) / 16; c += TL)
                 cp_async_16(reinterpret_cast<char*>(ring + (i % STAGES) * RECI) + 16 * c,
                             reinterpret_cast<const char*>(inf_g + (size_t)i * RECI) + 16 * c);
@@ -105,7 +107,7 @@ kalman_forward_rows2w_kernel(const R* __restrict__ info, const int* __restrict__
     for (int s2 = 0; s2 < STAGES - 1; ++s2) issue_info(i0 + s2);
     int mk_cur = mk[i0];
     bool changed_prev = false;
-    for (int i = i0; i < i1; ++i) {
+    for (int i = i0; i < i_stop; ++i) {
         const bool last = (i == Tx - 1);
         const bool keep = (i >= cr.begin);
         const int mk_next = (i + 1 < Tx) ? mk[i + 1] : 0;
@@ -374,6 +376,13 @@ kalman_forward_rows2w_kernel(const R* __restrict__ info, const int* __restrict__
         team_sync(bar);
     }
     asm volatile("cp.async.wait_all;\n" ::);
+    if (i1 == Tx && i_stop < Tx && act) {            // masked terminal frame: the carried state (Tx - 1 >= cr.begin)
+        sm_g[(size_t)(Tx - 1) * SMS + tl] = m;
+        R* so = sS_g + (size_t)(Tx - 1) * SSS + tl;
+#pragma unroll
+        for (int c = 0; c < n; ++c)
+            if (c <= tl) so[col_start(n, c) - c] = p[c];
+    }
     if (i1 < Tx && act) {                            // the state handed to the next chunk
         R* be = bnd_end + ((size_t)nn * C + ck + 1) * BREC;
         be[tl] = m;
