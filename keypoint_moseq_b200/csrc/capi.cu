@@ -1,4 +1,5 @@
 // Error reporting and version for the C-ABI (include/kpms_b200.h).
+#include <algorithm>
 #include <cstdlib>
 #include <atomic>
 #include <cstdarg>
@@ -65,12 +66,29 @@ static ChunkConfig g_chunk = [] {
     return c;
 }();
 ChunkConfig chunk_config() { return g_chunk; }
+// Chunks per chain for N chains when `slots` chunk tasks are resident on the device at once.  Tasks are equally long,
+// so the kernel runs in ceil(N C / slots) waves of (len / C + warm-up) steps: C minimises that product.  With fewer
+// chains than slots this is the old rule (one wave, C = slots / N: C2 -> 29); with about as many or more chains than
+// slots (C4 on one GPU: 1200 chains, 2368 filter slots, 1184 HMM slots) one chunk per chain would leave half of a
+// wave empty or spill a few tasks into a second full-length wave, and several shorter waves win.
 int chunks_for(int N, int slots, int len, int warmup) {
-    int C = g_chunk.chunks > 0 ? g_chunk.chunks : slots / (N > 0 ? N : 1);
-    if (warmup > 0 && C > len / (4 * warmup)) C = len / (4 * warmup);
-    if (C > KPMS_MAX_CHUNKS) C = KPMS_MAX_CHUNKS;
-    if (C < 1) C = 1;
-    return C;
+    if (g_chunk.chunks > 0) return g_chunk.chunks > KPMS_MAX_CHUNKS ? KPMS_MAX_CHUNKS : g_chunk.chunks;
+    if (N < 1) N = 1;
+    if (slots < 1) slots = 1;
+    int cmax = warmup > 0 ? len / (4 * warmup) : len;
+    if (cmax > KPMS_MAX_CHUNKS) cmax = KPMS_MAX_CHUNKS;
+    if (cmax < 1) cmax = 1;
+    auto cost_of = [&](int C) {
+        const long long waves = ((long long)N * C + slots - 1) / slots;
+        const long long steps = (len + C - 1) / C + (C > 1 ? warmup : 0);
+        return waves * steps;
+    };
+    long long best_cost = cost_of(1);
+    for (int C = 2; C <= cmax && (long long)N * C <= 64LL * slots; ++C) best_cost = std::min(best_cost, cost_of(C));
+    // the smallest C within 3 % of the optimum: the wave model ignores tails, so fewer, longer waves win a near-tie
+    for (int C = 1; C <= cmax; ++C)
+        if (cost_of(C) * 100 <= best_cost * 103) return C;
+    return 1;
 }
 
 }  // namespace kpms
