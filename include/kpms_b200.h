@@ -56,6 +56,10 @@ int kpms_profile_report(char* buf, size_t cap);
  * boundary discrepancy (float bits), the number of chains re-run forward, and the same two for
  * the backward recursion. */
 void kpms_set_time_chunking(int chunks, int warmup, double tol32, double tol64);
+/* The chunk count the library picks for N chains of `len` steps when `slots` chunk tasks are resident at once: the C
+ * that minimises ceil(N C / slots) * (len / C + warmup), smallest C within 3 % of the optimum, at most len / (4 warmup);
+ * the value forced by kpms_set_time_chunking when there is one.  Host-only (planning / tests). */
+int kpms_plan_chunks(int N, int slots, int len, int warmup);
 
 /* ---- discrete states: jax_moseq.models.arhmm.resample_discrete_stateseqs
  *      (utils.autoregression.ar_log_likelihood + utils.distributions.sample_hmm_stateseq);

@@ -25,6 +25,7 @@ SIGNATURES = {
     "kpms_profile_enable": (None, [_i]),
     "kpms_profile_report": (_i, [C.c_char_p, _sz]),
     "kpms_set_time_chunking": (None, [_i, _i, _d, _d]),
+    "kpms_plan_chunks": (_i, [_i, _i, _i, _i]),
     "kpms_hmm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "kpms_hmm_weights_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "kpms_ar_loglik": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -101,6 +101,8 @@ void kpms_set_time_chunking(int chunks, int warmup, double tol32, double tol64) 
     if (tol64 > 0) kpms::g_chunk.tol64 = tol64;
 }
 
+int kpms_plan_chunks(int N, int slots, int len, int warmup) { return kpms::chunks_for(N, slots, len, warmup); }
+
 long long kpms_launch_count(void) { return kpms::g_launches.load(); }
 
 void kpms_profile_enable(int on) { kpms::g_profile = on != 0; }

@@ -54,3 +54,37 @@ def test_supported_dims_table_and_up_front_validation():
         _lib.check_model_dims(9, 2, 100)
     with pytest.raises(_lib.KpmsError, match="num_states"):
         _lib.check_model_dims(10, 3, 0)
+
+
+def test_chunk_planner_minimises_waves_times_steps():
+    """csrc/capi.cu chunks_for through kpms_plan_chunks: with fewer chains than task slots one wave of slots / N chunks
+    (C2: 29 filter chunks); with about as many chains as slots (C4 on one GPU: 1200 chains, 2368 filter slots, 1184 HMM
+    slots) several shorter waves instead of one half-empty or two full-length ones; never beyond len / (4 warm-up);
+    always within 3 % of the brute-force optimum of the wave model; a forced count wins."""
+    import __graft_entry__
+    __graft_entry__.build()
+    from keypoint_moseq_b200 import _lib
+    lib = _lib.load()
+
+    def cost(N, slots, length, W, C):
+        return -(-N * C // slots) * (-(-length // C) + (W if C > 1 else 0))
+
+    assert lib.kpms_plan_chunks(80, 148 * 16, 10028, 64) == 29
+    assert lib.kpms_plan_chunks(80, 148 * 8, 10027, 64) == 14
+    assert lib.kpms_plan_chunks(1200, 148 * 16, 10028, 64) == 7
+    assert lib.kpms_plan_chunks(1200, 148 * 8, 10027, 64) == 7
+    assert lib.kpms_plan_chunks(1, 148 * 16, 100, 64) == 1                       # too short to cut
+    for N in (1, 4, 80, 150, 300, 550, 600, 1200, 5000):
+        for slots in (148 * 4, 148 * 8, 148 * 12, 148 * 16):
+            for length in (500, 10028, 100_000):
+                C = lib.kpms_plan_chunks(N, slots, length, 64)
+                cmax = max(1, length // 256)
+                assert 1 <= C <= cmax
+                best = min(cost(N, slots, length, 64, c) for c in range(1, cmax + 1) if N * c <= 64 * slots or c == 1)
+                assert cost(N, slots, length, 64, C) * 100 <= best * 103, (N, slots, length, C)
+    _lib.set_time_chunking(chunks=3)
+    try:
+        assert lib.kpms_plan_chunks(1200, 148 * 16, 10028, 64) == 3
+    finally:
+        _lib.set_time_chunking(chunks=0)
+    assert lib.kpms_plan_chunks(1200, 148 * 16, 10028, 64) == 7
