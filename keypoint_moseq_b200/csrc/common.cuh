@@ -130,12 +130,20 @@ __device__ __forceinline__ bool gamma_accept(double x, double u, double dd, doub
     return false;
 }
 
+// Marsaglia-Tsang constants of a shape parameter (a kernel whose draws all share one shape computes them once)
+struct GammaShape {
+    double a, dd, c;
+    bool boost;
+    __host__ __device__ explicit GammaShape(double a_) : a(a_), boost(a_ < 1.0) {
+        dd = (boost ? a_ + 1.0 : a_) - 1.0 / 3.0;
+        c = 1.0 / sqrt(9.0 * dd);
+    }
+};
+
 template <typename R>
-__device__ inline double gamma_draw(double a, const R* tape, Philox& g) {
-    const bool boost = a < 1.0;
-    const double a1 = boost ? a + 1.0 : a;
-    const double dd = a1 - 1.0 / 3.0;
-    const double c = 1.0 / sqrt(9.0 * dd);
+__device__ inline double gamma_draw(const GammaShape& sh, const R* tape, Philox& g) {
+    const bool boost = sh.boost;
+    const double a = sh.a, dd = sh.dd, c = sh.c;
     double out = dd;
     if (tape) {
 #pragma unroll 1
@@ -168,6 +176,11 @@ __device__ inline double gamma_draw(double a, const R* tape, Philox& g) {
         }
     }
     return out;
+}
+
+template <typename R>
+__device__ inline double gamma_draw(double a, const R* tape, Philox& g) {
+    return gamma_draw<R>(GammaShape(a), tape, g);
 }
 
 // ---------------------------------------------------------------------------

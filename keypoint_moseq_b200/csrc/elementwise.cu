@@ -16,11 +16,13 @@ template <typename R, int DK>
 __global__ void __launch_bounds__(256)
 scales_kernel(const R* __restrict__ Y, const R* __restrict__ x, const R* __restrict__ v,
               const R* __restrict__ h, const R* __restrict__ Ct, const R* __restrict__ sigmasq,
-              const R* __restrict__ prior, double nu_s, const R* __restrict__ g_tape, SeedArg seed,
+              const R* __restrict__ prior, double nu_s, GammaShape shape, const R* __restrict__ g_tape, SeedArg seed,
               long long frames, int k, int d, R* __restrict__ s_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R* Cs = reinterpret_cast<R*>(smem_raw);
+    double* isg = reinterpret_cast<double*>(Cs + align_up((size_t)k * DK * (d + 1), 2));     // 1 / sigmasq per keypoint
     for (int i = threadIdx.x; i < k * DK * (d + 1); i += blockDim.x) Cs[i] = Ct[i];
+    for (int i = threadIdx.x; i < k; i += blockDim.x) isg[i] = 1.0 / (double)sigmasq[i];
     __syncthreads();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= frames * k) return;
@@ -45,9 +47,11 @@ scales_kernel(const R* __restrict__ Y, const R* __restrict__ x, const R* __restr
         R df = Y[e * DK + c] - yb[c] - v[ft * DK + c];
         sq = fma(df, df, sq);
     }
-    const double variance = (double)sq / (double)sigmasq[j] + nu_s * (double)prior[e];
+    // (the Marsaglia-Tsang constants of the shared shape arrive as a kernel argument and 1 / sigmasq sits in shared
+    // memory: one double division per element, the final one, instead of three and a square root)
+    const double variance = fma((double)sq, isg[j], nu_s * (double)prior[e]);
     Philox gen(seed, KPMS_STREAM_S, (uint64_t)e);
-    const double gam = gamma_draw<R>(0.5 * (nu_s + KPMS_OBS_DOF(DK)), g_tape ? g_tape + e * KPMS_GAMMA_TAPE : nullptr, gen);
+    const double gam = gamma_draw<R>(shape, g_tape ? g_tape + e * KPMS_GAMMA_TAPE : nullptr, gen);
     s_out[e] = (R)(variance / (2.0 * gam));
 }
 
@@ -386,16 +390,18 @@ static int scales_impl(const void* Y, const void* x, const void* v, const void* 
                        int N, int T, int k, int Dk, int d, void* s_out, cudaStream_t st) {
     const long long frames = (long long)N * T;
     const long long elems = frames * k;
-    size_t smem = (size_t)k * Dk * (d + 1) * sizeof(R);
+    size_t smem = align_up((size_t)k * Dk * (d + 1), 2) * sizeof(R) + (size_t)k * sizeof(double);
     int blocks = (int)((elems + 255) / 256);
     KPMS_LAUNCH("resample_scales", st);
     if (Dk == 2)
         scales_kernel<R, 2><<<blocks, 256, smem, st>>>((const R*)Y, (const R*)x, (const R*)v, (const R*)h, (const R*)Ct,
-                                                       (const R*)sigmasq, (const R*)prior, nu_s, (const R*)g_tape, seed,
+                                                       (const R*)sigmasq, (const R*)prior, nu_s,
+                                                       GammaShape(0.5 * (nu_s + KPMS_OBS_DOF(2))), (const R*)g_tape, seed,
                                                        frames, k, d, (R*)s_out);
     else if (Dk == 3)
         scales_kernel<R, 3><<<blocks, 256, smem, st>>>((const R*)Y, (const R*)x, (const R*)v, (const R*)h, (const R*)Ct,
-                                                       (const R*)sigmasq, (const R*)prior, nu_s, (const R*)g_tape, seed,
+                                                       (const R*)sigmasq, (const R*)prior, nu_s,
+                                                       GammaShape(0.5 * (nu_s + KPMS_OBS_DOF(3))), (const R*)g_tape, seed,
                                                        frames, k, d, (R*)s_out);
     else return set_error(-3, "resample_scales: keypoint dimension must be 2 or 3, got %d", Dk);
     return check_launch("resample_scales");

@@ -520,11 +520,34 @@ def _sweep_device(Y, mask, prior, st, pr, hypparams, seed64, seed_loc, seed_dev,
             import torch.distributed as dist
             dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
         gram, counts, obsvar = unpack_statistics(packed, K, d, L)
-        pr["betas"], pr["pi"] = resample_hdp_transitions(
-            counts, pr["betas"], th["alpha"], th["kappa"], th["gamma"], seed64,
-            tp.get("u_crp"), tp.get("u_bin"), tp.get("g_beta"), tp.get("g_pi"), seed_dev=seed_dev)
+        # The transition draw (five short kernels on K CTAs) and the AR draw (K warps) are independent and each leaves
+        # most of the device idle: the former runs on a second stream beside the latter (KPMS_PARAM_FORK=0: in line).
+        trans_side = _side_stream(st["x"].device, "trans") if (_param_fork_enabled() and st["x"].is_cuda) else None
+        if trans_side is not None:
+            main = torch.cuda.current_stream()
+            fork_ev = torch.cuda.Event()
+            fork_ev.record(main)
+            trans_side.wait_event(fork_ev)
+            betas_in = pr["betas"]
+            with torch.cuda.stream(trans_side):
+                pr["betas"], pr["pi"] = resample_hdp_transitions(
+                    counts, betas_in, th["alpha"], th["kappa"], th["gamma"], seed64,
+                    tp.get("u_crp"), tp.get("u_bin"), tp.get("g_beta"), tp.get("g_pi"), seed_dev=seed_dev)
+                trans_done = torch.cuda.Event()
+                trans_done.record(trans_side)
+            for t_ in (counts, betas_in):                    # read on the side stream, owned by the main one
+                if isinstance(t_, torch.Tensor) and t_.is_cuda:
+                    t_.record_stream(trans_side)
+            for t_ in (pr["betas"], pr["pi"]):               # and the other way round
+                t_.record_stream(main)
+        else:
+            pr["betas"], pr["pi"] = resample_hdp_transitions(
+                counts, pr["betas"], th["alpha"], th["kappa"], th["gamma"], seed64,
+                tp.get("u_crp"), tp.get("u_bin"), tp.get("g_beta"), tp.get("g_pi"), seed_dev=seed_dev)
         pr["Ab"], pr["Q"] = resample_ar_params(gram, ah["nu_0"], ah["S_0"], ah["M_0"], ah["K_0"], seed64,
                                                tp.get("w_G"), tp.get("w_B"), tp.get("g_chi"), seed_dev=seed_dev)
+        if trans_side is not None:
+            torch.cuda.current_stream().wait_event(trans_done)
         if obs is not None:
             pr["sigmasq"] = resample_obs_variance(obsvar, oh["nu_sigma"], oh["sigmasq_0"], obs[0].shape[3], seed64,
                                                   tp.get("g_sig"), seed_dev=seed_dev)
@@ -615,6 +638,11 @@ def graph_kernel_launches():
 def graphs_enabled():
     import os
     return os.environ.get("KPMS_GRAPH", "1") != "0"
+
+
+def _param_fork_enabled():
+    import os
+    return os.environ.get("KPMS_PARAM_FORK", "1") != "0"
 
 
 def _overlap_enabled():
