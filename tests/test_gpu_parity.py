@@ -307,6 +307,39 @@ def test_full_sweep_with_mask_holes(dtype, tol, chunks, chunking):
     assert np.abs(_np(out["states"]["s"]) / st_ref["s"] - 1).max() < tol * 10
 
 
+def _odd_problem(case):
+    if case == "six_valid_frames":                       # a row barely above the reference's min_fragment_length = 4
+        data, _, model = small_problem(seed=32, d=4, L=3, K=8, k=5, D=2, kappa=1e2)
+        m = data["mask"].copy()
+        m[1, 6:] = 0
+        return dict(data, mask=m), model
+    if case == "one_short_chain":                        # N = 1, T = 70
+        data, _, model = small_problem(seed=33, recordings=1, frames=40, seg_length=40, d=4, L=3, K=8, k=5, D=2, kappa=1e2)
+        return data, model
+    data, _, model = small_problem(seed=34, d=10, L=3, K=20, k=25, D=3, kappa=1e2)       # 25 keypoints in 3D
+    return data, model
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, F64_TOL), (torch.float32, F32_TOL)])
+@pytest.mark.parametrize("case", ["six_valid_frames", "one_short_chain", "many_keypoints_3d"])
+def test_full_sweep_odd_shapes(case, dtype, tol):
+    """Edges of the input space: a row with six valid frames, a single 70-frame chain, 25 keypoints in 3D (the
+    shared-memory staging of the per-frame kernels scales with k D)."""
+    g = _gibbs()
+    data, model = _odd_problem(case)
+    tape = tape_for(data, model)
+    data, model, tape = _cast_problem(data, model, tape, dtype)
+    st_ref, pr_ref, _ = oracle_sweep(data, model, tape)
+    dd, dm = _to_dev(data, model, dtype)
+    out = g.resample_model(dd, **dm, draws=tape)
+    assert np.array_equal(_np(out["states"]["z"]), st_ref["z"])
+    for key in ("Ab", "Q", "betas", "pi"):
+        assert rel_err(_np(out["params"][key]), pr_ref[key]) < max(tol, 1e-7), key
+    assert rel_err(_np(out["states"]["x"]), st_ref["x"]) < tol
+    assert rel_err(_np(out["states"]["v"]), st_ref["v"]) < tol
+    assert np.abs(_np(out["states"]["s"]) / st_ref["s"] - 1).max() < tol * 10
+
+
 def test_philox_sweeps_are_finite_and_reproducible():
     g = _gibbs()
     data, _, model = small_problem(seed=9, d=4, L=3, K=12, k=5, D=2, kappa=1e2, frames=600, seg_length=300)
