@@ -241,8 +241,21 @@ def test_full_sweep_wide_states(dtype, tol):
 
 
 def _compiled_pairs():
+    """(latent_dim, nlags) pairs listed in csrc/common.cuh - read from the source so that collecting the tests does
+    not need the built library (test_compiled_pairs_match_the_library checks the list against kpms_supported_dims)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "keypoint_moseq_b200", "csrc", "common.cuh")).read()
+    pairs = set()
+    for line in re.findall(r"#define\s+KPMS_DL_GROUP_\d+\(X\)(.*)", text):
+        pairs.update((int(a), int(b)) for a, b in re.findall(r"X\((\d+),\s*(\d+)\)", line))
+    return sorted(pairs)
+
+
+def test_compiled_pairs_match_the_library():
     from keypoint_moseq_b200 import _lib
-    return sorted(_lib.supported_dims())
+    assert _compiled_pairs() == sorted(_lib.supported_dims())
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, F64_TOL), (torch.float32, F32_TOL)])
