@@ -522,7 +522,10 @@ def _sweep_device(Y, mask, prior, st, pr, hypparams, seed64, seed_loc, seed_dev,
         gram, counts, obsvar = unpack_statistics(packed, K, d, L)
         # The transition draw (five short kernels on K CTAs) and the AR draw (K warps) are independent and each leaves
         # most of the device idle: the former runs on a second stream beside the latter (KPMS_PARAM_FORK=0: in line).
-        trans_side = _side_stream(st["x"].device, "trans") if (_param_fork_enabled() and st["x"].is_cuda) else None
+        # Single-process sweeps only: the fork was measured and validated without a process group (13.92 against
+        # 14.02 ms at C2); sharded sweeps, whose graph also holds the all-reduce, keep the in-line order.
+        trans_side = (_side_stream(st["x"].device, "trans")
+                      if (_param_fork_enabled() and group is None and st["x"].is_cuda) else None)
         if trans_side is not None:
             main = torch.cuda.current_stream()
             fork_ev = torch.cuda.Event()
