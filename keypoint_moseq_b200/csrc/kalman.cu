@@ -5,9 +5,12 @@
 //
 // The FFBS is split so that only the covariance recursion is serial:
 //   K1a obs_info      (parallel over frames)  J_t = C~' R_t^-1 C~ -> chol, r_t = C~' R_t^-1 (y~_t - d~)
-//   K1b forward       (serial, CTA per chain) covariance-form filter, stashes (m_t, P_t)
-//   K1c backprep      (parallel, warp/frame)  G_t = P_t A' P'^-1, chol(Sigma_t), h_t = m_t - G_t(A m_t + b) + L_t w_t
-//   K1d affine        (serial, warp per chain) xi_t = G_t xi_{t+1} + h_t
+//   K1b forward       (serial per (chain, time chunk)) covariance-form filter, stashes (m_t, P_t): one warp with a
+//                     covariance row per lane for n <= 32, a two-warp team for n <= 64 in float32
+//                     (kalman_rows_wide.cuh), the 256-thread shared-memory kernel otherwise
+//   K1c backprep      (parallel over frames)  G_t = P_t A' P'^-1, chol(Sigma_t), h_t = m_t - G_t(A m_t + b) + L_t w_t,
+//                     in the two-stage form of kalman_split.cuh (nlags = 1: kalman_rows2.cuh)
+//   K1d affine        (serial, warp per (chain, chunk)) xi_t = G_t xi_{t+1} + h_t
 // which draws exactly the sample mu_t + chol(Sigma_t) w_t of the sequential sampler.
 //
 // Frame index i = t - (L-1), i in [0, Tx), Tx = T - L + 1.  z[i] governs the transition i -> i+1.

@@ -1,9 +1,10 @@
-// K1c, register-blocked: backward preparation with TWO matrix rows per lane.
+// K1c, register-blocked one-stage form: backward preparation with TWO matrix rows per lane.  Round 1's default for
+// every shape; since round 2 the two-stage kernel (kalman_split.cuh) handles nlags >= 2 and this one nlags = 1.
 //
-// The one-row-per-lane kernel (kalman_backprep_rows_kernel) is bound by shared-memory operand
-// traffic: every FMA consumes one operand that another lane published, delivered by 16-byte
+// The one-row-per-lane kernel it replaced (kalman_backprep_rows_kernel, removed) was bound by shared-memory operand
+// traffic: every FMA consumed one operand that another lane published, delivered by 16-byte
 // broadcasts at two floats per lane per wavefront, so the shared-memory pipe (1 wavefront / clk)
-// saturates at half the FMA rate (ncu: 1 750 wavefronts per frame, 60 % of the run time).  Here a lane
+// saturated at half the FMA rate (ncu: 1 750 wavefronts per frame, 60 % of the run time).  Here a lane
 // owns rows gl and gl + NH (NH = ceil(n/2)) of its frame, so every broadcast operand feeds two FMAs,
 // and a warp carries FPW = 32 / GW frames (GW = lanes per frame, the power of two >= NH): n = 30 ->
 // 15 active lanes per frame, two frames per warp; n = 12 -> four frames per warp; n = 48 -> one.
