@@ -612,3 +612,28 @@ def test_npz_checkpoint_snapshots_are_appended_not_rewritten(tmp_path, monkeypat
     assert sorted(kio.load_hdf5(f)["model_snapshots"], key=int) == ["0", "5"]
     kio.save_hdf5(f, snap(7), "model_snapshots/7", exist_ok=True)
     assert sorted(kio.load_hdf5(f)["model_snapshots"], key=int) == ["0", "5", "7"]
+
+
+def test_async_host_copy_passes_host_trees_through():
+    """util.AsyncHostCopy without a device: host leaves pass through as NumPy arrays, the post-processing hook runs
+    on the settled tree, non-tensor leaves are untouched (the CUDA path is covered by
+    tests/test_gpu_fitting.py::test_async_checkpoints_write_the_same_snapshots)."""
+    import torch
+    from keypoint_moseq_b200.util import AsyncHostCopy
+    tree = {"states": {"x": torch.arange(6.0).reshape(2, 3), "z": torch.arange(4, dtype=torch.int32)},
+            "params": {"pi": np.eye(2)}, "seed": np.array([1, 2], np.uint32), "hypparams": {"kappa": 1e4, "name": "a"},
+            "list": [torch.ones(2), 3]}
+    seen = []
+
+    def post(host):
+        seen.append(True)
+        host["states"]["z"] = np.asarray(host["states"]["z"]).astype(np.int64)
+        return host
+
+    out = AsyncHostCopy(tree, post).result()
+    assert seen == [True]
+    assert isinstance(out["states"]["x"], np.ndarray) and out["states"]["z"].dtype == np.int64
+    np.testing.assert_array_equal(out["states"]["x"], np.arange(6.0).reshape(2, 3))
+    np.testing.assert_array_equal(out["params"]["pi"], np.eye(2))
+    assert out["hypparams"] == {"kappa": 1e4, "name": "a"} and out["list"][1] == 3
+    np.testing.assert_array_equal(out["list"][0], np.ones(2))
